@@ -1,0 +1,328 @@
+// C-ABI of libdge_b200.so (include/dge_b200.h) and the per-view orchestration that
+// replaces CudaRasterizer::Rasterizer::{forward,backward,apply_weights,markVisible}
+// (DGR/cuda_rasterizer/rasterizer_impl.cu:128-447).
+#include <cstdio>
+#include <cstring>
+#include "../../include/dge_b200.h"
+#include "common.cuh"
+
+namespace dge {
+
+static thread_local char g_err[512] = "";
+
+static int fail(const char* where, cudaError_t e) {
+  snprintf(g_err, sizeof(g_err), "dge_b200: %s: %s (%d)", where, cudaGetErrorString(e), (int)e);
+  return -(int)(e == cudaSuccess ? 1 : e);
+}
+static int fail_msg(const char* msg) {
+  snprintf(g_err, sizeof(g_err), "dge_b200: %s", msg);
+  return -1;
+}
+
+#define CK(where, expr)                               \
+  do {                                                \
+    cudaError_t _e = (expr);                          \
+    if (_e != cudaSuccess) return fail(where, _e);    \
+  } while (0)
+// debug=True in the reference = synchronise and check after every stage (auxiliary.h:166-173)
+#define STAGE(where, expr)                                                   \
+  do {                                                                       \
+    CK(where, (expr));                                                       \
+    if (debug) CK(where " (debug sync)", cudaStreamSynchronize(stream));     \
+  } while (0)
+
+// ------------------------------------------------------------------- carving -----
+template <typename T>
+static void take(char*& p, T*& out, size_t count) {
+  uintptr_t a = (reinterpret_cast<uintptr_t>(p) + 255) & ~uintptr_t(255);
+  out = reinterpret_cast<T*>(a);
+  p = reinterpret_cast<char*>(out + count);
+}
+
+size_t carve_geom(char* base, int P, GeomState* st) {
+  GeomState s;
+  char* p = base;
+  const size_t n = (size_t)P;
+  take(p, s.means2D, n);
+  take(p, s.conic_opacity, n);
+  take(p, s.rgb_depth, n);
+  take(p, s.rect, n);
+  take(p, s.clamped, n);
+  take(p, s.sort_key[0], n);
+  take(p, s.sort_key[1], n);
+  take(p, s.sort_val[0], n);
+  take(p, s.sort_val[1], n);
+  take(p, s.offsets, n);
+  take(p, s.block_sums, (n + 255) / 256 + 1);
+  take(p, s.counters, 64);
+  s.sort_ws_bytes = sort_workspace_bytes((uint32_t)P);
+  take(p, s.sort_ws, s.sort_ws_bytes / sizeof(uint32_t));
+  if (st) *st = s;
+  return (size_t)(p - base) + 256;
+}
+
+size_t carve_binning(char* base, int R, int width, int height, BinState* st) {
+  (void)width;
+  (void)height;
+  BinState s;
+  char* p = base;
+  const size_t n = (size_t)(R > 0 ? R : 1);
+  take(p, s.point_list, n);
+  take(p, s.tile_ids, n);
+  take(p, s.key_alt, n);
+  take(p, s.val_alt, n);
+  s.sort_ws_bytes = sort_workspace_bytes((uint32_t)n);
+  take(p, s.sort_ws, s.sort_ws_bytes / sizeof(uint32_t));
+  if (st) *st = s;
+  return (size_t)(p - base) + 256;
+}
+
+size_t carve_image(char* base, int width, int height, ImgState* st) {
+  ImgState s;
+  char* p = base;
+  const size_t N = (size_t)width * height;
+  const size_t T = (size_t)((width + DGE_TILE - 1) / DGE_TILE) * ((height + DGE_TILE - 1) / DGE_TILE);
+  take(p, s.final_T, N);
+  take(p, s.n_contrib, N);
+  take(p, s.ranges, T);
+  if (st) *st = s;
+  return (size_t)(p - base) + 256;
+}
+
+// Pinned word + event used to bring num_rendered to the host without draining the stream:
+// the wait covers preprocess only; the depth sort queued behind it keeps the GPU busy.
+struct HostSlot {
+  uint32_t* pinned = nullptr;
+  cudaEvent_t ev = nullptr;
+};
+static thread_local HostSlot g_slot;
+
+static cudaError_t ensure_slot() {
+  if (g_slot.pinned) return cudaSuccess;
+  cudaError_t e = cudaHostAlloc((void**)&g_slot.pinned, 64, cudaHostAllocDefault);
+  if (e != cudaSuccess) return e;
+  return cudaEventCreateWithFlags(&g_slot.ev, cudaEventDisableTiming);
+}
+
+static ViewParams make_view(int P, int D, int M, int width, int height, const float* viewmatrix,
+                            const float* projmatrix, const float* cam_pos, float tan_fovx,
+                            float tan_fovy, float scale_modifier) {
+  ViewParams vp;
+  vp.view = viewmatrix;
+  vp.proj = projmatrix;
+  vp.campos = cam_pos;
+  vp.tan_fovx = tan_fovx;
+  vp.tan_fovy = tan_fovy;
+  // rasterizer_impl.cu:190-191, host float arithmetic
+  vp.focal_y = height / (2.0f * tan_fovy);
+  vp.focal_x = width / (2.0f * tan_fovx);
+  vp.scale_modifier = scale_modifier;
+  vp.W = width;
+  vp.H = height;
+  vp.grid_x = (width + DGE_TILE - 1) / DGE_TILE;
+  vp.grid_y = (height + DGE_TILE - 1) / DGE_TILE;
+  vp.P = P;
+  vp.D = D;
+  vp.M = M;
+  return vp;
+}
+
+// Shared front half of forward and apply_weights: K1(/K13) .. K5.
+static int bin_view(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge_alloc_fn imageBuffer,
+                    void* ctx, const ViewParams& vp, const float* means3D, const float* shs,
+                    const float* colors_precomp, int colors_mode, const float* opacities,
+                    const float* scales, const float* rotations, const float* cov3D_precomp,
+                    bool prefiltered, int* radii, bool debug, cudaStream_t stream, GeomState& g,
+                    BinState& b, ImgState& img) {
+  if (vp.grid_x > 65535 || vp.grid_y > 65535) return fail_msg("image too large (tile grid > 65535)");
+  if (cov3D_precomp == nullptr && (scales == nullptr || rotations == nullptr))
+    return fail_msg("need scales+rotations or cov3D_precomp");
+  CK("pinned slot", ensure_slot());
+  char* gp = geometryBuffer(ctx, carve_geom(nullptr, vp.P, nullptr));
+  char* ip = imageBuffer(ctx, carve_image(nullptr, vp.W, vp.H, nullptr));
+  if (!gp || !ip) return fail_msg("scratch allocator returned NULL");
+  carve_geom(gp, vp.P, &g);
+  carve_image(ip, vp.W, vp.H, &img);
+  STAGE("preprocess", launch_preprocess(vp, means3D, scales, rotations, opacities, shs, cov3D_precomp,
+                                        colors_precomp, colors_mode, prefiltered, radii, g, stream));
+  CK("num_rendered copy", cudaMemcpyAsync(g_slot.pinned, g.counters, sizeof(uint32_t),
+                                          cudaMemcpyDeviceToHost, stream));
+  CK("event record", cudaEventRecord(g_slot.ev, stream));
+  STAGE("depth sort", launch_depth_sort(vp.P, g, stream));
+  CK("num_rendered wait", cudaEventSynchronize(g_slot.ev));
+  const uint32_t R = *g_slot.pinned;
+  if (R >= (1u << 30)) return fail_msg("num_rendered exceeds 2^30 instances");
+  char* bp = binningBuffer(ctx, carve_binning(nullptr, (int)R, vp.W, vp.H, nullptr));
+  if (!bp) return fail_msg("scratch allocator returned NULL");
+  carve_binning(bp, (int)R, vp.W, vp.H, &b);
+  STAGE("binning", launch_binning(vp, (int)R, g, b, img, stream));
+  return (int)R;
+}
+
+}  // namespace dge
+
+using namespace dge;
+
+extern "C" {
+
+const char* dge_last_error(void) { return g_err; }
+int dge_abi_version(void) { return 1; }
+
+size_t dge_geom_bytes(int P) { return carve_geom(nullptr, P, nullptr); }
+size_t dge_binning_bytes(int R, int width, int height) {
+  return carve_binning(nullptr, R, width, height, nullptr);
+}
+size_t dge_image_bytes(int width, int height) { return carve_image(nullptr, width, height, nullptr); }
+size_t dge_backward_scratch_bytes(int P) { return sizeof(float) * ACC_STRIDE * (size_t)P + 256; }
+
+int dge_rasterize_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer,
+                          dge_alloc_fn imageBuffer, void* alloc_ctx, int P, int D, int M,
+                          const float* background, int width, int height, const float* means3D,
+                          const float* shs, const float* colors_precomp, const float* opacities,
+                          const float* scales, float scale_modifier, const float* rotations,
+                          const float* cov3D_precomp, const float* viewmatrix,
+                          const float* projmatrix, const float* cam_pos, float tan_fovx,
+                          float tan_fovy, int prefiltered, float* out_color, float* out_depth,
+                          int* radii, int debug, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (width <= 0 || height <= 0) return fail_msg("empty image");
+  const size_t N = (size_t)width * height;
+  if (P == 0) {  // rasterize_points.cu:72: kernels skipped, outputs stay zero
+    CK("memset", cudaMemsetAsync(out_color, 0, 3 * N * sizeof(float), stream));
+    CK("memset", cudaMemsetAsync(out_depth, 0, N * sizeof(float), stream));
+    return 0;
+  }
+  if (shs == nullptr && colors_precomp == nullptr) return fail_msg("need shs or colors_precomp");
+  const ViewParams vp = make_view(P, D, M, width, height, viewmatrix, projmatrix, cam_pos, tan_fovx,
+                                  tan_fovy, scale_modifier);
+  GeomState g;
+  BinState b;
+  ImgState img;
+  const int R = bin_view(geometryBuffer, binningBuffer, imageBuffer, alloc_ctx, vp, means3D, shs,
+                         colors_precomp, colors_precomp ? 1 : 0, opacities, scales, rotations,
+                         cov3D_precomp, prefiltered != 0, radii, debug != 0, stream, g, b, img);
+  if (R < 0) return R;
+  STAGE("render forward",
+        launch_render_forward(vp, g, b, img, background, out_color, out_depth, stream));
+  return R;
+}
+
+int dge_rasterize_backward(dge_alloc_fn scratchBuffer, void* alloc_ctx, int P, int D, int M, int R,
+                           const float* background, int width, int height, const float* means3D,
+                           const float* shs, const float* colors_precomp, const float* scales,
+                           float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                           const float* viewmatrix, const float* projmatrix, const float* campos,
+                           float tan_fovx, float tan_fovy, const int* radii, char* geom_buffer,
+                           char* binning_buffer, char* image_buffer, const float* dL_dpix,
+                           float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+                           float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale,
+                           float* dL_drot, int debug, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (P == 0) return 0;
+  if (!dL_dmean2D || !dL_dmean3D) return fail_msg("dL_dmean2D and dL_dmean3D are required");
+  const ViewParams vp = make_view(P, D, M, width, height, viewmatrix, projmatrix, campos, tan_fovx,
+                                  tan_fovy, scale_modifier);
+  GeomState g;
+  BinState b;
+  ImgState img;
+  carve_geom(geom_buffer, P, &g);
+  carve_binning(binning_buffer, R, width, height, &b);
+  carve_image(image_buffer, width, height, &img);
+  const size_t acc_bytes = sizeof(float) * ACC_STRIDE * (size_t)P;
+  char* sp = scratchBuffer(alloc_ctx, acc_bytes + 256);
+  if (!sp) return fail_msg("scratch allocator returned NULL");
+  float* acc = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sp) + 255) & ~uintptr_t(255));
+  CK("memset acc", cudaMemsetAsync(acc, 0, acc_bytes, stream));
+  if (R > 0)
+    STAGE("render backward", launch_render_backward(vp, g, b, img, background, dL_dpix, acc, stream));
+  (void)colors_precomp;
+  STAGE("geometry backward",
+        launch_geom_backward(vp, means3D, scales, rotations, shs, cov3D_precomp, radii, g, acc,
+                             dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D,
+                             dL_dsh, dL_dscale, dL_drot, stream));
+  return 0;
+}
+
+int dge_apply_weights(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer,
+                      dge_alloc_fn imageBuffer, void* alloc_ctx, int P, int D, int M,
+                      const float* background, int width, int height, const float* means3D,
+                      const float* shs, float* weights, const float* opacities, const float* scales,
+                      float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                      const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                      float tan_fovx, float tan_fovy, int prefiltered, const float* image_weights,
+                      int* radii, int* cnt, int num_channels, int debug, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  (void)background;
+  (void)shs;
+  if (P == 0) return 0;
+  if (width <= 0 || height <= 0) return fail_msg("empty image");
+  if (num_channels < 1 || num_channels > 3) return fail_msg("Unsupported number of channels");
+  const ViewParams vp = make_view(P, D, M, width, height, viewmatrix, projmatrix, cam_pos, tan_fovx,
+                                  tan_fovy, scale_modifier);
+  GeomState g;
+  BinState b;
+  ImgState img;
+  // rasterizer_impl.cu:381-389: `weights` travels as colors_precomp, so SH is skipped (K13)
+  const int R = bin_view(geometryBuffer, binningBuffer, imageBuffer, alloc_ctx, vp, means3D, nullptr,
+                         nullptr, /*colors_mode=*/2, opacities, scales, rotations, cov3D_precomp,
+                         prefiltered != 0, radii, debug != 0, stream, g, b, img);
+  if (R < 0) return R;
+  if (R > 0)
+    STAGE("apply_weights blend", launch_apply_weights_render(vp, g, b, img, weights, cnt,
+                                                             image_weights, num_channels, stream));
+  return R;
+}
+
+int dge_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream_) {
+  if (P == 0) return 0;
+  CK("mark_visible",
+     launch_mark_visible(P, means3D, viewmatrix, projmatrix, present, (cudaStream_t)stream_));
+  return 0;
+}
+
+void dge_geom_pointers(char* chunk, int P, void** out) {
+  GeomState g;
+  carve_geom(chunk, P, &g);
+  out[0] = g.means2D;
+  out[1] = g.conic_opacity;
+  out[2] = g.rgb_depth;
+  out[3] = g.rect;
+  out[4] = g.clamped;
+  out[5] = g.sort_val[0];
+  out[6] = g.offsets;
+  out[7] = g.counters;
+}
+void dge_binning_pointers(char* chunk, int R, int width, int height, void** out) {
+  BinState b;
+  carve_binning(chunk, R, width, height, &b);
+  out[0] = b.point_list;
+  out[1] = b.tile_ids;
+}
+void dge_image_pointers(char* chunk, int width, int height, void** out) {
+  ImgState s;
+  carve_image(chunk, width, height, &s);
+  out[0] = s.final_T;
+  out[1] = s.n_contrib;
+  out[2] = s.ranges;
+}
+
+int dge_debug_sorted_keys(char* geom_buffer, char* binning_buffer, int P, int R, int width,
+                          int height, uint64_t* keys_out, void* stream_) {
+  GeomState g;
+  BinState b;
+  carve_geom(geom_buffer, P, &g);
+  carve_binning(binning_buffer, R, width, height, &b);
+  CK("debug keys", launch_debug_keys(g, b, R, keys_out, (cudaStream_t)stream_));
+  return 0;
+}
+
+int dge_fused_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n,
+                   float lr, float beta1, float beta2, float eps, int step, const uint8_t* mask,
+                   int stride, void* stream_) {
+  CK("fused adam", launch_fused_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step,
+                                     mask, stride, (cudaStream_t)stream_));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,172 @@
+// K14: DGE's local-editing mask back-projection.
+//
+// Replaces renderCUDA_apply_weights<CH> (DGR/cuda_rasterizer/apply_weights.cu:239-356):
+// walk each tile's list front to back with exactly the forward blend's alpha / T tests and,
+// for every contributing (pixel, Gaussian) pair, add the pixel's mask value to
+// weights[gid*CH+ch] and 1 to cnt[gid] once PER CHANNEL (apply_weights.cu:331-334).
+// The reference issues CH float + CH int atomics per pair; here each thread owns a 2x2
+// quad, sums its pixels, the warp reduces (REDUX for the count, shuffles for the floats)
+// and one lane per value issues the atomic. With 0/1 masks the float sums are integers
+// below 2^24, so the result is bit-identical to the reference whatever the order.
+// The out-of-image read of image_weights in the reference (apply_weights.cu:279-283, before
+// its `inside` test) is guarded here; those values are never used.
+#include "common.cuh"
+
+namespace dge {
+
+constexpr int AW_THREADS = 64;
+constexpr int AW_BATCH = 128;
+
+#define MUL(a, b) __fmul_rn((a), (b))
+#define ADD(a, b) __fadd_rn((a), (b))
+#define FMA(a, b, c) __fmaf_rn((a), (b), (c))
+
+template <int CH>
+__global__ void __launch_bounds__(AW_THREADS) apply_weights_kernel(
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
+    const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity,
+    const float* __restrict__ image_weights, float* __restrict__ weights, int* __restrict__ cnt) {
+  __shared__ float4 s_a[AW_BATCH];  // x, y, conic.x, conic.y
+  __shared__ float4 s_b[AW_BATCH];  // conic.z, power threshold, opacity, gid bits
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int qx = tid & 7, qy = tid >> 3;
+  const int px0 = blockIdx.x * DGE_TILE + 2 * qx, py0 = blockIdx.y * DGE_TILE + 2 * qy;
+  const float fx0 = (float)px0, fx1 = (float)(px0 + 1), fy0 = (float)py0, fy1 = (float)(py0 + 1);
+  const size_t HW = (size_t)H * W;
+  const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
+
+  float T[4], Cw[4][CH];
+  bool done[4];
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    const int x = px0 + (p & 1), y = py0 + (p >> 1);
+    const bool inside = x < W && y < H;
+    T[p] = 1.0f;
+    done[p] = !inside;
+#pragma unroll
+    for (int c = 0; c < CH; c++) Cw[p][c] = inside ? image_weights[c * HW + (size_t)y * W + x] : 0.0f;
+  }
+
+  for (uint32_t base = range.x; base < range.y; base += AW_BATCH) {
+    const bool all_done = done[0] && done[1] && done[2] && done[3];
+    if (__syncthreads_and(all_done)) break;
+    const int count = min((uint32_t)AW_BATCH, range.y - base);
+    for (int k = tid; k < count; k += AW_THREADS) {
+      const uint32_t gid = point_list[base + k];
+      const float2 xy = means2D[gid];
+      const float4 co = conic_opacity[gid];
+      const float thr =
+          co.w > 0.0f ? -(__logf(255.0f * co.w) + 0.01f) : __int_as_float(0x7f800000);
+      s_a[k] = make_float4(xy.x, xy.y, co.x, co.y);
+      s_b[k] = make_float4(co.z, thr, co.w, __uint_as_float(gid));
+    }
+    __syncthreads();
+    if (__all_sync(0xFFFFFFFFu, all_done)) continue;
+    for (int j = 0; j < count; j++) {
+      const float4 a = s_a[j];
+      const float4 b = s_b[j];
+      const float dx0 = ADD(a.x, -fx0), dx1 = ADD(a.x, -fx1);
+      const float dy0 = ADD(a.y, -fy0), dy1 = ADD(a.y, -fy1);
+      const float bx0 = MUL(dx0, a.z), bx1 = MUL(dx1, a.z);
+      const float cx0 = MUL(dx0, a.w), cx1 = MUL(dx1, a.w);
+      const float ay0 = MUL(dy0, MUL(dy0, b.x)), ay1 = MUL(dy1, MUL(dy1, b.x));
+      float power[4];
+      power[0] = FMA(FMA(dx0, bx0, ay0), -0.5f, -MUL(dy0, cx0));
+      power[1] = FMA(FMA(dx1, bx1, ay0), -0.5f, -MUL(dy0, cx1));
+      power[2] = FMA(FMA(dx0, bx0, ay1), -0.5f, -MUL(dy1, cx0));
+      power[3] = FMA(FMA(dx1, bx1, ay1), -0.5f, -MUL(dy1, cx1));
+      bool any = false;
+      bool cand[4];
+#pragma unroll
+      for (int p = 0; p < 4; p++) {
+        cand[p] = !done[p] && !(power[p] > 0.0f) && !(power[p] < b.y);
+        any |= cand[p];
+      }
+      if (!__any_sync(0xFFFFFFFFu, any)) continue;
+      float wsum[CH];
+#pragma unroll
+      for (int c = 0; c < CH; c++) wsum[c] = 0.0f;
+      int n = 0;
+#pragma unroll
+      for (int p = 0; p < 4; p++) {
+        if (!cand[p]) continue;
+        const float alpha = fminf(0.99f, MUL(b.z, expf(power[p])));
+        if (alpha < 1.0f / 255.0f) continue;
+        const float test_T = MUL(T[p], ADD(1.0f, -alpha));
+        if (test_T < 0.0001f) {
+          done[p] = true;
+          continue;
+        }
+#pragma unroll
+        for (int c = 0; c < CH; c++) wsum[c] += Cw[p][c];
+        n += 1;
+        T[p] = test_T;
+      }
+      const int total = __reduce_add_sync(0xFFFFFFFFu, n);
+      if (total == 0) continue;
+#pragma unroll
+      for (int c = 0; c < CH; c++)
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) wsum[c] += __shfl_xor_sync(0xFFFFFFFFu, wsum[c], o);
+      const uint32_t gid = __float_as_uint(b.w);
+      if (lane == 0) atomicAdd(cnt + gid, total * CH);
+#pragma unroll
+      for (int c = 0; c < CH; c++)
+        if (lane == c + 1) atomicAdd(weights + (size_t)gid * CH + c, wsum[c]);
+    }
+  }
+}
+
+cudaError_t launch_apply_weights_render(const ViewParams& vp, const GeomState& g, const BinState& b,
+                                        const ImgState& img, float* weights, int* cnt,
+                                        const float* image_weights, int num_channels,
+                                        cudaStream_t stream) {
+  dim3 grid(vp.grid_x, vp.grid_y);
+#define AW_LAUNCH(CH)                                                                          \
+  apply_weights_kernel<CH><<<grid, AW_THREADS, 0, stream>>>(img.ranges, b.point_list, vp.W, vp.H, \
+                                                            g.means2D, g.conic_opacity,        \
+                                                            image_weights, weights, cnt)
+  if (num_channels == 1) AW_LAUNCH(1);
+  else if (num_channels == 2) AW_LAUNCH(2);
+  else if (num_channels == 3) AW_LAUNCH(3);
+  else return cudaErrorInvalidValue;  // the reference prints and exit(-1)s (apply_weights.cu:377-380)
+#undef AW_LAUNCH
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ fused Adam (N3) -----
+// torch.optim.Adam (gaussiansplatting/scene/gaussian_model.py:374): no weight decay, no
+// amsgrad; bias corrections as torch's single-tensor path:
+//   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2
+//   p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+__global__ void __launch_bounds__(256) fused_adam_kernel(float* __restrict__ p,
+                                                         const float* __restrict__ g,
+                                                         float* __restrict__ m, float* __restrict__ v,
+                                                         size_t n, float step_size, float inv_bc2_sqrt,
+                                                         float beta1, float beta2, float eps,
+                                                         const uint8_t* __restrict__ mask, int stride) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float grad = g[i];
+  if (mask != nullptr && !mask[i / stride]) grad = 0.0f;
+  const float mi = beta1 * m[i] + (1.0f - beta1) * grad;
+  const float vi = beta2 * v[i] + (1.0f - beta2) * grad * grad;
+  m[i] = mi;
+  v[i] = vi;
+  p[i] -= step_size * (mi / (sqrtf(vi) * inv_bc2_sqrt + eps));
+}
+
+cudaError_t launch_fused_adam(float* param, const float* grad, float* m, float* v, size_t n, float lr,
+                              float beta1, float beta2, float eps, int step, const uint8_t* mask,
+                              int stride, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  fused_adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+      param, grad, m, v, n, step_size, inv_bc2_sqrt, beta1, beta2, eps, mask, stride > 0 ? stride : 1);
+  return cudaGetLastError();
+}
+
+}  // namespace dge

@@ -1,0 +1,210 @@
+// K2-K5: instance lists per tile, front-to-back.
+//
+// Replaces InclusiveSum + duplicateWithKeys + SortPairs + identifyTileRanges
+// (DGR/cuda_rasterizer/rasterizer_impl.cu:67-125, :229-271). The reference
+// sorts R (tile|depth) 64-bit keys in 6 byte passes (152 B/instance). The same
+// stable order (tile, depth bits, Gaussian id) is produced here with far less
+// traffic by sorting the P Gaussians by depth bits ONCE (4 passes over P
+// items), emitting instances in that order, and stable-partitioning them by
+// tile id (ceil(log2(T)/8) passes over R 8-byte pairs): 8 + 16*passes B/instance.
+// Stability of both sorts makes the resulting point_list / ranges bit-identical
+// to the reference's (ties in depth keep Gaussian-id order, exactly as CUB's
+// stable sort of the id-ordered unsorted list does).
+#include "common.cuh"
+
+namespace dge {
+
+constexpr int SCAN_THREADS = 256;
+
+__device__ __forceinline__ uint32_t rect_count(ushort4 r) {
+  return (uint32_t)(r.z - r.x) * (uint32_t)(r.w - r.y);
+}
+
+// block sums of tiles_touched taken in depth order
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(
+    int P, const uint32_t* __restrict__ order, const ushort4* __restrict__ rect,
+    uint32_t* __restrict__ block_sums) {
+  const int r = blockIdx.x * SCAN_THREADS + threadIdx.x;
+  uint32_t c = 0;
+  if (r < P) c = rect_count(rect[order[r]]);
+  c = __reduce_add_sync(0xFFFFFFFFu, c);
+  __shared__ uint32_t ws[SCAN_THREADS / 32];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_THREADS / 32; i++) t += ws[i];
+    block_sums[blockIdx.x] = t;
+  }
+}
+
+// in-place exclusive scan of the block sums (single CTA, 1024 threads, carried chunks)
+__global__ void __launch_bounds__(1024) scan_block_sums_kernel(int n, uint32_t* __restrict__ sums) {
+  __shared__ uint32_t ws[32];
+  __shared__ uint32_t carry_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const uint32_t v = i < n ? sums[i] : 0;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) ws[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = ws[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, o);
+        if (lane >= o) w += y;
+      }
+      ws[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const uint32_t carry = carry_s;
+    const uint32_t wbase = warp ? ws[warp - 1] : 0;
+    if (i < n) sums[i] = carry + wbase + x - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + wbase + x;
+    __syncthreads();
+  }
+}
+
+// Emits the (tile id, Gaussian id) pairs of 256 depth-consecutive Gaussians.
+// Offsets come from a CTA scan + the scanned block sums; each warp then writes its
+// Gaussians' instances cooperatively (lane k handles the k-th instance of the warp,
+// source Gaussian found by a 5-step search over the warp's 32 offsets) so the stores
+// are coalesced however skewed the per-Gaussian tile counts are.
+__global__ void __launch_bounds__(SCAN_THREADS) expand_kernel(
+    int P, int grid_x, const uint32_t* __restrict__ order, const ushort4* __restrict__ rect,
+    const uint32_t* __restrict__ block_prefix, uint32_t* __restrict__ offsets,
+    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+  __shared__ uint32_t ws[SCAN_THREADS / 32];
+  __shared__ uint32_t s_off[SCAN_THREADS / 32][33];
+  __shared__ uint32_t s_gid[SCAN_THREADS / 32][32];
+  __shared__ ushort4 s_rect[SCAN_THREADS / 32][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = blockIdx.x * SCAN_THREADS + threadIdx.x;
+  uint32_t gid = 0;
+  ushort4 rc = make_ushort4(0, 0, 0, 0);
+  if (r < P) {
+    gid = order[r];
+    rc = rect[gid];
+  }
+  const uint32_t cnt = rect_count(rc);
+  uint32_t x = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) ws[warp] = x;
+  __syncthreads();
+  uint32_t wbase = block_prefix[blockIdx.x];
+#pragma unroll
+  for (int w = 0; w < SCAN_THREADS / 32; w++)
+    if (w < warp) wbase += ws[w];
+  const uint32_t incl = wbase + x;
+  if (r < P) offsets[r] = incl;
+  s_off[warp][lane] = incl - cnt;
+  s_gid[warp][lane] = gid;
+  s_rect[warp][lane] = rc;
+  if (lane == 31) s_off[warp][32] = incl;
+  __syncwarp();
+  const uint32_t wstart = s_off[warp][0];
+  const uint32_t wtotal = s_off[warp][32] - wstart;
+  for (uint32_t k = lane; k < wtotal; k += 32) {
+    const uint32_t target = wstart + k;
+    int l = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1)
+      if (s_off[warp][l + step] <= target) l += step;
+    const uint32_t j = target - s_off[warp][l];
+    const ushort4 q = s_rect[warp][l];
+    const uint32_t w = q.z - q.x;
+    const uint32_t ty = q.y + j / w, tx = q.x + j % w;
+    keys_out[target] = ty * (uint32_t)grid_x + tx;
+    vals_out[target] = s_gid[warp][l];
+  }
+}
+
+// identifyTileRanges (DGR/cuda_rasterizer/rasterizer_impl.cu:105-125) on 32-bit tile ids
+__global__ void __launch_bounds__(256) tile_ranges_kernel(uint32_t R,
+                                                         const uint32_t* __restrict__ tile_ids,
+                                                         uint2* __restrict__ ranges) {
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= R) return;
+  const uint32_t cur = tile_ids[i];
+  if (i == 0) {
+    ranges[cur].x = 0;
+  } else {
+    const uint32_t prev = tile_ids[i - 1];
+    if (cur != prev) {
+      ranges[prev].y = i;
+      ranges[cur].x = i;
+    }
+  }
+  if (i == R - 1) ranges[cur].y = R;
+}
+
+__global__ void debug_keys_kernel(uint32_t R, const uint32_t* __restrict__ tile_ids,
+                                  const uint32_t* __restrict__ point_list,
+                                  const float4* __restrict__ rgb_depth,
+                                  uint64_t* __restrict__ keys_out) {
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= R) return;
+  keys_out[i] = ((uint64_t)tile_ids[i] << 32) | __float_as_uint(rgb_depth[point_list[i]].w);
+}
+
+cudaError_t launch_depth_sort(int P, GeomState& g, cudaStream_t stream) {
+  // culled Gaussians carry key 0xFFFFFFFF and tile count 0: they sort last and emit nothing
+  return sort_pairs(g.sort_key, g.sort_val, (uint32_t)P, 32, /*iota=*/true, g.sort_ws,
+                    g.sort_ws_bytes, stream);
+}
+
+static int tile_bits(int T) {
+  int bits = 0;
+  while (bits < 32 && (1ll << bits) < (long long)T) bits++;
+  return bits;
+}
+
+cudaError_t launch_binning(const ViewParams& vp, int R, GeomState& g, BinState& b, ImgState& img,
+                           cudaStream_t stream) {
+  const int T = vp.grid_x * vp.grid_y;
+  cudaError_t e = cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)T, stream);
+  if (e != cudaSuccess || R == 0) return e;
+  const int P = vp.P;
+  const int blocks = (P + SCAN_THREADS - 1) / SCAN_THREADS;
+  const uint32_t* order = g.sort_val[0];
+  scan_reduce_kernel<<<blocks, SCAN_THREADS, 0, stream>>>(P, order, g.rect, g.block_sums);
+  scan_block_sums_kernel<<<1, 1024, 0, stream>>>(blocks, g.block_sums);
+  const int bits = tile_bits(T);
+  const int passes = sort_num_passes(bits);
+  uint32_t* keys[2] = {b.tile_ids, b.key_alt};
+  uint32_t* vals[2] = {b.point_list, b.val_alt};
+  expand_kernel<<<blocks, SCAN_THREADS, 0, stream>>>(P, vp.grid_x, order, g.rect, g.block_sums,
+                                                     g.offsets, keys[passes & 1], vals[passes & 1]);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (passes > 0) {
+    e = sort_pairs(keys, vals, (uint32_t)R, bits, /*iota=*/false, b.sort_ws, b.sort_ws_bytes, stream);
+    if (e != cudaSuccess) return e;
+  }
+  tile_ranges_kernel<<<(R + 255) / 256, 256, 0, stream>>>((uint32_t)R, b.tile_ids, img.ranges);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_debug_keys(const GeomState& g, const BinState& b, int R, uint64_t* keys_out,
+                              cudaStream_t stream) {
+  if (R == 0) return cudaSuccess;
+  debug_keys_kernel<<<(R + 255) / 256, 256, 0, stream>>>((uint32_t)R, b.tile_ids, b.point_list,
+                                                         g.rgb_depth, keys_out);
+  return cudaGetLastError();
+}
+
+}  // namespace dge

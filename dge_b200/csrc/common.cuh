@@ -1,0 +1,124 @@
+// Shared declarations of the dge_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#define DGE_TILE 16            // DGR/cuda_rasterizer/config.h:16-17 (BLOCK_X/BLOCK_Y)
+#define DGE_NUM_SMS 148
+
+namespace dge {
+
+// ---------------------------------------------------------------- scratch ---
+// Our own layout of the three opaque blobs (the reference's is
+// DGR/cuda_rasterizer/rasterizer_impl.cu:135-175). All sub-arrays 256-B aligned.
+struct GeomState {
+  float2* means2D;        // [P] pixel-space centre
+  float4* conic_opacity;  // [P] conic.x, conic.y, conic.z, opacity
+  float4* rgb_depth;      // [P] r, g, b, view-space depth
+  ushort4* rect;          // [P] tile rect min.x, min.y, max.x, max.y (all 0 <=> culled)
+  uint8_t* clamped;       // [P] bit ch set <=> SH colour channel clamped at 0
+  uint32_t* sort_key[2];  // [P] depth bits (0xFFFFFFFF for culled), ping-pong
+  uint32_t* sort_val[2];  // [P] Gaussian ids, ping-pong; sort_val[0] ends up depth-sorted
+  uint32_t* offsets;      // [P] inclusive scan of tiles_touched in depth order
+  uint32_t* block_sums;   // [scan blocks]
+  uint32_t* counters;     // [64] counters[0] = num_rendered
+  uint32_t* sort_ws;      // radix-sort workspace (tickets, histograms, look-back status)
+  size_t sort_ws_bytes;
+};
+
+struct BinState {
+  uint32_t* point_list;   // [R] Gaussian ids sorted by (tile, depth, id)   (= val[0])
+  uint32_t* tile_ids;     // [R] tile id of each sorted instance            (= key[0])
+  uint32_t* key_alt;      // [R] ping-pong
+  uint32_t* val_alt;      // [R] ping-pong
+  uint32_t* sort_ws;
+  size_t sort_ws_bytes;
+};
+
+struct ImgState {
+  float* final_T;         // [N]
+  uint32_t* n_contrib;    // [N]
+  uint2* ranges;          // [T]
+};
+
+size_t carve_geom(char* base, int P, GeomState* st);
+size_t carve_binning(char* base, int R, int width, int height, BinState* st);
+size_t carve_image(char* base, int width, int height, ImgState* st);
+
+// ------------------------------------------------------------------- sort ---
+// Stable LSD onesweep radix sort of (u32 key, u32 value) pairs on key bits
+// [0, num_bits). Result lands in (keys[0], vals[0]) when the number of passes
+// is even, which sort_pairs guarantees by issuing a plain copy pass otherwise.
+// vals[0] == nullptr on entry means "values are 0..n-1" (no iota kernel).
+size_t sort_workspace_bytes(uint32_t n);
+cudaError_t sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int num_bits,
+                       bool iota_values, uint32_t* ws, size_t ws_bytes, cudaStream_t stream);
+int sort_num_passes(int num_bits);
+
+// ----------------------------------------------------------------- stages ---
+struct ViewParams {
+  const float* view;    // device, 16 floats, flat index [4*col+row] (auxiliary.h:58-77)
+  const float* proj;    // device, 16 floats
+  const float* campos;  // device, 3 floats
+  float tan_fovx, tan_fovy, focal_x, focal_y;
+  float scale_modifier;
+  int W, H, grid_x, grid_y;
+  int P, D, M;
+};
+
+// colors_mode: 0 = SH -> rgb, 1 = copy colors_precomp into rgb_depth, 2 = no colour (apply_weights)
+cudaError_t launch_preprocess(const ViewParams& vp, const float* means3D, const float* scales,
+                              const float* rotations, const float* opacities, const float* shs,
+                              const float* cov3D_precomp, const float* colors_precomp,
+                              int colors_mode, bool prefiltered, int* radii, GeomState& g,
+                              cudaStream_t stream);
+cudaError_t launch_mark_visible(int P, const float* means3D, const float* view, const float* proj,
+                                uint8_t* present, cudaStream_t stream);
+// depth sort -> scan -> expand -> tile sort -> ranges. R already known on host.
+cudaError_t launch_depth_sort(int P, GeomState& g, cudaStream_t stream);
+cudaError_t launch_binning(const ViewParams& vp, int R, GeomState& g, BinState& b, ImgState& img,
+                           cudaStream_t stream);
+cudaError_t launch_render_forward(const ViewParams& vp, const GeomState& g, const BinState& b,
+                                  ImgState& img, const float* background, float* out_color,
+                                  float* out_depth, cudaStream_t stream);
+// acc: [P][12] floats, zeroed by the caller: dmean2D.xy, dconic.xyz(w), dopacity, dcolor.rgb
+cudaError_t launch_render_backward(const ViewParams& vp, const GeomState& g, const BinState& b,
+                                   const ImgState& img, const float* background,
+                                   const float* dL_dpix, float* acc, cudaStream_t stream);
+cudaError_t launch_geom_backward(const ViewParams& vp, const float* means3D, const float* scales,
+                                 const float* rotations, const float* shs, const float* cov3D_precomp,
+                                 const int* radii, const GeomState& g, const float* acc,
+                                 float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                                 float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
+                                 float* dL_dscale, float* dL_drot, cudaStream_t stream);
+cudaError_t launch_apply_weights_render(const ViewParams& vp, const GeomState& g, const BinState& b,
+                                        const ImgState& img, float* weights, int* cnt,
+                                        const float* image_weights, int num_channels,
+                                        cudaStream_t stream);
+cudaError_t launch_debug_keys(const GeomState& g, const BinState& b, int R, uint64_t* keys_out,
+                              cudaStream_t stream);
+cudaError_t launch_fused_adam(float* param, const float* grad, float* m, float* v, size_t n, float lr,
+                              float beta1, float beta2, float eps, int step, const uint8_t* mask,
+                              int stride, cudaStream_t stream);
+
+// per-Gaussian accumulator slots written by the backward blend
+enum { ACC_MEAN_X = 0, ACC_MEAN_Y, ACC_CONIC_X, ACC_CONIC_Y, ACC_CONIC_W, ACC_OPACITY, ACC_R, ACC_G,
+       ACC_B, ACC_STRIDE = 12 };
+
+// Tile rect of a Gaussian, bit-exact with getRect (DGR/cuda_rasterizer/auxiliary.h:46-56) as
+// compiled for sm_100a: two separate float adds (+16, -1), *0.0625, truncation, clamp.
+__device__ __forceinline__ void tile_rect(float px, float py, int radius, int grid_x, int grid_y,
+                                          int& min_x, int& min_y, int& max_x, int& max_y) {
+  const float r = (float)radius;
+  int a = (int)(__fmul_rn(__fadd_rn(px, -r), 0.0625f));
+  int b = (int)(__fmul_rn(__fadd_rn(py, -r), 0.0625f));
+  int c = (int)(__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(px, r), 16.0f), -1.0f), 0.0625f));
+  int d = (int)(__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(py, r), 16.0f), -1.0f), 0.0625f));
+  min_x = min(grid_x, max(0, a));
+  min_y = min(grid_y, max(0, b));
+  max_x = min(grid_x, max(0, c));
+  max_y = min(grid_y, max(0, d));
+}
+
+}  // namespace dge

@@ -1,0 +1,337 @@
+// K8 + K9 + K10 fused: per-Gaussian backward.
+//
+// Replaces computeCov2DCUDA (DGR/cuda_rasterizer/backward.cu:144-274), the backward
+// preprocessCUDA with its SH and cov3D helpers (backward.cu:20-139, :278-396) and the nine
+// torch::zeros fills of the glue (DGR/rasterize_points.cu:120-128): one pass reads the
+// blend-stage sums acc[P][12] and writes EVERY output row (zeros for culled Gaussians), so
+// no separate zero-fill and no second read of the per-Gaussian inputs is needed. cov3D is
+// recomputed from scale/rotation (bit-identical to the forward) instead of being stored.
+#include "common.cuh"
+#include "math_ref.cuh"
+
+namespace dge {
+
+// GLM-style column-major 3x3: m[col][row]; product as glm::operator* (type_mat3x3.inl)
+struct M3 {
+  float m[3][3];
+};
+__device__ __forceinline__ M3 mul(const M3& A, const M3& B) {
+  M3 R;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+      R.m[i][j] = A.m[0][j] * B.m[i][0] + A.m[1][j] * B.m[i][1] + A.m[2][j] * B.m[i][2];
+  return R;
+}
+
+__device__ __forceinline__ void store3(float* p, size_t idx, float a, float b, float c) {
+  p[3 * idx] = a;
+  p[3 * idx + 1] = b;
+  p[3 * idx + 2] = c;
+}
+
+__global__ void __launch_bounds__(256) geom_backward_kernel(
+    ViewParams vp, const float* __restrict__ means3D, const float* __restrict__ scales,
+    const float* __restrict__ rotations, const float* __restrict__ shs,
+    const float* __restrict__ cov3D_precomp, const int* __restrict__ radii,
+    const uint8_t* __restrict__ clamped, const float* __restrict__ acc,
+    float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic, float* __restrict__ dL_dopacity,
+    float* __restrict__ dL_dcolor, float* __restrict__ dL_dmean3D, float* __restrict__ dL_dcov3D,
+    float* __restrict__ dL_dsh, float* __restrict__ dL_dscale, float* __restrict__ dL_drot) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= vp.P) return;
+  const size_t i = (size_t)idx;
+  const int M = vp.M;
+
+  if (!(radii[idx] > 0)) {
+    // rows the reference leaves at torch::zeros
+    store3(dL_dmean2D, i, 0.f, 0.f, 0.f);
+    store3(dL_dmean3D, i, 0.f, 0.f, 0.f);
+    if (dL_dopacity) dL_dopacity[i] = 0.f;
+    if (dL_dconic) reinterpret_cast<float4*>(dL_dconic)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (dL_dcolor) store3(dL_dcolor, i, 0.f, 0.f, 0.f);
+    if (dL_dcov3D)
+      for (int k = 0; k < 6; k++) dL_dcov3D[6 * i + k] = 0.f;
+    if (dL_dsh)
+      for (int k = 0; k < 3 * M; k++) dL_dsh[3 * M * i + k] = 0.f;
+    if (dL_dscale) store3(dL_dscale, i, 0.f, 0.f, 0.f);
+    if (dL_drot) reinterpret_cast<float4*>(dL_drot)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+
+  const float4 a0 = __ldg(reinterpret_cast<const float4*>(acc) + 3 * i);
+  const float4 a1 = __ldg(reinterpret_cast<const float4*>(acc) + 3 * i + 1);
+  const float4 a2 = __ldg(reinterpret_cast<const float4*>(acc) + 3 * i + 2);
+  const float dm2x = a0.x, dm2y = a0.y;
+  const float dcon_x = a0.z, dcon_y = a0.w, dcon_w = a1.x;
+  const float dop = a1.y;
+  float dcol[3] = {a1.z, a1.w, a2.x};
+
+  store3(dL_dmean2D, i, dm2x, dm2y, 0.f);
+  if (dL_dopacity) dL_dopacity[i] = dop;
+  if (dL_dconic) reinterpret_cast<float4*>(dL_dconic)[i] = make_float4(dcon_x, dcon_y, 0.f, dcon_w);
+  if (dL_dcolor) store3(dL_dcolor, i, dcol[0], dcol[1], dcol[2]);
+
+  float V[16], Pm[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    V[k] = __ldg(vp.view + k);
+    Pm[k] = __ldg(vp.proj + k);
+  }
+  const float mx = __ldg(means3D + 3 * i), my = __ldg(means3D + 3 * i + 1),
+              mz = __ldg(means3D + 3 * i + 2);
+
+  // ---------------- cov3D (forward value) ----------------
+  float c3[6];
+  float4 q = make_float4(0, 0, 0, 0);
+  float sc[3] = {0, 0, 0};
+  if (cov3D_precomp != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) c3[k] = __ldg(cov3D_precomp + 6 * i + k);
+  } else {
+    q = __ldg(reinterpret_cast<const float4*>(rotations) + i);
+    sc[0] = __ldg(scales + 3 * i);
+    sc[1] = __ldg(scales + 3 * i + 1);
+    sc[2] = __ldg(scales + 3 * i + 2);
+    cov3d_from_scale_rot(sc[0], sc[1], sc[2], vp.scale_modifier, q, c3);
+  }
+
+  // ---------------- K8: conic -> cov2D -> cov3D, mean (backward.cu:144-274) ----------------
+  float tx = V[0] * mx + V[4] * my + V[8] * mz + V[12];
+  float ty = V[1] * mx + V[5] * my + V[9] * mz + V[13];
+  const float tz = V[2] * mx + V[6] * my + V[10] * mz + V[14];
+  const float limx = 1.3f * vp.tan_fovx, limy = 1.3f * vp.tan_fovy;
+  const float txtz = tx / tz, tytz = ty / tz;
+  tx = fminf(limx, fmaxf(-limx, txtz)) * tz;
+  ty = fminf(limy, fmaxf(-limy, tytz)) * tz;
+  const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
+  const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
+  const float hx = vp.focal_x, hy = vp.focal_y;
+
+  M3 J, Wm, Vrk;
+  J.m[0][0] = hx / tz; J.m[0][1] = 0.f; J.m[0][2] = -(hx * tx) / (tz * tz);
+  J.m[1][0] = 0.f; J.m[1][1] = hy / tz; J.m[1][2] = -(hy * ty) / (tz * tz);
+  J.m[2][0] = 0.f; J.m[2][1] = 0.f; J.m[2][2] = 0.f;
+  Wm.m[0][0] = V[0]; Wm.m[0][1] = V[4]; Wm.m[0][2] = V[8];
+  Wm.m[1][0] = V[1]; Wm.m[1][1] = V[5]; Wm.m[1][2] = V[9];
+  Wm.m[2][0] = V[2]; Wm.m[2][1] = V[6]; Wm.m[2][2] = V[10];
+  Vrk.m[0][0] = c3[0]; Vrk.m[0][1] = c3[1]; Vrk.m[0][2] = c3[2];
+  Vrk.m[1][0] = c3[1]; Vrk.m[1][1] = c3[3]; Vrk.m[1][2] = c3[4];
+  Vrk.m[2][0] = c3[2]; Vrk.m[2][1] = c3[4]; Vrk.m[2][2] = c3[5];
+  const M3 Tm = mul(Wm, J);
+  // cov2D = T^T * Vrk^T * T ; only [0][0], [0][1], [1][1] needed. Vrk symmetric.
+  float TV[2][3];  // (T^T Vrk)[row j of T^T = col j of T][k]
+#pragma unroll
+  for (int j = 0; j < 2; j++)
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+      TV[j][k] = Tm.m[j][0] * Vrk.m[0][k] + Tm.m[j][1] * Vrk.m[1][k] + Tm.m[j][2] * Vrk.m[2][k];
+  const float a = TV[0][0] * Tm.m[0][0] + TV[0][1] * Tm.m[0][1] + TV[0][2] * Tm.m[0][2] + 0.3f;
+  const float b = TV[1][0] * Tm.m[0][0] + TV[1][1] * Tm.m[0][1] + TV[1][2] * Tm.m[0][2];
+  const float c = TV[1][0] * Tm.m[1][0] + TV[1][1] * Tm.m[1][1] + TV[1][2] * Tm.m[1][2] + 0.3f;
+
+  const float denom = a * c - b * b;
+  float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
+  const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+  float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float T00 = Tm.m[0][0], T01 = Tm.m[0][1], T02 = Tm.m[0][2];
+  const float T10 = Tm.m[1][0], T11 = Tm.m[1][1], T12 = Tm.m[1][2];
+  if (denom2inv != 0.f) {
+    dL_da = denom2inv * (-c * c * dcon_x + 2 * b * c * dcon_y + (denom - a * c) * dcon_w);
+    dL_dc = denom2inv * (-a * a * dcon_w + 2 * a * b * dcon_y + (denom - a * c) * dcon_x);
+    dL_db = denom2inv * 2 * (b * c * dcon_x - (denom + 2 * b * b) * dcon_y + a * b * dcon_w);
+    dcov[0] = T00 * T00 * dL_da + T00 * T10 * dL_db + T10 * T10 * dL_dc;
+    dcov[3] = T01 * T01 * dL_da + T01 * T11 * dL_db + T11 * T11 * dL_dc;
+    dcov[5] = T02 * T02 * dL_da + T02 * T12 * dL_db + T12 * T12 * dL_dc;
+    dcov[1] = 2 * T00 * T01 * dL_da + (T00 * T11 + T01 * T10) * dL_db + 2 * T10 * T11 * dL_dc;
+    dcov[2] = 2 * T00 * T02 * dL_da + (T00 * T12 + T02 * T10) * dL_db + 2 * T10 * T12 * dL_dc;
+    dcov[4] = 2 * T02 * T01 * dL_da + (T01 * T12 + T02 * T11) * dL_db + 2 * T11 * T12 * dL_dc;
+  }
+  if (dL_dcov3D)
+#pragma unroll
+    for (int k = 0; k < 6; k++) dL_dcov3D[6 * i + k] = dcov[k];
+
+  // dL/dT (upper 2x3), TV[j][k] = sum_l T[j][l] Vrk[l][k]
+  const float dT00 = 2 * TV[0][0] * dL_da + TV[1][0] * dL_db;
+  const float dT01 = 2 * TV[0][1] * dL_da + TV[1][1] * dL_db;
+  const float dT02 = 2 * TV[0][2] * dL_da + TV[1][2] * dL_db;
+  const float dT10 = 2 * TV[1][0] * dL_dc + TV[0][0] * dL_db;
+  const float dT11 = 2 * TV[1][1] * dL_dc + TV[0][1] * dL_db;
+  const float dT12 = 2 * TV[1][2] * dL_dc + TV[0][2] * dL_db;
+  const float dJ00 = Wm.m[0][0] * dT00 + Wm.m[0][1] * dT01 + Wm.m[0][2] * dT02;
+  const float dJ02 = Wm.m[2][0] * dT00 + Wm.m[2][1] * dT01 + Wm.m[2][2] * dT02;
+  const float dJ11 = Wm.m[1][0] * dT10 + Wm.m[1][1] * dT11 + Wm.m[1][2] * dT12;
+  const float dJ12 = Wm.m[2][0] * dT10 + Wm.m[2][1] * dT11 + Wm.m[2][2] * dT12;
+  const float itz = 1.f / tz, itz2 = itz * itz, itz3 = itz2 * itz;
+  const float dtx = x_grad_mul * -hx * itz2 * dJ02;
+  const float dty = y_grad_mul * -hy * itz2 * dJ12;
+  const float dtz = -hx * itz2 * dJ00 - hy * itz2 * dJ11 + (2 * hx * tx) * itz3 * dJ02 +
+                    (2 * hy * ty) * itz3 * dJ12;
+  // transformVec4x3Transpose (auxiliary.h:89-97)
+  float dmean[3] = {V[0] * dtx + V[1] * dty + V[2] * dtz, V[4] * dtx + V[5] * dty + V[6] * dtz,
+                    V[8] * dtx + V[9] * dty + V[10] * dtz};
+
+  // ---------------- K9: projection (backward.cu:366-387) ----------------
+  {
+    const float mhw = Pm[3] * mx + Pm[7] * my + Pm[11] * mz + Pm[15];
+    const float m_w = 1.0f / (mhw + 0.0000001f);
+    const float mul1 = (Pm[0] * mx + Pm[4] * my + Pm[8] * mz + Pm[12]) * m_w * m_w;
+    const float mul2 = (Pm[1] * mx + Pm[5] * my + Pm[9] * mz + Pm[13]) * m_w * m_w;
+    dmean[0] += (Pm[0] * m_w - Pm[3] * mul1) * dm2x + (Pm[1] * m_w - Pm[3] * mul2) * dm2y;
+    dmean[1] += (Pm[4] * m_w - Pm[7] * mul1) * dm2x + (Pm[5] * m_w - Pm[7] * mul2) * dm2y;
+    dmean[2] += (Pm[8] * m_w - Pm[11] * mul1) * dm2x + (Pm[9] * m_w - Pm[11] * mul2) * dm2y;
+  }
+
+  // ---------------- K9: SH (backward.cu:20-139) ----------------
+  if (shs != nullptr && dL_dsh != nullptr) {
+    const float* sh = shs + 3 * (size_t)M * i;
+    float* dsh = dL_dsh + 3 * (size_t)M * i;
+    const float ox = mx - __ldg(vp.campos), oy = my - __ldg(vp.campos + 1),
+                oz = mz - __ldg(vp.campos + 2);
+    const float len = sqrtf(ox * ox + oy * oy + oz * oz);
+    const float x = ox / len, y = oy / len, z = oz / len;
+    const uint8_t cl = clamped[i];
+    float dRGB[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) dRGB[ch] = (cl >> ch) & 1 ? 0.f : dcol[ch];
+    float dRGBdx[3] = {0, 0, 0}, dRGBdy[3] = {0, 0, 0}, dRGBdz[3] = {0, 0, 0};
+    const int D = vp.D;
+    auto SH = [&](int k, int ch) { return __ldg(sh + 3 * k + ch); };
+    auto put = [&](int k, float coef) {
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) dsh[3 * k + ch] = coef * dRGB[ch];
+    };
+    put(0, SH_C0);
+    int written = 1;
+    if (D > 0) {
+      put(1, -SH_C1 * y);
+      put(2, SH_C1 * z);
+      put(3, -SH_C1 * x);
+      written = 4;
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) {
+        dRGBdx[ch] = -SH_C1 * SH(3, ch);
+        dRGBdy[ch] = -SH_C1 * SH(1, ch);
+        dRGBdz[ch] = SH_C1 * SH(2, ch);
+      }
+      if (D > 1) {
+        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+        put(4, SH_C2_0 * xy);
+        put(5, SH_C2_1 * yz);
+        put(6, SH_C2_2 * (2.f * zz - xx - yy));
+        put(7, SH_C2_3 * xz);
+        put(8, SH_C2_4 * (xx - yy));
+        written = 9;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+          dRGBdx[ch] += SH_C2_0 * y * SH(4, ch) + SH_C2_2 * 2.f * -x * SH(6, ch) +
+                        SH_C2_3 * z * SH(7, ch) + SH_C2_4 * 2.f * x * SH(8, ch);
+          dRGBdy[ch] += SH_C2_0 * x * SH(4, ch) + SH_C2_1 * z * SH(5, ch) +
+                        SH_C2_2 * 2.f * -y * SH(6, ch) + SH_C2_4 * 2.f * -y * SH(8, ch);
+          dRGBdz[ch] += SH_C2_1 * y * SH(5, ch) + SH_C2_2 * 2.f * 2.f * z * SH(6, ch) +
+                        SH_C2_3 * x * SH(7, ch);
+        }
+        if (D > 2) {
+          put(9, SH_C3_0 * y * (3.f * xx - yy));
+          put(10, SH_C3_1 * xy * z);
+          put(11, SH_C3_2 * y * (4.f * zz - xx - yy));
+          put(12, SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy));
+          put(13, SH_C3_4 * x * (4.f * zz - xx - yy));
+          put(14, SH_C3_5 * z * (xx - yy));
+          put(15, SH_C3_6 * x * (xx - 3.f * yy));
+          written = 16;
+#pragma unroll
+          for (int ch = 0; ch < 3; ch++) {
+            dRGBdx[ch] += SH_C3_0 * SH(9, ch) * 3.f * 2.f * xy + SH_C3_1 * SH(10, ch) * yz +
+                          SH_C3_2 * SH(11, ch) * -2.f * xy + SH_C3_3 * SH(12, ch) * -3.f * 2.f * xz +
+                          SH_C3_4 * SH(13, ch) * (-3.f * xx + 4.f * zz - yy) +
+                          SH_C3_5 * SH(14, ch) * 2.f * xz + SH_C3_6 * SH(15, ch) * 3.f * (xx - yy);
+            dRGBdy[ch] += SH_C3_0 * SH(9, ch) * 3.f * (xx - yy) + SH_C3_1 * SH(10, ch) * xz +
+                          SH_C3_2 * SH(11, ch) * (-3.f * yy + 4.f * zz - xx) +
+                          SH_C3_3 * SH(12, ch) * -3.f * 2.f * yz + SH_C3_4 * SH(13, ch) * -2.f * xy +
+                          SH_C3_5 * SH(14, ch) * -2.f * yz + SH_C3_6 * SH(15, ch) * -3.f * 2.f * xy;
+            dRGBdz[ch] += SH_C3_1 * SH(10, ch) * xy + SH_C3_2 * SH(11, ch) * 4.f * 2.f * yz +
+                          SH_C3_3 * SH(12, ch) * 3.f * (2.f * zz - xx - yy) +
+                          SH_C3_4 * SH(13, ch) * 4.f * 2.f * xz + SH_C3_5 * SH(14, ch) * (xx - yy);
+          }
+        }
+      }
+    }
+    for (int k = written; k < M; k++) put(k, 0.f);  // rows torch::zeros left untouched
+    const float ddx = dRGBdx[0] * dRGB[0] + dRGBdx[1] * dRGB[1] + dRGBdx[2] * dRGB[2];
+    const float ddy = dRGBdy[0] * dRGB[0] + dRGBdy[1] * dRGB[1] + dRGBdy[2] * dRGB[2];
+    const float ddz = dRGBdz[0] * dRGB[0] + dRGBdz[1] * dRGB[1] + dRGBdz[2] * dRGB[2];
+    // dnormvdv (auxiliary.h:107-117)
+    const float sum2 = ox * ox + oy * oy + oz * oz;
+    const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+    dmean[0] += ((+sum2 - ox * ox) * ddx - oy * ox * ddy - oz * ox * ddz) * invsum32;
+    dmean[1] += (-ox * oy * ddx + (sum2 - oy * oy) * ddy - oz * oy * ddz) * invsum32;
+    dmean[2] += (-ox * oz * ddx - oy * oz * ddy + (sum2 - oz * oz) * ddz) * invsum32;
+  } else if (dL_dsh != nullptr) {
+    for (int k = 0; k < 3 * M; k++) dL_dsh[3 * M * i + k] = 0.f;
+  }
+  store3(dL_dmean3D, i, dmean[0], dmean[1], dmean[2]);
+
+  // ---------------- K9: cov3D -> scale, rotation (backward.cu:278-341) ----------------
+  if (scales != nullptr && cov3D_precomp == nullptr) {
+    const float r = q.x, x = q.y, y = q.z, z = q.w;
+    M3 R;
+    R.m[0][0] = 1.f - 2.f * (y * y + z * z); R.m[0][1] = 2.f * (x * y - r * z); R.m[0][2] = 2.f * (x * z + r * y);
+    R.m[1][0] = 2.f * (x * y + r * z); R.m[1][1] = 1.f - 2.f * (x * x + z * z); R.m[1][2] = 2.f * (y * z - r * x);
+    R.m[2][0] = 2.f * (x * z - r * y); R.m[2][1] = 2.f * (y * z + r * x); R.m[2][2] = 1.f - 2.f * (x * x + y * y);
+    const float s[3] = {vp.scale_modifier * sc[0], vp.scale_modifier * sc[1], vp.scale_modifier * sc[2]};
+    M3 Mm;  // M = S * R : M[col i][row j] = s_j * R[i][j]
+#pragma unroll
+    for (int ci = 0; ci < 3; ci++)
+#pragma unroll
+      for (int rj = 0; rj < 3; rj++) Mm.m[ci][rj] = s[rj] * R.m[ci][rj];
+    M3 dS;
+    dS.m[0][0] = dcov[0]; dS.m[0][1] = 0.5f * dcov[1]; dS.m[0][2] = 0.5f * dcov[2];
+    dS.m[1][0] = 0.5f * dcov[1]; dS.m[1][1] = dcov[3]; dS.m[1][2] = 0.5f * dcov[4];
+    dS.m[2][0] = 0.5f * dcov[2]; dS.m[2][1] = 0.5f * dcov[4]; dS.m[2][2] = dcov[5];
+    M3 dM = mul(Mm, dS);
+#pragma unroll
+    for (int ci = 0; ci < 3; ci++)
+#pragma unroll
+      for (int rj = 0; rj < 3; rj++) dM.m[ci][rj] *= 2.0f;
+    // Rt[k] = (R[0][k], R[1][k], R[2][k]); dMt[k] = (dM[0][k], dM[1][k], dM[2][k])
+    float dMt[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+      for (int l = 0; l < 3; l++) dMt[k][l] = dM.m[l][k];
+    float dscale[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+      dscale[k] = R.m[0][k] * dMt[k][0] + R.m[1][k] * dMt[k][1] + R.m[2][k] * dMt[k][2];
+    if (dL_dscale) store3(dL_dscale, i, dscale[0], dscale[1], dscale[2]);
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+      for (int l = 0; l < 3; l++) dMt[k][l] *= s[k];
+    float4 dq;
+    dq.x = 2 * z * (dMt[0][1] - dMt[1][0]) + 2 * y * (dMt[2][0] - dMt[0][2]) + 2 * x * (dMt[1][2] - dMt[2][1]);
+    dq.y = 2 * y * (dMt[1][0] + dMt[0][1]) + 2 * z * (dMt[2][0] + dMt[0][2]) + 2 * r * (dMt[1][2] - dMt[2][1]) - 4 * x * (dMt[2][2] + dMt[1][1]);
+    dq.z = 2 * x * (dMt[1][0] + dMt[0][1]) + 2 * r * (dMt[2][0] - dMt[0][2]) + 2 * z * (dMt[1][2] + dMt[2][1]) - 4 * y * (dMt[2][2] + dMt[0][0]);
+    dq.w = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) - 4 * z * (dMt[1][1] + dMt[0][0]);
+    if (dL_drot) reinterpret_cast<float4*>(dL_drot)[i] = dq;
+  } else {
+    if (dL_dscale) store3(dL_dscale, i, 0.f, 0.f, 0.f);
+    if (dL_drot) reinterpret_cast<float4*>(dL_drot)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+cudaError_t launch_geom_backward(const ViewParams& vp, const float* means3D, const float* scales,
+                                 const float* rotations, const float* shs, const float* cov3D_precomp,
+                                 const int* radii, const GeomState& g, const float* acc,
+                                 float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                                 float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
+                                 float* dL_dscale, float* dL_drot, cudaStream_t stream) {
+  geom_backward_kernel<<<(vp.P + 255) / 256, 256, 0, stream>>>(
+      vp, means3D, scales, rotations, shs, cov3D_precomp, radii, g.clamped, acc, dL_dmean2D,
+      dL_dconic, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot);
+  return cudaGetLastError();
+}
+
+}  // namespace dge

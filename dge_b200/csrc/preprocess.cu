@@ -1,0 +1,268 @@
+// K1 / K13 / K12: per-Gaussian projection, EWA covariance, SH colour, tile rect.
+//
+// Replaces preprocessCUDA (DGR/cuda_rasterizer/forward.cu:155-256), its clone
+// preprocessCUDA_apply_weights (DGR/cuda_rasterizer/apply_weights.cu:148-234) and
+// checkFrustum (DGR/cuda_rasterizer/rasterizer_impl.cu:53-63).
+//
+// Tile assignment and the depth bits that go into the sort key must be BIT-EXACT
+// with the reference, so every floating-point operation below is written with
+// explicit round-to-nearest intrinsics in the order the reference's own build
+// (nvcc 12.9, -fmad=true, sm_100a) contracts them — read off its SASS
+// (cuobjdump -sass of oracle/_ref/forward.o; see DESIGN.md "bit-exact preprocess").
+// The same sequence is restated on the CPU in oracle/splat_oracle.c.
+#include <cstdio>
+#include "common.cuh"
+#include "math_ref.cuh"
+
+namespace dge {
+
+// DGR/cuda_rasterizer/forward.cu:74-113 computeCov2D. t = view-space mean.
+__device__ __forceinline__ float3 cov2d_ref(float tx, float ty, float tz, const ViewParams& vp,
+                                            const float* V, const float* c) {
+  const float limx = MUL(vp.tan_fovx, 1.3f), limy = MUL(vp.tan_fovy, 1.3f);
+  const float txtz = __fdiv_rn(tx, tz), tytz = __fdiv_rn(ty, tz);
+  const float cx = fminf(fmaxf(txtz, -limx), limx);
+  const float cy = fminf(fmaxf(tytz, -limy), limy);
+  const float tz2 = MUL(tz, tz);
+  const float J00 = __fdiv_rn(vp.focal_x, tz);
+  const float J02 = __fdiv_rn(MUL(MUL(tz, -cx), vp.focal_x), tz2);
+  const float J11 = __fdiv_rn(vp.focal_y, tz);
+  const float J12 = __fdiv_rn(MUL(MUL(tz, -cy), vp.focal_y), tz2);
+  // T = W * J ; T0j = fma(W2j, J02, W0j*J00), T1j = fma(W2j, J12, W1j*J11)
+  const float T00 = FMA(V[2], J02, MUL(V[0], J00));
+  const float T01 = FMA(V[6], J02, MUL(V[4], J00));
+  const float T02 = FMA(V[10], J02, MUL(V[8], J00));
+  const float T10 = FMA(V[2], J12, MUL(V[1], J11));
+  const float T11 = FMA(V[6], J12, MUL(V[5], J11));
+  const float T12 = FMA(V[10], J12, MUL(V[9], J11));
+  // A = T^T * Vrk^T ; A[k][j] = fma(Tj2, Vrk[2][k], fma(Tj0, Vrk[0][k], Tj1*Vrk[1][k]))
+  const float A00 = dot3_ref(T00, c[0], T01, c[1], T02, c[2]);
+  const float A10 = dot3_ref(T00, c[1], T01, c[3], T02, c[4]);
+  const float A20 = dot3_ref(T00, c[2], T01, c[4], T02, c[5]);
+  const float A01 = dot3_ref(T10, c[0], T11, c[1], T12, c[2]);
+  const float A11 = dot3_ref(T10, c[1], T11, c[3], T12, c[4]);
+  const float A21 = dot3_ref(T10, c[2], T11, c[4], T12, c[5]);
+  // cov[i][j] = fma(A[2][j], T[i][2], fma(A[0][j], T[i][0], A[1][j]*T[i][1]))
+  float3 cov;
+  cov.x = ADD(dot3_ref(T00, A00, T01, A10, T02, A20), 0.3f);
+  cov.y = dot3_ref(T00, A01, T01, A11, T02, A21);
+  cov.z = ADD(dot3_ref(T10, A01, T11, A11, T12, A21), 0.3f);
+  return cov;
+}
+
+// DGR/cuda_rasterizer/forward.cu:20-71 computeColorFromSH; sh = 3*M floats of this Gaussian.
+// Returns result BEFORE the +0.5 in res[3].
+template <typename F>
+__device__ __forceinline__ void sh_to_rgb_ref(int deg, float dx, float dy, float dz, F sh,
+                                              float res[3]) {
+  const float len = __fsqrt_rn(FMA(dz, dz, FMA(dx, dx, MUL(dy, dy))));
+  const float x = __fdiv_rn(dx, len), y = __fdiv_rn(dy, len), z = __fdiv_rn(dz, len);
+#pragma unroll
+  for (int c = 0; c < 3; c++) res[c] = MUL(sh(0, c), SH_C0);
+  if (deg > 0) {
+    const float t1 = MUL(y, SH_C1), t2 = MUL(z, SH_C1), t3 = MUL(x, SH_C1);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      float r = FMA(-t1, sh(1, c), res[c]);
+      r = FMA(t2, sh(2, c), r);
+      res[c] = FMA(-t3, sh(3, c), r);
+    }
+    if (deg > 1) {
+      const float xx = MUL(x, x), yy = MUL(y, y), zz = MUL(z, z);
+      const float xy = MUL(y, x), yz = MUL(z, y), xz = MUL(z, x);
+      const float zz2 = ADD(zz, zz);
+      const float k4 = MUL(xy, SH_C2_0), k5 = MUL(yz, SH_C2_1);
+      const float k6 = MUL(ADD(-yy, ADD(-xx, zz2)), SH_C2_2);
+      const float k7 = MUL(xz, SH_C2_3);
+      const float xx_m_yy = ADD(xx, -yy);
+      const float k8 = MUL(xx_m_yy, SH_C2_4);
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        float r = FMA(k4, sh(4, c), res[c]);
+        r = FMA(k5, sh(5, c), r);
+        r = FMA(k6, sh(6, c), r);
+        r = FMA(k7, sh(7, c), r);
+        res[c] = FMA(k8, sh(8, c), r);
+      }
+      if (deg > 2) {
+        const float k9 = MUL(MUL(y, SH_C3_0), FMA(xx, 3.0f, -yy));
+        const float k10 = MUL(MUL(xy, SH_C3_1), z);
+        const float f4 = ADD(-yy, FMA(zz, 4.0f, -xx));  // 4zz - xx - yy
+        const float k11 = MUL(MUL(y, SH_C3_2), f4);
+        const float k12 = MUL(MUL(z, SH_C3_3), FMA(yy, -3.0f, FMA(xx, -3.0f, zz2)));
+        const float k13 = MUL(f4, MUL(x, SH_C3_4));
+        const float k14 = MUL(xx_m_yy, MUL(z, SH_C3_5));
+        const float k15 = MUL(MUL(x, SH_C3_6), FMA(yy, -3.0f, xx));
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          float r = FMA(k9, sh(9, c), res[c]);
+          r = FMA(k10, sh(10, c), r);
+          r = FMA(k11, sh(11, c), r);
+          r = FMA(k12, sh(12, c), r);
+          r = FMA(k13, sh(13, c), r);
+          r = FMA(k14, sh(14, c), r);
+          res[c] = FMA(k15, sh(15, c), r);
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg((const float4*)p); }
+
+// One thread per Gaussian, 256 per CTA. Loads: xyz/scale 3 coalesced scalar streams,
+// quaternion one float4, SH 12 float4 (M==16) issued together only by surviving lanes.
+__global__ void __launch_bounds__(256) preprocess_kernel(
+    ViewParams vp, const float* __restrict__ means3D, const float* __restrict__ scales,
+    const float* __restrict__ rotations, const float* __restrict__ opacities,
+    const float* __restrict__ shs, const float* __restrict__ cov3D_precomp,
+    const float* __restrict__ colors_precomp, int colors_mode, bool prefiltered,
+    int* __restrict__ radii, GeomState g) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t tiles = 0;
+  if (idx < vp.P) {
+    float V[16], Pm[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      V[i] = __ldg(vp.view + i);
+      Pm[i] = __ldg(vp.proj + i);
+    }
+    int radius = 0;
+    ushort4 rect = make_ushort4(0, 0, 0, 0);
+    uint32_t key = 0xFFFFFFFFu;
+    const float px = __ldg(means3D + 3 * idx), py = __ldg(means3D + 3 * idx + 1),
+                pz = __ldg(means3D + 3 * idx + 2);
+    // in_frustum (auxiliary.h:139-164): near-plane test only
+    const float depth = xform_row(V, 2, px, py, pz);
+    if (depth > 0.2f) {
+      const float hw = ADD(xform_row(Pm, 3, px, py, pz), 0.0000001f);
+      const float p_w = __frcp_rn(hw);
+      const float projx = MUL(xform_row(Pm, 0, px, py, pz), p_w);
+      const float projy = MUL(xform_row(Pm, 1, px, py, pz), p_w);
+      float cov3[6];
+      if (cov3D_precomp != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) cov3[i] = __ldg(cov3D_precomp + 6 * (size_t)idx + i);
+      } else {
+        const float4 q = ldg4(rotations + 4 * (size_t)idx);
+        cov3d_from_scale_rot(__ldg(scales + 3 * idx), __ldg(scales + 3 * idx + 1),
+                             __ldg(scales + 3 * idx + 2), vp.scale_modifier, q, cov3);
+      }
+      const float tx = xform_row(V, 0, px, py, pz), ty = xform_row(V, 1, px, py, pz);
+      const float3 cov = cov2d_ref(tx, ty, depth, vp, V, cov3);
+      const float det = FMA(cov.x, cov.z, -MUL(cov.y, cov.y));
+      if (det != 0.0f) {
+        const float inv = __frcp_rn(det);
+        const float mid = MUL(ADD(cov.x, cov.z), 0.5f);
+        const float s = __fsqrt_rn(fmaxf(FMA(mid, mid, -det), 0.1f));
+        const float lam = fmaxf(ADD(mid, s), ADD(mid, -s));
+        const int rad = (int)ceilf(MUL(__fsqrt_rn(lam), 3.0f));
+        // ndc2Pix in FP64 (auxiliary.h:41-44): ((v + 1.0) * S - 1.0) * 0.5 with one DFMA
+        const float pix_x =
+            (float)__dmul_rn(__fma_rn(__dadd_rn((double)projx, 1.0), (double)vp.W, -1.0), 0.5);
+        const float pix_y =
+            (float)__dmul_rn(__fma_rn(__dadd_rn((double)projy, 1.0), (double)vp.H, -1.0), 0.5);
+        int x0, y0, x1, y1;
+        tile_rect(pix_x, pix_y, rad, vp.grid_x, vp.grid_y, x0, y0, x1, y1);
+        const uint32_t cnt = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
+        if (cnt != 0) {
+          float rgb[3];
+          if (colors_mode == 0) {
+            const float ddx = ADD(px, -__ldg(vp.campos)), ddy = ADD(py, -__ldg(vp.campos + 1)),
+                        ddz = ADD(pz, -__ldg(vp.campos + 2));
+            if (vp.M == 16) {
+              float4 v[12];
+              const float* base = shs + 48 * (size_t)idx;
+#pragma unroll
+              for (int i = 0; i < 12; i++) v[i] = ldg4(base + 4 * i);
+              const float* f = reinterpret_cast<const float*>(v);
+              sh_to_rgb_ref(vp.D, ddx, ddy, ddz, [&](int k, int c) { return f[3 * k + c]; }, rgb);
+            } else {
+              const float* base = shs + 3 * (size_t)vp.M * idx;
+              sh_to_rgb_ref(vp.D, ddx, ddy, ddz,
+                            [&](int k, int c) { return __ldg(base + 3 * k + c); }, rgb);
+            }
+            uint8_t cl = 0;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+              rgb[c] = ADD(rgb[c], 0.5f);
+              if (rgb[c] < 0.0f) cl |= (1u << c);
+              rgb[c] = fmaxf(rgb[c], 0.0f);
+            }
+            g.clamped[idx] = cl;
+          } else if (colors_mode == 1) {
+            // forward.cu:241-247 / rasterizer_impl.cu:274-275: precomputed colours are blended
+            // as given; staged into the same record the blend kernels read.
+#pragma unroll
+            for (int c = 0; c < 3; c++) rgb[c] = __ldg(colors_precomp + 3 * (size_t)idx + c);
+          } else {
+            rgb[0] = rgb[1] = rgb[2] = 0.0f;  // apply_weights blends no colour
+          }
+          g.means2D[idx] = make_float2(pix_x, pix_y);
+          g.conic_opacity[idx] =
+              make_float4(MUL(cov.z, inv), MUL(cov.y, -inv), MUL(cov.x, inv), __ldg(opacities + idx));
+          g.rgb_depth[idx] = make_float4(rgb[0], rgb[1], rgb[2], depth);
+          radius = rad;
+          rect = make_ushort4(x0, y0, x1, y1);
+          key = __float_as_uint(depth);
+          tiles = cnt;
+        }
+      }
+    } else if (prefiltered) {
+      // auxiliary.h:156-160: the reference traps here
+      printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+      __trap();
+    }
+    radii[idx] = radius;
+    g.rect[idx] = rect;
+    g.sort_key[0][idx] = key;
+  }
+  // num_rendered = sum of tiles_touched (integer, order-independent)
+  uint32_t s = __reduce_add_sync(0xFFFFFFFFu, tiles);
+  __shared__ uint32_t warp_sum[8];
+  if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += warp_sum[i];
+    if (t) atomicAdd(g.counters, t);
+  }
+}
+
+cudaError_t launch_preprocess(const ViewParams& vp, const float* means3D, const float* scales,
+                              const float* rotations, const float* opacities, const float* shs,
+                              const float* cov3D_precomp, const float* colors_precomp,
+                              int colors_mode, bool prefiltered, int* radii, GeomState& g,
+                              cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(g.counters, 0, 64 * sizeof(uint32_t), stream);
+  if (e != cudaSuccess) return e;
+  const int blocks = (vp.P + 255) / 256;
+  preprocess_kernel<<<blocks, 256, 0, stream>>>(vp, means3D, scales, rotations, opacities, shs,
+                                                cov3D_precomp, colors_precomp, colors_mode, prefiltered,
+                                                radii, g);
+  return cudaGetLastError();
+}
+
+// K12 checkFrustum (DGR/cuda_rasterizer/rasterizer_impl.cu:53-63)
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
+                                    const float* __restrict__ view,
+                                    uint8_t* __restrict__ present) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  float V[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) V[i] = __ldg(view + i);
+  const float px = __ldg(means3D + 3 * idx), py = __ldg(means3D + 3 * idx + 1),
+              pz = __ldg(means3D + 3 * idx + 2);
+  present[idx] = xform_row(V, 2, px, py, pz) > 0.2f ? 1 : 0;
+}
+
+cudaError_t launch_mark_visible(int P, const float* means3D, const float* view, const float* proj,
+                                uint8_t* present, cudaStream_t stream) {
+  (void)proj;  // the reference's side-frustum test is commented out (auxiliary.h:154)
+  mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, view, present);
+  return cudaGetLastError();
+}
+
+}  // namespace dge

@@ -1,0 +1,209 @@
+// K7: backward of the per-tile alpha blend.
+//
+// Replaces renderCUDA<3> backward (DGR/cuda_rasterizer/backward.cu:399-557). Same
+// per-pixel recurrences (T /= 1-alpha walking back to front, accum_rec, the
+// background term) and the same skip decisions as the forward (identical `power`
+// and alpha arithmetic), but:
+//  * the traversal starts at the tile's largest n_contrib instead of the end of the
+//    tile list, so occluded instances are never touched;
+//  * each thread owns a 2x2 quad and sums its pixels' contributions in registers;
+//  * the nine per-Gaussian partial gradients are reduced across the warp with a
+//    transposing butterfly (14 shuffles instead of 45) and leave the SM as ONE
+//    red.global instruction per warp and Gaussian (9 active lanes) instead of the
+//    reference's 9 atomics per contributing (pixel, Gaussian) pair;
+//  * warps in which no lane touches a Gaussian skip the reduction (ballot).
+// Sums are accumulated into acc[P][12] (see ACC_* in common.cuh); the per-Gaussian
+// kernel in geom_bwd.cu turns them into the reference's output tensors.
+#include "common.cuh"
+
+namespace dge {
+
+constexpr int RB_THREADS = 64;
+constexpr int RB_BATCH = 128;
+
+#define MUL(a, b) __fmul_rn((a), (b))
+#define ADD(a, b) __fadd_rn((a), (b))
+#define FMA(a, b, c) __fmaf_rn((a), (b), (c))
+
+__device__ __forceinline__ float power_threshold_b(float opacity) {
+  return opacity > 0.0f ? -(__logf(255.0f * opacity) + 0.01f) : __int_as_float(0x7f800000);
+}
+
+__global__ void __launch_bounds__(RB_THREADS) render_backward_kernel(
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
+    const float* __restrict__ background, const float2* __restrict__ means2D,
+    const float4* __restrict__ conic_opacity, const float4* __restrict__ rgb_depth,
+    const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
+    const float* __restrict__ dL_dpixels, float* __restrict__ acc) {
+  __shared__ float4 s_a[RB_BATCH];  // x, y, conic.x, conic.y
+  __shared__ float4 s_b[RB_BATCH];  // conic.z, power threshold, opacity, gid (bits)
+  __shared__ float4 s_c[RB_BATCH];  // r, g, b, unused
+  __shared__ uint32_t s_max[RB_THREADS / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int qx = tid & 7, qy = tid >> 3;
+  const int px0 = blockIdx.x * DGE_TILE + 2 * qx, py0 = blockIdx.y * DGE_TILE + 2 * qy;
+  const float fx0 = (float)px0, fx1 = (float)(px0 + 1), fy0 = (float)py0, fy1 = (float)(py0 + 1);
+  const size_t HW = (size_t)H * W;
+  const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
+
+  float T[4], T_final[4], accum[4][3], last_color[4][3], last_alpha[4], dpix[4][3], bg_dot[4];
+  uint32_t last[4];
+  const float bg0 = __ldg(background), bg1 = __ldg(background + 1), bg2 = __ldg(background + 2);
+  uint32_t tmax = 0;
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    const int x = px0 + (p & 1), y = py0 + (p >> 1);
+    const bool inside = x < W && y < H;
+    const size_t pix = (size_t)y * W + x;
+    T_final[p] = inside ? final_Ts[pix] : 0.0f;
+    T[p] = T_final[p];
+    last[p] = inside ? n_contrib[pix] : 0;
+    tmax = max(tmax, last[p]);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      dpix[p][c] = inside ? dL_dpixels[c * HW + pix] : 0.0f;
+      accum[p][c] = 0.0f;
+      last_color[p][c] = 0.0f;
+    }
+    last_alpha[p] = 0.0f;
+    bg_dot[p] = bg0 * dpix[p][0] + bg1 * dpix[p][1] + bg2 * dpix[p][2];
+  }
+  const uint32_t wmax = __reduce_max_sync(0xFFFFFFFFu, tmax);
+  if (lane == 0) s_max[tid >> 5] = wmax;
+  __syncthreads();
+  uint32_t bmax = 0;
+#pragma unroll
+  for (int w = 0; w < RB_THREADS / 32; w++) bmax = max(bmax, s_max[w]);
+
+  const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+
+  // positions hi-1 ... 0 of the tile list, back to front, in batches
+  for (uint32_t hi = bmax; hi > 0; hi -= min(hi, (uint32_t)RB_BATCH)) {
+    const int count = min(hi, (uint32_t)RB_BATCH);
+    __syncthreads();
+    for (int k = tid; k < count; k += RB_THREADS) {
+      const uint32_t gid = point_list[range.x + hi - 1 - k];
+      const float2 xy = means2D[gid];
+      const float4 co = conic_opacity[gid];
+      const float4 cd = rgb_depth[gid];
+      s_a[k] = make_float4(xy.x, xy.y, co.x, co.y);
+      s_b[k] = make_float4(co.z, power_threshold_b(co.w), co.w, __uint_as_float(gid));
+      s_c[k] = cd;
+    }
+    __syncthreads();
+    if (hi - count >= wmax) continue;  // nothing in this batch reaches this warp (warp-uniform)
+    for (int j = 0; j < count; j++) {
+      const uint32_t pos = hi - 1 - j;  // 0-based list position
+      const float4 a = s_a[j];
+      const float4 b = s_b[j];
+      const float dx0 = ADD(a.x, -fx0), dx1 = ADD(a.x, -fx1);
+      const float dy0 = ADD(a.y, -fy0), dy1 = ADD(a.y, -fy1);
+      const float bx0 = MUL(dx0, a.z), bx1 = MUL(dx1, a.z);
+      const float cx0 = MUL(dx0, a.w), cx1 = MUL(dx1, a.w);
+      const float ay0 = MUL(dy0, MUL(dy0, b.x)), ay1 = MUL(dy1, MUL(dy1, b.x));
+      float power[4];
+      power[0] = FMA(FMA(dx0, bx0, ay0), -0.5f, -MUL(dy0, cx0));
+      power[1] = FMA(FMA(dx1, bx1, ay0), -0.5f, -MUL(dy0, cx1));
+      power[2] = FMA(FMA(dx0, bx0, ay1), -0.5f, -MUL(dy1, cx0));
+      power[3] = FMA(FMA(dx1, bx1, ay1), -0.5f, -MUL(dy1, cx1));
+      bool cand[4];
+      bool any = false;
+#pragma unroll
+      for (int p = 0; p < 4; p++) {
+        cand[p] = pos < last[p] && !(power[p] > 0.0f) && !(power[p] < b.y);
+        any |= cand[p];
+      }
+      if (!__any_sync(0xFFFFFFFFu, any)) continue;
+
+      float g[9];
+#pragma unroll
+      for (int i = 0; i < 9; i++) g[i] = 0.0f;
+      bool touched = false;
+      if (any) {
+        const float opacity = b.z;
+        const float4 cd = s_c[j];
+        const float col[3] = {cd.x, cd.y, cd.z};
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+          if (!cand[p]) continue;
+          const float G = expf(power[p]);
+          const float alpha = fminf(0.99f, MUL(opacity, G));
+          if (alpha < 1.0f / 255.0f) continue;
+          touched = true;
+          const float dx = (p & 1) ? dx1 : dx0, dy = (p >> 1) ? dy1 : dy0;
+          const float inv = __frcp_rn(1.0f - alpha);
+          T[p] = T[p] * inv;
+          const float w = alpha * T[p];
+          float dL_dalpha = 0.0f;
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            accum[p][c] = last_alpha[p] * last_color[p][c] + (1.0f - last_alpha[p]) * accum[p][c];
+            last_color[p][c] = col[c];
+            dL_dalpha += (col[c] - accum[p][c]) * dpix[p][c];
+            g[ACC_R + c] += w * dpix[p][c];
+          }
+          dL_dalpha *= T[p];
+          last_alpha[p] = alpha;
+          dL_dalpha += (-T_final[p] * inv) * bg_dot[p];
+          const float dL_dG = opacity * dL_dalpha;
+          const float gdx = G * dx, gdy = G * dy;
+          const float dG_ddelx = -gdx * a.z - gdy * a.w;
+          const float dG_ddely = -gdy * b.x - gdx * a.w;
+          g[ACC_MEAN_X] += dL_dG * dG_ddelx * ddelx_dx;
+          g[ACC_MEAN_Y] += dL_dG * dG_ddely * ddely_dy;
+          g[ACC_CONIC_X] += -0.5f * gdx * dx * dL_dG;
+          g[ACC_CONIC_Y] += -0.5f * gdx * dy * dL_dG;
+          g[ACC_CONIC_W] += -0.5f * gdy * dy * dL_dG;
+          g[ACC_OPACITY] += G * dL_dalpha;
+        }
+      }
+      if (!__any_sync(0xFFFFFFFFu, touched)) continue;
+
+      // ---- transposing butterfly: g[0..7] -> lane L holds the warp total of g[L>>2]
+      const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+      float w4[4], w2[2], z;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const float send = h16 ? g[i] : g[i + 4];
+        const float keep = h16 ? g[i + 4] : g[i];
+        w4[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 16);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        const float send = h8 ? w4[i] : w4[i + 2];
+        const float keep = h8 ? w4[i + 2] : w4[i];
+        w2[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 8);
+      }
+      {
+        const float send = h4 ? w2[0] : w2[1];
+        const float keep = h4 ? w2[1] : w2[0];
+        z = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 4);
+      }
+      z += __shfl_xor_sync(0xFFFFFFFFu, z, 2);
+      z += __shfl_xor_sync(0xFFFFFFFFu, z, 1);
+      float z8 = g[8];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) z8 += __shfl_xor_sync(0xFFFFFFFFu, z8, o);
+      // lanes 0,4,...,28 own slots 0..7, lane 1 owns slot 8: one red.global for all nine
+      const uint32_t gid = __float_as_uint(b.w);
+      const bool owner = (lane & 3) == 0 || lane == 1;
+      if (owner) {
+        const int slot = lane == 1 ? 8 : (lane >> 2);
+        atomicAdd(acc + (size_t)gid * ACC_STRIDE + slot, lane == 1 ? z8 : z);
+      }
+    }
+  }
+}
+
+cudaError_t launch_render_backward(const ViewParams& vp, const GeomState& g, const BinState& b,
+                                   const ImgState& img, const float* background,
+                                   const float* dL_dpix, float* acc, cudaStream_t stream) {
+  dim3 grid(vp.grid_x, vp.grid_y);
+  render_backward_kernel<<<grid, RB_THREADS, 0, stream>>>(
+      img.ranges, b.point_list, vp.W, vp.H, background, g.means2D, g.conic_opacity, g.rgb_depth,
+      img.final_T, img.n_contrib, dL_dpix, acc);
+  return cudaGetLastError();
+}
+
+}  // namespace dge

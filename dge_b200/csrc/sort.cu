@@ -1,0 +1,237 @@
+// Hand-written stable onesweep LSD radix sort of (u32 key, u32 value) pairs.
+//
+// Replaces the two cub::DeviceRadixSort::SortPairs call sites of the reference
+// (DGR/cuda_rasterizer/rasterizer_impl.cu:256-261, :420-425); no CUB/Thrust.
+// One upfront histogram kernel for all passes, then one kernel per 8-bit digit:
+// every CTA ranks its 4096-item tile with warp match-any (stable), publishes its
+// digit counts, resolves its global base by decoupled look-back over the
+// predecessors' (flag|count) words, reorders the tile through shared memory and
+// writes each digit run coalesced. CTAs take their tile index from an atomic
+// ticket so that every predecessor of a running CTA is itself running or done.
+#include "common.cuh"
+
+namespace dge {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_IPT = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;  // 4096 items per CTA
+constexpr int MAX_PASSES = 4;
+constexpr uint32_t FLAG_AGG = 1u << 30, FLAG_PREFIX = 2u << 30, FLAG_MASK = 3u << 30;
+
+int sort_num_passes(int num_bits) { return (num_bits + RADIX_BITS - 1) / RADIX_BITS; }
+
+static inline uint32_t sort_num_tiles(uint32_t n) { return (n + SORT_TILE - 1) / SORT_TILE; }
+
+// workspace: [tickets: 64 u32][hist: MAX_PASSES*RADIX u32][status: MAX_PASSES*tiles*RADIX u32]
+size_t sort_workspace_bytes(uint32_t n) {
+  return sizeof(uint32_t) * (64 + (size_t)MAX_PASSES * RADIX + (size_t)MAX_PASSES * sort_num_tiles(n) * RADIX);
+}
+
+__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Digit histograms of every pass in one read of the keys.
+__global__ void __launch_bounds__(256) sort_histogram_kernel(const uint32_t* __restrict__ keys,
+                                                             uint32_t n, int num_passes,
+                                                             int num_bits,
+                                                             uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[MAX_PASSES * RADIX];
+  for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t k = keys[i];
+    for (int p = 0; p < num_passes; p++) {
+      const int shift = p * RADIX_BITS;
+      const int bits = min(RADIX_BITS, num_bits - shift);
+      const uint32_t d = (k >> shift) & ((1u << bits) - 1u);
+      atomicAdd(&sh[p * RADIX + d], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < num_passes * RADIX; i += blockDim.x)
+    if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(
+    const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
+    uint32_t digit_mask, const uint32_t* __restrict__ hist, uint32_t* status, uint32_t* ticket) {
+  __shared__ uint32_t s_cnt[SORT_WARPS][RADIX];  // per-warp digit counters -> warp bases
+  __shared__ uint32_t s_excl[RADIX];             // CTA-local exclusive digit prefix
+  __shared__ uint32_t s_base[RADIX];             // global base of each digit for this CTA, minus s_excl
+  __shared__ uint32_t s_keys[SORT_TILE];
+  __shared__ uint32_t s_vals[SORT_TILE];
+  __shared__ uint32_t s_warp_tot[SORT_WARPS];
+  __shared__ uint32_t s_tile;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&s_cnt[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t tile_base = tile * SORT_TILE;
+  const uint32_t tile_n = min((uint32_t)SORT_TILE, n - tile_base);
+
+  // ---- load (warp-striped: item order is (warp, i, lane), monotonic in the input index)
+  uint32_t key[SORT_IPT], val[SORT_IPT];
+  uint16_t rank[SORT_IPT];
+  const uint32_t warp_base = warp * (32 * SORT_IPT);
+#pragma unroll
+  for (int i = 0; i < SORT_IPT; i++) {
+    const uint32_t li = warp_base + i * 32 + lane;
+    if (li < tile_n) {
+      key[i] = keys_in[tile_base + li];
+      val[i] = vals_in ? vals_in[tile_base + li] : (tile_base + li);
+    } else {
+      key[i] = 0xFFFFFFFFu;
+      val[i] = 0;
+    }
+  }
+  // ---- stable rank inside the warp's sequence, digit by digit
+  const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int i = 0; i < SORT_IPT; i++) {
+    const uint32_t li = warp_base + i * 32 + lane;
+    const bool valid = li < tile_n;
+    const uint32_t d = valid ? ((key[i] >> shift) & digit_mask) : RADIX;  // RADIX = "none"
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+    const int leader = __ffs(peers) - 1;
+    uint32_t prev = 0;
+    if (valid && lane == leader) {
+      prev = s_cnt[warp][d];
+      s_cnt[warp][d] = prev + __popc(peers);
+    }
+    prev = __shfl_sync(0xFFFFFFFFu, prev, leader);
+    rank[i] = (uint16_t)(prev + __popc(peers & lt_mask));
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // ---- per digit: scan over warps, publish, look back, CTA-local digit prefix
+  uint32_t my_count = 0;  // thread d owns digit d (RADIX == SORT_THREADS)
+  {
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++) {
+      const uint32_t t = s_cnt[w][tid];
+      s_cnt[w][tid] = run;
+      run += t;
+    }
+    my_count = run;
+  }
+  uint32_t* my_status = status + (size_t)tile * RADIX + tid;
+  st_relaxed(my_status, (tile == 0 ? FLAG_PREFIX : FLAG_AGG) | my_count);
+  // CTA-local exclusive scan over digits (while the look-back words propagate)
+  {
+    uint32_t x = my_count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp_tot[warp] = x;
+    __syncthreads();
+    uint32_t wbase = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++)
+      if (w < warp) wbase += s_warp_tot[w];
+    s_excl[tid] = wbase + x - my_count;
+  }
+  // global digit base = (digits below, whole input) + (same digit, earlier tiles)
+  {
+    // exclusive prefix of the global histogram, recomputed per CTA (256 adds via warp scan)
+    const uint32_t h = hist[tid];
+    uint32_t x = h;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+      if (lane >= o) x += y;
+    }
+    __syncthreads();  // s_warp_tot reuse
+    if (lane == 31) s_warp_tot[warp] = x;
+    __syncthreads();
+    uint32_t wbase = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++)
+      if (w < warp) wbase += s_warp_tot[w];
+    uint32_t base = wbase + x - h;
+    if (tile > 0) {
+      uint32_t excl = 0;
+      int64_t b = (int64_t)tile - 1;
+      while (true) {
+        const uint32_t s = ld_relaxed(status + (size_t)b * RADIX + tid);
+        const uint32_t f = s & FLAG_MASK;
+        if (f == 0) continue;  // not published yet
+        excl += s & ~FLAG_MASK;
+        if (f == FLAG_PREFIX) break;
+        b--;
+      }
+      st_relaxed(my_status, FLAG_PREFIX | (excl + my_count));
+      base += excl;
+    }
+    s_base[tid] = base - s_excl[tid];
+  }
+  __syncthreads();
+
+  // ---- reorder through shared memory, then write digit runs coalesced
+#pragma unroll
+  for (int i = 0; i < SORT_IPT; i++) {
+    const uint32_t li = warp_base + i * 32 + lane;
+    if (li < tile_n) {
+      const uint32_t d = (key[i] >> shift) & digit_mask;
+      const uint32_t pos = s_excl[d] + s_cnt[warp][d] + rank[i];
+      s_keys[pos] = key[i];
+      s_vals[pos] = val[i];
+    }
+  }
+  __syncthreads();
+  for (uint32_t p = tid; p < tile_n; p += SORT_THREADS) {
+    const uint32_t k = s_keys[p];
+    const uint32_t d = (k >> shift) & digit_mask;
+    const uint32_t dst = s_base[d] + p;
+    keys_out[dst] = k;
+    vals_out[dst] = s_vals[p];
+  }
+}
+
+// Input in (keys[passes&1], vals[passes&1]); output in (keys[0], vals[0]).
+cudaError_t sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int num_bits,
+                       bool iota_values, uint32_t* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  if (n >= (1u << 30)) return cudaErrorInvalidValue;
+  const int passes = sort_num_passes(num_bits);
+  if (passes < 1 || passes > MAX_PASSES) return cudaErrorInvalidValue;
+  const uint32_t tiles = sort_num_tiles(n);
+  const size_t need = sizeof(uint32_t) * (64 + (size_t)MAX_PASSES * RADIX + (size_t)passes * tiles * RADIX);
+  if (need > ws_bytes) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(ws, 0, need, stream);
+  if (e != cudaSuccess) return e;
+  uint32_t* tickets = ws;
+  uint32_t* hist = ws + 64;
+  uint32_t* status = hist + MAX_PASSES * RADIX;
+  int cur = passes & 1;
+  const int hist_blocks = (int)min((uint32_t)(DGE_NUM_SMS * 4), (n + 2047) / 2048);
+  sort_histogram_kernel<<<hist_blocks, 256, 0, stream>>>(keys[cur], n, passes, num_bits, hist);
+  for (int p = 0; p < passes; p++) {
+    const int shift = p * RADIX_BITS;
+    const int bits = (num_bits - shift) < RADIX_BITS ? (num_bits - shift) : RADIX_BITS;
+    const uint32_t* vin = (p == 0 && iota_values) ? nullptr : vals[cur];
+    onesweep_kernel<<<tiles, SORT_THREADS, 0, stream>>>(
+        keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift, (1u << bits) - 1u,
+        hist + p * RADIX, status + (size_t)p * tiles * RADIX, tickets + p);
+    cur ^= 1;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace dge

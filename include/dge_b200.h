@@ -1,0 +1,145 @@
+/*
+ * dge_b200 — C-ABI of the B200-native differentiable Gaussian-splatting
+ * rasterizer that replaces DGE's `diff_gaussian_rasterization` hot path.
+ *
+ * Every entry point below is the drop-in for one function of the reference's
+ * torch-free CUDA library (`CudaRasterizer::Rasterizer`,
+ * gaussiansplatting/submodules/diff-gaussian-rasterization/cuda_rasterizer/
+ * rasterizer.h, abbreviated DGR/ below) or of its torch glue
+ * (DGR/rasterize_points.cu). Plain pointers and sizes only: all pointers are
+ * DEVICE pointers unless the name says `host`; the library allocates nothing
+ * persistent — scratch comes from the caller through the three allocator
+ * callbacks exactly like the reference's std::function<char*(size_t)> trio.
+ *
+ * Return value: >= 0 on success (dge_rasterize_forward returns num_rendered),
+ * < 0 on failure; dge_last_error() then returns a thread-local message.
+ * Streams are passed as void* (a cudaStream_t); NULL is the legacy stream.
+ */
+#ifndef DGE_B200_H_
+#define DGE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Scratch allocator: must return a device pointer to at least `bytes` bytes,
+ * 256-byte aligned, valid until the matching backward has run.
+ * Replaces std::function<char*(size_t)> (DGR/cuda_rasterizer/rasterizer.h:32-34,
+ * bound to torch tensors by resizeFunctional, DGR/rasterize_points.cu:27-33). */
+typedef char* (*dge_alloc_fn)(void* ctx, size_t bytes);
+
+const char* dge_last_error(void);
+/* ABI version of this header; bumped on any signature change. */
+int dge_abi_version(void);
+
+/* Replaces CudaRasterizer::Rasterizer::forward (DGR/cuda_rasterizer/rasterizer.h:31-56,
+ * rasterizer_impl.cu:179-285). Same argument meaning and order; additions:
+ * `alloc_ctx` (passed back to the three callbacks) and `stream`.
+ * NULL / empty semantics as the reference: shs==NULL <=> colors_precomp given,
+ * scales/rotations==NULL <=> cov3D_precomp given.
+ * out_color [3,H,W], out_depth [1,H,W], radii [P] (int32) are fully written. */
+int dge_rasterize_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer,
+                          dge_alloc_fn imageBuffer, void* alloc_ctx,
+                          int P, int D, int M, const float* background,
+                          int width, int height, const float* means3D,
+                          const float* shs, const float* colors_precomp,
+                          const float* opacities, const float* scales,
+                          float scale_modifier, const float* rotations,
+                          const float* cov3D_precomp, const float* viewmatrix,
+                          const float* projmatrix, const float* cam_pos,
+                          float tan_fovx, float tan_fovy, int prefiltered,
+                          float* out_color, float* out_depth, int* radii,
+                          int debug, void* stream);
+
+/* Replaces CudaRasterizer::Rasterizer::backward (DGR/cuda_rasterizer/rasterizer.h:58-87,
+ * rasterizer_impl.cu:289-341) TOGETHER WITH the nine torch::zeros fills of
+ * RasterizeGaussiansBackwardCUDA (DGR/rasterize_points.cu:120-128): every output
+ * below is fully written by the call (zeros for culled Gaussians), so the
+ * caller passes uninitialised memory. dL_dconic [P,4] and dL_dcolor [P,3] are
+ * the reference's intermediates; any output pointer except dL_dmean2D,
+ * dL_dmean3D may be NULL when the caller does not need it.
+ * dL_dmean2D is [P,3] with .z = 0 (DGR/rasterize_points.cu:121).
+ * `scratchBuffer` provides dge_backward_scratch_bytes(P) bytes that only need to
+ * live until the call's work on `stream` has finished (the blend-stage sums). */
+int dge_rasterize_backward(dge_alloc_fn scratchBuffer, void* alloc_ctx,
+                           int P, int D, int M, int R, const float* background,
+                           int width, int height, const float* means3D,
+                           const float* shs, const float* colors_precomp,
+                           const float* scales, float scale_modifier,
+                           const float* rotations, const float* cov3D_precomp,
+                           const float* viewmatrix, const float* projmatrix,
+                           const float* campos, float tan_fovx, float tan_fovy,
+                           const int* radii, char* geom_buffer,
+                           char* binning_buffer, char* image_buffer,
+                           const float* dL_dpix, float* dL_dmean2D,
+                           float* dL_dconic, float* dL_dopacity,
+                           float* dL_dcolor, float* dL_dmean3D,
+                           float* dL_dcov3D, float* dL_dsh, float* dL_dscale,
+                           float* dL_drot, int debug, void* stream);
+
+/* Replaces CudaRasterizer::Rasterizer::apply_weights (DGR/cuda_rasterizer/rasterizer.h:89-112,
+ * rasterizer_impl.cu:343-447): DGE's mask back-projection. `weights` [P,CH] f32
+ * and `cnt` [P] i32 are accumulated IN PLACE; image_weights is [CH,H,W],
+ * CH = num_channels in {1,2,3}. */
+int dge_apply_weights(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer,
+                      dge_alloc_fn imageBuffer, void* alloc_ctx, int P, int D,
+                      int M, const float* background, int width, int height,
+                      const float* means3D, const float* shs, float* weights,
+                      const float* opacities, const float* scales,
+                      float scale_modifier, const float* rotations,
+                      const float* cov3D_precomp, const float* viewmatrix,
+                      const float* projmatrix, const float* cam_pos,
+                      float tan_fovx, float tan_fovy, int prefiltered,
+                      const float* image_weights, int* radii, int* cnt,
+                      int num_channels, int debug, void* stream);
+
+/* Replaces CudaRasterizer::Rasterizer::markVisible (DGR/cuda_rasterizer/rasterizer.h:24-29,
+ * rasterizer_impl.cu:128-133). present is uint8[P] (bool). */
+int dge_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                     const float* projmatrix, uint8_t* present, void* stream);
+
+/* Scratch sizes (the reference's required<GeometryState/BinningState/ImageState>,
+ * DGR/cuda_rasterizer/rasterizer_impl.h:66-72). The layouts are ours. */
+size_t dge_geom_bytes(int P);
+size_t dge_binning_bytes(int R, int width, int height);
+size_t dge_image_bytes(int width, int height);
+size_t dge_backward_scratch_bytes(int P);
+
+/* Inspection of the opaque scratch blobs — used by the parity tests to compare
+ * every intermediate with the reference's (DGR/cuda_rasterizer/rasterizer_impl.cu:135-175).
+ * geom: out[0]=means2D float2[P], out[1]=conic_opacity float4[P],
+ *       out[2]=rgb_depth float4[P] (r,g,b,view-space depth), out[3]=rect
+ *       ushort4[P] (min.x,min.y,max.x,max.y), out[4]=clamped uint8[P] (bit ch),
+ *       out[5]=depth_order uint32[P] (Gaussian ids sorted by depth bits),
+ *       out[6]=point_offsets uint32[P] (inclusive, in depth order),
+ *       out[7]=num_rendered uint32[1]
+ * binning: out[0]=point_list uint32[R], out[1]=tile ids (sorted) uint32[R]
+ * image: out[0]=final_T float[N], out[1]=n_contrib uint32[N], out[2]=ranges uint2[T] */
+void dge_geom_pointers(char* chunk, int P, void** out);
+void dge_binning_pointers(char* chunk, int R, int width, int height, void** out);
+void dge_image_pointers(char* chunk, int width, int height, void** out);
+
+/* Rebuilds the reference's sorted 64-bit key list ((tile<<32)|depth bits,
+ * DGR/cuda_rasterizer/rasterizer_impl.cu:88-93) from our binning state, for
+ * bit-exact comparison. keys_out is uint64[R]. */
+int dge_debug_sorted_keys(char* geom_buffer, char* binning_buffer, int P, int R,
+                          int width, int height, uint64_t* keys_out,
+                          void* stream);
+
+/* ---- fit-step helpers ----
+ * Fused Adam over one flat fp32 parameter block (torch.optim.Adam semantics,
+ * gaussiansplatting/scene/gaussian_model.py:374: eps=1e-15, no weight decay,
+ * no amsgrad), with the optional per-Gaussian grad mask of
+ * gaussian_model.py:837-856 (mask uint8[n/stride] or NULL). In place. */
+int dge_fused_adam(float* param, const float* grad, float* exp_avg,
+                   float* exp_avg_sq, size_t n, float lr, float beta1,
+                   float beta2, float eps, int step, const uint8_t* mask,
+                   int stride, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGE_B200_H_ */

@@ -1,0 +1,150 @@
+// TEST INFRASTRUCTURE — not part of the product path.
+//
+// extern "C" shim over the UNMODIFIED reference rasterizer
+// (CudaRasterizer::Rasterizer, DGR/cuda_rasterizer/rasterizer.h:20-113) so
+// that tests/, __graft_entry__.smoke() and bench.py's reference arm can drive
+// the reference's own CUDA code (rebuilt for sm_100a by oracle/Makefile from
+// the sources where they lie under /root/reference) through ctypes.
+// Nothing under dge_b200/ may load the resulting oracle/_ref/libref_rast.so.
+//
+// The reference headers are included at build time via -I; no reference
+// source is copied into this repository.
+#include <cstdint>
+#include <cstdio>
+#include <functional>
+#include <stdexcept>
+#include <cuda_runtime.h>
+#include "rasterizer.h"
+#include "rasterizer_impl.h"
+
+typedef char* (*ref_alloc_fn)(size_t);
+
+static thread_local char g_err[512];
+
+extern "C" {
+
+const char* ref_last_error() { return g_err; }
+
+// DGR/cuda_rasterizer/rasterizer.h:31-56 (Rasterizer::forward)
+int ref_forward(ref_alloc_fn geom, ref_alloc_fn binning, ref_alloc_fn img,
+                int P, int D, int M, const float* background, int width,
+                int height, const float* means3D, const float* shs,
+                const float* colors_precomp, const float* opacities,
+                const float* scales, float scale_modifier,
+                const float* rotations, const float* cov3D_precomp,
+                const float* viewmatrix, const float* projmatrix,
+                const float* cam_pos, float tan_fovx, float tan_fovy,
+                int prefiltered, float* out_color, float* out_depth,
+                int* radii, int debug) {
+  try {
+    return CudaRasterizer::Rasterizer::forward(
+        geom, binning, img, P, D, M, background, width, height, means3D, shs,
+        colors_precomp, opacities, scales, scale_modifier, rotations,
+        cov3D_precomp, viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy,
+        prefiltered != 0, out_color, out_depth, radii, debug != 0);
+  } catch (const std::exception& e) {
+    snprintf(g_err, sizeof(g_err), "%s", e.what());
+    return -1;
+  }
+}
+
+// DGR/cuda_rasterizer/rasterizer.h:58-87 (Rasterizer::backward)
+int ref_backward(int P, int D, int M, int R, const float* background,
+                 int width, int height, const float* means3D,
+                 const float* shs, const float* colors_precomp,
+                 const float* scales, float scale_modifier,
+                 const float* rotations, const float* cov3D_precomp,
+                 const float* viewmatrix, const float* projmatrix,
+                 const float* campos, float tan_fovx, float tan_fovy,
+                 const int* radii, char* geom_buffer, char* binning_buffer,
+                 char* image_buffer, const float* dL_dpix, float* dL_dmean2D,
+                 float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+                 float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
+                 float* dL_dscale, float* dL_drot, int debug) {
+  try {
+    CudaRasterizer::Rasterizer::backward(
+        P, D, M, R, background, width, height, means3D, shs, colors_precomp,
+        scales, scale_modifier, rotations, cov3D_precomp, viewmatrix,
+        projmatrix, campos, tan_fovx, tan_fovy, radii, geom_buffer,
+        binning_buffer, image_buffer, dL_dpix, dL_dmean2D, dL_dconic,
+        dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale,
+        dL_drot, debug != 0);
+    return 0;
+  } catch (const std::exception& e) {
+    snprintf(g_err, sizeof(g_err), "%s", e.what());
+    return -1;
+  }
+}
+
+// DGR/cuda_rasterizer/rasterizer.h:89-112 (Rasterizer::apply_weights)
+int ref_apply_weights(ref_alloc_fn geom, ref_alloc_fn binning,
+                      ref_alloc_fn img, int P, int D, int M,
+                      const float* background, int width, int height,
+                      const float* means3D, const float* shs, float* weights,
+                      const float* opacities, const float* scales,
+                      float scale_modifier, const float* rotations,
+                      const float* cov3D_precomp, const float* viewmatrix,
+                      const float* projmatrix, const float* cam_pos,
+                      float tan_fovx, float tan_fovy, int prefiltered,
+                      const float* image_weights, int* radii, int* cnt,
+                      int num_channels, int debug) {
+  try {
+    CudaRasterizer::Rasterizer::apply_weights(
+        geom, binning, img, P, D, M, background, width, height, means3D, shs,
+        weights, opacities, scales, scale_modifier, rotations, cov3D_precomp,
+        viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy, prefiltered != 0,
+        image_weights, radii, cnt, num_channels, debug != 0);
+    return 0;
+  } catch (const std::exception& e) {
+    snprintf(g_err, sizeof(g_err), "%s", e.what());
+    return -1;
+  }
+}
+
+// DGR/cuda_rasterizer/rasterizer.h:24-29 (Rasterizer::markVisible)
+void ref_mark_visible(int P, float* means3D, float* viewmatrix,
+                      float* projmatrix, bool* present) {
+  CudaRasterizer::Rasterizer::markVisible(P, means3D, viewmatrix, projmatrix,
+                                          present);
+}
+
+// Where the reference keeps each intermediate inside its opaque byte blobs
+// (DGR/cuda_rasterizer/rasterizer_impl.cu:135-175 fromChunk). Lets the golden
+// generator read every intermediate without restating the layout.
+// out[0..9] = depths, clamped, internal_radii, means2D, cov3D, conic_opacity,
+//             rgb, tiles_touched, scanning_space, point_offsets
+void ref_geom_pointers(char* chunk, size_t P, void** out) {
+  CudaRasterizer::GeometryState g =
+      CudaRasterizer::GeometryState::fromChunk(chunk, P);
+  out[0] = g.depths;
+  out[1] = g.clamped;
+  out[2] = g.internal_radii;
+  out[3] = g.means2D;
+  out[4] = g.cov3D;
+  out[5] = g.conic_opacity;
+  out[6] = g.rgb;
+  out[7] = g.tiles_touched;
+  out[8] = g.scanning_space;
+  out[9] = g.point_offsets;
+}
+
+// out[0..3] = point_list, point_list_unsorted, point_list_keys,
+//             point_list_keys_unsorted
+void ref_binning_pointers(char* chunk, size_t R, void** out) {
+  CudaRasterizer::BinningState b =
+      CudaRasterizer::BinningState::fromChunk(chunk, R);
+  out[0] = b.point_list;
+  out[1] = b.point_list_unsorted;
+  out[2] = b.point_list_keys;
+  out[3] = b.point_list_keys_unsorted;
+}
+
+// out[0..2] = accum_alpha (final_T), n_contrib, ranges
+void ref_img_pointers(char* chunk, size_t N, void** out) {
+  CudaRasterizer::ImageState s = CudaRasterizer::ImageState::fromChunk(chunk, N);
+  out[0] = s.accum_alpha;
+  out[1] = s.n_contrib;
+  out[2] = s.ranges;
+}
+
+}  // extern "C"
