@@ -37,6 +37,9 @@ _SIGNATURES = {
     "dge_binning_pointers": (None, [_p, _i, _i, _i, C.POINTER(_p)]),
     "dge_image_pointers": (None, [_p, _i, _i, C.POINTER(_p)]),
     "dge_debug_sorted_keys": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
+    "dge_launch_count": (C.c_ulonglong, []),
+    "dge_profile_enable": (None, [C.c_uint]),
+    "dge_profile_read": (_i, [C.POINTER(C.c_float), C.POINTER(_i)]),
     "dge_fused_adam": (_i, [_p, _p, _p, _p, C.c_size_t, _f, _f, _f, _f, _i, _p, _i, _p]),
 }
 EXPORTS = tuple(_SIGNATURES)

@@ -6,9 +6,35 @@
 #include "../../include/dge_b200.h"
 #include "common.cuh"
 
+#include <vector>
+
 namespace dge {
 
+unsigned long long g_kernel_launches = 0;
+
 static thread_local char g_err[512] = "";
+
+// ---- optional per-stage CUDA-event timing on the launching stream (bench.py roofline) ----
+enum { ST_PREPROCESS = 0, ST_DEPTH_SORT, ST_BINNING, ST_RENDER_FWD, ST_RENDER_BWD, ST_GEOM_BWD,
+       ST_APPLY_WEIGHTS, ST_COUNT };
+static unsigned g_profile_mask = 0;
+struct EvPair { cudaEvent_t a, b; };
+static std::vector<EvPair> g_ev_free;
+static std::vector<EvPair> g_ev_used[ST_COUNT];
+struct StageScope {
+  int st; cudaStream_t s; bool on; EvPair ev;
+  StageScope(int st_, cudaStream_t s_) : st(st_), s(s_), on((g_profile_mask >> st_) & 1u) {
+    if (!on) return;
+    if (g_ev_free.empty()) { cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); }
+    else { ev = g_ev_free.back(); g_ev_free.pop_back(); }
+    cudaEventRecord(ev.a, s);
+  }
+  ~StageScope() {
+    if (!on) return;
+    cudaEventRecord(ev.b, s);
+    g_ev_used[st].push_back(ev);
+  }
+};
 
 static int fail(const char* where, cudaError_t e) {
   snprintf(g_err, sizeof(g_err), "dge_b200: %s: %s (%d)", where, cudaGetErrorString(e), (int)e);
@@ -25,9 +51,12 @@ static int fail_msg(const char* msg) {
     if (_e != cudaSuccess) return fail(where, _e);    \
   } while (0)
 // debug=True in the reference = synchronise and check after every stage (auxiliary.h:166-173)
-#define STAGE(where, expr)                                                   \
+#define STAGE(st, where, expr)                                               \
   do {                                                                       \
-    CK(where, (expr));                                                       \
+    {                                                                        \
+      StageScope _scope(st, stream);                                         \
+      CK(where, (expr));                                                     \
+    }                                                                        \
     if (debug) CK(where " (debug sync)", cudaStreamSynchronize(stream));     \
   } while (0)
 
@@ -143,19 +172,19 @@ static int bin_view(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge
   if (!gp || !ip) return fail_msg("scratch allocator returned NULL");
   carve_geom(gp, vp.P, &g);
   carve_image(ip, vp.W, vp.H, &img);
-  STAGE("preprocess", launch_preprocess(vp, means3D, scales, rotations, opacities, shs, cov3D_precomp,
+  STAGE(ST_PREPROCESS, "preprocess", launch_preprocess(vp, means3D, scales, rotations, opacities, shs, cov3D_precomp,
                                         colors_precomp, colors_mode, prefiltered, radii, g, stream));
   CK("num_rendered copy", cudaMemcpyAsync(g_slot.pinned, g.counters, sizeof(uint32_t),
                                           cudaMemcpyDeviceToHost, stream));
   CK("event record", cudaEventRecord(g_slot.ev, stream));
-  STAGE("depth sort", launch_depth_sort(vp.P, g, stream));
+  STAGE(ST_DEPTH_SORT, "depth sort", launch_depth_sort(vp.P, g, stream));
   CK("num_rendered wait", cudaEventSynchronize(g_slot.ev));
   const uint32_t R = *g_slot.pinned;
   if (R >= (1u << 30)) return fail_msg("num_rendered exceeds 2^30 instances");
   char* bp = binningBuffer(ctx, carve_binning(nullptr, (int)R, vp.W, vp.H, nullptr));
   if (!bp) return fail_msg("scratch allocator returned NULL");
   carve_binning(bp, (int)R, vp.W, vp.H, &b);
-  STAGE("binning", launch_binning(vp, (int)R, g, b, img, stream));
+  STAGE(ST_BINNING, "binning", launch_binning(vp, (int)R, g, b, img, stream));
   return (int)R;
 }
 
@@ -167,6 +196,28 @@ extern "C" {
 
 const char* dge_last_error(void) { return g_err; }
 int dge_abi_version(void) { return 1; }
+unsigned long long dge_launch_count(void) { return g_kernel_launches; }
+
+void dge_profile_enable(unsigned stage_mask) { g_profile_mask = stage_mask; }
+// Sums (and clears) the event-timed durations recorded since the last call.
+// ms_out / count_out have DGE_NUM_STAGES entries. Synchronises on the recorded events.
+int dge_profile_read(float* ms_out, int* count_out) {
+  for (int st = 0; st < ST_COUNT; st++) {
+    float total = 0.f;
+    for (const EvPair& ev : g_ev_used[st]) {
+      cudaError_t e = cudaEventSynchronize(ev.b);
+      float ms = 0.f;
+      if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ev.a, ev.b);
+      if (e != cudaSuccess) return fail("profile read", e);
+      total += ms;
+      g_ev_free.push_back(ev);
+    }
+    ms_out[st] = total;
+    count_out[st] = (int)g_ev_used[st].size();
+    g_ev_used[st].clear();
+  }
+  return 0;
+}
 
 size_t dge_geom_bytes(int P) { return carve_geom(nullptr, P, nullptr); }
 size_t dge_binning_bytes(int R, int width, int height) {
@@ -202,7 +253,7 @@ int dge_rasterize_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffe
                          colors_precomp, colors_precomp ? 1 : 0, opacities, scales, rotations,
                          cov3D_precomp, prefiltered != 0, radii, debug != 0, stream, g, b, img);
   if (R < 0) return R;
-  STAGE("render forward",
+  STAGE(ST_RENDER_FWD, "render forward",
         launch_render_forward(vp, g, b, img, background, out_color, out_depth, stream));
   return R;
 }
@@ -234,9 +285,9 @@ int dge_rasterize_backward(dge_alloc_fn scratchBuffer, void* alloc_ctx, int P, i
   float* acc = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sp) + 255) & ~uintptr_t(255));
   CK("memset acc", cudaMemsetAsync(acc, 0, acc_bytes, stream));
   if (R > 0)
-    STAGE("render backward", launch_render_backward(vp, g, b, img, background, dL_dpix, acc, stream));
+    STAGE(ST_RENDER_BWD, "render backward", launch_render_backward(vp, g, b, img, background, dL_dpix, acc, stream));
   (void)colors_precomp;
-  STAGE("geometry backward",
+  STAGE(ST_GEOM_BWD, "geometry backward",
         launch_geom_backward(vp, means3D, scales, rotations, shs, cov3D_precomp, radii, g, acc,
                              dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D,
                              dL_dsh, dL_dscale, dL_drot, stream));
@@ -268,7 +319,7 @@ int dge_apply_weights(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer,
                          prefiltered != 0, radii, debug != 0, stream, g, b, img);
   if (R < 0) return R;
   if (R > 0)
-    STAGE("apply_weights blend", launch_apply_weights_render(vp, g, b, img, weights, cnt,
+    STAGE(ST_APPLY_WEIGHTS, "apply_weights blend", launch_apply_weights_render(vp, g, b, img, weights, cnt,
                                                              image_weights, num_channels, stream));
   return R;
 }

@@ -131,6 +131,7 @@ cudaError_t launch_apply_weights_render(const ViewParams& vp, const GeomState& g
   else if (num_channels == 3) AW_LAUNCH(3);
   else return cudaErrorInvalidValue;  // the reference prints and exit(-1)s (apply_weights.cu:377-380)
 #undef AW_LAUNCH
+  DGE_LAUNCHED(1);
   return cudaGetLastError();
 }
 
@@ -166,6 +167,7 @@ cudaError_t launch_fused_adam(float* param, const float* grad, float* m, float* 
   const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
   fused_adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
       param, grad, m, v, n, step_size, inv_bc2_sqrt, beta1, beta2, eps, mask, stride > 0 ? stride : 1);
+  DGE_LAUNCHED(1);
   return cudaGetLastError();
 }
 

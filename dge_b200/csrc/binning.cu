@@ -190,12 +190,14 @@ cudaError_t launch_binning(const ViewParams& vp, int R, GeomState& g, BinState& 
   uint32_t* vals[2] = {b.point_list, b.val_alt};
   expand_kernel<<<blocks, SCAN_THREADS, 0, stream>>>(P, vp.grid_x, order, g.rect, g.block_sums,
                                                      g.offsets, keys[passes & 1], vals[passes & 1]);
+  DGE_LAUNCHED(3);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (passes > 0) {
     e = sort_pairs(keys, vals, (uint32_t)R, bits, /*iota=*/false, b.sort_ws, b.sort_ws_bytes, stream);
     if (e != cudaSuccess) return e;
   }
   tile_ranges_kernel<<<(R + 255) / 256, 256, 0, stream>>>((uint32_t)R, b.tile_ids, img.ranges);
+  DGE_LAUNCHED(1);
   return cudaGetLastError();
 }
 

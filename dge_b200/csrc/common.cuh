@@ -9,6 +9,10 @@
 
 namespace dge {
 
+// Number of kernels this library has launched (read by bench.py through dge_launch_count()).
+extern unsigned long long g_kernel_launches;
+#define DGE_LAUNCHED(n) (::dge::g_kernel_launches += (n))
+
 // ---------------------------------------------------------------- scratch ---
 // Our own layout of the three opaque blobs (the reference's is
 // DGR/cuda_rasterizer/rasterizer_impl.cu:135-175). All sub-arrays 256-B aligned.

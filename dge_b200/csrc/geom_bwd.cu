@@ -331,6 +331,7 @@ cudaError_t launch_geom_backward(const ViewParams& vp, const float* means3D, con
   geom_backward_kernel<<<(vp.P + 255) / 256, 256, 0, stream>>>(
       vp, means3D, scales, rotations, shs, cov3D_precomp, radii, g.clamped, acc, dL_dmean2D,
       dL_dconic, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot);
+  DGE_LAUNCHED(1);
   return cudaGetLastError();
 }
 

@@ -241,6 +241,7 @@ cudaError_t launch_preprocess(const ViewParams& vp, const float* means3D, const 
   preprocess_kernel<<<blocks, 256, 0, stream>>>(vp, means3D, scales, rotations, opacities, shs,
                                                 cov3D_precomp, colors_precomp, colors_mode, prefiltered,
                                                 radii, g);
+  DGE_LAUNCHED(1);
   return cudaGetLastError();
 }
 
@@ -262,6 +263,7 @@ cudaError_t launch_mark_visible(int P, const float* means3D, const float* view, 
                                 uint8_t* present, cudaStream_t stream) {
   (void)proj;  // the reference's side-frustum test is commented out (auxiliary.h:154)
   mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, view, present);
+  DGE_LAUNCHED(1);
   return cudaGetLastError();
 }
 

@@ -132,8 +132,8 @@ __global__ void __launch_bounds__(RB_THREADS) render_backward_kernel(
           if (alpha < 1.0f / 255.0f) continue;
           touched = true;
           const float dx = (p & 1) ? dx1 : dx0, dy = (p >> 1) ? dy1 : dy0;
-          const float inv = __frcp_rn(1.0f - alpha);
-          T[p] = T[p] * inv;
+          const float one_m = 1.0f - alpha;
+          T[p] = __fdiv_rn(T[p], one_m);  // same recurrence as the reference (backward.cu:505)
           const float w = alpha * T[p];
           float dL_dalpha = 0.0f;
 #pragma unroll
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(RB_THREADS) render_backward_kernel(
           }
           dL_dalpha *= T[p];
           last_alpha[p] = alpha;
-          dL_dalpha += (-T_final[p] * inv) * bg_dot[p];
+          dL_dalpha += __fdiv_rn(-T_final[p], one_m) * bg_dot[p];
           const float dL_dG = opacity * dL_dalpha;
           const float gdx = G * dx, gdy = G * dy;
           const float dG_ddelx = -gdx * a.z - gdy * a.w;
@@ -203,6 +203,7 @@ cudaError_t launch_render_backward(const ViewParams& vp, const GeomState& g, con
   render_backward_kernel<<<grid, RB_THREADS, 0, stream>>>(
       img.ranges, b.point_list, vp.W, vp.H, background, g.means2D, g.conic_opacity, g.rgb_depth,
       img.final_T, img.n_contrib, dL_dpix, acc);
+  DGE_LAUNCHED(1);
   return cudaGetLastError();
 }
 

@@ -144,6 +144,7 @@ cudaError_t launch_render_forward(const ViewParams& vp, const GeomState& g, cons
   render_forward_kernel<<<grid, RF_THREADS, 0, stream>>>(
       img.ranges, b.point_list, vp.W, vp.H, g.means2D, g.conic_opacity, g.rgb_depth, background,
       img.final_T, img.n_contrib, out_color, out_depth);
+  DGE_LAUNCHED(1);
   return cudaGetLastError();
 }
 

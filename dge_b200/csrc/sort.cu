@@ -231,6 +231,7 @@ cudaError_t sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int num
         hist + p * RADIX, status + (size_t)p * tiles * RADIX, tickets + p);
     cur ^= 1;
   }
+  DGE_LAUNCHED(1 + passes);
   return cudaGetLastError();
 }
 

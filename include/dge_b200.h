@@ -129,6 +129,16 @@ int dge_debug_sorted_keys(char* geom_buffer, char* binning_buffer, int P, int R,
                           int width, int height, uint64_t* keys_out,
                           void* stream);
 
+/* ---- measurement hooks (bench.py) ----
+ * Kernels launched by this library so far (all entry points, this process). */
+unsigned long long dge_launch_count(void);
+/* Per-stage CUDA-event timing on the launching stream. Bit s of stage_mask enables stage s:
+ * 0 preprocess, 1 depth sort, 2 binning (scan+expand+tile sort+ranges), 3 blend forward,
+ * 4 blend backward, 5 per-Gaussian backward, 6 apply_weights blend. */
+#define DGE_NUM_STAGES 7
+void dge_profile_enable(unsigned stage_mask);
+int dge_profile_read(float* ms_out, int* count_out);
+
 /* ---- fit-step helpers ----
  * Fused Adam over one flat fp32 parameter block (torch.optim.Adam semantics,
  * gaussiansplatting/scene/gaussian_model.py:374: eps=1e-15, no weight decay,

@@ -1,0 +1,206 @@
+"""Helpers shared by the tests: run the product (dge_b200), the reference rebuilt for sm_100a
+(oracle/_ref via oracle/ref.py) and the CPU oracle on the same seeded inputs."""
+import ctypes as C
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from dge_b200 import scene  # noqa: E402
+
+
+def tans(cam):
+    return math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5)
+
+
+def to_dev(g, dev):
+    return scene.Gaussians(*[t.to(dev) for t in g])
+
+
+def ours_forward(g, cam, bg, dev, sh_degree=3, scale_modifier=1.0, colors_precomp=None, cov3D_precomp=None,
+                 requires_grad=False, debug=False):
+    """Calls the public API (GaussianRasterizer.forward) and returns (outputs, leaves, ctx dict)."""
+    from dge_b200 import diff_gaussian_rasterization as dgr
+    gd = to_dev(g, dev)
+    cam_d = scene.camera_to(cam, dev)
+    rs = scene.raster_settings(cam_d, bg.to(dev), sh_degree, scale_modifier, debug, module=dgr)
+    leaves = {k: getattr(gd, k).clone().requires_grad_(requires_grad) for k in gd._fields}
+    means2D = torch.zeros_like(leaves["means3D"], requires_grad=requires_grad)
+    leaves["means2D"] = means2D
+    kw = {}
+    if colors_precomp is not None:
+        leaves["colors_precomp"] = colors_precomp.to(dev).clone().requires_grad_(requires_grad)
+        kw.update(shs=None, colors_precomp=leaves["colors_precomp"])
+    else:
+        kw.update(shs=leaves["shs"], colors_precomp=None)
+    if cov3D_precomp is not None:
+        leaves["cov3D_precomp"] = cov3D_precomp.to(dev).clone().requires_grad_(requires_grad)
+        kw.update(scales=None, rotations=None, cov3D_precomp=leaves["cov3D_precomp"])
+    else:
+        kw.update(scales=leaves["scales"], rotations=leaves["rotations"], cov3D_precomp=None)
+    rast = dgr.GaussianRasterizer(rs)
+    color, radii, depth = rast(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"], **kw)
+    return (color, radii, depth), leaves, rs
+
+
+def ours_intermediates(rs, g, dev, colors_precomp=None, cov3D_precomp=None):
+    """Runs the library's forward directly and reads every intermediate out of the scratch blobs,
+    under the reference's names."""
+    from dge_b200 import _lib as L
+    from dge_b200 import diff_gaussian_rasterization as dgr
+    gd = to_dev(g, dev)
+    e = torch.empty(0, dtype=torch.float32, device=dev)
+    cp = e if colors_precomp is None else colors_precomp.to(dev)
+    c3 = e if cov3D_precomp is None else cov3D_precomp.to(dev)
+    sh = gd.shs if colors_precomp is None else e
+    sc, ro = (gd.scales, gd.rotations) if cov3D_precomp is None else (e, e)
+    R, color, depth, radii, geom, binning, img = dgr._forward_call(rs, gd.means3D, cp, gd.opacities, sc, ro, c3, sh)
+    lib = L.load()
+    P = gd.means3D.shape[0]
+    H, W = int(rs.image_height), int(rs.image_width)
+    N, T = H * W, ((W + 15) // 16) * ((H + 15) // 16)
+
+    def view(base, p, dtype, count):
+        off = p - base.data_ptr()
+        nb = count * torch.empty(0, dtype=dtype).element_size()
+        return base[off:off + nb].view(dtype)
+
+    gp = (C.c_void_p * 8)()
+    lib.dge_geom_pointers(geom.data_ptr(), P, gp)
+    o = {"num_rendered": R, "radii": radii, "out_color": color, "out_depth": depth}
+    o["means2D"] = view(geom, gp[0], torch.float32, 2 * P).view(P, 2)
+    o["conic_opacity"] = view(geom, gp[1], torch.float32, 4 * P).view(P, 4)
+    rd = view(geom, gp[2], torch.float32, 4 * P).view(P, 4)
+    o["rgb"], o["depths"] = rd[:, :3], rd[:, 3]
+    o["rect"] = view(geom, gp[3], torch.int16, 4 * P).view(P, 4).to(torch.int32) & 0xFFFF
+    cl = view(geom, gp[4], torch.uint8, P)
+    o["clamped"] = torch.stack([(cl >> c) & 1 for c in range(3)], 1)
+    o["depth_order"] = view(geom, gp[5], torch.int32, P)
+    o["tiles_touched"] = (o["rect"][:, 2] - o["rect"][:, 0]) * (o["rect"][:, 3] - o["rect"][:, 1])
+    if R > 0:
+        bp = (C.c_void_p * 2)()
+        lib.dge_binning_pointers(binning.data_ptr(), R, W, H, bp)
+        o["point_list"] = view(binning, bp[0], torch.int32, R)
+        keys = torch.empty(R, dtype=torch.int64, device=dev)
+        L.check(lib.dge_debug_sorted_keys(geom.data_ptr(), binning.data_ptr(), P, R, W, H, keys.data_ptr(),
+                                          L.stream_ptr(dev)), "debug keys")
+        o["keys"] = keys
+    ip = (C.c_void_p * 3)()
+    lib.dge_image_pointers(img.data_ptr(), W, H, ip)
+    o["final_T"] = view(img, ip[0], torch.float32, N).view(H, W)
+    o["n_contrib"] = view(img, ip[1], torch.int32, N).view(H, W)
+    o["ranges"] = view(img, ip[2], torch.int32, 2 * T).view(T, 2)
+    torch.cuda.synchronize()
+    res = {k: (v.detach().cpu().numpy().copy() if isinstance(v, torch.Tensor) else v) for k, v in o.items()}
+    vis = res["radii"] > 0
+    for k in ("depths", "clamped", "means2D", "conic_opacity", "rgb"):
+        res[k][~vis] = 0
+    return res
+
+
+def ref_forward(g, cam, bg, dev, sh_degree=3, scale_modifier=1.0, colors_precomp=None, cov3D_precomp=None):
+    """The reference (oracle/_ref) on the same inputs; returns (dict of intermediates, saved state)."""
+    from oracle import ref
+    gd = to_dev(g, dev)
+    cam_d = scene.camera_to(cam, dev)
+    tfx, tfy = tans(cam)
+    e = torch.empty(0, dtype=torch.float32, device=dev)
+    cp = e if colors_precomp is None else colors_precomp.to(dev).contiguous()
+    c3 = e if cov3D_precomp is None else cov3D_precomp.to(dev).contiguous()
+    sh = gd.shs if colors_precomp is None else e
+    sc, ro = (gd.scales, gd.rotations) if cov3D_precomp is None else (e, e)
+    H, W = cam.image_height, cam.image_width
+    bgd = bg.to(dev)
+    args = dict(bg=bgd, means3D=gd.means3D, colors=cp, opacity=gd.opacities, scales=sc, rotations=ro,
+                scale_modifier=scale_modifier, cov3D_precomp=c3, viewmatrix=cam_d.world_view_transform,
+                projmatrix=cam_d.full_proj_transform, tan_fovx=tfx, tan_fovy=tfy, H=H, W=W, sh=sh, degree=sh_degree,
+                campos=cam_d.camera_center, prefiltered=False, debug=False)
+    R, color, depth, radii, geom, binning, img = ref.rasterize_gaussians(**args)
+    torch.cuda.synchronize()
+    inter = ref.intermediates(gd.means3D.shape[0], R, H, W, geom, binning, img, radii)
+    inter.update(num_rendered=R, out_color=color.cpu().numpy(), out_depth=depth.cpu().numpy())
+    state = dict(args=args, R=R, radii=radii, geom=geom, binning=binning, img=img)
+    return inter, state
+
+
+def ref_backward(state, dL_dcolor):
+    from oracle import ref
+    a = state["args"]
+    out = ref.rasterize_gaussians_backward(a["bg"], a["means3D"], state["radii"], a["colors"], a["scales"], a["rotations"],
+                                           a["scale_modifier"], a["cov3D_precomp"], a["viewmatrix"], a["projmatrix"],
+                                           a["tan_fovx"], a["tan_fovy"], dL_dcolor, a["sh"], a["degree"], a["campos"],
+                                           state["geom"], state["R"], state["binning"], state["img"], False)
+    torch.cuda.synchronize()
+    names = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscales",
+             "dL_drotations", "dL_dconic"]
+    return {n: t.cpu().numpy() for n, t in zip(names, out)}
+
+
+def oracle_forward(g, cam, bg, sh_degree=3, scale_modifier=1.0, colors_precomp=None, cov3D_precomp=None):
+    from oracle import oracle
+    tfx, tfy = tans(cam)
+    kw = {}
+    if colors_precomp is None:
+        kw["shs"] = g.shs.numpy()
+    else:
+        kw["colors_precomp"] = colors_precomp.numpy()
+    if cov3D_precomp is None:
+        kw.update(scales=g.scales.numpy(), rotations=g.rotations.numpy())
+    else:
+        kw["cov3D_precomp"] = cov3D_precomp.numpy()
+    return oracle.forward(g.means3D.numpy(), g.opacities.numpy(), cam.world_view_transform.numpy(),
+                          cam.full_proj_transform.numpy(), cam.camera_center.numpy(), bg.numpy(), cam.image_width,
+                          cam.image_height, tfx, tfy, sh_degree=sh_degree, scale_modifier=scale_modifier, **kw)
+
+
+def oracle_backward(fw, dL, g, cam, bg, sh_degree=3, scale_modifier=1.0, colors_precomp=None, cov3D_precomp=None):
+    from oracle import oracle
+    tfx, tfy = tans(cam)
+    kw = {}
+    if colors_precomp is None:
+        kw["shs"] = g.shs.numpy()
+    else:
+        kw["colors_precomp"] = colors_precomp.numpy()
+    if cov3D_precomp is None:
+        kw.update(scales=g.scales.numpy(), rotations=g.rotations.numpy())
+    else:
+        kw["cov3D_precomp"] = cov3D_precomp.numpy()
+    return oracle.backward(fw, dL.numpy(), g.means3D.numpy(), cam.world_view_transform.numpy(),
+                           cam.full_proj_transform.numpy(), cam.camera_center.numpy(), bg.numpy(), cam.image_width,
+                           cam.image_height, tfx, tfy, sh_degree=sh_degree, scale_modifier=scale_modifier, **kw)
+
+
+def rel_err(a, b):
+    """max|a-b| / max|b| — the per-tensor relative error used for atomically summed gradients."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)) if b.size else 0.0
+
+
+BIT_EXACT = ("radii", "tiles_touched", "means2D", "depths", "conic_opacity", "rgb", "clamped", "keys", "point_list",
+             "ranges", "n_contrib", "final_T", "out_color", "out_depth")
+
+
+def compare_exact(a, b, names=BIT_EXACT):
+    """Returns {name: number of differing elements} comparing raw bits."""
+    bad = {}
+    for n in names:
+        if n not in a or n not in b:
+            continue
+        x, y = np.ascontiguousarray(a[n]), np.ascontiguousarray(b[n])
+        if x.dtype.kind == "f":
+            x, y = x.view(np.uint32), np.ascontiguousarray(y.astype(np.float32)).view(np.uint32)
+        else:
+            x, y = x.astype(np.int64), y.astype(np.int64)
+        if x.shape != y.shape:
+            bad[n] = -1
+            continue
+        d = int((x != y).sum())
+        if d:
+            bad[n] = d
+    return bad
