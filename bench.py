@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py — fwd+bwd views/s of the DGE 3D-fit step (BASELINE.json metric).
+
+Workload (config 2 of BASELINE.json / SURVEY.md §8d): 1 M synthetic Gaussians (randgauss-v1),
+SH degree 3, a batch of 20 edited views per GPU at 512x512, L1 loss to fixed random targets,
+forward + backward through the rasterizer for every view, one Adam step over the 59
+floats/Gaussian per step. One process per GPU; with N>1 each rank fits 20 views per step
+against its replica and the gradients + densification statistics are all-reduced (weak scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0). `value` = views/s with the step's inputs resident in HBM;
+`e2e` = the same step through the public API with cameras/targets in pinned HOST memory and
+the loss read back every step. `--impl reference` drives the UNMODIFIED reference rasterizer
+rebuilt for sm_100a (oracle/_ref; the reference ships no CPU rasterizer) through the same
+harness with torch.optim.Adam, on one GPU.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: P, W, H, views per GPU per step, seed
+    "config2": dict(P=1_000_000, W=512, H=512, V=20, seed=1236,
+                    desc="DGE global edit fit: 1M Gaussians, 20 views/step/GPU at 512x512, fwd+bwd+Adam"),
+    "config1": dict(P=16_384, W=256, H=256, V=1, seed=1235, desc="16k Gaussians, one 256x256 view (parity config)"),
+    "tiny": dict(P=50_000, W=256, H=256, V=4, seed=1240, desc="smoke-sized"),
+}
+
+
+# --------------------------------------------------------------------------- clocks -----
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ reference arm -----
+def make_reference_rasterize():
+    """autograd.Function around the reference's _C calls, mirroring
+    DGR/diff_gaussian_rasterization/__init__.py:50-225 (the reference's own binding cannot be
+    imported: its _C is a torch extension that needs ~5 min of nvcc per build)."""
+    from oracle import ref
+
+    class RefRasterize(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, means3D, means2D, sh, opacities, scales, rotations, rs):
+            e = torch.empty(0, dtype=torch.float32, device=means3D.device)
+            R, color, depth, radii, geom, binning, img = ref.rasterize_gaussians(
+                rs.bg, means3D, e, opacities, scales, rotations, rs.scale_modifier, e, rs.viewmatrix, rs.projmatrix,
+                rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, sh, rs.sh_degree, rs.campos,
+                rs.prefiltered, rs.debug)
+            ctx.rs, ctx.R = rs, R
+            ctx.save_for_backward(means3D, scales, rotations, radii, sh, geom, binning, img)
+            return color, radii, depth
+
+        @staticmethod
+        def backward(ctx, grad_color, _gr, _gd):
+            rs = ctx.rs
+            means3D, scales, rotations, radii, sh, geom, binning, img = ctx.saved_tensors
+            e = torch.empty(0, dtype=torch.float32, device=means3D.device)
+            (g_m2d, _g_col, g_op, g_m3d, _g_cov, g_sh, g_sc, g_rot, _g_con) = ref.rasterize_gaussians_backward(
+                rs.bg, means3D, radii, e, scales, rotations, rs.scale_modifier, e, rs.viewmatrix, rs.projmatrix,
+                rs.tanfovx, rs.tanfovy, grad_color, sh, rs.sh_degree, rs.campos, geom, ctx.R, binning, img, rs.debug)
+            return g_m3d, g_m2d, g_sh, g_op, g_sc, g_rot, None
+
+    def rasterize(rs, means3D, means2D, shs, opacities, scales, rotations):
+        return RefRasterize.apply(means3D, means2D, shs, opacities, scales, rotations, rs)
+
+    return rasterize
+
+
+# -------------------------------------------------------------------- cpu baseline -----
+def cpu_baseline(cfg, g, cam, target):
+    """The CPU restatement (oracle/, kind "port") on ONE view of the same workload, fwd+bwd."""
+    from oracle import oracle
+    import numpy as np
+    tfx, tfy = math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5)
+    a = dict(shs=g.shs.numpy(), scales=g.scales.numpy(), rotations=g.rotations.numpy())
+    common = (cam.world_view_transform.numpy(), cam.full_proj_transform.numpy(), cam.camera_center.numpy(),
+              np.zeros(3, np.float32), cfg["W"], cfg["H"], tfx, tfy)
+    t0 = time.perf_counter()
+    fw = oracle.forward(g.means3D.numpy(), g.opacities.numpy(), *common, **a)
+    dL = np.sign(fw["out_color"] - target.numpy()).astype(np.float32) / (3.0 * cfg["W"] * cfg["H"])
+    oracle.backward(fw, dL, g.means3D.numpy(), *common, **a)
+    dt = time.perf_counter() - t0
+    return {"value": 1.0 / dt, "unit": "views/s", "cores": int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1)),
+            "kind": "port",
+            "sample": f"1 view fwd+bwd of the same workload ({cfg['P']} Gaussians, {cfg['W']}x{cfg['H']}) with oracle/splat_oracle.c "
+                      f"(per-Gaussian and forward stages OpenMP, backward blend single-threaded); {dt:.1f} s"}
+
+
+def algorithmic_bytes(stage, P, Pv, R, Npix, T, n_pass=6):
+    """SURVEY.md §8d, per view, with the reference's stage decomposition."""
+    return {
+        "preprocess": 20 * P + 291 * Pv,
+        "binning": 16 * P + 12 * Pv + (28 + 24 * n_pass) * R + 16 * T,  # K2+K3+K4+K5 (depth sort + binning here)
+        "render_fwd": 44 * R + 24 * Npix + 8 * T,
+        "render_bwd": 40 * R + 20 * Npix + 8 * T + 44 * Pv,
+        "geom_bwd": 8 * P + 615 * Pv + 284 * (P - Pv),
+    }[stage]
+
+
+STAGE_NAMES = ["preprocess", "depth_sort", "binning", "render_fwd", "render_bwd", "geom_bwd", "apply_weights"]
+KERNEL_OF_STAGE = {"preprocess": "preprocess_kernel", "render_fwd": "render_forward_kernel",
+                   "render_bwd": "render_backward_kernel", "geom_bwd": "geom_backward_kernel",
+                   "binning": "onesweep_kernel+expand_kernel", "depth_sort": "onesweep_kernel"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="config2", choices=list(CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference" and rank != 0:
+        return 0  # the reference is a single-GPU program: rank 0 alone runs it
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback of the product path)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    import torch.distributed as dist
+    if world > 1 and args.impl == "ours":
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world if args.impl == "ours" else 1
+
+    from dge_b200 import fit, scene
+    from dge_b200 import _lib as L
+    from dge_b200 import diff_gaussian_rasterization as dgr
+
+    P, W, H, V = cfg["P"], cfg["W"], cfg["H"], cfg["V"]
+    g = scene.make_gaussians(P, seed=cfg["seed"])
+    # every rank fits its own 20 views of a ring of 20*n_gpus cameras (view i -> rank i mod world)
+    ring = scene.ring_cameras(V * n_gpus, W, H)
+    mine = fit.shard_views(V * n_gpus, rank if args.impl == "ours" else 0, n_gpus)
+    gen = torch.Generator().manual_seed(cfg["seed"] + 17)
+    targets_all = [torch.rand(3, H, W, generator=gen) for _ in range(V * n_gpus)]
+    cams_host = [scene.Camera(*[t.pin_memory() if isinstance(t, torch.Tensor) else t for t in ring[i]]) for i in mine]
+    targets_host = [targets_all[i].pin_memory() for i in mine]
+    cams_dev = [scene.camera_to(c, dev) for c in cams_host]
+    targets_dev = [t.to(dev) for t in targets_host]
+    bg = torch.zeros(3, device=dev)
+
+    if args.impl == "ours":
+        model = fit.FitModel(g, dev, fused_adam=True)
+        rasterize, module = fit.default_rasterize, dgr
+    else:
+        model = fit.FitModel(g, dev, fused_adam=False)
+        rasterize, module = make_reference_rasterize(), dgr
+    lib = L.load()
+
+    def step(host):
+        return fit.fit_step(model, cams_host if host else cams_dev, targets_host if host else targets_dev, bg,
+                            global_batch=V * n_gpus, rasterize=rasterize, settings_module=module, host_inputs=host)
+
+    def barrier():
+        if world > 1 and args.impl == "ours":
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    barrier()
+
+    # ---- diagnostic pass (untimed): per-stage device time, R and P_v of this rank's views
+    stage_ms, stats = {}, {}
+    if args.impl == "ours":
+        import ctypes as C
+        lib.dge_profile_enable((1 << 7) - 1)
+        step(False)
+        torch.cuda.synchronize()
+        ms, cnt = (C.c_float * 7)(), (C.c_int * 7)()
+        L.check(lib.dge_profile_read(ms, cnt), "profile read")
+        stage_ms = {n: ms[i] / max(cnt[i], 1) for i, n in enumerate(STAGE_NAMES) if cnt[i]}
+        lib.dge_profile_enable(0)
+        with torch.no_grad():
+            a = model.activations()
+            Rs, Pvs = [], []
+            for cam in cams_dev[:4]:
+                rs = scene.raster_settings(cam, bg, 3, module=dgr)
+                e = torch.empty(0, device=dev)
+                R, _c, _d, radii, *_ = dgr._forward_call(rs, a["means3D"], e, a["opacities"], a["scales"], a["rotations"], e, a["shs"])
+                Rs.append(R)
+                Pvs.append(int((radii > 0).sum()))
+        stats = {"P": P, "P_visible": sum(Pvs) / len(Pvs), "R": sum(Rs) / len(Rs), "views_sampled": len(Rs)}
+        dominant = max((k for k in stage_ms if k in ("preprocess", "render_fwd", "render_bwd", "geom_bwd", "binning")),
+                       key=lambda k: stage_ms[k])
+        lib.dge_profile_enable(1 << STAGE_NAMES.index(dominant))
+        lib.dge_profile_read((C.c_float * 7)(), (C.c_int * 7)())
+    barrier()
+
+    # ---- timed region 1: K steps, inputs resident in HBM
+    launches0 = lib.dge_launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(False)
+    e1.record()
+    barrier()
+    ms_resident = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = lib.dge_launch_count() - launches0
+    roof = None
+    if args.impl == "ours":
+        import ctypes as C
+        ms, cnt = (C.c_float * 7)(), (C.c_int * 7)()
+        L.check(lib.dge_profile_read(ms, cnt), "profile read")
+        lib.dge_profile_enable(0)
+        i = STAGE_NAMES.index(dominant)
+        avg_ms = ms[i] / max(cnt[i], 1)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak, which = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+        T = ((W + 15) // 16) * ((H + 15) // 16)
+        abytes = algorithmic_bytes(dominant, P, stats["P_visible"], stats["R"], W * H, T)
+        achieved = abytes / (avg_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(KERNEL_OF_STAGE[dominant])
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "kernel": KERNEL_OF_STAGE[dominant], "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": which,
+                "avg_launch_ms": avg_ms, "launches_timed": int(cnt[i]), "algorithmic_bytes_per_launch": abytes,
+                "note": "blend kernels are issue/atomic bound, not HBM bound (SURVEY.md §8d); see DESIGN.md"}
+
+    # ---- timed region 2: K steps end to end (pinned host inputs copied inside, loss read back)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    last_loss = None
+    for _ in range(args.steps):
+        last_loss = float(step(True).item())
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+
+    t = torch.tensor([ms_resident, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1 and args.impl == "ours":
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_resident, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1 and args.impl == "ours":
+            dist.destroy_process_group()
+        return 0
+
+    views = V * n_gpus * args.steps
+    value = views / (ms_resident * 1e-3)
+    e2e_value = views / (ms_e2e * 1e-3)
+    h2d = V * (3 * H * W * 4 + (16 + 16 + 3) * 4)
+    out = {
+        "metric": "fwd+bwd views/s @1M Gaussians 512^2 (DGE 3D-fit step incl. Adam)", "value": value, "unit": "views/s",
+        "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_resident / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.config}: {cfg['desc']}", "gaussians": P, "resolution": [W, H],
+                   "views_per_step_per_gpu": V, "global_batch": V * n_gpus, "sh_degree": 3, "parallelism": f"dp{n_gpus} (views)",
+                   "l2": "per-view working set (inputs 236 MB + scratch) exceeds the 126 MB L2; no explicit flush",
+                   "scene": "randgauss-v1", **stats},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps, "loss": last_loss},
+        "gpu_launches": int(launches),
+    }
+    if args.impl == "ours":
+        out["roofline"] = roof
+        out["stages_ms_per_view"] = stage_ms
+        if not args.no_cpu_baseline:
+            try:
+                out["cpu_baseline"] = cpu_baseline(cfg, g, ring[0], targets_all[0])
+            except Exception as ex:  # the checker is optional for the number, never for the tests
+                out["cpu_baseline"] = {"value": None, "unit": "views/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+    else:
+        out["impl"] = "reference"
+        out["gpu_launches"] = None
+        out["cpu_baseline"] = {"value": value, "unit": "views/s", "cores": os.cpu_count(), "kind": "reference",
+                               "sample": "the reference ships no CPU rasterizer; this arm runs its UNMODIFIED CUDA code rebuilt "
+                                         "for sm_100a (oracle/_ref) on one B200 of the same box, same harness, torch.optim.Adam"}
+    print(json.dumps(out))
+    if world > 1 and args.impl == "ours":
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

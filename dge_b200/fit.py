@@ -1,0 +1,182 @@
+"""View-sharded 3D-fit step.
+
+One process per GPU, every rank holds a full Gaussian replica. A step renders this rank's
+share of the batch of edited views (forward + backward through the rasterizer), reduces the
+parameter gradients and the densification statistics over the ranks with ONE NCCL
+all-reduce (SUM) over a flat fp32 buffer plus one small MAX for the radii, and applies Adam
+on every replica. What DGE does per view and that does not depend on the view is hoisted:
+
+  * activations (exp / sigmoid / normalize / cat of gaussiansplatting/scene/gaussian_model.py:
+    221-258) run once per step; the views back-propagate into detached leaves and one
+    backward through the activations follows (DGE re-runs them for every render()).
+  * the screen-space gradient tap `means2D` (gaussian_renderer/__init__.py:60-69) is one
+    tensor shared by the step's views, so its .grad IS the per-step sum DGE builds in
+    on_before_optimizer_step (threestudio/systems/DGE.py:269-276).
+  * the six parameter tensors, their .grad and the screen-space gradient are views into flat
+    buffers: autograd accumulates straight into the buffer NCCL reduces in place, and the
+    fused Adam (csrc/apply_weights.cu: fused_adam_kernel) sweeps contiguous slices.
+"""
+import math
+from typing import Callable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from . import diff_gaussian_rasterization as dgr
+from . import scene
+
+# name, floats per Gaussian, shape tail — gaussian_model.py:341-372 (param groups, same order)
+GROUPS = [("xyz", 3, (3,)), ("f_dc", 3, (1, 3)), ("f_rest", 45, (15, 3)), ("opacity", 1, (1,)),
+          ("scaling", 3, (3,)), ("rotation", 4, (4,))]
+FLOATS_PER_GAUSSIAN = sum(g[1] for g in GROUPS)  # 59
+# configs/dge.yaml + gaussiansplatting/arguments/__init__.py defaults
+DEFAULT_LRS = {"xyz": 0.00016, "f_dc": 0.0025, "f_rest": 0.0025 / 20.0, "opacity": 0.05, "scaling": 0.005,
+               "rotation": 0.001}
+MASKED_GROUPS = ("xyz", "f_dc", "f_rest", "opacity", "scaling")  # gaussian_model.py:848 (no rotation)
+
+
+def inverse_sigmoid(x):
+    return torch.log(x / (1 - x))
+
+
+class FitModel:
+    """Flat-buffer replica of GaussianModel's optimisable state."""
+
+    def __init__(self, gaussians: scene.Gaussians, device, lrs=None, fused_adam=True, sh_degree=3):
+        P = gaussians.means3D.shape[0]
+        self.P, self.device, self.sh_degree = P, device, sh_degree
+        self.lrs = dict(DEFAULT_LRS if lrs is None else lrs)
+        self.fused_adam = fused_adam
+        n = FLOATS_PER_GAUSSIAN * P
+        self.flat = torch.empty(n, dtype=torch.float32, device=device)
+        # gradient buffer: 59P parameter grads followed by the 3P screen-space gradient sum
+        self.flat_grad = torch.zeros(n + 3 * P, dtype=torch.float32, device=device)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=device)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=device)
+        self.step_count = 0
+        self.slices = {}
+        self.params = {}
+        off = 0
+        raw = {
+            "xyz": gaussians.means3D, "f_dc": gaussians.shs[:, :1, :], "f_rest": gaussians.shs[:, 1:, :],
+            "opacity": inverse_sigmoid(gaussians.opacities), "scaling": torch.log(gaussians.scales),
+            "rotation": gaussians.rotations,
+        }
+        for name, k, tail in GROUPS:
+            sl = slice(off, off + k * P)
+            self.slices[name] = sl
+            p = self.flat[sl].view(P, *tail)
+            p.copy_(raw[name].to(device).reshape(P, *tail))
+            p.requires_grad_(True)  # a leaf: `flat` itself never requires grad
+            p.grad = self.flat_grad[sl].view(P, *tail)
+            self.params[name] = p
+            off += k * P
+        self.means2D = torch.zeros(P, 3, dtype=torch.float32, device=device, requires_grad=True)
+        self.means2D.grad = self.flat_grad[n:].view(P, 3)
+        # densification statistics (gaussian_model.py:338-339, 811-815; DGE.py:277-284)
+        self.xyz_gradient_accum = torch.zeros(P, 1, device=device)
+        self.denom = torch.zeros(P, 1, device=device)
+        self.max_radii2D = torch.zeros(P, dtype=torch.int32, device=device)
+        self.grad_mask: Optional[torch.Tensor] = None  # uint8 [P], local editing
+        if not fused_adam:
+            # the reference's optimiser, verbatim (gaussian_model.py:374)
+            groups = [{"params": [self.params[nm]], "lr": self.lrs[nm], "name": nm} for nm, _, _ in GROUPS]
+            self.optimizer = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+
+    # -- gaussian_model.py:221-258
+    def activations(self):
+        p = self.params
+        return {
+            "means3D": p["xyz"],
+            "shs": torch.cat((p["f_dc"], p["f_rest"]), dim=1),
+            "opacities": torch.sigmoid(p["opacity"]),
+            "scales": torch.exp(p["scaling"]),
+            "rotations": torch.nn.functional.normalize(p["rotation"]),
+        }
+
+    def set_grad_mask(self, mask: Optional[torch.Tensor]):
+        self.grad_mask = None if mask is None else mask.to(self.device).to(torch.uint8).contiguous()
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    def adam_step(self):
+        self.step_count += 1
+        if not self.fused_adam:
+            if self.grad_mask is not None:  # the reference's hooks (gaussian_model.py:837-856)
+                m = self.grad_mask.to(torch.float32)
+                for nm in MASKED_GROUPS:
+                    g = self.params[nm].grad
+                    g.mul_(m.view(-1, *([1] * (g.ndim - 1))))
+            self.optimizer.step()
+            return
+        lib = L.load()
+        st = L.stream_ptr(self.device)
+        for name, k, _ in GROUPS:
+            sl = self.slices[name]
+            mask = self.grad_mask if (self.grad_mask is not None and name in MASKED_GROUPS) else None
+            L.check(lib.dge_fused_adam(self.flat[sl].data_ptr(), self.flat_grad[sl].data_ptr(),
+                                       self.exp_avg[sl].data_ptr(), self.exp_avg_sq[sl].data_ptr(), k * self.P,
+                                       self.lrs[name], 0.9, 0.999, 1e-15, self.step_count, L.ptr(mask), k, st),
+                    "fused adam")
+
+
+def shard_views(num_views: int, rank: int, world: int) -> List[int]:
+    """View i of the step's batch goes to rank i mod world."""
+    return list(range(rank, num_views, world))
+
+
+def default_rasterize(rs, means3D, means2D, shs, opacities, scales, rotations):
+    return dgr.GaussianRasterizer(rs)(means3D=means3D, means2D=means2D, shs=shs, colors_precomp=None,
+                                      opacities=opacities, scales=scales, rotations=rotations, cov3D_precomp=None)
+
+
+def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence[torch.Tensor], bg: torch.Tensor,
+             global_batch: int, rasterize: Callable = default_rasterize, settings_module=dgr,
+             process_group=None, lambda_l1: float = 10.0, host_inputs: bool = False, update_stats: bool = True):
+    """One optimisation step over this rank's views. `cameras`/`targets` are this rank's share;
+    `global_batch` the number of views in the whole step (L1 is a mean over the global batch,
+    DGE.py:672). With host_inputs the cameras/targets live in pinned host memory and are copied
+    inside the step. Returns the step's loss as a 0-d device tensor (already globally reduced)."""
+    dev = model.device
+    model.zero_grad()
+    acts_graph = model.activations()
+    acts = {k: v.detach().requires_grad_(True) for k, v in acts_graph.items()}
+    loss = torch.zeros((), device=dev)
+    radii_max = torch.zeros(model.P, dtype=torch.int32, device=dev)
+    H, W = cameras[0].image_height, cameras[0].image_width
+    scale = lambda_l1 / float(global_batch * 3 * H * W)
+    for cam, target in zip(cameras, targets):
+        if host_inputs:
+            cam = scene.camera_to(cam, dev, non_blocking=True)
+            target = target.to(dev, non_blocking=True)
+        rs = scene.raster_settings(cam, bg, model.sh_degree, module=settings_module)
+        color, radii, _depth = rasterize(rs, acts["means3D"], model.means2D, acts["shs"], acts["opacities"],
+                                         acts["scales"], acts["rotations"])
+        lv = (color - target).abs().sum() * scale
+        lv.backward()
+        loss = loss + lv.detach()
+        radii_max = torch.maximum(radii_max, radii)
+    # one backward through the activations for the whole step
+    through = [k for k in acts_graph if acts_graph[k].grad_fn is not None and acts[k].grad is not None]
+    if through:
+        torch.autograd.backward([acts_graph[k] for k in through], [acts[k].grad for k in through])
+    # xyz has no activation: its detached leaf's grad goes straight into the flat buffer
+    if acts["means3D"].grad is not None:
+        model.params["xyz"].grad.add_(acts["means3D"].grad)
+    world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+    if world > 1:
+        # THE collective: 59P parameter grads + 3P screen-space grads in one SUM
+        dist.all_reduce(model.flat_grad, op=dist.ReduceOp.SUM, group=process_group)
+        dist.all_reduce(radii_max, op=dist.ReduceOp.MAX, group=process_group)
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=process_group)
+    if update_stats:
+        with torch.no_grad():  # DGE.py:266-284, gaussian_model.py:811-815
+            vis = radii_max > 0
+            model.max_radii2D = torch.where(vis, torch.maximum(model.max_radii2D, radii_max), model.max_radii2D)
+            gnorm = model.means2D.grad[:, :2].norm(dim=-1, keepdim=True)
+            model.xyz_gradient_accum += torch.where(vis[:, None], gnorm, torch.zeros_like(gnorm))
+            model.denom += vis[:, None].to(model.denom.dtype)
+    model.adam_step()
+    return loss

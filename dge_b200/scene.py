@@ -127,7 +127,7 @@ def raster_settings(cam, bg, sh_degree=3, scale_modifier=1.0, debug=False, modul
         prefiltered=False, debug=debug)
 
 
-def camera_to(cam, device):
-    return cam._replace(world_view_transform=cam.world_view_transform.to(device),
-                        full_proj_transform=cam.full_proj_transform.to(device),
-                        camera_center=cam.camera_center.to(device))
+def camera_to(cam, device, non_blocking=False):
+    return cam._replace(world_view_transform=cam.world_view_transform.to(device, non_blocking=non_blocking),
+                        full_proj_transform=cam.full_proj_transform.to(device, non_blocking=non_blocking),
+                        camera_center=cam.camera_center.to(device, non_blocking=non_blocking))

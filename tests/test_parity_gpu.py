@@ -1,0 +1,263 @@
+"""Parity of the CUDA path (called through the public API / C-ABI) against
+ (1) the UNMODIFIED reference rebuilt for sm_100a (oracle/_ref) run live on the same inputs,
+ (2) the CPU restatement (oracle/splat_oracle.c),
+ (3) the committed golden fixtures produced by the reference (tests/golden/).
+Bit-exact: radii, tile counts, means2D, depths, conic/opacity, rgb, clamp mask, sorted 64-bit
+keys, point_list, tile ranges, n_contrib, final_T and — since the blend follows the
+reference's operation order — the images. Gradients: max|a-b| <= 1e-4 * max|ref| per tensor
+(float atomics are summed in a different order; BASELINE.json north_star)."""
+import glob
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from dge_b200 import scene
+from tests import util
+
+pytestmark = pytest.mark.gpu
+GRAD_TOL = 1e-4
+IMG_TOL = 1e-5
+GRAD_PAIRS = [("means3D", "dL_dmeans3D"), ("means2D", "dL_dmeans2D"), ("shs", "dL_dsh"), ("opacities", "dL_dopacity"),
+              ("scales", "dL_dscales"), ("rotations", "dL_drotations")]
+
+CASES = [
+    # P, W, H, seed, scale_median, bg, views
+    (16384, 256, 256, 1235, 0.012, (0.0, 0.0, 0.0), 2),     # BASELINE.json configs[0]
+    (5000, 200, 120, 7, 0.05, (0.3, 0.1, 0.7), 2),          # ragged edge tiles, coloured background
+    (2000, 33, 17, 8, 0.1, (1.0, 1.0, 1.0), 1),             # image smaller than 3 tiles
+    (200000, 512, 512, 1236, 0.012, (0.0, 0.0, 0.0), 1),    # config-2 shape, reduced P
+]
+
+
+def _ref_available():
+    from oracle import ref
+    return ref.available()
+
+
+@pytest.mark.parametrize("P,W,H,seed,sm,bgv,V", CASES)
+def test_forward_backward_vs_reference_and_oracle(cuda, P, W, H, seed, sm, bgv, V):
+    if not _ref_available():
+        pytest.skip("oracle/_ref/libref_rast.so not built")
+    g = scene.make_gaussians(P, seed=seed, scale_median=sm)
+    bg = torch.tensor(bgv, dtype=torch.float32)
+    for ci, cam in enumerate(scene.ring_cameras(V, W, H)):
+        (color, radii, depth), leaves, rs = util.ours_forward(g, cam, bg, cuda, requires_grad=True)
+        mine = util.ours_intermediates(rs, g, cuda)
+        refi, state = util.ref_forward(g, cam, bg, cuda)
+        assert mine["num_rendered"] == refi["num_rendered"]
+        assert util.compare_exact(mine, refi) == {}
+        assert np.array_equal(color.detach().cpu().numpy(), refi["out_color"])
+        assert np.array_equal(radii.cpu().numpy(), refi["radii"])
+        # CPU restatement: integer / per-Gaussian stages bit-exact, images within tolerance
+        of = util.oracle_forward(g, cam, bg)
+        assert util.compare_exact(of, mine, names=("radii", "tiles_touched", "means2D", "depths", "conic_opacity", "rgb",
+                                                   "clamped", "keys", "point_list", "ranges", "n_contrib")) == {}
+        assert np.abs(of["out_color"] - mine["out_color"]).max() <= IMG_TOL
+        assert np.abs(of["out_depth"] - mine["out_depth"]).max() <= IMG_TOL * max(1.0, float(np.abs(of["out_depth"]).max()))
+        assert np.abs(of["final_T"] - mine["final_T"]).max() <= IMG_TOL
+        # backward
+        dL = scene.upstream_grad(W, H, seed + 1 + ci) * 50
+        (color * dL.to(cuda)).sum().backward()
+        rb = util.ref_backward(state, dL.to(cuda))
+        ob = util.oracle_backward(of, dL, g, cam, bg)
+        for leaf, name in GRAD_PAIRS:
+            got = leaves[leaf].grad.cpu().numpy()
+            assert util.rel_err(got, rb[name]) <= GRAD_TOL, (name, "vs reference")
+            assert util.rel_err(got, ob[name]) <= GRAD_TOL, (name, "vs oracle")
+        # culled Gaussians get exact zeros (the reference's torch::zeros rows)
+        culled = refi["radii"] <= 0
+        for leaf, _ in GRAD_PAIRS:
+            assert not leaves[leaf].grad.cpu().numpy()[culled].any()
+
+
+def test_precomputed_colors_and_cov3d(cuda):
+    """colors_precomp / cov3D_precomp paths (DGE's mask render: DGE.py:198-204 uses override_color)."""
+    if not _ref_available():
+        pytest.skip("oracle/_ref/libref_rast.so not built")
+    P, W, H = 6000, 160, 96
+    g = scene.make_gaussians(P, seed=21, scale_median=0.04)
+    cam = scene.ring_cameras(3, W, H)[2]
+    bg = torch.tensor([0.2, 0.4, 0.6])
+    gen = torch.Generator().manual_seed(4)
+    colors = torch.rand(P, 3, generator=gen)
+    for kw in (dict(colors_precomp=colors), dict(cov3D_precomp=_all_cov3d(g)), dict(colors_precomp=colors, cov3D_precomp=_all_cov3d(g))):
+        (color, radii, depth), leaves, rs = util.ours_forward(g, cam, bg, cuda, requires_grad=True, **kw)
+        refi, state = util.ref_forward(g, cam, bg, cuda, **kw)
+        assert np.array_equal(color.detach().cpu().numpy(), refi["out_color"])
+        assert np.array_equal(depth.detach().cpu().numpy(), refi["out_depth"])
+        assert np.array_equal(radii.cpu().numpy(), refi["radii"])
+        dL = scene.upstream_grad(W, H, 77) * 50
+        (color * dL.to(cuda)).sum().backward()
+        rb = util.ref_backward(state, dL.to(cuda))
+        assert util.rel_err(leaves["means3D"].grad.cpu().numpy(), rb["dL_dmeans3D"]) <= GRAD_TOL
+        assert util.rel_err(leaves["opacities"].grad.cpu().numpy(), rb["dL_dopacity"]) <= GRAD_TOL
+        if "colors_precomp" in kw:
+            assert util.rel_err(leaves["colors_precomp"].grad.cpu().numpy(), rb["dL_dcolors"]) <= GRAD_TOL
+            assert leaves["shs"].grad is None
+        if "cov3D_precomp" in kw:
+            assert util.rel_err(leaves["cov3D_precomp"].grad.cpu().numpy(), rb["dL_dcov3D"]) <= GRAD_TOL
+            assert leaves["scales"].grad is None and leaves["rotations"].grad is None
+
+
+def _all_cov3d(g):
+    """cov3D of every Gaussian (the reference's computeCov3D, evaluated by the oracle for a camera that sees all)."""
+    R = torch.zeros(g.means3D.shape[0], 3, 3)
+    r, x, y, z = g.rotations.unbind(1)
+    R[:, 0, 0], R[:, 0, 1], R[:, 0, 2] = 1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y)
+    R[:, 1, 0], R[:, 1, 1], R[:, 1, 2] = 2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x)
+    R[:, 2, 0], R[:, 2, 1], R[:, 2, 2] = 2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)
+    M = R * g.scales[:, None, :]
+    S = M @ M.transpose(1, 2)
+    return torch.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], 1).contiguous()
+
+
+@pytest.mark.parametrize("CH", [1, 3])
+def test_apply_weights_vs_reference(cuda, CH):
+    """DGE mask back-projection over several views, accumulated in place (DGE.py:112-147). Binary masks:
+    float sums are exact integers, so weights and cnt must be IDENTICAL to the reference's."""
+    if not _ref_available():
+        pytest.skip("oracle/_ref/libref_rast.so not built")
+    from dge_b200 import diff_gaussian_rasterization as dgr
+    from oracle import ref
+    P, W, H, V = 30000, 200, 136, 3
+    g = scene.make_gaussians(P, seed=31, scale_median=0.03)
+    gd = util.to_dev(g, cuda)
+    mask = scene.disc_mask(W, H, radius=50).repeat(CH, 1, 1).contiguous().to(cuda)
+    w_ours = torch.zeros(P, CH, device=cuda)
+    c_ours = torch.zeros(P, 1, dtype=torch.int32, device=cuda)
+    w_ref, c_ref = torch.zeros_like(w_ours), torch.zeros_like(c_ours)
+    w_or, c_or = np.zeros((P, CH)), np.zeros(P, np.int64)
+    bg = torch.zeros(3, device=cuda)
+    e = torch.empty(0, device=cuda)
+    from oracle import oracle
+    for cam in scene.ring_cameras(V, W, H):
+        cam_d = scene.camera_to(cam, cuda)
+        rs = scene.raster_settings(cam_d, bg, 0, module=dgr)
+        # positional call, as GaussianModel.apply_weights does (gaussian_model.py:821-832)
+        dgr.GaussianRasterizer(rs).apply_weights(gd.means3D, None, gd.opacities, None, w_ours, gd.scales, gd.rotations, None,
+                                                 c_ours, mask)
+        tfx, tfy = util.tans(cam)
+        ref.apply_weights(bg, gd.means3D, w_ref, gd.opacities, gd.scales, gd.rotations, 1.0, e, cam_d.world_view_transform,
+                          cam_d.full_proj_transform, tfx, tfy, H, W, e, 0, cam_d.camera_center, False, mask, c_ref, False)
+        w_or, c_or = oracle.apply_weights(g.means3D.numpy(), g.opacities.numpy(), cam.world_view_transform.numpy(),
+                                          cam.full_proj_transform.numpy(), cam.camera_center.numpy(), W, H, tfx, tfy,
+                                          mask.cpu().numpy(), w_or, c_or, scales=g.scales.numpy(), rotations=g.rotations.numpy())
+    torch.cuda.synchronize()
+    assert c_ours.sum().item() > 0
+    assert torch.equal(c_ours, c_ref)
+    assert torch.equal(w_ours, w_ref)
+    assert np.array_equal(c_ours.cpu().numpy().reshape(-1), c_or)
+    assert np.array_equal(w_ours.cpu().numpy().astype(np.float64), w_or)
+    # DGE's selection (DGE.py:149-152) is therefore identical too
+    sel = (w_ours / (c_ours + 1e-7)) > 0.8
+    assert torch.equal(sel, (w_ref / (c_ref + 1e-7)) > 0.8)
+
+
+def test_mark_visible_and_edge_cases(cuda):
+    from dge_b200 import diff_gaussian_rasterization as dgr
+    g = scene.make_gaussians(5000, seed=41)
+    cam = scene.camera_to(scene.ring_cameras(1, 64, 64)[0], cuda)
+    bg = torch.zeros(3, device=cuda)
+    rs = scene.raster_settings(cam, bg, 3, module=dgr)
+    rast = dgr.GaussianRasterizer(rs)
+    gd = util.to_dev(g, cuda)
+    vis = rast.markVisible(gd.means3D)
+    pv = torch.cat([gd.means3D, torch.ones(5000, 1, device=cuda)], 1) @ cam.world_view_transform
+    assert vis.dtype == torch.bool and (vis != (pv[:, 2] > 0.2)).sum().item() <= 2  # fp contraction at the threshold
+    # exactly-one-of checks (DGR/diff_gaussian_rasterization/__init__.py:271-283)
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        rast(gd.means3D, torch.zeros_like(gd.means3D), gd.opacities, scales=gd.scales, rotations=gd.rotations)
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair"):
+        rast(gd.means3D, torch.zeros_like(gd.means3D), gd.opacities, shs=gd.shs, scales=gd.scales)
+    with pytest.raises(RuntimeError, match="means3D must have dimensions"):
+        rast(gd.means3D.view(-1), torch.zeros_like(gd.means3D), gd.opacities, shs=gd.shs, scales=gd.scales, rotations=gd.rotations)
+    # empty input: zeros, as the reference's glue (rasterize_points.cu:72)
+    e3 = torch.zeros(0, 3, device=cuda)
+    color, radii, depth = rast(e3, e3, torch.zeros(0, 1, device=cuda), shs=torch.zeros(0, 16, 3, device=cuda),
+                               scales=e3, rotations=torch.zeros(0, 4, device=cuda))
+    assert color.shape == (3, 64, 64) and not color.any() and radii.numel() == 0
+    # everything behind the camera: background only, no instances
+    behind = gd.means3D.clone()
+    behind[:, :] = cam.camera_center * 3  # the camera looks at the origin from camera_center
+    color, radii, depth = rast(behind, torch.zeros_like(behind), gd.opacities, shs=gd.shs, scales=gd.scales, rotations=gd.rotations)
+    assert not radii.any() and not color.any() and not depth.any()
+
+
+def test_golden_fixtures(cuda):
+    """The CUDA path against the committed outputs of the reference (no oracle/_ref needed)."""
+    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+    if not files:
+        pytest.skip("no golden fixtures committed yet")
+    from dge_b200 import diff_gaussian_rasterization as dgr
+    for f in files:
+        z = np.load(f)
+        g = scene.Gaussians(*[torch.from_numpy(z[f"in_{k}"]) for k in scene.Gaussians._fields])
+        W, H, deg = int(z["in_W"]), int(z["in_H"]), int(z["in_deg"])
+        cam = scene.Camera(H, W, 2 * math.atan(float(z["in_tanfovx"])), 2 * math.atan(float(z["in_tanfovy"])),
+                           torch.from_numpy(z["in_view"]), torch.from_numpy(z["in_proj"]), torch.from_numpy(z["in_campos"]))
+        bg = torch.from_numpy(z["in_bg"])
+        cam_d = scene.camera_to(cam, cuda)
+        rs = dgr.GaussianRasterizationSettings(H, W, float(z["in_tanfovx"]), float(z["in_tanfovy"]), bg.to(cuda), 1.0,
+                                               cam_d.world_view_transform, cam_d.full_proj_transform, deg,
+                                               cam_d.camera_center, False, False)
+        mine = util.ours_intermediates(rs, g, cuda)
+        gold = {k[3:]: z[k] for k in z.files if k.startswith("fw_")}
+        assert util.compare_exact(mine, gold) == {}, f
+        leaves = {k: getattr(g, k).to(cuda).requires_grad_(True) for k in g._fields}
+        m2d = torch.zeros(g.means3D.shape[0], 3, device=cuda, requires_grad=True)
+        color, radii, depth = dgr.GaussianRasterizer(rs)(leaves["means3D"], m2d, leaves["opacities"], shs=leaves["shs"],
+                                                         scales=leaves["scales"], rotations=leaves["rotations"])
+        (color * torch.from_numpy(z["in_dL"]).to(cuda)).sum().backward()
+        leaves["means2D"] = m2d
+        for leaf, name in GRAD_PAIRS:
+            assert util.rel_err(leaves[leaf].grad.cpu().numpy(), z["bw_" + name]) <= GRAD_TOL, (f, name)
+        w = torch.zeros(g.means3D.shape[0], 1, device=cuda)
+        c = torch.zeros(g.means3D.shape[0], 1, dtype=torch.int32, device=cuda)
+        rs0 = rs._replace(bg=torch.zeros(3, device=cuda), sh_degree=0)
+        dgr.GaussianRasterizer(rs0).apply_weights(leaves["means3D"].detach(), None, leaves["opacities"].detach(), None, w,
+                                                  leaves["scales"].detach(), leaves["rotations"].detach(), None, c,
+                                                  torch.from_numpy(z["in_mask"]).to(cuda))
+        assert np.array_equal(w.cpu().numpy(), z["aw_weights"]) and np.array_equal(c.cpu().numpy(), z["aw_cnt"]), f
+
+
+def test_full_size_properties(cuda):
+    """BASELINE.json config 2 at full size (1M Gaussians, 512x512): size-independent properties.
+    Sortedness of the key list, ranges partition it, rendering is deterministic, the image is
+    linear in the colours (colors_precomp path), and summing culled+visible gradients over two
+    disjoint colour perturbations matches the joint one (backward linearity in dL/dcolor)."""
+    from dge_b200 import diff_gaussian_rasterization as dgr
+    P, W, H = 1_000_000, 512, 512
+    g = scene.make_gaussians(P, seed=1236)
+    cam = scene.ring_cameras(20, W, H)[3]
+    bg = torch.zeros(3)
+    (color, radii, depth), leaves, rs = util.ours_forward(g, cam, bg, cuda, requires_grad=True)
+    mine = util.ours_intermediates(rs, g, cuda)
+    keys = mine["keys"].astype(np.uint64)
+    assert (keys[1:] >= keys[:-1]).all()
+    R = mine["num_rendered"]
+    assert R == int(mine["tiles_touched"].sum()) == len(mine["point_list"])
+    tiles = (keys >> np.uint64(32)).astype(np.int64)
+    rg = mine["ranges"].astype(np.int64)
+    cnt = np.bincount(tiles, minlength=rg.shape[0])
+    assert np.array_equal(rg[:, 1] - rg[:, 0], cnt)
+    nonempty = cnt > 0
+    assert (tiles[rg[nonempty, 0]] == np.nonzero(nonempty)[0]).all()
+    # within a tile, equal depth keys keep Gaussian-id order (stability)
+    same = keys[1:] == keys[:-1]
+    assert (mine["point_list"][1:][same] > mine["point_list"][:-1][same]).all()
+    assert np.array_equal(mine["out_color"], color.detach().cpu().numpy())  # two runs, same bits
+    assert (mine["n_contrib"] <= (rg[:, 1] - rg[:, 0]).reshape(H // 16, W // 16).repeat(16, 0).repeat(16, 1)).all()
+    # backward linearity in the upstream gradient
+    d1, d2 = scene.upstream_grad(W, H, 1).to(cuda) * 50, scene.upstream_grad(W, H, 2).to(cuda) * 50
+    grads = []
+    for d in (d1, d2, d1 + d2):
+        for v in leaves.values():
+            v.grad = None
+        (color * d).sum().backward(retain_graph=True)
+        grads.append({k: v.grad.clone() for k, v in leaves.items() if v.grad is not None})
+    for k in grads[0]:
+        s = grads[0][k] + grads[1][k]
+        assert util.rel_err(s.cpu().numpy(), grads[2][k].cpu().numpy()) <= 2e-4, k
