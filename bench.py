@@ -19,7 +19,6 @@ import argparse
 import json
 import math
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -40,40 +39,46 @@ CONFIGS = {
 
 # --------------------------------------------------------------------------- clocks -----
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons DURING the timed region (B200_PROFILING.md) through
+    NVML in a background thread: a polling `nvidia-smi -lms` process contends for the driver
+    and slows the measured step, NVML queries do not."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+    def __init__(self, gpu_index, period=0.02):
+        self.gpu, self.period, self.sm, self.bits, self.ok = gpu_index, period, [], 0, False
+        self.stop_flag = threading.Event()
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+            self.t = threading.Thread(target=self._loop, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
+        except Exception as ex:
+            self.err = str(ex)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _loop(self):
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                self.bits |= self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "?")]}
+        self.stop_flag.set()
         self.t.join(timeout=2)
-        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None, "sm_max_mhz": float(self.max),
+                "reasons": sorted(n for b, n in self.REASONS.items() if self.bits & b), "samples": len(sm)}
 
 
 # ------------------------------------------------------------------ reference arm -----
@@ -156,6 +161,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="config2", choices=list(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=3, help="CUDA streams the views of a step are pipelined on (ours)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
 
@@ -200,7 +206,8 @@ def main():
 
     def step(host):
         return fit.fit_step(model, cams_host if host else cams_dev, targets_host if host else targets_dev, bg,
-                            global_batch=V * n_gpus, rasterize=rasterize, settings_module=module, host_inputs=host)
+                            global_batch=V * n_gpus, rasterize=rasterize, settings_module=module, host_inputs=host,
+                            num_streams=args.streams if args.impl == "ours" else 1)
 
     def barrier():
         if world > 1 and args.impl == "ours":
@@ -310,6 +317,7 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.config}: {cfg['desc']}", "gaussians": P, "resolution": [W, H],
                    "views_per_step_per_gpu": V, "global_batch": V * n_gpus, "sh_degree": 3, "parallelism": f"dp{n_gpus} (views)",
+                   "streams_per_gpu": args.streams if args.impl == "ours" else 1,
                    "l2": "per-view working set (inputs 236 MB + scratch) exceeds the 126 MB L2; no explicit flush",
                    "scene": "randgauss-v1", **stats},
         "clocks": clocks,

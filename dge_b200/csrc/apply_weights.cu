@@ -10,28 +10,22 @@
 // below 2^24, so the result is bit-identical to the reference whatever the order.
 // The out-of-image read of image_weights in the reference (apply_weights.cu:279-283, before
 // its `inside` test) is guarded here; those values are never used.
-#include "common.cuh"
+#include "blend.cuh"
 
 namespace dge {
 
-constexpr int AW_THREADS = 64;
-constexpr int AW_BATCH = 128;
-
-#define MUL(a, b) __fmul_rn((a), (b))
-#define ADD(a, b) __fadd_rn((a), (b))
-#define FMA(a, b, c) __fmaf_rn((a), (b), (c))
-
 template <int CH>
-__global__ void __launch_bounds__(AW_THREADS) apply_weights_kernel(
+__global__ void __launch_bounds__(BL_THREADS) apply_weights_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
-    const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity,
+    const float4* __restrict__ means2D, const float4* __restrict__ conic_opacity,
     const float* __restrict__ image_weights, float* __restrict__ weights, int* __restrict__ cnt) {
-  __shared__ float4 s_a[AW_BATCH];  // x, y, conic.x, conic.y
-  __shared__ float4 s_b[AW_BATCH];  // conic.z, power threshold, opacity, gid bits
-  const int tid = threadIdx.x, lane = tid & 31;
+  __shared__ BlendSmem s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int qx = tid & 7, qy = tid >> 3;
   const int px0 = blockIdx.x * DGE_TILE + 2 * qx, py0 = blockIdx.y * DGE_TILE + 2 * qy;
   const float fx0 = (float)px0, fx1 = (float)(px0 + 1), fy0 = (float)py0, fy1 = (float)(py0 + 1);
+  const float X0 = (float)(blockIdx.x * DGE_TILE), X1 = X0 + 15.0f;
+  const float Y0 = (float)(blockIdx.y * DGE_TILE + 8 * warp), Y1 = Y0 + 7.0f;
   const size_t HW = (size_t)H * W;
   const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
 
@@ -47,62 +41,48 @@ __global__ void __launch_bounds__(AW_THREADS) apply_weights_kernel(
     for (int c = 0; c < CH; c++) Cw[p][c] = inside ? image_weights[c * HW + (size_t)y * W + x] : 0.0f;
   }
 
-  for (uint32_t base = range.x; base < range.y; base += AW_BATCH) {
+  for (uint32_t base = range.x; base < range.y; base += BL_BATCH) {
     const bool all_done = done[0] && done[1] && done[2] && done[3];
     if (__syncthreads_and(all_done)) break;
-    const int count = min((uint32_t)AW_BATCH, range.y - base);
-    for (int k = tid; k < count; k += AW_THREADS) {
-      const uint32_t gid = point_list[base + k];
-      const float2 xy = means2D[gid];
-      const float4 co = conic_opacity[gid];
-      const float thr =
-          co.w > 0.0f ? -(__logf(255.0f * co.w) + 0.01f) : __int_as_float(0x7f800000);
-      s_a[k] = make_float4(xy.x, xy.y, co.x, co.y);
-      s_b[k] = make_float4(co.z, thr, co.w, __uint_as_float(gid));
-    }
+    const int count = min((uint32_t)BL_BATCH, range.y - base);
+    stage_batch<false>(s, tid, count, [&](int k) { return base + k; }, point_list, means2D,
+                       conic_opacity, (const float4*)nullptr);
     __syncthreads();
     if (__all_sync(0xFFFFFFFFu, all_done)) continue;
-    for (int j = 0; j < count; j++) {
-      const float4 a = s_a[j];
-      const float4 b = s_b[j];
-      const float dx0 = ADD(a.x, -fx0), dx1 = ADD(a.x, -fx1);
-      const float dy0 = ADD(a.y, -fy0), dy1 = ADD(a.y, -fy1);
-      const float bx0 = MUL(dx0, a.z), bx1 = MUL(dx1, a.z);
-      const float cx0 = MUL(dx0, a.w), cx1 = MUL(dx1, a.w);
-      const float ay0 = MUL(dy0, MUL(dy0, b.x)), ay1 = MUL(dy1, MUL(dy1, b.x));
-      float power[4];
-      power[0] = FMA(FMA(dx0, bx0, ay0), -0.5f, -MUL(dy0, cx0));
-      power[1] = FMA(FMA(dx1, bx1, ay0), -0.5f, -MUL(dy0, cx1));
-      power[2] = FMA(FMA(dx0, bx0, ay1), -0.5f, -MUL(dy1, cx0));
-      power[3] = FMA(FMA(dx1, bx1, ay1), -0.5f, -MUL(dy1, cx1));
+    const int n = compact_batch(s, warp, lane, count, X0, X1, Y0, Y1, [](int) { return true; });
+    for (int i = 0; i < n; i++) {
+      const int j = s.list[warp][i];
+      const float4 a = s.a[j];
+      const float4 b = s.b[j];
+      const Quad q = quad_power(a, b.x, fx0, fx1, fy0, fy1);
       bool any = false;
       bool cand[4];
 #pragma unroll
       for (int p = 0; p < 4; p++) {
-        cand[p] = !done[p] && !(power[p] > 0.0f) && !(power[p] < b.y);
+        cand[p] = !done[p] && !(q.power[p] > 0.0f) && !(q.power[p] < b.y);
         any |= cand[p];
       }
       if (!__any_sync(0xFFFFFFFFu, any)) continue;
       float wsum[CH];
 #pragma unroll
       for (int c = 0; c < CH; c++) wsum[c] = 0.0f;
-      int n = 0;
+      int nhit = 0;
 #pragma unroll
       for (int p = 0; p < 4; p++) {
         if (!cand[p]) continue;
-        const float alpha = fminf(0.99f, MUL(b.z, expf(power[p])));
+        const float alpha = fminf(0.99f, BMUL(b.z, expf(q.power[p])));
         if (alpha < 1.0f / 255.0f) continue;
-        const float test_T = MUL(T[p], ADD(1.0f, -alpha));
+        const float test_T = BMUL(T[p], BADD(1.0f, -alpha));
         if (test_T < 0.0001f) {
           done[p] = true;
           continue;
         }
 #pragma unroll
         for (int c = 0; c < CH; c++) wsum[c] += Cw[p][c];
-        n += 1;
+        nhit += 1;
         T[p] = test_T;
       }
-      const int total = __reduce_add_sync(0xFFFFFFFFu, n);
+      const int total = __reduce_add_sync(0xFFFFFFFFu, nhit);
       if (total == 0) continue;
 #pragma unroll
       for (int c = 0; c < CH; c++)
@@ -123,7 +103,7 @@ cudaError_t launch_apply_weights_render(const ViewParams& vp, const GeomState& g
                                         cudaStream_t stream) {
   dim3 grid(vp.grid_x, vp.grid_y);
 #define AW_LAUNCH(CH)                                                                          \
-  apply_weights_kernel<CH><<<grid, AW_THREADS, 0, stream>>>(img.ranges, b.point_list, vp.W, vp.H, \
+  apply_weights_kernel<CH><<<grid, BL_THREADS, 0, stream>>>(img.ranges, b.point_list, vp.W, vp.H, \
                                                             g.means2D, g.conic_opacity,        \
                                                             image_weights, weights, cnt)
   if (num_channels == 1) AW_LAUNCH(1);

@@ -17,7 +17,8 @@ extern unsigned long long g_kernel_launches;
 // Our own layout of the three opaque blobs (the reference's is
 // DGR/cuda_rasterizer/rasterizer_impl.cu:135-175). All sub-arrays 256-B aligned.
 struct GeomState {
-  float2* means2D;        // [P] pixel-space centre
+  float4* means2D;        // [P] pixel-space centre x, y and half-extents hx, hy of the box outside
+                          //     which alpha < 1/255 for certain (conservative; -inf = never visible)
   float4* conic_opacity;  // [P] conic.x, conic.y, conic.z, opacity
   float4* rgb_depth;      // [P] r, g, b, view-space depth
   ushort4* rect;          // [P] tile rect min.x, min.y, max.x, max.y (all 0 <=> culled)

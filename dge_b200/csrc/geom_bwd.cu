@@ -53,8 +53,15 @@ __global__ void __launch_bounds__(256) geom_backward_kernel(
     if (dL_dcolor) store3(dL_dcolor, i, 0.f, 0.f, 0.f);
     if (dL_dcov3D)
       for (int k = 0; k < 6; k++) dL_dcov3D[6 * i + k] = 0.f;
-    if (dL_dsh)
-      for (int k = 0; k < 3 * M; k++) dL_dsh[3 * M * i + k] = 0.f;
+    if (dL_dsh) {
+      if (M == 16) {
+#pragma unroll
+        for (int j = 0; j < 12; j++)
+          reinterpret_cast<float4*>(dL_dsh + 48 * i)[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        for (int k = 0; k < 3 * M; k++) dL_dsh[3 * M * i + k] = 0.f;
+      }
+    }
     if (dL_dscale) store3(dL_dscale, i, 0.f, 0.f, 0.f);
     if (dL_drot) reinterpret_cast<float4*>(dL_drot)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     return;
@@ -184,6 +191,9 @@ __global__ void __launch_bounds__(256) geom_backward_kernel(
   }
 
   // ---------------- K9: SH (backward.cu:20-139) ----------------
+  // colour = sum_k b_k(dir) * sh_k, so dL/dsh_k = b_k * dL/dRGB and
+  // dL/ddir = sum_k grad(b_k) * (sh_k . dL/dRGB): the reference's dRGBdx/dy/dz sums, regrouped
+  // so that the 48 SH floats are consumed as they arrive from 12 vector loads.
   if (shs != nullptr && dL_dsh != nullptr) {
     const float* sh = shs + 3 * (size_t)M * i;
     float* dsh = dL_dsh + 3 * (size_t)M * i;
@@ -195,73 +205,77 @@ __global__ void __launch_bounds__(256) geom_backward_kernel(
     float dRGB[3];
 #pragma unroll
     for (int ch = 0; ch < 3; ch++) dRGB[ch] = (cl >> ch) & 1 ? 0.f : dcol[ch];
-    float dRGBdx[3] = {0, 0, 0}, dRGBdy[3] = {0, 0, 0}, dRGBdz[3] = {0, 0, 0};
     const int D = vp.D;
-    auto SH = [&](int k, int ch) { return __ldg(sh + 3 * k + ch); };
-    auto put = [&](int k, float coef) {
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    float b[16], gx[16], gy[16], gz[16];
 #pragma unroll
-      for (int ch = 0; ch < 3; ch++) dsh[3 * k + ch] = coef * dRGB[ch];
-    };
-    put(0, SH_C0);
-    int written = 1;
+    for (int k = 0; k < 16; k++) b[k] = gx[k] = gy[k] = gz[k] = 0.f;
+    b[0] = SH_C0;
     if (D > 0) {
-      put(1, -SH_C1 * y);
-      put(2, SH_C1 * z);
-      put(3, -SH_C1 * x);
-      written = 4;
-#pragma unroll
-      for (int ch = 0; ch < 3; ch++) {
-        dRGBdx[ch] = -SH_C1 * SH(3, ch);
-        dRGBdy[ch] = -SH_C1 * SH(1, ch);
-        dRGBdz[ch] = SH_C1 * SH(2, ch);
-      }
-      if (D > 1) {
-        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-        put(4, SH_C2_0 * xy);
-        put(5, SH_C2_1 * yz);
-        put(6, SH_C2_2 * (2.f * zz - xx - yy));
-        put(7, SH_C2_3 * xz);
-        put(8, SH_C2_4 * (xx - yy));
-        written = 9;
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-          dRGBdx[ch] += SH_C2_0 * y * SH(4, ch) + SH_C2_2 * 2.f * -x * SH(6, ch) +
-                        SH_C2_3 * z * SH(7, ch) + SH_C2_4 * 2.f * x * SH(8, ch);
-          dRGBdy[ch] += SH_C2_0 * x * SH(4, ch) + SH_C2_1 * z * SH(5, ch) +
-                        SH_C2_2 * 2.f * -y * SH(6, ch) + SH_C2_4 * 2.f * -y * SH(8, ch);
-          dRGBdz[ch] += SH_C2_1 * y * SH(5, ch) + SH_C2_2 * 2.f * 2.f * z * SH(6, ch) +
-                        SH_C2_3 * x * SH(7, ch);
-        }
-        if (D > 2) {
-          put(9, SH_C3_0 * y * (3.f * xx - yy));
-          put(10, SH_C3_1 * xy * z);
-          put(11, SH_C3_2 * y * (4.f * zz - xx - yy));
-          put(12, SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy));
-          put(13, SH_C3_4 * x * (4.f * zz - xx - yy));
-          put(14, SH_C3_5 * z * (xx - yy));
-          put(15, SH_C3_6 * x * (xx - 3.f * yy));
-          written = 16;
-#pragma unroll
-          for (int ch = 0; ch < 3; ch++) {
-            dRGBdx[ch] += SH_C3_0 * SH(9, ch) * 3.f * 2.f * xy + SH_C3_1 * SH(10, ch) * yz +
-                          SH_C3_2 * SH(11, ch) * -2.f * xy + SH_C3_3 * SH(12, ch) * -3.f * 2.f * xz +
-                          SH_C3_4 * SH(13, ch) * (-3.f * xx + 4.f * zz - yy) +
-                          SH_C3_5 * SH(14, ch) * 2.f * xz + SH_C3_6 * SH(15, ch) * 3.f * (xx - yy);
-            dRGBdy[ch] += SH_C3_0 * SH(9, ch) * 3.f * (xx - yy) + SH_C3_1 * SH(10, ch) * xz +
-                          SH_C3_2 * SH(11, ch) * (-3.f * yy + 4.f * zz - xx) +
-                          SH_C3_3 * SH(12, ch) * -3.f * 2.f * yz + SH_C3_4 * SH(13, ch) * -2.f * xy +
-                          SH_C3_5 * SH(14, ch) * -2.f * yz + SH_C3_6 * SH(15, ch) * -3.f * 2.f * xy;
-            dRGBdz[ch] += SH_C3_1 * SH(10, ch) * xy + SH_C3_2 * SH(11, ch) * 4.f * 2.f * yz +
-                          SH_C3_3 * SH(12, ch) * 3.f * (2.f * zz - xx - yy) +
-                          SH_C3_4 * SH(13, ch) * 4.f * 2.f * xz + SH_C3_5 * SH(14, ch) * (xx - yy);
-          }
-        }
-      }
+      b[1] = -SH_C1 * y; b[2] = SH_C1 * z; b[3] = -SH_C1 * x;
+      gy[1] = -SH_C1; gz[2] = SH_C1; gx[3] = -SH_C1;
     }
-    for (int k = written; k < M; k++) put(k, 0.f);  // rows torch::zeros left untouched
-    const float ddx = dRGBdx[0] * dRGB[0] + dRGBdx[1] * dRGB[1] + dRGBdx[2] * dRGB[2];
-    const float ddy = dRGBdy[0] * dRGB[0] + dRGBdy[1] * dRGB[1] + dRGBdy[2] * dRGB[2];
-    const float ddz = dRGBdz[0] * dRGB[0] + dRGBdz[1] * dRGB[1] + dRGBdz[2] * dRGB[2];
+    if (D > 1) {
+      b[4] = SH_C2_0 * xy; b[5] = SH_C2_1 * yz; b[6] = SH_C2_2 * (2.f * zz - xx - yy);
+      b[7] = SH_C2_3 * xz; b[8] = SH_C2_4 * (xx - yy);
+      gx[4] = SH_C2_0 * y; gy[4] = SH_C2_0 * x;
+      gy[5] = SH_C2_1 * z; gz[5] = SH_C2_1 * y;
+      gx[6] = SH_C2_2 * 2.f * -x; gy[6] = SH_C2_2 * 2.f * -y; gz[6] = SH_C2_2 * 2.f * 2.f * z;
+      gx[7] = SH_C2_3 * z; gz[7] = SH_C2_3 * x;
+      gx[8] = SH_C2_4 * 2.f * x; gy[8] = SH_C2_4 * 2.f * -y;
+    }
+    if (D > 2) {
+      b[9] = SH_C3_0 * y * (3.f * xx - yy); b[10] = SH_C3_1 * xy * z;
+      b[11] = SH_C3_2 * y * (4.f * zz - xx - yy); b[12] = SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy);
+      b[13] = SH_C3_4 * x * (4.f * zz - xx - yy); b[14] = SH_C3_5 * z * (xx - yy);
+      b[15] = SH_C3_6 * x * (xx - 3.f * yy);
+      gx[9] = SH_C3_0 * 3.f * 2.f * xy; gy[9] = SH_C3_0 * 3.f * (xx - yy);
+      gx[10] = SH_C3_1 * yz; gy[10] = SH_C3_1 * xz; gz[10] = SH_C3_1 * xy;
+      gx[11] = SH_C3_2 * -2.f * xy; gy[11] = SH_C3_2 * (-3.f * yy + 4.f * zz - xx); gz[11] = SH_C3_2 * 4.f * 2.f * yz;
+      gx[12] = SH_C3_3 * -3.f * 2.f * xz; gy[12] = SH_C3_3 * -3.f * 2.f * yz; gz[12] = SH_C3_3 * 3.f * (2.f * zz - xx - yy);
+      gx[13] = SH_C3_4 * (-3.f * xx + 4.f * zz - yy); gy[13] = SH_C3_4 * -2.f * xy; gz[13] = SH_C3_4 * 4.f * 2.f * xz;
+      gx[14] = SH_C3_5 * 2.f * xz; gy[14] = SH_C3_5 * -2.f * yz; gz[14] = SH_C3_5 * (xx - yy);
+      gx[15] = SH_C3_6 * 3.f * (xx - yy); gy[15] = SH_C3_6 * -3.f * 2.f * xy;
+    }
+    float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+    if (M == 16) {
+      float4 v[12];
+#pragma unroll
+      for (int j = 0; j < 12; j++) v[j] = __ldg(reinterpret_cast<const float4*>(sh) + j);
+      const float* f = reinterpret_cast<const float*>(v);
+#pragma unroll
+      for (int k = 1; k < 16; k++) {
+        const float sk = f[3 * k] * dRGB[0] + f[3 * k + 1] * dRGB[1] + f[3 * k + 2] * dRGB[2];
+        ddx += gx[k] * sk;
+        ddy += gy[k] * sk;
+        ddz += gz[k] * sk;
+      }
+#pragma unroll
+      for (int j = 0; j < 12; j++) {
+        float4 o;
+        o.x = b[(4 * j) / 3] * dRGB[(4 * j) % 3];
+        o.y = b[(4 * j + 1) / 3] * dRGB[(4 * j + 1) % 3];
+        o.z = b[(4 * j + 2) / 3] * dRGB[(4 * j + 2) % 3];
+        o.w = b[(4 * j + 3) / 3] * dRGB[(4 * j + 3) % 3];
+        reinterpret_cast<float4*>(dsh)[j] = o;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; k++) {  // compile-time k keeps b/gx/gy/gz in registers
+        if (k < M) {
+          if (k >= 1) {
+            const float sk = __ldg(sh + 3 * k) * dRGB[0] + __ldg(sh + 3 * k + 1) * dRGB[1] + __ldg(sh + 3 * k + 2) * dRGB[2];
+            ddx += gx[k] * sk;
+            ddy += gy[k] * sk;
+            ddz += gz[k] * sk;
+          }
+#pragma unroll
+          for (int ch = 0; ch < 3; ch++) dsh[3 * k + ch] = b[k] * dRGB[ch];
+        }
+      }
+      for (int k = 16; k < M; k++)
+        for (int ch = 0; ch < 3; ch++) dsh[3 * k + ch] = 0.f;
+    }
     // dnormvdv (auxiliary.h:107-117)
     const float sum2 = ox * ox + oy * oy + oz * oz;
     const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);

@@ -198,9 +198,26 @@ __global__ void __launch_bounds__(256) preprocess_kernel(
           } else {
             rgb[0] = rgb[1] = rgb[2] = 0.0f;  // apply_weights blends no colour
           }
-          g.means2D[idx] = make_float2(pix_x, pix_y);
-          g.conic_opacity[idx] =
-              make_float4(MUL(cov.z, inv), MUL(cov.y, -inv), MUL(cov.x, inv), __ldg(opacities + idx));
+          const float con_x = MUL(cov.z, inv), con_y = MUL(cov.y, -inv), con_z = MUL(cov.x, inv);
+          const float opac = __ldg(opacities + idx);
+          // Conservative screen-space box of {alpha >= 1/255}: power >= -ln(255 o) bounds the
+          // quadratic form, whose extreme |dx|, |dy| are sqrt(2t cz/det), sqrt(2t cx/det). Used by
+          // the blend kernels only to SKIP work; every skipped pair fails the exact test too.
+          float hx = __int_as_float(0xff800000), hy = hx;  // -inf: never visible
+          if (opac > 0.0f) {
+            const float k2 = 2.0f * (logf(255.0f * opac) + 0.02f);
+            const float dc = con_x * con_z - con_y * con_y;
+            if (k2 > 0.0f) {
+              if (dc > 0.0f) {
+                hx = sqrtf(k2 * con_z / dc) * 1.0001f + 0.01f;
+                hy = sqrtf(k2 * con_x / dc) * 1.0001f + 0.01f;
+              } else {
+                hx = hy = __int_as_float(0x7f800000);
+              }
+            }
+          }
+          g.means2D[idx] = make_float4(pix_x, pix_y, hx, hy);
+          g.conic_opacity[idx] = make_float4(con_x, con_y, con_z, opac);
           g.rgb_depth[idx] = make_float4(rgb[0], rgb[1], rgb[2], depth);
           radius = rad;
           rect = make_ushort4(x0, y0, x1, y1);

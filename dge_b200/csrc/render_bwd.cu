@@ -11,39 +11,29 @@
 //    transposing butterfly (14 shuffles instead of 45) and leave the SM as ONE
 //    red.global instruction per warp and Gaussian (9 active lanes) instead of the
 //    reference's 9 atomics per contributing (pixel, Gaussian) pair;
-//  * warps in which no lane touches a Gaussian skip the reduction (ballot).
+//  * warps in which no lane touches a Gaussian skip the reduction (ballot), and each warp only
+//    visits the records whose conservative alpha >= 1/255 box overlaps its half-tile (blend.cuh).
 // Sums are accumulated into acc[P][12] (see ACC_* in common.cuh); the per-Gaussian
 // kernel in geom_bwd.cu turns them into the reference's output tensors.
-#include "common.cuh"
+#include "blend.cuh"
 
 namespace dge {
 
-constexpr int RB_THREADS = 64;
-constexpr int RB_BATCH = 128;
-
-#define MUL(a, b) __fmul_rn((a), (b))
-#define ADD(a, b) __fadd_rn((a), (b))
-#define FMA(a, b, c) __fmaf_rn((a), (b), (c))
-
-__device__ __forceinline__ float power_threshold_b(float opacity) {
-  return opacity > 0.0f ? -(__logf(255.0f * opacity) + 0.01f) : __int_as_float(0x7f800000);
-}
-
-__global__ void __launch_bounds__(RB_THREADS) render_backward_kernel(
+__global__ void __launch_bounds__(BL_THREADS) render_backward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
-    const float* __restrict__ background, const float2* __restrict__ means2D,
+    const float* __restrict__ background, const float4* __restrict__ means2D,
     const float4* __restrict__ conic_opacity, const float4* __restrict__ rgb_depth,
     const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
     const float* __restrict__ dL_dpixels, float* __restrict__ acc) {
-  __shared__ float4 s_a[RB_BATCH];  // x, y, conic.x, conic.y
-  __shared__ float4 s_b[RB_BATCH];  // conic.z, power threshold, opacity, gid (bits)
-  __shared__ float4 s_c[RB_BATCH];  // r, g, b, unused
-  __shared__ uint32_t s_max[RB_THREADS / 32];
+  __shared__ BlendSmem s;
+  __shared__ uint32_t s_max[BL_WARPS];
 
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int qx = tid & 7, qy = tid >> 3;
   const int px0 = blockIdx.x * DGE_TILE + 2 * qx, py0 = blockIdx.y * DGE_TILE + 2 * qy;
   const float fx0 = (float)px0, fx1 = (float)(px0 + 1), fy0 = (float)py0, fy1 = (float)(py0 + 1);
+  const float X0 = (float)(blockIdx.x * DGE_TILE), X1 = X0 + 15.0f;
+  const float Y0 = (float)(blockIdx.y * DGE_TILE + 8 * warp), Y1 = Y0 + 7.0f;
   const size_t HW = (size_t)H * W;
   const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
 
@@ -70,48 +60,36 @@ __global__ void __launch_bounds__(RB_THREADS) render_backward_kernel(
     bg_dot[p] = bg0 * dpix[p][0] + bg1 * dpix[p][1] + bg2 * dpix[p][2];
   }
   const uint32_t wmax = __reduce_max_sync(0xFFFFFFFFu, tmax);
-  if (lane == 0) s_max[tid >> 5] = wmax;
+  if (lane == 0) s_max[warp] = wmax;
   __syncthreads();
   uint32_t bmax = 0;
 #pragma unroll
-  for (int w = 0; w < RB_THREADS / 32; w++) bmax = max(bmax, s_max[w]);
+  for (int w = 0; w < BL_WARPS; w++) bmax = max(bmax, s_max[w]);
 
   const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
 
   // positions hi-1 ... 0 of the tile list, back to front, in batches
-  for (uint32_t hi = bmax; hi > 0; hi -= min(hi, (uint32_t)RB_BATCH)) {
-    const int count = min(hi, (uint32_t)RB_BATCH);
+  for (uint32_t hi = bmax; hi > 0; hi -= min(hi, (uint32_t)BL_BATCH)) {
+    const int count = min(hi, (uint32_t)BL_BATCH);
     __syncthreads();
-    for (int k = tid; k < count; k += RB_THREADS) {
-      const uint32_t gid = point_list[range.x + hi - 1 - k];
-      const float2 xy = means2D[gid];
-      const float4 co = conic_opacity[gid];
-      const float4 cd = rgb_depth[gid];
-      s_a[k] = make_float4(xy.x, xy.y, co.x, co.y);
-      s_b[k] = make_float4(co.z, power_threshold_b(co.w), co.w, __uint_as_float(gid));
-      s_c[k] = cd;
-    }
+    stage_batch<true>(s, tid, count, [&](int k) { return range.x + hi - 1 - k; }, point_list,
+                      means2D, conic_opacity, rgb_depth);
     __syncthreads();
     if (hi - count >= wmax) continue;  // nothing in this batch reaches this warp (warp-uniform)
-    for (int j = 0; j < count; j++) {
+    const int n = compact_batch(s, warp, lane, count, X0, X1, Y0, Y1,
+                                [&](int k) { return hi - 1 - k < wmax; });
+    for (int i = 0; i < n; i++) {
+      const int j = s.list[warp][i];
       const uint32_t pos = hi - 1 - j;  // 0-based list position
-      const float4 a = s_a[j];
-      const float4 b = s_b[j];
-      const float dx0 = ADD(a.x, -fx0), dx1 = ADD(a.x, -fx1);
-      const float dy0 = ADD(a.y, -fy0), dy1 = ADD(a.y, -fy1);
-      const float bx0 = MUL(dx0, a.z), bx1 = MUL(dx1, a.z);
-      const float cx0 = MUL(dx0, a.w), cx1 = MUL(dx1, a.w);
-      const float ay0 = MUL(dy0, MUL(dy0, b.x)), ay1 = MUL(dy1, MUL(dy1, b.x));
-      float power[4];
-      power[0] = FMA(FMA(dx0, bx0, ay0), -0.5f, -MUL(dy0, cx0));
-      power[1] = FMA(FMA(dx1, bx1, ay0), -0.5f, -MUL(dy0, cx1));
-      power[2] = FMA(FMA(dx0, bx0, ay1), -0.5f, -MUL(dy1, cx0));
-      power[3] = FMA(FMA(dx1, bx1, ay1), -0.5f, -MUL(dy1, cx1));
+      const float4 a = s.a[j];
+      const float4 b = s.b[j];
+      const Quad q = quad_power(a, b.x, fx0, fx1, fy0, fy1);
+      const float dx0 = q.dx0, dx1 = q.dx1, dy0 = q.dy0, dy1 = q.dy1;
       bool cand[4];
       bool any = false;
 #pragma unroll
       for (int p = 0; p < 4; p++) {
-        cand[p] = pos < last[p] && !(power[p] > 0.0f) && !(power[p] < b.y);
+        cand[p] = pos < last[p] && !(q.power[p] > 0.0f) && !(q.power[p] < b.y);
         any |= cand[p];
       }
       if (!__any_sync(0xFFFFFFFFu, any)) continue;
@@ -122,13 +100,13 @@ __global__ void __launch_bounds__(RB_THREADS) render_backward_kernel(
       bool touched = false;
       if (any) {
         const float opacity = b.z;
-        const float4 cd = s_c[j];
+        const float4 cd = s.c[j];
         const float col[3] = {cd.x, cd.y, cd.z};
 #pragma unroll
         for (int p = 0; p < 4; p++) {
           if (!cand[p]) continue;
-          const float G = expf(power[p]);
-          const float alpha = fminf(0.99f, MUL(opacity, G));
+          const float G = expf(q.power[p]);
+          const float alpha = fminf(0.99f, BMUL(opacity, G));
           if (alpha < 1.0f / 255.0f) continue;
           touched = true;
           const float dx = (p & 1) ? dx1 : dx0, dy = (p >> 1) ? dy1 : dy0;
@@ -200,7 +178,7 @@ cudaError_t launch_render_backward(const ViewParams& vp, const GeomState& g, con
                                    const ImgState& img, const float* background,
                                    const float* dL_dpix, float* acc, cudaStream_t stream) {
   dim3 grid(vp.grid_x, vp.grid_y);
-  render_backward_kernel<<<grid, RB_THREADS, 0, stream>>>(
+  render_backward_kernel<<<grid, BL_THREADS, 0, stream>>>(
       img.ranges, b.point_list, vp.W, vp.H, background, g.means2D, g.conic_opacity, g.rgb_depth,
       img.final_T, img.n_contrib, dL_dpix, acc);
   DGE_LAUNCHED(1);

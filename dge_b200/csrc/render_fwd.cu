@@ -12,38 +12,26 @@
 //  * a per-Gaussian power threshold (staged next to the conic) rejects pairs whose
 //    alpha is certainly < 1/255 before the expf; it is conservative by a margin far
 //    above expf's error, so no decision of the reference is ever changed;
-//  * Gaussians are staged in batches of 128 records of 48 B.
-#include "common.cuh"
+//  * Gaussians are staged in batches of 128 records; each warp visits only the records whose
+//    conservative alpha >= 1/255 box overlaps its 16x8 half-tile (blend.cuh).
+#include "blend.cuh"
 
 namespace dge {
 
-constexpr int RF_THREADS = 64;
-constexpr int RF_BATCH = 128;
-
-#define MUL(a, b) __fmul_rn((a), (b))
-#define ADD(a, b) __fadd_rn((a), (b))
-#define FMA(a, b, c) __fmaf_rn((a), (b), (c))
-
-// Lower bound on `power` below which opacity*exp(power) < 1/255 for certain.
-// 0.01 of slack in the exponent is ~1% in alpha; expf and __logf err by < 1e-6.
-__device__ __forceinline__ float power_threshold(float opacity) {
-  return opacity > 0.0f ? -(__logf(255.0f * opacity) + 0.01f) : __int_as_float(0x7f800000);
-}
-
-__global__ void __launch_bounds__(RF_THREADS) render_forward_kernel(
+__global__ void __launch_bounds__(BL_THREADS) render_forward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
-    const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity,
+    const float4* __restrict__ means2D, const float4* __restrict__ conic_opacity,
     const float4* __restrict__ rgb_depth, const float* __restrict__ background,
     float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
     float* __restrict__ out_depth) {
-  __shared__ float4 s_a[RF_BATCH];  // x, y, conic.x, conic.y
-  __shared__ float4 s_b[RF_BATCH];  // conic.z, power threshold, opacity, unused
-  __shared__ float4 s_c[RF_BATCH];  // r, g, b, depth
-
-  const int tid = threadIdx.x;
+  __shared__ BlendSmem s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int qx = tid & 7, qy = tid >> 3;
   const int px0 = blockIdx.x * DGE_TILE + 2 * qx, py0 = blockIdx.y * DGE_TILE + 2 * qy;
   const float fx0 = (float)px0, fx1 = (float)(px0 + 1), fy0 = (float)py0, fy1 = (float)(py0 + 1);
+  // the warp's half-tile, in pixel-centre coordinates
+  const float X0 = (float)(blockIdx.x * DGE_TILE), X1 = X0 + 15.0f;
+  const float Y0 = (float)(blockIdx.y * DGE_TILE + 8 * warp), Y1 = Y0 + 7.0f;
   // pixel p = 2*row + col inside the quad
   bool inside[4];
   inside[0] = px0 < W && py0 < H;
@@ -64,60 +52,46 @@ __global__ void __launch_bounds__(RF_THREADS) render_forward_kernel(
     done[p] = !inside[p];
   }
 
-  for (uint32_t base = range.x; base < range.y; base += RF_BATCH) {
+  for (uint32_t base = range.x; base < range.y; base += BL_BATCH) {
     const bool all_done = done[0] && done[1] && done[2] && done[3];
     if (__syncthreads_and(all_done)) break;
-    const int count = min((uint32_t)RF_BATCH, range.y - base);
-    for (int k = tid; k < count; k += RF_THREADS) {
-      const uint32_t gid = point_list[base + k];
-      const float2 xy = means2D[gid];
-      const float4 co = conic_opacity[gid];
-      s_a[k] = make_float4(xy.x, xy.y, co.x, co.y);
-      s_b[k] = make_float4(co.z, power_threshold(co.w), co.w, 0.0f);
-      s_c[k] = rgb_depth[gid];
-    }
+    const int count = min((uint32_t)BL_BATCH, range.y - base);
+    stage_batch<true>(s, tid, count, [&](int k) { return base + k; }, point_list, means2D,
+                      conic_opacity, rgb_depth);
     __syncthreads();
-    if (!all_done) {
-      for (int j = 0; j < count; j++) {
-        const float4 a = s_a[j];
-        const float2 b = *reinterpret_cast<const float2*>(&s_b[j]);
-        const float dx0 = ADD(a.x, -fx0), dx1 = ADD(a.x, -fx1);
-        const float dy0 = ADD(a.y, -fy0), dy1 = ADD(a.y, -fy1);
-        const float bx0 = MUL(dx0, a.z), bx1 = MUL(dx1, a.z);  // conic.x * dx
-        const float cx0 = MUL(dx0, a.w), cx1 = MUL(dx1, a.w);  // conic.y * dx
-        const float ay0 = MUL(dy0, MUL(dy0, b.x)), ay1 = MUL(dy1, MUL(dy1, b.x));
-        float power[4];
-        power[0] = FMA(FMA(dx0, bx0, ay0), -0.5f, -MUL(dy0, cx0));
-        power[1] = FMA(FMA(dx1, bx1, ay0), -0.5f, -MUL(dy0, cx1));
-        power[2] = FMA(FMA(dx0, bx0, ay1), -0.5f, -MUL(dy1, cx0));
-        power[3] = FMA(FMA(dx1, bx1, ay1), -0.5f, -MUL(dy1, cx1));
-        bool cand[4];
-        bool any = false;
+    if (__all_sync(0xFFFFFFFFu, all_done)) continue;  // this half-tile is saturated
+    const int n = compact_batch(s, warp, lane, count, X0, X1, Y0, Y1, [](int) { return true; });
+    for (int i = 0; i < n; i++) {
+      const int j = s.list[warp][i];
+      const float4 a = s.a[j];
+      const float2 b = *reinterpret_cast<const float2*>(&s.b[j]);
+      const Quad q = quad_power(a, b.x, fx0, fx1, fy0, fy1);
+      bool cand[4];
+      bool any = false;
 #pragma unroll
-        for (int p = 0; p < 4; p++) {
-          cand[p] = !done[p] && !(power[p] > 0.0f) && !(power[p] < b.y);
-          any |= cand[p];
-        }
-        if (!any) continue;
-        const float opacity = s_b[j].z;
-        const float4 cd = s_c[j];
+      for (int p = 0; p < 4; p++) {
+        cand[p] = !done[p] && !(q.power[p] > 0.0f) && !(q.power[p] < b.y);
+        any |= cand[p];
+      }
+      if (!any) continue;
+      const float opacity = s.b[j].z;
+      const float4 cd = s.c[j];
 #pragma unroll
-        for (int p = 0; p < 4; p++) {
-          if (!cand[p]) continue;
-          const float alpha = fminf(0.99f, MUL(opacity, expf(power[p])));
-          if (alpha < 1.0f / 255.0f) continue;
-          const float test_T = MUL(T[p], ADD(1.0f, -alpha));
-          if (test_T < 0.0001f) {
-            done[p] = true;
-            continue;
-          }
-          C[p][0] = FMA(T[p], MUL(alpha, cd.x), C[p][0]);
-          C[p][1] = FMA(T[p], MUL(alpha, cd.y), C[p][1]);
-          C[p][2] = FMA(T[p], MUL(alpha, cd.z), C[p][2]);
-          Dp[p] = FMA(T[p], MUL(alpha, cd.w), Dp[p]);
-          T[p] = test_T;
-          last[p] = base - range.x + j + 1;
+      for (int p = 0; p < 4; p++) {
+        if (!cand[p]) continue;
+        const float alpha = fminf(0.99f, BMUL(opacity, expf(q.power[p])));
+        if (alpha < 1.0f / 255.0f) continue;
+        const float test_T = BMUL(T[p], BADD(1.0f, -alpha));
+        if (test_T < 0.0001f) {
+          done[p] = true;
+          continue;
         }
+        C[p][0] = BFMA(T[p], BMUL(alpha, cd.x), C[p][0]);
+        C[p][1] = BFMA(T[p], BMUL(alpha, cd.y), C[p][1]);
+        C[p][2] = BFMA(T[p], BMUL(alpha, cd.z), C[p][2]);
+        Dp[p] = BFMA(T[p], BMUL(alpha, cd.w), Dp[p]);
+        T[p] = test_T;
+        last[p] = base - range.x + j + 1;
       }
     }
   }
@@ -130,9 +104,9 @@ __global__ void __launch_bounds__(RF_THREADS) render_forward_kernel(
     const size_t pix = (size_t)(py0 + (p >> 1)) * W + (px0 + (p & 1));
     final_T[pix] = T[p];
     n_contrib[pix] = last[p];
-    out_color[pix] = FMA(bg0, T[p], C[p][0]);
-    out_color[HW + pix] = FMA(bg1, T[p], C[p][1]);
-    out_color[2 * HW + pix] = FMA(bg2, T[p], C[p][2]);
+    out_color[pix] = BFMA(bg0, T[p], C[p][0]);
+    out_color[HW + pix] = BFMA(bg1, T[p], C[p][1]);
+    out_color[2 * HW + pix] = BFMA(bg2, T[p], C[p][2]);
     out_depth[pix] = Dp[p];
   }
 }
@@ -141,7 +115,7 @@ cudaError_t launch_render_forward(const ViewParams& vp, const GeomState& g, cons
                                   ImgState& img, const float* background, float* out_color,
                                   float* out_depth, cudaStream_t stream) {
   dim3 grid(vp.grid_x, vp.grid_y);
-  render_forward_kernel<<<grid, RF_THREADS, 0, stream>>>(
+  render_forward_kernel<<<grid, BL_THREADS, 0, stream>>>(
       img.ranges, b.point_list, vp.W, vp.H, g.means2D, g.conic_opacity, g.rgb_depth, background,
       img.final_T, img.n_contrib, out_color, out_depth);
   DGE_LAUNCHED(1);

@@ -134,30 +134,71 @@ def default_rasterize(rs, means3D, means2D, shs, opacities, scales, rotations):
 
 def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence[torch.Tensor], bg: torch.Tensor,
              global_batch: int, rasterize: Callable = default_rasterize, settings_module=dgr,
-             process_group=None, lambda_l1: float = 10.0, host_inputs: bool = False, update_stats: bool = True):
+             process_group=None, lambda_l1: float = 10.0, host_inputs: bool = False, update_stats: bool = True,
+             num_streams: int = 1):
     """One optimisation step over this rank's views. `cameras`/`targets` are this rank's share;
     `global_batch` the number of views in the whole step (L1 is a mean over the global batch,
     DGE.py:672). With host_inputs the cameras/targets live in pinned host memory and are copied
-    inside the step. Returns the step's loss as a 0-d device tensor (already globally reduced)."""
+    inside the step. Returns the step's loss as a 0-d device tensor (already globally reduced).
+
+    Views are independent until the optimiser step, so with num_streams > 1 they are issued
+    round-robin on that many CUDA streams: one view's latency-bound stages (sorts, the tail of
+    the blend over the densest tiles) overlap another view's kernels. Each stream accumulates
+    into its own gradient leaves; the partial sums are added on the main stream afterwards."""
     dev = model.device
     model.zero_grad()
     acts_graph = model.activations()
-    acts = {k: v.detach().requires_grad_(True) for k, v in acts_graph.items()}
-    loss = torch.zeros((), device=dev)
-    radii_max = torch.zeros(model.P, dtype=torch.int32, device=dev)
     H, W = cameras[0].image_height, cameras[0].image_width
     scale = lambda_l1 / float(global_batch * 3 * H * W)
-    for cam, target in zip(cameras, targets):
-        if host_inputs:
-            cam = scene.camera_to(cam, dev, non_blocking=True)
-            target = target.to(dev, non_blocking=True)
-        rs = scene.raster_settings(cam, bg, model.sh_degree, module=settings_module)
-        color, radii, _depth = rasterize(rs, acts["means3D"], model.means2D, acts["shs"], acts["opacities"],
-                                         acts["scales"], acts["rotations"])
-        lv = (color - target).abs().sum() * scale
-        lv.backward()
-        loss = loss + lv.detach()
-        radii_max = torch.maximum(radii_max, radii)
+    S = max(1, min(num_streams, len(cameras)))
+    main = torch.cuda.current_stream(dev) if dev.type == "cuda" else None
+    if S > 1:
+        if len(getattr(model, "_streams", [])) < S:
+            model._streams = [torch.cuda.Stream(dev) for _ in range(S)]
+        streams = model._streams[:S]
+        for st in streams:
+            st.wait_stream(main)
+    else:
+        streams = [None]
+
+    lanes = []  # per stream: detached activation leaves, means2D tap, loss and radii accumulators
+    for st in streams:
+        with torch.cuda.stream(st) if st is not None else _null():
+            acts = {k: v.detach().requires_grad_(True) for k, v in acts_graph.items()}
+            m2d = model.means2D if S == 1 else torch.zeros_like(model.means2D, requires_grad=True)
+            lanes.append(dict(acts=acts, m2d=m2d, loss=torch.zeros((), device=dev),
+                              radii=torch.zeros(model.P, dtype=torch.int32, device=dev)))
+    for i, (cam, target) in enumerate(zip(cameras, targets)):
+        lane, st = lanes[i % S], streams[i % S]
+        with torch.cuda.stream(st) if st is not None else _null():
+            if host_inputs:
+                cam = scene.camera_to(cam, dev, non_blocking=True)
+                target = target.to(dev, non_blocking=True)
+            rs = scene.raster_settings(cam, bg, model.sh_degree, module=settings_module)
+            a = lane["acts"]
+            color, radii, _depth = rasterize(rs, a["means3D"], lane["m2d"], a["shs"], a["opacities"], a["scales"],
+                                             a["rotations"])
+            lv = (color - target).abs().sum() * scale
+            lv.backward()
+            lane["loss"] += lv.detach()
+            torch.maximum(lane["radii"], radii, out=lane["radii"])
+    if S > 1:
+        for st in streams:
+            main.wait_stream(st)
+    # fold the per-stream partial sums (main stream)
+    acts = lanes[0]["acts"]
+    loss, radii_max = lanes[0]["loss"], lanes[0]["radii"]
+    for lane in lanes[1:]:
+        for k in acts:
+            if lane["acts"][k].grad is not None:
+                acts[k].grad.add_(lane["acts"][k].grad)
+        loss = loss + lane["loss"]
+        radii_max = torch.maximum(radii_max, lane["radii"])
+    if S > 1:
+        g2 = model.means2D.grad
+        for lane in lanes:
+            if lane["m2d"].grad is not None:
+                g2.add_(lane["m2d"].grad)
     # one backward through the activations for the whole step
     through = [k for k in acts_graph if acts_graph[k].grad_fn is not None and acts[k].grad is not None]
     if through:
@@ -180,3 +221,11 @@ def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence
             model.denom += vis[:, None].to(model.denom.dtype)
     model.adam_step()
     return loss
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

@@ -110,7 +110,7 @@ size_t dge_backward_scratch_bytes(int P);
 
 /* Inspection of the opaque scratch blobs — used by the parity tests to compare
  * every intermediate with the reference's (DGR/cuda_rasterizer/rasterizer_impl.cu:135-175).
- * geom: out[0]=means2D float2[P], out[1]=conic_opacity float4[P],
+ * geom: out[0]=means2D float4[P] (x, y, cull half-extents hx, hy), out[1]=conic_opacity float4[P],
  *       out[2]=rgb_depth float4[P] (r,g,b,view-space depth), out[3]=rect
  *       ushort4[P] (min.x,min.y,max.x,max.y), out[4]=clamped uint8[P] (bit ch),
  *       out[5]=depth_order uint32[P] (Gaussian ids sorted by depth bits),

@@ -74,7 +74,7 @@ def ours_intermediates(rs, g, dev, colors_precomp=None, cov3D_precomp=None):
     gp = (C.c_void_p * 8)()
     lib.dge_geom_pointers(geom.data_ptr(), P, gp)
     o = {"num_rendered": R, "radii": radii, "out_color": color, "out_depth": depth}
-    o["means2D"] = view(geom, gp[0], torch.float32, 2 * P).view(P, 2)
+    o["means2D"] = view(geom, gp[0], torch.float32, 4 * P).view(P, 4)[:, :2]
     o["conic_opacity"] = view(geom, gp[1], torch.float32, 4 * P).view(P, 4)
     rd = view(geom, gp[2], torch.float32, 4 * P).view(P, 4)
     o["rgb"], o["depths"] = rd[:, :3], rd[:, 3]
