@@ -44,7 +44,7 @@ class ClockSampler:
     and slows the measured step, NVML queries do not."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index, period=0.02):
+    def __init__(self, gpu_index, period=0.1):
         self.gpu, self.period, self.sm, self.bits, self.ok = gpu_index, period, [], 0, False
         self.stop_flag = threading.Event()
 
@@ -156,7 +156,7 @@ KERNEL_OF_STAGE = {"preprocess": "preprocess_kernel", "render_fwd": "render_forw
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="config2", choices=list(CONFIGS))
@@ -310,7 +310,7 @@ def main():
     views = V * n_gpus * args.steps
     value = views / (ms_resident * 1e-3)
     e2e_value = views / (ms_e2e * 1e-3)
-    h2d = V * (3 * H * W * 4 + (16 + 16 + 3) * 4)
+    h2d = n_gpus * V * (3 * H * W * 4 + (16 + 16 + 3) * 4)  # whole job: every rank copies its own views
     out = {
         "metric": "fwd+bwd views/s @1M Gaussians 512^2 (DGE 3D-fit step incl. Adam)", "value": value, "unit": "views/s",
         "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_resident / args.steps,
@@ -321,7 +321,7 @@ def main():
                    "l2": "per-view working set (inputs 236 MB + scratch) exceeds the 126 MB L2; no explicit flush",
                    "scene": "randgauss-v1", **stats},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+        "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * n_gpus,
                 "ms_per_step": ms_e2e / args.steps, "loss": last_loss},
         "gpu_launches": int(launches),
     }

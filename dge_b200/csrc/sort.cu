@@ -19,6 +19,7 @@ constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_IPT = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;  // 4096 items per CTA
 constexpr int MAX_PASSES = 4;
+constexpr int LB_WINDOW = 16;
 constexpr uint32_t FLAG_AGG = 1u << 30, FLAG_PREFIX = 2u << 30, FLAG_MASK = 3u << 30;
 
 int sort_num_passes(int num_bits) { return (num_bits + RADIX_BITS - 1) / RADIX_BITS; }
@@ -166,15 +167,27 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(
       if (w < warp) wbase += s_warp_tot[w];
     uint32_t base = wbase + x - h;
     if (tile > 0) {
+      // Decoupled look-back, LB_WINDOW predecessors per round trip: every CTA of a single-wave
+      // grid publishes its aggregate at about the same time, so a one-at-a-time walk costs one L2
+      // latency per predecessor (the pass time was proportional to the tile count). Loading a
+      // window of status words at once divides the number of serialised latencies by the window.
       uint32_t excl = 0;
       int64_t b = (int64_t)tile - 1;
-      while (true) {
-        const uint32_t s = ld_relaxed(status + (size_t)b * RADIX + tid);
-        const uint32_t f = s & FLAG_MASK;
-        if (f == 0) continue;  // not published yet
-        excl += s & ~FLAG_MASK;
-        if (f == FLAG_PREFIX) break;
-        b--;
+      bool found = false;
+      while (!found) {
+        uint32_t w[LB_WINDOW];
+#pragma unroll
+        for (int i = 0; i < LB_WINDOW; i++)
+          w[i] = (b - i >= 0) ? ld_relaxed(status + (size_t)(b - i) * RADIX + tid) : FLAG_PREFIX;
+#pragma unroll
+        for (int i = 0; i < LB_WINDOW; i++) {
+          if (found) break;
+          uint32_t v = w[i];
+          while ((v & FLAG_MASK) == 0) v = ld_relaxed(status + (size_t)(b - i) * RADIX + tid);
+          excl += v & ~FLAG_MASK;
+          found = (v & FLAG_MASK) == FLAG_PREFIX;
+        }
+        b -= LB_WINDOW;
       }
       st_relaxed(my_status, FLAG_PREFIX | (excl + my_count));
       base += excl;
