@@ -34,6 +34,7 @@ CONFIGS = {
                     desc="DGE global edit fit: 1M Gaussians, 20 views/step/GPU at 512x512, fwd+bwd+Adam"),
     "config1": dict(P=16_384, W=256, H=256, V=1, seed=1235, desc="16k Gaussians, one 256x256 view (parity config)"),
     "tiny": dict(P=50_000, W=256, H=256, V=4, seed=1240, desc="smoke-sized"),
+    "hostbound": dict(P=2_000, W=64, H=64, V=20, seed=1241, desc="negligible GPU work: measures host overhead per view"),
 }
 
 

@@ -10,7 +10,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_build", "libdge_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 3
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
@@ -25,7 +25,7 @@ _SIGNATURES = {
                                    _p, _p, _f, _p, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p, _i, _p]),
     "dge_rasterize_backward": (_i, [ALLOC_FN, _p, _i, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _f, _p, _p,
                                     _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
-                                    _p, _p, _i, _p]),
+                                    _p, _p, _i, _i, _p]),
     "dge_apply_weights": (_i, [ALLOC_FN, ALLOC_FN, ALLOC_FN, _p, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p,
                                _p, _f, _p, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p, _i, _i, _p]),
     "dge_mark_visible": (_i, [_i, _p, _p, _p, _p, _p]),
@@ -40,6 +40,12 @@ _SIGNATURES = {
     "dge_launch_count": (C.c_ulonglong, []),
     "dge_profile_enable": (None, [C.c_uint]),
     "dge_profile_read": (_i, [C.POINTER(C.c_float), C.POINTER(_i)]),
+    "dge_fit_forward": (_i, [ALLOC_FN, ALLOC_FN, ALLOC_FN, _p, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _f, _p, _p,
+                             _f, _f, _p, _p, _p, _p, _p]),
+    "dge_fit_backward_blend": (_i, [_i, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "dge_fit_backward_geom": (_i, [_i, _i, _i, _i, _p, _i, _i, _f, _p, C.c_size_t, _p, _p, _p, _p, _p, _p, _p, _p,
+                                   _p, _p, _i, _p]),
+    "dge_l1_loss_grad": (_i, [_p, _p, C.c_size_t, _f, _p, _p, _p]),
     "dge_fused_adam": (_i, [_p, _p, _p, _p, C.c_size_t, _f, _f, _f, _f, _i, _p, _i, _p]),
 }
 EXPORTS = tuple(_SIGNATURES)

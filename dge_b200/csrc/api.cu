@@ -162,7 +162,7 @@ static int bin_view(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge
                     const float* colors_precomp, int colors_mode, const float* opacities,
                     const float* scales, const float* rotations, const float* cov3D_precomp,
                     bool prefiltered, int* radii, bool debug, cudaStream_t stream, GeomState& g,
-                    BinState& b, ImgState& img) {
+                    BinState& b, ImgState& img, float* acc_init = nullptr) {
   if (vp.grid_x > 65535 || vp.grid_y > 65535) return fail_msg("image too large (tile grid > 65535)");
   if (cov3D_precomp == nullptr && (scales == nullptr || rotations == nullptr))
     return fail_msg("need scales+rotations or cov3D_precomp");
@@ -173,7 +173,7 @@ static int bin_view(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge
   carve_geom(gp, vp.P, &g);
   carve_image(ip, vp.W, vp.H, &img);
   STAGE(ST_PREPROCESS, "preprocess", launch_preprocess(vp, means3D, scales, rotations, opacities, shs, cov3D_precomp,
-                                        colors_precomp, colors_mode, prefiltered, radii, g, stream));
+                                        colors_precomp, colors_mode, prefiltered, radii, g, acc_init, stream));
   CK("num_rendered copy", cudaMemcpyAsync(g_slot.pinned, g.counters, sizeof(uint32_t),
                                           cudaMemcpyDeviceToHost, stream));
   CK("event record", cudaEventRecord(g_slot.ev, stream));
@@ -195,7 +195,7 @@ using namespace dge;
 extern "C" {
 
 const char* dge_last_error(void) { return g_err; }
-int dge_abi_version(void) { return 1; }
+int dge_abi_version(void) { return 3; }
 unsigned long long dge_launch_count(void) { return g_kernel_launches; }
 
 void dge_profile_enable(unsigned stage_mask) { g_profile_mask = stage_mask; }
@@ -258,6 +258,61 @@ int dge_rasterize_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffe
   return R;
 }
 
+// ---- fit-step entry points (include/dge_b200.h "fit step") ----
+int dge_fit_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge_alloc_fn imageBuffer,
+                        void* alloc_ctx, int P, int D, int M, const float* background, int width,
+                        int height, const float* means3D, const float* shs, const float* opacities,
+                        const float* scales, float scale_modifier, const float* rotations,
+                        const float* cam, float tan_fovx, float tan_fovy, float* out_color,
+                        float* out_depth, int* radii, float* acc, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool debug = false;
+  if (P == 0 || width <= 0 || height <= 0) return fail_msg("empty problem");
+  const ViewParams vp = make_view(P, D, M, width, height, cam, cam + 16, cam + 32, tan_fovx, tan_fovy,
+                                  scale_modifier);
+  GeomState g;
+  BinState b;
+  ImgState img;
+  const int R = bin_view(geometryBuffer, binningBuffer, imageBuffer, alloc_ctx, vp, means3D, shs, nullptr, 0,
+                         opacities, scales, rotations, nullptr, false, radii, debug, stream, g, b, img, acc);
+  if (R < 0) return R;
+  STAGE(ST_RENDER_FWD, "render forward",
+        launch_render_forward(vp, g, b, img, background, out_color, out_depth, stream));
+  return R;
+}
+
+int dge_fit_backward_blend(int P, int R, const float* background, int width, int height, char* geom_buffer,
+                           char* binning_buffer, char* image_buffer, const float* dL_dpix, float* acc,
+                           void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool debug = false;
+  if (P == 0 || R == 0) return 0;
+  const ViewParams vp = make_view(P, 0, 0, width, height, nullptr, nullptr, nullptr, 1.f, 1.f, 1.f);
+  GeomState g;
+  BinState b;
+  ImgState img;
+  carve_geom(geom_buffer, P, &g);
+  carve_binning(binning_buffer, R, width, height, &b);
+  carve_image(image_buffer, width, height, &img);
+  STAGE(ST_RENDER_BWD, "render backward", launch_render_backward(vp, g, b, img, background, dL_dpix, acc, stream));
+  return 0;
+}
+
+int dge_fit_backward_geom(int P, int D, int M, int V, const float* cams, int width, int height,
+                          float scale_modifier, const float* acc, size_t acc_stride_floats,
+                          const float* means3D, const float* shs, const float* scales, const float* rotations,
+                          float* dL_dmean3D, float* dL_dmean2D, float* dL_dsh, float* dL_dopacity,
+                          float* dL_dscale, float* dL_drot, int accumulate, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool debug = false;
+  if (P == 0) return 0;
+  STAGE(ST_GEOM_BWD, "batched geometry backward",
+        launch_geom_backward_batched(P, D, M, V, cams, width, height, scale_modifier, acc, acc_stride_floats,
+                                     means3D, shs, scales, rotations, dL_dmean3D, dL_dmean2D, dL_dsh,
+                                     dL_dopacity, dL_dscale, dL_drot, accumulate != 0, stream));
+  return 0;
+}
+
 int dge_rasterize_backward(dge_alloc_fn scratchBuffer, void* alloc_ctx, int P, int D, int M, int R,
                            const float* background, int width, int height, const float* means3D,
                            const float* shs, const float* colors_precomp, const float* scales,
@@ -267,7 +322,7 @@ int dge_rasterize_backward(dge_alloc_fn scratchBuffer, void* alloc_ctx, int P, i
                            char* binning_buffer, char* image_buffer, const float* dL_dpix,
                            float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
                            float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale,
-                           float* dL_drot, int debug, void* stream_) {
+                           float* dL_drot, int accumulate, int debug, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (P == 0) return 0;
   if (!dL_dmean2D || !dL_dmean3D) return fail_msg("dL_dmean2D and dL_dmean3D are required");
@@ -290,7 +345,7 @@ int dge_rasterize_backward(dge_alloc_fn scratchBuffer, void* alloc_ctx, int P, i
   STAGE(ST_GEOM_BWD, "geometry backward",
         launch_geom_backward(vp, means3D, scales, rotations, shs, cov3D_precomp, radii, g, acc,
                              dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D,
-                             dL_dsh, dL_dscale, dL_drot, stream));
+                             dL_dsh, dL_dscale, dL_drot, accumulate != 0, stream));
   return 0;
 }
 
@@ -365,6 +420,12 @@ int dge_debug_sorted_keys(char* geom_buffer, char* binning_buffer, int P, int R,
   carve_geom(geom_buffer, P, &g);
   carve_binning(binning_buffer, R, width, height, &b);
   CK("debug keys", launch_debug_keys(g, b, R, keys_out, (cudaStream_t)stream_));
+  return 0;
+}
+
+int dge_l1_loss_grad(const float* image, const float* target, size_t n, float scale, float* grad,
+                     float* loss_accum, void* stream_) {
+  CK("l1 loss", launch_l1_loss_grad(image, target, n, scale, grad, loss_accum, (cudaStream_t)stream_));
   return 0;
 }
 

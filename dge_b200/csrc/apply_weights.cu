@@ -151,4 +151,40 @@ cudaError_t launch_fused_adam(float* param, const float* grad, float* m, float* 
   return cudaGetLastError();
 }
 
+
+// Fused L1 loss and its gradient for one rendered view (DGE.py:672: 10 * L1 over the batch):
+// grad = scale * sign(image - target), *loss_accum += scale * sum|image - target|.
+// Replaces sub / abs / sum / mul and their four backward kernels.
+__global__ void __launch_bounds__(256) l1_loss_grad_kernel(const float* __restrict__ image,
+                                                           const float* __restrict__ target, size_t n,
+                                                           float scale, float* __restrict__ grad,
+                                                           float* __restrict__ loss_accum) {
+  float local = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float d = image[i] - target[i];
+    local += fabsf(d);
+    grad[i] = d > 0.f ? scale : (d < 0.f ? -scale : 0.f);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, o);
+  __shared__ float ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += ws[i];
+    atomicAdd(loss_accum, t * scale);
+  }
+}
+
+cudaError_t launch_l1_loss_grad(const float* image, const float* target, size_t n, float scale,
+                                float* grad, float* loss_accum, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)((n + 256 * 8 - 1) / (256 * 8));
+  l1_loss_grad_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, stream>>>(image, target, n, scale, grad, loss_accum);
+  DGE_LAUNCHED(1);
+  return cudaGetLastError();
+}
+
 }  // namespace dge

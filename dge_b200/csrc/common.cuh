@@ -77,7 +77,14 @@ cudaError_t launch_preprocess(const ViewParams& vp, const float* means3D, const 
                               const float* rotations, const float* opacities, const float* shs,
                               const float* cov3D_precomp, const float* colors_precomp,
                               int colors_mode, bool prefiltered, int* radii, GeomState& g,
-                              cudaStream_t stream);
+                              float* acc_init, cudaStream_t stream);
+// fit step: per-Gaussian backward of V views in one pass (cams: V records of 40 floats)
+cudaError_t launch_geom_backward_batched(int P, int D, int M, int V, const float* cams, int W, int H,
+                                         float scale_modifier, const float* acc, size_t acc_stride,
+                                         const float* means3D, const float* shs, const float* scales,
+                                         const float* rotations, float* dL_dmean3D, float* dL_dmean2D,
+                                         float* dL_dsh, float* dL_dopacity, float* dL_dscale,
+                                         float* dL_drot, bool accumulate, cudaStream_t stream);
 cudaError_t launch_mark_visible(int P, const float* means3D, const float* view, const float* proj,
                                 uint8_t* present, cudaStream_t stream);
 // depth sort -> scan -> expand -> tile sort -> ranges. R already known on host.
@@ -96,7 +103,9 @@ cudaError_t launch_geom_backward(const ViewParams& vp, const float* means3D, con
                                  const int* radii, const GeomState& g, const float* acc,
                                  float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
                                  float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
-                                 float* dL_dscale, float* dL_drot, cudaStream_t stream);
+                                 float* dL_dscale, float* dL_drot, bool accumulate, cudaStream_t stream);
+cudaError_t launch_l1_loss_grad(const float* image, const float* target, size_t n, float scale,
+                                float* grad, float* loss_accum, cudaStream_t stream);
 cudaError_t launch_apply_weights_render(const ViewParams& vp, const GeomState& g, const BinState& b,
                                         const ImgState& img, float* weights, int* cnt,
                                         const float* image_weights, int num_channels,
@@ -109,7 +118,7 @@ cudaError_t launch_fused_adam(float* param, const float* grad, float* m, float* 
 
 // per-Gaussian accumulator slots written by the backward blend
 enum { ACC_MEAN_X = 0, ACC_MEAN_Y, ACC_CONIC_X, ACC_CONIC_Y, ACC_CONIC_W, ACC_OPACITY, ACC_R, ACC_G,
-       ACC_B, ACC_STRIDE = 12 };
+       ACC_B, ACC_FLAGS = 11, ACC_STRIDE = 12 };
 
 // Tile rect of a Gaussian, bit-exact with getRect (DGR/cuda_rasterizer/auxiliary.h:46-56) as
 // compiled for sm_100a: two separate float adds (+16, -1), *0.0625, truncation, clamp.

@@ -30,80 +30,38 @@ __device__ __forceinline__ void store3(float* p, size_t idx, float a, float b, f
   p[3 * idx + 1] = b;
   p[3 * idx + 2] = c;
 }
-
-__global__ void __launch_bounds__(256) geom_backward_kernel(
-    ViewParams vp, const float* __restrict__ means3D, const float* __restrict__ scales,
-    const float* __restrict__ rotations, const float* __restrict__ shs,
-    const float* __restrict__ cov3D_precomp, const int* __restrict__ radii,
-    const uint8_t* __restrict__ clamped, const float* __restrict__ acc,
-    float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic, float* __restrict__ dL_dopacity,
-    float* __restrict__ dL_dcolor, float* __restrict__ dL_dmean3D, float* __restrict__ dL_dcov3D,
-    float* __restrict__ dL_dsh, float* __restrict__ dL_dscale, float* __restrict__ dL_drot) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= vp.P) return;
-  const size_t i = (size_t)idx;
-  const int M = vp.M;
-
-  if (!(radii[idx] > 0)) {
-    // rows the reference leaves at torch::zeros
-    store3(dL_dmean2D, i, 0.f, 0.f, 0.f);
-    store3(dL_dmean3D, i, 0.f, 0.f, 0.f);
-    if (dL_dopacity) dL_dopacity[i] = 0.f;
-    if (dL_dconic) reinterpret_cast<float4*>(dL_dconic)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (dL_dcolor) store3(dL_dcolor, i, 0.f, 0.f, 0.f);
-    if (dL_dcov3D)
-      for (int k = 0; k < 6; k++) dL_dcov3D[6 * i + k] = 0.f;
-    if (dL_dsh) {
-      if (M == 16) {
-#pragma unroll
-        for (int j = 0; j < 12; j++)
-          reinterpret_cast<float4*>(dL_dsh + 48 * i)[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      } else {
-        for (int k = 0; k < 3 * M; k++) dL_dsh[3 * M * i + k] = 0.f;
-      }
-    }
-    if (dL_dscale) store3(dL_dscale, i, 0.f, 0.f, 0.f);
-    if (dL_drot) reinterpret_cast<float4*>(dL_drot)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    return;
-  }
-
-  const float4 a0 = __ldg(reinterpret_cast<const float4*>(acc) + 3 * i);
-  const float4 a1 = __ldg(reinterpret_cast<const float4*>(acc) + 3 * i + 1);
-  const float4 a2 = __ldg(reinterpret_cast<const float4*>(acc) + 3 * i + 2);
-  const float dm2x = a0.x, dm2y = a0.y;
-  const float dcon_x = a0.z, dcon_y = a0.w, dcon_w = a1.x;
-  const float dop = a1.y;
-  float dcol[3] = {a1.z, a1.w, a2.x};
-
-  store3(dL_dmean2D, i, dm2x, dm2y, 0.f);
-  if (dL_dopacity) dL_dopacity[i] = dop;
-  if (dL_dconic) reinterpret_cast<float4*>(dL_dconic)[i] = make_float4(dcon_x, dcon_y, 0.f, dcon_w);
-  if (dL_dcolor) store3(dL_dcolor, i, dcol[0], dcol[1], dcol[2]);
-
-  float V[16], Pm[16];
-#pragma unroll
-  for (int k = 0; k < 16; k++) {
-    V[k] = __ldg(vp.view + k);
-    Pm[k] = __ldg(vp.proj + k);
-  }
-  const float mx = __ldg(means3D + 3 * i), my = __ldg(means3D + 3 * i + 1),
-              mz = __ldg(means3D + 3 * i + 2);
-
-  // ---------------- cov3D (forward value) ----------------
-  float c3[6];
-  float4 q = make_float4(0, 0, 0, 0);
-  float sc[3] = {0, 0, 0};
-  if (cov3D_precomp != nullptr) {
-#pragma unroll
-    for (int k = 0; k < 6; k++) c3[k] = __ldg(cov3D_precomp + 6 * i + k);
+// ACC = true: add into the caller's running sums (fit step: gradients of all views of a step
+// accumulate in place, no per-view tensors and no separate add pass); false: overwrite.
+template <bool ACC>
+__device__ __forceinline__ void out3(float* p, size_t idx, float a, float b, float c) {
+  if (ACC) {
+    p[3 * idx] += a;
+    p[3 * idx + 1] += b;
+    p[3 * idx + 2] += c;
   } else {
-    q = __ldg(reinterpret_cast<const float4*>(rotations) + i);
-    sc[0] = __ldg(scales + 3 * i);
-    sc[1] = __ldg(scales + 3 * i + 1);
-    sc[2] = __ldg(scales + 3 * i + 2);
-    cov3d_from_scale_rot(sc[0], sc[1], sc[2], vp.scale_modifier, q, c3);
+    store3(p, idx, a, b, c);
   }
+}
+template <bool ACC>
+__device__ __forceinline__ void out4(float* p, size_t idx, float4 v) {
+  float4* q = reinterpret_cast<float4*>(p) + idx;
+  if (ACC) {
+    const float4 o = *q;
+    v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+  }
+  *q = v;
+}
 
+
+// ---- K8 + projection part of K9 for ONE view (backward.cu:144-274, :366-387): given the
+// blend-stage sums of this Gaussian, the view's camera and the Gaussian's cov3D, returns the
+// view's contribution to dL/dmean3D (without the SH term) and dL/dcov3D.
+__device__ __forceinline__ void view_geom_backward(float mx, float my, float mz, const float* c3,
+                                                   const float* V, const float* Pm, float tan_fovx,
+                                                   float tan_fovy, float focal_x, float focal_y,
+                                                   float dm2x, float dm2y, float dcon_x, float dcon_y,
+                                                   float dcon_w, float dmean[3], float dcov[6]) {
+  struct { float tan_fovx, tan_fovy, focal_x, focal_y; } vp = {tan_fovx, tan_fovy, focal_x, focal_y};
   // ---------------- K8: conic -> cov2D -> cov3D, mean (backward.cu:144-274) ----------------
   float tx = V[0] * mx + V[4] * my + V[8] * mz + V[12];
   float ty = V[1] * mx + V[5] * my + V[9] * mz + V[13];
@@ -141,7 +99,8 @@ __global__ void __launch_bounds__(256) geom_backward_kernel(
   const float denom = a * c - b * b;
   float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
   const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
-  float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 6; k++) dcov[k] = 0.f;
   const float T00 = Tm.m[0][0], T01 = Tm.m[0][1], T02 = Tm.m[0][2];
   const float T10 = Tm.m[1][0], T11 = Tm.m[1][1], T12 = Tm.m[1][2];
   if (denom2inv != 0.f) {
@@ -155,10 +114,6 @@ __global__ void __launch_bounds__(256) geom_backward_kernel(
     dcov[2] = 2 * T00 * T02 * dL_da + (T00 * T12 + T02 * T10) * dL_db + 2 * T10 * T12 * dL_dc;
     dcov[4] = 2 * T02 * T01 * dL_da + (T01 * T12 + T02 * T11) * dL_db + 2 * T11 * T12 * dL_dc;
   }
-  if (dL_dcov3D)
-#pragma unroll
-    for (int k = 0; k < 6; k++) dL_dcov3D[6 * i + k] = dcov[k];
-
   // dL/dT (upper 2x3), TV[j][k] = sum_l T[j][l] Vrk[l][k]
   const float dT00 = 2 * TV[0][0] * dL_da + TV[1][0] * dL_db;
   const float dT01 = 2 * TV[0][1] * dL_da + TV[1][1] * dL_db;
@@ -176,8 +131,9 @@ __global__ void __launch_bounds__(256) geom_backward_kernel(
   const float dtz = -hx * itz2 * dJ00 - hy * itz2 * dJ11 + (2 * hx * tx) * itz3 * dJ02 +
                     (2 * hy * ty) * itz3 * dJ12;
   // transformVec4x3Transpose (auxiliary.h:89-97)
-  float dmean[3] = {V[0] * dtx + V[1] * dty + V[2] * dtz, V[4] * dtx + V[5] * dty + V[6] * dtz,
-                    V[8] * dtx + V[9] * dty + V[10] * dtz};
+  dmean[0] = V[0] * dtx + V[1] * dty + V[2] * dtz;
+  dmean[1] = V[4] * dtx + V[5] * dty + V[6] * dtz;
+  dmean[2] = V[8] * dtx + V[9] * dty + V[10] * dtz;
 
   // ---------------- K9: projection (backward.cu:366-387) ----------------
   {
@@ -190,24 +146,13 @@ __global__ void __launch_bounds__(256) geom_backward_kernel(
     dmean[2] += (Pm[8] * m_w - Pm[11] * mul1) * dm2x + (Pm[9] * m_w - Pm[11] * mul2) * dm2y;
   }
 
-  // ---------------- K9: SH (backward.cu:20-139) ----------------
-  // colour = sum_k b_k(dir) * sh_k, so dL/dsh_k = b_k * dL/dRGB and
-  // dL/ddir = sum_k grad(b_k) * (sh_k . dL/dRGB): the reference's dRGBdx/dy/dz sums, regrouped
-  // so that the 48 SH floats are consumed as they arrive from 12 vector loads.
-  if (shs != nullptr && dL_dsh != nullptr) {
-    const float* sh = shs + 3 * (size_t)M * i;
-    float* dsh = dL_dsh + 3 * (size_t)M * i;
-    const float ox = mx - __ldg(vp.campos), oy = my - __ldg(vp.campos + 1),
-                oz = mz - __ldg(vp.campos + 2);
-    const float len = sqrtf(ox * ox + oy * oy + oz * oz);
-    const float x = ox / len, y = oy / len, z = oz / len;
-    const uint8_t cl = clamped[i];
-    float dRGB[3];
-#pragma unroll
-    for (int ch = 0; ch < 3; ch++) dRGB[ch] = (cl >> ch) & 1 ? 0.f : dcol[ch];
-    const int D = vp.D;
+}
+
+// SH basis b_k(dir) and its gradient w.r.t. the (normalised) direction, degree <= D
+// (the coefficients of DGR/cuda_rasterizer/backward.cu:44-128, regrouped per basis function).
+__device__ __forceinline__ void sh_basis_grad(int D, float x, float y, float z, float b[16],
+                                              float gx[16], float gy[16], float gz[16]) {
     const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-    float b[16], gx[16], gy[16], gz[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) b[k] = gx[k] = gy[k] = gz[k] = 0.f;
     b[0] = SH_C0;
@@ -237,64 +182,17 @@ __global__ void __launch_bounds__(256) geom_backward_kernel(
       gx[14] = SH_C3_5 * 2.f * xz; gy[14] = SH_C3_5 * -2.f * yz; gz[14] = SH_C3_5 * (xx - yy);
       gx[15] = SH_C3_6 * 3.f * (xx - yy); gy[15] = SH_C3_6 * -3.f * 2.f * xy;
     }
-    float ddx = 0.f, ddy = 0.f, ddz = 0.f;
-    if (M == 16) {
-      float4 v[12];
-#pragma unroll
-      for (int j = 0; j < 12; j++) v[j] = __ldg(reinterpret_cast<const float4*>(sh) + j);
-      const float* f = reinterpret_cast<const float*>(v);
-#pragma unroll
-      for (int k = 1; k < 16; k++) {
-        const float sk = f[3 * k] * dRGB[0] + f[3 * k + 1] * dRGB[1] + f[3 * k + 2] * dRGB[2];
-        ddx += gx[k] * sk;
-        ddy += gy[k] * sk;
-        ddz += gz[k] * sk;
-      }
-#pragma unroll
-      for (int j = 0; j < 12; j++) {
-        float4 o;
-        o.x = b[(4 * j) / 3] * dRGB[(4 * j) % 3];
-        o.y = b[(4 * j + 1) / 3] * dRGB[(4 * j + 1) % 3];
-        o.z = b[(4 * j + 2) / 3] * dRGB[(4 * j + 2) % 3];
-        o.w = b[(4 * j + 3) / 3] * dRGB[(4 * j + 3) % 3];
-        reinterpret_cast<float4*>(dsh)[j] = o;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 16; k++) {  // compile-time k keeps b/gx/gy/gz in registers
-        if (k < M) {
-          if (k >= 1) {
-            const float sk = __ldg(sh + 3 * k) * dRGB[0] + __ldg(sh + 3 * k + 1) * dRGB[1] + __ldg(sh + 3 * k + 2) * dRGB[2];
-            ddx += gx[k] * sk;
-            ddy += gy[k] * sk;
-            ddz += gz[k] * sk;
-          }
-#pragma unroll
-          for (int ch = 0; ch < 3; ch++) dsh[3 * k + ch] = b[k] * dRGB[ch];
-        }
-      }
-      for (int k = 16; k < M; k++)
-        for (int ch = 0; ch < 3; ch++) dsh[3 * k + ch] = 0.f;
-    }
-    // dnormvdv (auxiliary.h:107-117)
-    const float sum2 = ox * ox + oy * oy + oz * oz;
-    const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
-    dmean[0] += ((+sum2 - ox * ox) * ddx - oy * ox * ddy - oz * ox * ddz) * invsum32;
-    dmean[1] += (-ox * oy * ddx + (sum2 - oy * oy) * ddy - oz * oy * ddz) * invsum32;
-    dmean[2] += (-ox * oz * ddx - oy * oz * ddy + (sum2 - oz * oz) * ddz) * invsum32;
-  } else if (dL_dsh != nullptr) {
-    for (int k = 0; k < 3 * M; k++) dL_dsh[3 * M * i + k] = 0.f;
-  }
-  store3(dL_dmean3D, i, dmean[0], dmean[1], dmean[2]);
+}
 
-  // ---------------- K9: cov3D -> scale, rotation (backward.cu:278-341) ----------------
-  if (scales != nullptr && cov3D_precomp == nullptr) {
+// cov3D -> scale, quaternion backward (backward.cu:278-341); no quaternion-norm Jacobian.
+__device__ __forceinline__ void cov3d_backward(float4 q, const float* sc, float scale_modifier,
+                                               const float* dcov, float dscale[3], float4& dq) {
     const float r = q.x, x = q.y, y = q.z, z = q.w;
     M3 R;
     R.m[0][0] = 1.f - 2.f * (y * y + z * z); R.m[0][1] = 2.f * (x * y - r * z); R.m[0][2] = 2.f * (x * z + r * y);
     R.m[1][0] = 2.f * (x * y + r * z); R.m[1][1] = 1.f - 2.f * (x * x + z * z); R.m[1][2] = 2.f * (y * z - r * x);
     R.m[2][0] = 2.f * (x * z - r * y); R.m[2][1] = 2.f * (y * z + r * x); R.m[2][2] = 1.f - 2.f * (x * x + y * y);
-    const float s[3] = {vp.scale_modifier * sc[0], vp.scale_modifier * sc[1], vp.scale_modifier * sc[2]};
+    const float s[3] = {scale_modifier * sc[0], scale_modifier * sc[1], scale_modifier * sc[2]};
     M3 Mm;  // M = S * R : M[col i][row j] = s_j * R[i][j]
 #pragma unroll
     for (int ci = 0; ci < 3; ci++)
@@ -315,25 +213,333 @@ __global__ void __launch_bounds__(256) geom_backward_kernel(
     for (int k = 0; k < 3; k++)
 #pragma unroll
       for (int l = 0; l < 3; l++) dMt[k][l] = dM.m[l][k];
-    float dscale[3];
 #pragma unroll
     for (int k = 0; k < 3; k++)
       dscale[k] = R.m[0][k] * dMt[k][0] + R.m[1][k] * dMt[k][1] + R.m[2][k] * dMt[k][2];
-    if (dL_dscale) store3(dL_dscale, i, dscale[0], dscale[1], dscale[2]);
 #pragma unroll
     for (int k = 0; k < 3; k++)
 #pragma unroll
       for (int l = 0; l < 3; l++) dMt[k][l] *= s[k];
-    float4 dq;
     dq.x = 2 * z * (dMt[0][1] - dMt[1][0]) + 2 * y * (dMt[2][0] - dMt[0][2]) + 2 * x * (dMt[1][2] - dMt[2][1]);
     dq.y = 2 * y * (dMt[1][0] + dMt[0][1]) + 2 * z * (dMt[2][0] + dMt[0][2]) + 2 * r * (dMt[1][2] - dMt[2][1]) - 4 * x * (dMt[2][2] + dMt[1][1]);
     dq.z = 2 * x * (dMt[1][0] + dMt[0][1]) + 2 * r * (dMt[2][0] - dMt[0][2]) + 2 * z * (dMt[1][2] + dMt[2][1]) - 4 * y * (dMt[2][2] + dMt[0][0]);
     dq.w = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) - 4 * z * (dMt[1][1] + dMt[0][0]);
-    if (dL_drot) reinterpret_cast<float4*>(dL_drot)[i] = dq;
+}
+
+template <bool ACC>
+__global__ void __launch_bounds__(256) geom_backward_kernel(
+    ViewParams vp, const float* __restrict__ means3D, const float* __restrict__ scales,
+    const float* __restrict__ rotations, const float* __restrict__ shs,
+    const float* __restrict__ cov3D_precomp, const int* __restrict__ radii,
+    const uint8_t* __restrict__ clamped, const float* __restrict__ acc,
+    float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic, float* __restrict__ dL_dopacity,
+    float* __restrict__ dL_dcolor, float* __restrict__ dL_dmean3D, float* __restrict__ dL_dcov3D,
+    float* __restrict__ dL_dsh, float* __restrict__ dL_dscale, float* __restrict__ dL_drot) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= vp.P) return;
+  const size_t i = (size_t)idx;
+  const int M = vp.M;
+
+  if (!(radii[idx] > 0)) {
+    if (ACC) return;  // nothing to add
+    // rows the reference leaves at torch::zeros
+    store3(dL_dmean2D, i, 0.f, 0.f, 0.f);
+    store3(dL_dmean3D, i, 0.f, 0.f, 0.f);
+    if (dL_dopacity) dL_dopacity[i] = 0.f;
+    if (dL_dconic) reinterpret_cast<float4*>(dL_dconic)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (dL_dcolor) store3(dL_dcolor, i, 0.f, 0.f, 0.f);
+    if (dL_dcov3D)
+      for (int k = 0; k < 6; k++) dL_dcov3D[6 * i + k] = 0.f;
+    if (dL_dsh) {
+      if (M == 16) {
+#pragma unroll
+        for (int j = 0; j < 12; j++)
+          reinterpret_cast<float4*>(dL_dsh + 48 * i)[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        for (int k = 0; k < 3 * M; k++) dL_dsh[3 * M * i + k] = 0.f;
+      }
+    }
+    if (dL_dscale) store3(dL_dscale, i, 0.f, 0.f, 0.f);
+    if (dL_drot) reinterpret_cast<float4*>(dL_drot)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+
+  const float4 a0 = __ldg(reinterpret_cast<const float4*>(acc) + 3 * i);
+  const float4 a1 = __ldg(reinterpret_cast<const float4*>(acc) + 3 * i + 1);
+  const float4 a2 = __ldg(reinterpret_cast<const float4*>(acc) + 3 * i + 2);
+  const float dm2x = a0.x, dm2y = a0.y;
+  const float dcon_x = a0.z, dcon_y = a0.w, dcon_w = a1.x;
+  const float dop = a1.y;
+  float dcol[3] = {a1.z, a1.w, a2.x};
+
+  out3<ACC>(dL_dmean2D, i, dm2x, dm2y, 0.f);
+  if (dL_dopacity) {
+    if (ACC) dL_dopacity[i] += dop; else dL_dopacity[i] = dop;
+  }
+  if (dL_dconic) out4<ACC>(dL_dconic, i, make_float4(dcon_x, dcon_y, 0.f, dcon_w));
+  if (dL_dcolor) out3<ACC>(dL_dcolor, i, dcol[0], dcol[1], dcol[2]);
+
+  float V[16], Pm[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    V[k] = __ldg(vp.view + k);
+    Pm[k] = __ldg(vp.proj + k);
+  }
+  const float mx = __ldg(means3D + 3 * i), my = __ldg(means3D + 3 * i + 1),
+              mz = __ldg(means3D + 3 * i + 2);
+
+  // ---------------- cov3D (forward value) ----------------
+  float c3[6];
+  float4 q = make_float4(0, 0, 0, 0);
+  float sc[3] = {0, 0, 0};
+  if (cov3D_precomp != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) c3[k] = __ldg(cov3D_precomp + 6 * i + k);
   } else {
+    q = __ldg(reinterpret_cast<const float4*>(rotations) + i);
+    sc[0] = __ldg(scales + 3 * i);
+    sc[1] = __ldg(scales + 3 * i + 1);
+    sc[2] = __ldg(scales + 3 * i + 2);
+    cov3d_from_scale_rot(sc[0], sc[1], sc[2], vp.scale_modifier, q, c3);
+  }
+
+  // ---------------- K8 + projection (backward.cu:144-274, :366-387) ----------------
+  float dmean[3], dcov[6];
+  view_geom_backward(mx, my, mz, c3, V, Pm, vp.tan_fovx, vp.tan_fovy, vp.focal_x, vp.focal_y, dm2x, dm2y,
+                     dcon_x, dcon_y, dcon_w, dmean, dcov);
+  if (dL_dcov3D)
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      if (ACC) dL_dcov3D[6 * i + k] += dcov[k]; else dL_dcov3D[6 * i + k] = dcov[k];
+    }
+
+  // ---------------- K9: SH (backward.cu:20-139) ----------------
+  // colour = sum_k b_k(dir) * sh_k, so dL/dsh_k = b_k * dL/dRGB and
+  // dL/ddir = sum_k grad(b_k) * (sh_k . dL/dRGB): the reference's dRGBdx/dy/dz sums, regrouped
+  // so that the 48 SH floats are consumed as they arrive from 12 vector loads.
+  if (shs != nullptr && dL_dsh != nullptr) {
+    const float* sh = shs + 3 * (size_t)M * i;
+    float* dsh = dL_dsh + 3 * (size_t)M * i;
+    const float ox = mx - __ldg(vp.campos), oy = my - __ldg(vp.campos + 1),
+                oz = mz - __ldg(vp.campos + 2);
+    const float len = sqrtf(ox * ox + oy * oy + oz * oz);
+    const float x = ox / len, y = oy / len, z = oz / len;
+    const uint8_t cl = clamped[i];
+    float dRGB[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) dRGB[ch] = (cl >> ch) & 1 ? 0.f : dcol[ch];
+    const int D = vp.D;
+    float b[16], gx[16], gy[16], gz[16];
+    sh_basis_grad(D, x, y, z, b, gx, gy, gz);
+    float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+    if (M == 16) {
+      float4 v[12];
+#pragma unroll
+      for (int j = 0; j < 12; j++) v[j] = __ldg(reinterpret_cast<const float4*>(sh) + j);
+      const float* f = reinterpret_cast<const float*>(v);
+#pragma unroll
+      for (int k = 1; k < 16; k++) {
+        const float sk = f[3 * k] * dRGB[0] + f[3 * k + 1] * dRGB[1] + f[3 * k + 2] * dRGB[2];
+        ddx += gx[k] * sk;
+        ddy += gy[k] * sk;
+        ddz += gz[k] * sk;
+      }
+#pragma unroll
+      for (int j = 0; j < 12; j++) {
+        float4 o;
+        o.x = b[(4 * j) / 3] * dRGB[(4 * j) % 3];
+        o.y = b[(4 * j + 1) / 3] * dRGB[(4 * j + 1) % 3];
+        o.z = b[(4 * j + 2) / 3] * dRGB[(4 * j + 2) % 3];
+        o.w = b[(4 * j + 3) / 3] * dRGB[(4 * j + 3) % 3];
+        out4<ACC>(dsh, j, o);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; k++) {  // compile-time k keeps b/gx/gy/gz in registers
+        if (k < M) {
+          if (k >= 1) {
+            const float sk = __ldg(sh + 3 * k) * dRGB[0] + __ldg(sh + 3 * k + 1) * dRGB[1] + __ldg(sh + 3 * k + 2) * dRGB[2];
+            ddx += gx[k] * sk;
+            ddy += gy[k] * sk;
+            ddz += gz[k] * sk;
+          }
+#pragma unroll
+          for (int ch = 0; ch < 3; ch++) {
+            if (ACC) dsh[3 * k + ch] += b[k] * dRGB[ch]; else dsh[3 * k + ch] = b[k] * dRGB[ch];
+          }
+        }
+      }
+      if (!ACC)
+        for (int k = 16; k < M; k++)
+          for (int ch = 0; ch < 3; ch++) dsh[3 * k + ch] = 0.f;
+    }
+    // dnormvdv (auxiliary.h:107-117)
+    const float sum2 = ox * ox + oy * oy + oz * oz;
+    const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+    dmean[0] += ((+sum2 - ox * ox) * ddx - oy * ox * ddy - oz * ox * ddz) * invsum32;
+    dmean[1] += (-ox * oy * ddx + (sum2 - oy * oy) * ddy - oz * oy * ddz) * invsum32;
+    dmean[2] += (-ox * oz * ddx - oy * oz * ddy + (sum2 - oz * oz) * ddz) * invsum32;
+  } else if (dL_dsh != nullptr && !ACC) {
+    for (int k = 0; k < 3 * M; k++) dL_dsh[3 * M * i + k] = 0.f;
+  }
+  out3<ACC>(dL_dmean3D, i, dmean[0], dmean[1], dmean[2]);
+
+  // ---------------- K9: cov3D -> scale, rotation (backward.cu:278-341) ----------------
+  if (scales != nullptr && cov3D_precomp == nullptr) {
+    float dscale[3];
+    float4 dq;
+    cov3d_backward(q, sc, vp.scale_modifier, dcov, dscale, dq);
+    if (dL_dscale) out3<ACC>(dL_dscale, i, dscale[0], dscale[1], dscale[2]);
+    if (dL_drot) out4<ACC>(dL_drot, i, dq);
+  } else if (!ACC) {
     if (dL_dscale) store3(dL_dscale, i, 0.f, 0.f, 0.f);
     if (dL_drot) reinterpret_cast<float4*>(dL_drot)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+}
+
+// ---- fit step: the per-Gaussian backward of ALL views of a step in one pass -------------------
+// The per-view outputs of K8/K9 are 62 floats per Gaussian, their inputs 59; what differs from view
+// to view is only the 9 blend-stage sums (48-byte acc row incl. flags) and the camera. Running K8/K9
+// once per view therefore moves ~780 B/Gaussian/view when accumulating; looping over the views
+// inside the thread keeps the 62 sums in registers and moves 52 B/Gaussian/view + 484 B once.
+// dL/dscale and dL/dq are linear in dL/dcov3D, so that part runs once on the summed dL/dcov3D.
+constexpr int CAM_FLOATS = 40;   // view[16] | proj[16] | campos[3] | tan_fovx | tan_fovy | pad[3]
+constexpr int MAX_BATCH_VIEWS = 64;
+
+__global__ void __launch_bounds__(128) geom_backward_batched_kernel(
+    int P, int D, int M, int V, const float* __restrict__ cams, int W, int H, float scale_modifier,
+    const float* __restrict__ acc, size_t acc_stride, const float* __restrict__ means3D,
+    const float* __restrict__ shs, const float* __restrict__ scales, const float* __restrict__ rotations,
+    float* __restrict__ dL_dmean3D, float* __restrict__ dL_dmean2D, float* __restrict__ dL_dsh,
+    float* __restrict__ dL_dopacity, float* __restrict__ dL_dscale, float* __restrict__ dL_drot,
+    bool accumulate) {
+  extern __shared__ float s_cam[];
+  for (int k = threadIdx.x; k < V * CAM_FLOATS; k += blockDim.x) s_cam[k] = cams[k];
+  __syncthreads();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  const size_t i = (size_t)idx;
+  const float mx = __ldg(means3D + 3 * i), my = __ldg(means3D + 3 * i + 1), mz = __ldg(means3D + 3 * i + 2);
+  const float4 q = __ldg(reinterpret_cast<const float4*>(rotations) + i);
+  const float sc[3] = {__ldg(scales + 3 * i), __ldg(scales + 3 * i + 1), __ldg(scales + 3 * i + 2)};
+  float c3[6];
+  cov3d_from_scale_rot(sc[0], sc[1], sc[2], scale_modifier, q, c3);
+  const float* sh = shs + 3 * (size_t)M * i;
+
+  float dmean[3] = {0.f, 0.f, 0.f}, dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float dm2x = 0.f, dm2y = 0.f, dop = 0.f;
+  float dsh[48];
+#pragma unroll
+  for (int k = 0; k < 48; k++) dsh[k] = 0.f;
+  bool any = false;
+  for (int v = 0; v < V; v++) {
+    const float4* row = reinterpret_cast<const float4*>(acc + (size_t)v * acc_stride) + 3 * i;
+    const float4 a2 = __ldg(row + 2);
+    const uint32_t flags = __float_as_uint(a2.w);
+    if (!(flags & 1u)) continue;
+    const float4 a0 = __ldg(row), a1 = __ldg(row + 1);
+    any = true;
+    const float* cam = s_cam + v * CAM_FLOATS;
+    const float tan_fovx = cam[35], tan_fovy = cam[36];
+    const float focal_y = H / (2.0f * tan_fovy), focal_x = W / (2.0f * tan_fovx);
+    float vm[3], vc[6];
+    view_geom_backward(mx, my, mz, c3, cam, cam + 16, tan_fovx, tan_fovy, focal_x, focal_y, a0.x, a0.y, a0.z,
+                       a0.w, a1.x, vm, vc);
+#pragma unroll
+    for (int k = 0; k < 6; k++) dcov[k] += vc[k];
+    dm2x += a0.x;
+    dm2y += a0.y;
+    dop += a1.y;
+    // SH part (backward.cu:20-139)
+    const float ox = mx - cam[32], oy = my - cam[33], oz = mz - cam[34];
+    const float len = sqrtf(ox * ox + oy * oy + oz * oz);
+    const float x = ox / len, y = oy / len, z = oz / len;
+    float dRGB[3] = {a1.z, a1.w, a2.x};
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++)
+      if ((flags >> (1 + ch)) & 1u) dRGB[ch] = 0.f;
+    float b[16], gx[16], gy[16], gz[16];
+    sh_basis_grad(D, x, y, z, b, gx, gy, gz);
+    float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+    if (M == 16) {
+      float4 w4[12];
+#pragma unroll
+      for (int j = 0; j < 12; j++) w4[j] = __ldg(reinterpret_cast<const float4*>(sh) + j);
+      const float* f = reinterpret_cast<const float*>(w4);
+#pragma unroll
+      for (int k = 1; k < 16; k++) {
+        const float sk = f[3 * k] * dRGB[0] + f[3 * k + 1] * dRGB[1] + f[3 * k + 2] * dRGB[2];
+        ddx += gx[k] * sk;
+        ddy += gy[k] * sk;
+        ddz += gz[k] * sk;
+      }
+    } else {
+#pragma unroll
+      for (int k = 1; k < 16; k++)
+        if (k < M) {
+          const float sk = __ldg(sh + 3 * k) * dRGB[0] + __ldg(sh + 3 * k + 1) * dRGB[1] + __ldg(sh + 3 * k + 2) * dRGB[2];
+          ddx += gx[k] * sk;
+          ddy += gy[k] * sk;
+          ddz += gz[k] * sk;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++)
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) dsh[3 * k + ch] += b[k] * dRGB[ch];
+    const float sum2 = ox * ox + oy * oy + oz * oz;
+    const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+    dmean[0] += vm[0] + ((+sum2 - ox * ox) * ddx - oy * ox * ddy - oz * ox * ddz) * invsum32;
+    dmean[1] += vm[1] + (-ox * oy * ddx + (sum2 - oy * oy) * ddy - oz * oy * ddz) * invsum32;
+    dmean[2] += vm[2] + (-ox * oz * ddx - oy * oz * ddy + (sum2 - oz * oz) * ddz) * invsum32;
+  }
+  if (!any && accumulate) return;
+  float dscale[3] = {0.f, 0.f, 0.f};
+  float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (any) cov3d_backward(q, sc, scale_modifier, dcov, dscale, dq);
+  if (accumulate) {
+    out3<true>(dL_dmean3D, i, dmean[0], dmean[1], dmean[2]);
+    out3<true>(dL_dmean2D, i, dm2x, dm2y, 0.f);
+    dL_dopacity[i] += dop;
+    out3<true>(dL_dscale, i, dscale[0], dscale[1], dscale[2]);
+    out4<true>(dL_drot, i, dq);
+  } else {
+    out3<false>(dL_dmean3D, i, dmean[0], dmean[1], dmean[2]);
+    out3<false>(dL_dmean2D, i, dm2x, dm2y, 0.f);
+    dL_dopacity[i] = dop;
+    out3<false>(dL_dscale, i, dscale[0], dscale[1], dscale[2]);
+    out4<false>(dL_drot, i, dq);
+  }
+  float* o = dL_dsh + 3 * (size_t)M * i;
+  if (M == 16) {
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+      const float4 v4 = make_float4(dsh[4 * j], dsh[4 * j + 1], dsh[4 * j + 2], dsh[4 * j + 3]);
+      if (accumulate) out4<true>(o, j, v4); else out4<false>(o, j, v4);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 48; k++)
+      if (k < 3 * M) {
+        if (accumulate) o[k] += dsh[k]; else o[k] = dsh[k];
+      }
+    if (!accumulate)
+      for (int k = 48; k < 3 * M; k++) o[k] = 0.f;
+  }
+}
+
+cudaError_t launch_geom_backward_batched(int P, int D, int M, int V, const float* cams, int W, int H,
+                                         float scale_modifier, const float* acc, size_t acc_stride,
+                                         const float* means3D, const float* shs, const float* scales,
+                                         const float* rotations, float* dL_dmean3D, float* dL_dmean2D,
+                                         float* dL_dsh, float* dL_dopacity, float* dL_dscale,
+                                         float* dL_drot, bool accumulate, cudaStream_t stream) {
+  if (V < 1 || V > MAX_BATCH_VIEWS) return cudaErrorInvalidValue;
+  geom_backward_batched_kernel<<<(P + 127) / 128, 128, V * CAM_FLOATS * sizeof(float), stream>>>(
+      P, D, M, V, cams, W, H, scale_modifier, acc, acc_stride, means3D, shs, scales, rotations,
+      dL_dmean3D, dL_dmean2D, dL_dsh, dL_dopacity, dL_dscale, dL_drot, accumulate);
+  DGE_LAUNCHED(1);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_geom_backward(const ViewParams& vp, const float* means3D, const float* scales,
@@ -341,10 +547,16 @@ cudaError_t launch_geom_backward(const ViewParams& vp, const float* means3D, con
                                  const int* radii, const GeomState& g, const float* acc,
                                  float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
                                  float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
-                                 float* dL_dscale, float* dL_drot, cudaStream_t stream) {
-  geom_backward_kernel<<<(vp.P + 255) / 256, 256, 0, stream>>>(
-      vp, means3D, scales, rotations, shs, cov3D_precomp, radii, g.clamped, acc, dL_dmean2D,
-      dL_dconic, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot);
+                                 float* dL_dscale, float* dL_drot, bool accumulate,
+                                 cudaStream_t stream) {
+  if (accumulate)
+    geom_backward_kernel<true><<<(vp.P + 255) / 256, 256, 0, stream>>>(
+        vp, means3D, scales, rotations, shs, cov3D_precomp, radii, g.clamped, acc, dL_dmean2D,
+        dL_dconic, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot);
+  else
+    geom_backward_kernel<false><<<(vp.P + 255) / 256, 256, 0, stream>>>(
+        vp, means3D, scales, rotations, shs, cov3D_precomp, radii, g.clamped, acc, dL_dmean2D,
+        dL_dconic, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot);
   DGE_LAUNCHED(1);
   return cudaGetLastError();
 }

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(
     const float* __restrict__ rotations, const float* __restrict__ opacities,
     const float* __restrict__ shs, const float* __restrict__ cov3D_precomp,
     const float* __restrict__ colors_precomp, int colors_mode, bool prefiltered,
-    int* __restrict__ radii, GeomState g) {
+    int* __restrict__ radii, GeomState g, float4* __restrict__ acc_init) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t tiles = 0;
   if (idx < vp.P) {
@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(
       Pm[i] = __ldg(vp.proj + i);
     }
     int radius = 0;
+    uint8_t clamp_bits = 0;
     ushort4 rect = make_ushort4(0, 0, 0, 0);
     uint32_t key = 0xFFFFFFFFu;
     const float px = __ldg(means3D + 3 * idx), py = __ldg(means3D + 3 * idx + 1),
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(
               rgb[c] = fmaxf(rgb[c], 0.0f);
             }
             g.clamped[idx] = cl;
+            clamp_bits = cl;
           } else if (colors_mode == 1) {
             // forward.cu:241-247 / rasterizer_impl.cu:274-275: precomputed colours are blended
             // as given; staged into the same record the blend kernels read.
@@ -233,6 +235,15 @@ __global__ void __launch_bounds__(256) preprocess_kernel(
     radii[idx] = radius;
     g.rect[idx] = rect;
     g.sort_key[0][idx] = key;
+    if (acc_init != nullptr) {
+      // fit step: this view's row of blend-stage sums starts at zero and carries, in slot 11, what
+      // the batched per-Gaussian backward needs to know about this view: bit 0 visible, bits 1-3
+      // the SH clamp mask (instead of a separate memset and per-view radii / clamped arrays).
+      const uint32_t flags = radius > 0 ? (1u | ((uint32_t)clamp_bits << 1)) : 0u;
+      acc_init[3 * (size_t)idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+      acc_init[3 * (size_t)idx + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      acc_init[3 * (size_t)idx + 2] = make_float4(0.f, 0.f, 0.f, __uint_as_float(flags));
+    }
   }
   // num_rendered = sum of tiles_touched (integer, order-independent)
   uint32_t s = __reduce_add_sync(0xFFFFFFFFu, tiles);
@@ -251,13 +262,13 @@ cudaError_t launch_preprocess(const ViewParams& vp, const float* means3D, const 
                               const float* rotations, const float* opacities, const float* shs,
                               const float* cov3D_precomp, const float* colors_precomp,
                               int colors_mode, bool prefiltered, int* radii, GeomState& g,
-                              cudaStream_t stream) {
+                              float* acc_init, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(g.counters, 0, 64 * sizeof(uint32_t), stream);
   if (e != cudaSuccess) return e;
   const int blocks = (vp.P + 255) / 256;
   preprocess_kernel<<<blocks, 256, 0, stream>>>(vp, means3D, scales, rotations, opacities, shs,
                                                 cov3D_precomp, colors_precomp, colors_mode, prefiltered,
-                                                radii, g);
+                                                radii, g, reinterpret_cast<float4*>(acc_init));
   DGE_LAUNCHED(1);
   return cudaGetLastError();
 }

@@ -105,7 +105,7 @@ def _backward_call(rs, means3D, radii, colors_precomp, scales, rotations, cov3Ds
                 float(rs.tanfovx), float(rs.tanfovy), L.ptr(radii), L.ptr(geom), L.ptr(binning), L.ptr(img),
                 L.ptr(grad_out_color), L.ptr(dL_dmeans2D), None, L.ptr(dL_dopacity), L.ptr(dL_dcolors),
                 L.ptr(dL_dmeans3D), L.ptr(dL_dcov3D), L.ptr(dL_dsh), L.ptr(dL_dscales), L.ptr(dL_drotations),
-                int(bool(rs.debug)), L.stream_ptr(dev))
+                0, int(bool(rs.debug)), L.stream_ptr(dev))
         L.check(rc, "rasterize_gaussians_backward")
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
 

@@ -122,6 +122,135 @@ class FitModel:
                     "fused adam")
 
 
+CAM_FLOATS = 40  # view[16] | proj[16] | campos[3] | tan_fovx | tan_fovy | pad[3]  (include/dge_b200.h "fit step")
+
+
+def pack_camera(cam: scene.Camera) -> torch.Tensor:
+    """The camera as the pinned 40-float record the fit entry points take."""
+    rec = torch.zeros(CAM_FLOATS, dtype=torch.float32)
+    rec[0:16] = cam.world_view_transform.detach().cpu().reshape(-1)
+    rec[16:32] = cam.full_proj_transform.detach().cpu().reshape(-1)
+    rec[32:35] = cam.camera_center.detach().cpu().reshape(-1)
+    rec[35], rec[36] = math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5)
+    return rec.pin_memory() if torch.cuda.is_available() else rec
+
+
+class ViewLane:
+    """Everything one CUDA stream needs to push views through the C-ABI without touching the
+    allocator, autograd or Python object construction per view: fixed output / scratch buffers
+    (geom and image blobs have a fixed size for a given P, W, H; the binning blob only grows) and
+    allocator callbacks created once."""
+
+    def __init__(self, model: "FitModel", W: int, H: int, stream):
+        lib = L.load()
+        dev, P = model.device, model.P
+        self.stream, self.W, self.H, self.P = stream, W, H, P
+        f32 = dict(dtype=torch.float32, device=dev)
+        u8 = dict(dtype=torch.uint8, device=dev)
+        self.color = torch.empty(3, H, W, **f32)
+        self.depth = torch.empty(1, H, W, **f32)
+        self.dL = torch.empty(3, H, W, **f32)
+        self.radii = torch.empty(P, dtype=torch.int32, device=dev)
+        self.radii_max = torch.zeros(P, dtype=torch.int32, device=dev)
+        self.loss = torch.zeros((), **f32)
+        self.geom = torch.empty(lib.dge_geom_bytes(P), **u8)
+        self.img = torch.empty(lib.dge_image_bytes(W, H), **u8)
+        self.binning = torch.empty(0, **u8)
+        self.target_buf = torch.empty(3, H, W, **f32)  # staged target image (host_inputs)
+
+        def fixed(t):
+            ptr = t.data_ptr()
+            return L.ALLOC_FN(lambda _ctx, nbytes: ptr if nbytes <= t.numel() else 0)
+
+        def growing(_ctx, nbytes):
+            if nbytes > self.binning.numel():
+                with torch.cuda.stream(self.stream):
+                    self.binning = torch.empty(int(nbytes * 1.25) + 256, **u8)
+            return self.binning.data_ptr()
+
+        self.cb_geom, self.cb_img = fixed(self.geom), fixed(self.img)
+        self.cb_binning = L.ALLOC_FN(growing)
+        self.stream_ptr = L.C.c_void_p(stream.cuda_stream)
+
+    def reset(self):
+        self.loss.zero_()
+        self.radii_max.zero_()
+
+
+def _direct_views(model: FitModel, acts, cameras, targets, bg, scale, host_inputs, num_streams):
+    """The step's views through the C-ABI, round-robin over `num_streams` lanes (no autograd):
+    per view forward -> fused L1 loss+gradient -> blend backward into that view's acc rows; then ONE
+    batched per-Gaussian backward over all views. Returns (grads w.r.t. the activated tensors and the
+    screen-space tap, loss, max radii)."""
+    lib = L.load()
+    dev = model.device
+    H, W = cameras[0].image_height, cameras[0].image_width
+    V = len(cameras)
+    S = max(1, min(num_streams, V))
+    P = model.P
+    main = torch.cuda.current_stream(dev)
+    key = (W, H, S, V)
+    if getattr(model, "_lane_key", None) != key:
+        model._lanes = [ViewLane(model, W, H, torch.cuda.Stream(dev)) for _ in range(S)]
+        f32 = dict(dtype=torch.float32, device=dev)
+        model._acc = torch.empty(V, P, 12, **f32)          # blend-stage sums of every view of the step
+        model._cams = torch.empty(V, CAM_FLOATS, **f32)
+        model._act_grads = {"shs": torch.empty(P, 16, 3, **f32), "opacities": torch.empty(P, 1, **f32),
+                            "scales": torch.empty(P, 3, **f32), "rotations": torch.empty(P, 4, **f32)}
+        model._cam_cache = {}
+        model._lane_key = key
+    lanes, acc, cams_dev = model._lanes, model._acc, model._cams
+    a = {k: v.detach() for k, v in acts.items()}
+    ptrs = {k: v.data_ptr() for k, v in a.items()}
+    M = a["shs"].shape[1]
+    for ln in lanes:
+        ln.stream.wait_stream(main)
+        with torch.cuda.stream(ln.stream):
+            ln.reset()
+    bgp = bg.data_ptr()
+    n_img = 3 * H * W
+    for i, (cam, target) in enumerate(zip(cameras, targets)):
+        ln = lanes[i % S]
+        ck = cam.world_view_transform.data_ptr()
+        rec = model._cam_cache.get(ck)
+        if rec is None:
+            r = pack_camera(cam)
+            rec = model._cam_cache[ck] = (r, float(r[35]), float(r[36]))
+        rec, tfx, tfy = rec
+        with torch.cuda.stream(ln.stream):
+            cams_dev[i].copy_(rec, non_blocking=True)
+            if host_inputs:  # pinned host -> this lane's staging buffer, asynchronously on its stream
+                ln.target_buf.copy_(target, non_blocking=True)
+                target = ln.target_buf
+            cam_ptr, acc_ptr = cams_dev[i].data_ptr(), acc[i].data_ptr()
+            R = lib.dge_fit_forward(
+                ln.cb_geom, ln.cb_binning, ln.cb_img, None, P, model.sh_degree, M, bgp, W, H, ptrs["means3D"],
+                ptrs["shs"], ptrs["opacities"], ptrs["scales"], 1.0, ptrs["rotations"], cam_ptr, tfx,
+                tfy, ln.color.data_ptr(), ln.depth.data_ptr(), ln.radii.data_ptr(), acc_ptr, ln.stream_ptr)
+            L.check(R, "fit forward")
+            L.check(lib.dge_l1_loss_grad(ln.color.data_ptr(), target.data_ptr(), n_img, scale, ln.dL.data_ptr(),
+                                         ln.loss.data_ptr(), ln.stream_ptr), "l1 loss")
+            L.check(lib.dge_fit_backward_blend(P, R, bgp, W, H, ln.geom.data_ptr(), ln.binning.data_ptr(),
+                                               ln.img.data_ptr(), ln.dL.data_ptr(), acc_ptr, ln.stream_ptr),
+                    "fit backward blend")
+            torch.maximum(ln.radii_max, ln.radii, out=ln.radii_max)
+    for ln in lanes:
+        main.wait_stream(ln.stream)
+    g = dict(model._act_grads)
+    g["means3D"] = model.params["xyz"].grad      # xyz has no activation: straight into the flat buffer
+    g["means2D"] = model.means2D.grad
+    L.check(lib.dge_fit_backward_geom(
+        P, model.sh_degree, M, V, cams_dev.data_ptr(), W, H, 1.0, acc.data_ptr(), P * 12, ptrs["means3D"],
+        ptrs["shs"], ptrs["scales"], ptrs["rotations"], g["means3D"].data_ptr(), g["means2D"].data_ptr(),
+        g["shs"].data_ptr(), g["opacities"].data_ptr(), g["scales"].data_ptr(), g["rotations"].data_ptr(), 0,
+        L.stream_ptr(dev)), "fit backward geom")
+    loss, radii_max = lanes[0].loss.clone(), lanes[0].radii_max
+    for ln in lanes[1:]:
+        loss += ln.loss
+        radii_max = torch.maximum(radii_max, ln.radii_max)
+    return g, loss, radii_max
+
+
 def shard_views(num_views: int, rank: int, world: int) -> List[int]:
     """View i of the step's batch goes to rank i mod world."""
     return list(range(rank, num_views, world))
@@ -135,7 +264,7 @@ def default_rasterize(rs, means3D, means2D, shs, opacities, scales, rotations):
 def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence[torch.Tensor], bg: torch.Tensor,
              global_batch: int, rasterize: Callable = default_rasterize, settings_module=dgr,
              process_group=None, lambda_l1: float = 10.0, host_inputs: bool = False, update_stats: bool = True,
-             num_streams: int = 1):
+             num_streams: int = 1, direct: Optional[bool] = None):
     """One optimisation step over this rank's views. `cameras`/`targets` are this rank's share;
     `global_batch` the number of views in the whole step (L1 is a mean over the global batch,
     DGE.py:672). With host_inputs the cameras/targets live in pinned host memory and are copied
@@ -144,12 +273,24 @@ def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence
     Views are independent until the optimiser step, so with num_streams > 1 they are issued
     round-robin on that many CUDA streams: one view's latency-bound stages (sorts, the tail of
     the blend over the densest tiles) overlap another view's kernels. Each stream accumulates
-    into its own gradient leaves; the partial sums are added on the main stream afterwards."""
+    into its own gradient leaves; the partial sums are added on the main stream afterwards.
+
+    direct (default: on CUDA with the stock rasterizer) drives the C-ABI without autograd: fixed
+    per-stream buffers, one fused L1 loss+gradient kernel per view and a backward that adds into the
+    stream's running sums. The autograd path below is the reference-shaped one (per-view tensors,
+    torch ops for the loss, AccumulateGrad) and is what `rasterize` overrides go through."""
     dev = model.device
     model.zero_grad()
     acts_graph = model.activations()
     H, W = cameras[0].image_height, cameras[0].image_width
     scale = lambda_l1 / float(global_batch * 3 * H * W)
+    if direct is None:
+        direct = dev.type == "cuda" and rasterize is default_rasterize
+    if direct:
+        grads, loss, radii_max = _direct_views(model, acts_graph, cameras, targets, bg, scale, host_inputs, num_streams)
+        through = [k for k in acts_graph if acts_graph[k].grad_fn is not None]
+        torch.autograd.backward([acts_graph[k] for k in through], [grads[k] for k in through])
+        return _finish_step(model, loss, radii_max, process_group, update_stats)
     S = max(1, min(num_streams, len(cameras)))
     main = torch.cuda.current_stream(dev) if dev.type == "cuda" else None
     if S > 1:
@@ -206,6 +347,10 @@ def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence
     # xyz has no activation: its detached leaf's grad goes straight into the flat buffer
     if acts["means3D"].grad is not None:
         model.params["xyz"].grad.add_(acts["means3D"].grad)
+    return _finish_step(model, loss, radii_max, process_group, update_stats)
+
+
+def _finish_step(model, loss, radii_max, process_group, update_stats):
     world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
     if world > 1:
         # THE collective: 59P parameter grads + 3P screen-space grads in one SUM

@@ -63,7 +63,10 @@ int dge_rasterize_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffe
  * dL_dmean3D may be NULL when the caller does not need it.
  * dL_dmean2D is [P,3] with .z = 0 (DGR/rasterize_points.cu:121).
  * `scratchBuffer` provides dge_backward_scratch_bytes(P) bytes that only need to
- * live until the call's work on `stream` has finished (the blend-stage sums). */
+ * live until the call's work on `stream` has finished (the blend-stage sums).
+ * accumulate != 0: the outputs are running sums — rows of visible Gaussians are ADDED to,
+ * rows of culled Gaussians are left alone (what autograd's AccumulateGrad does with the
+ * reference's per-view tensors, DGE.py:170-239, without the per-view tensors). */
 int dge_rasterize_backward(dge_alloc_fn scratchBuffer, void* alloc_ctx,
                            int P, int D, int M, int R, const float* background,
                            int width, int height, const float* means3D,
@@ -78,7 +81,7 @@ int dge_rasterize_backward(dge_alloc_fn scratchBuffer, void* alloc_ctx,
                            float* dL_dconic, float* dL_dopacity,
                            float* dL_dcolor, float* dL_dmean3D,
                            float* dL_dcov3D, float* dL_dsh, float* dL_dscale,
-                           float* dL_drot, int debug, void* stream);
+                           float* dL_drot, int accumulate, int debug, void* stream);
 
 /* Replaces CudaRasterizer::Rasterizer::apply_weights (DGR/cuda_rasterizer/rasterizer.h:89-112,
  * rasterizer_impl.cu:343-447): DGE's mask back-projection. `weights` [P,CH] f32
@@ -139,7 +142,38 @@ unsigned long long dge_launch_count(void);
 void dge_profile_enable(unsigned stage_mask);
 int dge_profile_read(float* ms_out, int* count_out);
 
-/* ---- fit-step helpers (SURVEY.md §8f N3) ----
+/* ---- fit step: the views of one optimisation step --------------------
+ * `cam` is a device record of 40 floats: viewmatrix[16] | projmatrix[16] | campos[3] | tan_fovx |
+ * tan_fovy | pad[3]. `acc` is this view's [P][12] row block of blend-stage sums.
+ *
+ * dge_fit_forward = dge_rasterize_forward (SH colours, scale/rotation covariances) that also
+ * initialises `acc` (zeros + per-view visibility / clamp flags) from inside preprocess.
+ * dge_fit_backward_blend = the blend backward of the view into `acc` (K7 only).
+ * dge_fit_backward_geom = K8 + K9 of rasterizer_impl.cu:324-340 for ALL V views of the step in one
+ * pass over the Gaussians (acc of view v at acc + v*acc_stride_floats); with accumulate != 0 the six
+ * outputs are added to, otherwise every row is written. */
+int dge_fit_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge_alloc_fn imageBuffer,
+                    void* alloc_ctx, int P, int D, int M, const float* background, int width,
+                    int height, const float* means3D, const float* shs, const float* opacities,
+                    const float* scales, float scale_modifier, const float* rotations,
+                    const float* cam, float tan_fovx, float tan_fovy, float* out_color,
+                    float* out_depth, int* radii, float* acc, void* stream);
+int dge_fit_backward_blend(int P, int R, const float* background, int width, int height,
+                           char* geom_buffer, char* binning_buffer, char* image_buffer,
+                           const float* dL_dpix, float* acc, void* stream);
+int dge_fit_backward_geom(int P, int D, int M, int V, const float* cams, int width, int height,
+                          float scale_modifier, const float* acc, size_t acc_stride_floats,
+                          const float* means3D, const float* shs, const float* scales,
+                          const float* rotations, float* dL_dmean3D, float* dL_dmean2D,
+                          float* dL_dsh, float* dL_dopacity, float* dL_dscale, float* dL_drot,
+                          int accumulate, void* stream);
+
+/* ---- fit-step helpers (SURVEY.md §8f N1/N3) ----
+ * L1 loss of one rendered view and its gradient (threestudio/systems/DGE.py:672):
+ * grad[i] = scale * sign(image[i] - target[i]); *loss_accum += scale * sum |image - target|. */
+int dge_l1_loss_grad(const float* image, const float* target, size_t n, float scale,
+                     float* grad, float* loss_accum, void* stream);
+/*
  * Fused Adam over one flat fp32 parameter block (torch.optim.Adam semantics,
  * gaussiansplatting/scene/gaussian_model.py:374: eps=1e-15, no weight decay,
  * no amsgrad), with the optional per-Gaussian grad mask of
