@@ -21,9 +21,10 @@ __global__ void __launch_bounds__(BL_THREADS) apply_weights_kernel(
     const float* __restrict__ image_weights, float* __restrict__ weights, int* __restrict__ cnt) {
   __shared__ BlendSmem s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int qx = tid & 7, qy = tid >> 3;
-  const int px0 = blockIdx.x * DGE_TILE + 2 * qx, py0 = blockIdx.y * DGE_TILE + 2 * qy;
-  const float fx0 = (float)px0, fx1 = (float)(px0 + 1), fy0 = (float)py0, fy1 = (float)(py0 + 1);
+  // pixel p of this thread = (px0 + PX_STEP*(p&1), py0 + PY_STEP*(p>>1)): one pixel in each 8x4
+  // quadrant of the warp's 16x8 half-tile (see blend.cuh)
+  const int px0 = blockIdx.x * DGE_TILE + (lane & 7), py0 = blockIdx.y * DGE_TILE + 8 * warp + (lane >> 3);
+  const float fx0 = (float)px0, fx1 = (float)(px0 + PX_STEP), fy0 = (float)py0, fy1 = (float)(py0 + PY_STEP);
   const float X0 = (float)(blockIdx.x * DGE_TILE), X1 = X0 + 15.0f;
   const float Y0 = (float)(blockIdx.y * DGE_TILE + 8 * warp), Y1 = Y0 + 7.0f;
   const size_t HW = (size_t)H * W;
@@ -33,7 +34,7 @@ __global__ void __launch_bounds__(BL_THREADS) apply_weights_kernel(
   bool done[4];
 #pragma unroll
   for (int p = 0; p < 4; p++) {
-    const int x = px0 + (p & 1), y = py0 + (p >> 1);
+    const int x = px0 + PX_STEP * (p & 1), y = py0 + PY_STEP * (p >> 1);
     const bool inside = x < W && y < H;
     T[p] = 1.0f;
     done[p] = !inside;

@@ -439,6 +439,11 @@ __global__ void __launch_bounds__(128) geom_backward_batched_kernel(
     if (!(flags & 1u)) continue;
     const float4 a0 = __ldg(row), a1 = __ldg(row + 1);
     any = true;
+    // visible but untouched by any pixel of this view (occluded, or alpha < 1/255 everywhere):
+    // every term below is linear in these nine sums
+    if (a0.x == 0.f && a0.y == 0.f && a0.z == 0.f && a0.w == 0.f && a1.x == 0.f && a1.y == 0.f && a1.z == 0.f &&
+        a1.w == 0.f && a2.x == 0.f)
+      continue;
     const float* cam = s_cam + v * CAM_FLOATS;
     const float tan_fovx = cam[35], tan_fovy = cam[36];
     const float focal_y = H / (2.0f * tan_fovy), focal_x = W / (2.0f * tan_fovx);

@@ -29,9 +29,10 @@ __global__ void __launch_bounds__(BL_THREADS) render_backward_kernel(
   __shared__ uint32_t s_max[BL_WARPS];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int qx = tid & 7, qy = tid >> 3;
-  const int px0 = blockIdx.x * DGE_TILE + 2 * qx, py0 = blockIdx.y * DGE_TILE + 2 * qy;
-  const float fx0 = (float)px0, fx1 = (float)(px0 + 1), fy0 = (float)py0, fy1 = (float)(py0 + 1);
+  // pixel p of this thread = (px0 + PX_STEP*(p&1), py0 + PY_STEP*(p>>1)): one pixel in each 8x4
+  // quadrant of the warp's 16x8 half-tile (see blend.cuh)
+  const int px0 = blockIdx.x * DGE_TILE + (lane & 7), py0 = blockIdx.y * DGE_TILE + 8 * warp + (lane >> 3);
+  const float fx0 = (float)px0, fx1 = (float)(px0 + PX_STEP), fy0 = (float)py0, fy1 = (float)(py0 + PY_STEP);
   const float X0 = (float)(blockIdx.x * DGE_TILE), X1 = X0 + 15.0f;
   const float Y0 = (float)(blockIdx.y * DGE_TILE + 8 * warp), Y1 = Y0 + 7.0f;
   const size_t HW = (size_t)H * W;
@@ -43,7 +44,7 @@ __global__ void __launch_bounds__(BL_THREADS) render_backward_kernel(
   uint32_t tmax = 0;
 #pragma unroll
   for (int p = 0; p < 4; p++) {
-    const int x = px0 + (p & 1), y = py0 + (p >> 1);
+    const int x = px0 + PX_STEP * (p & 1), y = py0 + PY_STEP * (p >> 1);
     const bool inside = x < W && y < H;
     const size_t pix = (size_t)y * W + x;
     T_final[p] = inside ? final_Ts[pix] : 0.0f;
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(BL_THREADS) render_backward_kernel(
   for (int w = 0; w < BL_WARPS; w++) bmax = max(bmax, s_max[w]);
 
   const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+  const bool has_bg = bg0 != 0.0f || bg1 != 0.0f || bg2 != 0.0f;  // CTA-uniform
 
   // positions hi-1 ... 0 of the tile list, back to front, in batches
   for (uint32_t hi = bmax; hi > 0; hi -= min(hi, (uint32_t)BL_BATCH)) {
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(BL_THREADS) render_backward_kernel(
           }
           dL_dalpha *= T[p];
           last_alpha[p] = alpha;
-          dL_dalpha += __fdiv_rn(-T_final[p], one_m) * bg_dot[p];
+          if (has_bg) dL_dalpha += __fdiv_rn(-T_final[p], one_m) * bg_dot[p];  // zero for DGE's black background
           const float dL_dG = opacity * dL_dalpha;
           const float gdx = G * dx, gdy = G * dy;
           const float dG_ddelx = -gdx * a.z - gdy * a.w;

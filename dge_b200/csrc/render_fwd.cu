@@ -26,18 +26,17 @@ __global__ void __launch_bounds__(BL_THREADS) render_forward_kernel(
     float* __restrict__ out_depth) {
   __shared__ BlendSmem s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int qx = tid & 7, qy = tid >> 3;
-  const int px0 = blockIdx.x * DGE_TILE + 2 * qx, py0 = blockIdx.y * DGE_TILE + 2 * qy;
-  const float fx0 = (float)px0, fx1 = (float)(px0 + 1), fy0 = (float)py0, fy1 = (float)(py0 + 1);
+  // pixel p of this thread = (px0 + PX_STEP*(p&1), py0 + PY_STEP*(p>>1)): one pixel in each 8x4
+  // quadrant of the warp's 16x8 half-tile (see blend.cuh)
+  const int px0 = blockIdx.x * DGE_TILE + (lane & 7), py0 = blockIdx.y * DGE_TILE + 8 * warp + (lane >> 3);
+  const float fx0 = (float)px0, fx1 = (float)(px0 + PX_STEP), fy0 = (float)py0, fy1 = (float)(py0 + PY_STEP);
   // the warp's half-tile, in pixel-centre coordinates
   const float X0 = (float)(blockIdx.x * DGE_TILE), X1 = X0 + 15.0f;
   const float Y0 = (float)(blockIdx.y * DGE_TILE + 8 * warp), Y1 = Y0 + 7.0f;
   // pixel p = 2*row + col inside the quad
   bool inside[4];
-  inside[0] = px0 < W && py0 < H;
-  inside[1] = px0 + 1 < W && py0 < H;
-  inside[2] = px0 < W && py0 + 1 < H;
-  inside[3] = px0 + 1 < W && py0 + 1 < H;
+#pragma unroll
+  for (int p = 0; p < 4; p++) inside[p] = px0 + PX_STEP * (p & 1) < W && py0 + PY_STEP * (p >> 1) < H;
 
   const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
   float T[4], C[4][3], Dp[4];
@@ -101,7 +100,7 @@ __global__ void __launch_bounds__(BL_THREADS) render_forward_kernel(
 #pragma unroll
   for (int p = 0; p < 4; p++) {
     if (!inside[p]) continue;
-    const size_t pix = (size_t)(py0 + (p >> 1)) * W + (px0 + (p & 1));
+    const size_t pix = (size_t)(py0 + PY_STEP * (p >> 1)) * W + (px0 + PX_STEP * (p & 1));
     final_T[pix] = T[p];
     n_contrib[pix] = last[p];
     out_color[pix] = BFMA(bg0, T[p], C[p][0]);
