@@ -195,7 +195,7 @@ using namespace dge;
 extern "C" {
 
 const char* dge_last_error(void) { return g_err; }
-int dge_abi_version(void) { return 3; }
+int dge_abi_version(void) { return 4; }
 unsigned long long dge_launch_count(void) { return g_kernel_launches; }
 
 void dge_profile_enable(unsigned stage_mask) { g_profile_mask = stage_mask; }
@@ -281,9 +281,9 @@ int dge_fit_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge
   return R;
 }
 
-int dge_fit_backward_blend(int P, int R, const float* background, int width, int height, char* geom_buffer,
-                           char* binning_buffer, char* image_buffer, const float* dL_dpix, float* acc,
-                           void* stream_) {
+int dge_fit_backward_blend(int P, int R, const float* background, int background_is_black, int width,
+                           int height, char* geom_buffer, char* binning_buffer, char* image_buffer,
+                           const float* dL_dpix, float* acc, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool debug = false;
   if (P == 0 || R == 0) return 0;
@@ -294,7 +294,8 @@ int dge_fit_backward_blend(int P, int R, const float* background, int width, int
   carve_geom(geom_buffer, P, &g);
   carve_binning(binning_buffer, R, width, height, &b);
   carve_image(image_buffer, width, height, &img);
-  STAGE(ST_RENDER_BWD, "render backward", launch_render_backward(vp, g, b, img, background, dL_dpix, acc, stream));
+  STAGE(ST_RENDER_BWD, "render backward",
+        launch_render_backward(vp, g, b, img, background, dL_dpix, acc, background_is_black != 0, stream));
   return 0;
 }
 
@@ -340,7 +341,8 @@ int dge_rasterize_backward(dge_alloc_fn scratchBuffer, void* alloc_ctx, int P, i
   float* acc = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sp) + 255) & ~uintptr_t(255));
   CK("memset acc", cudaMemsetAsync(acc, 0, acc_bytes, stream));
   if (R > 0)
-    STAGE(ST_RENDER_BWD, "render backward", launch_render_backward(vp, g, b, img, background, dL_dpix, acc, stream));
+    STAGE(ST_RENDER_BWD, "render backward",
+          launch_render_backward(vp, g, b, img, background, dL_dpix, acc, /*black_background=*/false, stream));
   (void)colors_precomp;
   STAGE(ST_GEOM_BWD, "geometry backward",
         launch_geom_backward(vp, means3D, scales, rotations, shs, cov3D_precomp, radii, g, acc,

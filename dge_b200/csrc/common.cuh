@@ -97,7 +97,8 @@ cudaError_t launch_render_forward(const ViewParams& vp, const GeomState& g, cons
 // acc: [P][12] floats, zeroed by the caller: dmean2D.xy, dconic.xyz(w), dopacity, dcolor.rgb
 cudaError_t launch_render_backward(const ViewParams& vp, const GeomState& g, const BinState& b,
                                    const ImgState& img, const float* background,
-                                   const float* dL_dpix, float* acc, cudaStream_t stream);
+                                   const float* dL_dpix, float* acc, bool black_background,
+                                   cudaStream_t stream);
 cudaError_t launch_geom_backward(const ViewParams& vp, const float* means3D, const float* scales,
                                  const float* rotations, const float* shs, const float* cov3D_precomp,
                                  const int* radii, const GeomState& g, const float* acc,

@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(256) geom_backward_kernel(
 constexpr int CAM_FLOATS = 40;   // view[16] | proj[16] | campos[3] | tan_fovx | tan_fovy | pad[3]
 constexpr int MAX_BATCH_VIEWS = 64;
 
-__global__ void __launch_bounds__(128) geom_backward_batched_kernel(
+__global__ void __launch_bounds__(128, 4) geom_backward_batched_kernel(
     int P, int D, int M, int V, const float* __restrict__ cams, int W, int H, float scale_modifier,
     const float* __restrict__ acc, size_t acc_stride, const float* __restrict__ means3D,
     const float* __restrict__ shs, const float* __restrict__ scales, const float* __restrict__ rotations,

@@ -44,10 +44,16 @@ __device__ __forceinline__ void cov3d_from_scale_rot(float sx, float sy, float s
   const float R20 = ADD(xz_m_ry, xz_m_ry), R21 = ADD(yz_p_rx, yz_p_rx),
               R22 = ADD(1.0f, -ADD(xx_p_yy, xx_p_yy));
   const float s0 = MUL(sx, mod), s1 = MUL(sy, mod), s2 = MUL(sz, mod);
-  // M = S * R (the zero terms of the GLM product are value-neutral)
-  const float M00 = MUL(s0, R00), M01 = MUL(s1, R01), M02 = MUL(s2, R02);
-  const float M10 = MUL(s0, R10), M11 = MUL(s1, R11), M12 = MUL(s2, R12);
-  const float M20 = MUL(s0, R20), M21 = MUL(s1, R21), M22 = MUL(s2, R22);
+  // M = S * R as GLM evaluates it: M[i][j] = S[0][j]*R[i][0] + S[1][j]*R[i][1] + S[2][j]*R[i][2] with
+  // S diagonal. The literal-zero products are kept (the reference's SASS keeps them as FMUL/FFMA
+  // with RZ): they never change a value but they decide the SIGN of a zero result.
+  const float Z = 0.0f;
+  const float M00 = dot3_ref(s0, R00, Z, R01, Z, R02), M01 = dot3_ref(Z, R00, s1, R01, Z, R02),
+              M02 = dot3_ref(Z, R00, Z, R01, s2, R02);
+  const float M10 = dot3_ref(s0, R10, Z, R11, Z, R12), M11 = dot3_ref(Z, R10, s1, R11, Z, R12),
+              M12 = dot3_ref(Z, R10, Z, R11, s2, R12);
+  const float M20 = dot3_ref(s0, R20, Z, R21, Z, R22), M21 = dot3_ref(Z, R20, s1, R21, Z, R22),
+              M22 = dot3_ref(Z, R20, Z, R21, s2, R22);
   // Sigma[i][j] = M[j][0]*M[i][0] + M[j][1]*M[i][1] + M[j][2]*M[i][2]
   cov[0] = dot3_ref(M00, M00, M01, M01, M02, M02);
   cov[1] = dot3_ref(M10, M00, M11, M01, M12, M02);

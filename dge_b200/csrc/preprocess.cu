@@ -28,13 +28,15 @@ __device__ __forceinline__ float3 cov2d_ref(float tx, float ty, float tz, const 
   const float J02 = __fdiv_rn(MUL(MUL(tz, -cx), vp.focal_x), tz2);
   const float J11 = __fdiv_rn(vp.focal_y, tz);
   const float J12 = __fdiv_rn(MUL(MUL(tz, -cy), vp.focal_y), tz2);
-  // T = W * J ; T0j = fma(W2j, J02, W0j*J00), T1j = fma(W2j, J12, W1j*J11)
-  const float T00 = FMA(V[2], J02, MUL(V[0], J00));
-  const float T01 = FMA(V[6], J02, MUL(V[4], J00));
-  const float T02 = FMA(V[10], J02, MUL(V[8], J00));
-  const float T10 = FMA(V[2], J12, MUL(V[1], J11));
-  const float T11 = FMA(V[6], J12, MUL(V[5], J11));
-  const float T12 = FMA(V[10], J12, MUL(V[9], J11));
+  // T = W * J (GLM): T[i][j] = W[0][j]*J[i][0] + W[1][j]*J[i][1] + W[2][j]*J[i][2], J's literal zeros kept
+  // (they only decide the sign of zero results, as in the reference's SASS)
+  const float Z = 0.0f;
+  const float T00 = dot3_ref(V[0], J00, V[1], Z, V[2], J02);
+  const float T01 = dot3_ref(V[4], J00, V[5], Z, V[6], J02);
+  const float T02 = dot3_ref(V[8], J00, V[9], Z, V[10], J02);
+  const float T10 = dot3_ref(V[0], Z, V[1], J11, V[2], J12);
+  const float T11 = dot3_ref(V[4], Z, V[5], J11, V[6], J12);
+  const float T12 = dot3_ref(V[8], Z, V[9], J11, V[10], J12);
   // A = T^T * Vrk^T ; A[k][j] = fma(Tj2, Vrk[2][k], fma(Tj0, Vrk[0][k], Tj1*Vrk[1][k]))
   const float A00 = dot3_ref(T00, c[0], T01, c[1], T02, c[2]);
   const float A10 = dot3_ref(T00, c[1], T01, c[3], T02, c[4]);

@@ -19,7 +19,11 @@
 
 namespace dge {
 
-__global__ void __launch_bounds__(BL_THREADS) render_backward_kernel(
+// HAS_BG: a non-black background adds the -T_final/(1-alpha) * (bg . dL/dpixel) term to dL/dalpha
+// (backward.cu:526-529); for DGE's black background (DGE.py:87) that term, its division and
+// eight registers of per-pixel state disappear at compile time.
+template <bool HAS_BG>
+__global__ void __launch_bounds__(BL_THREADS, 9) render_backward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
     const float* __restrict__ background, const float4* __restrict__ means2D,
     const float4* __restrict__ conic_opacity, const float4* __restrict__ rgb_depth,
@@ -38,7 +42,11 @@ __global__ void __launch_bounds__(BL_THREADS) render_backward_kernel(
   const size_t HW = (size_t)H * W;
   const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
 
-  float T[4], T_final[4], accum[4][3], last_color[4][3], last_alpha[4], dpix[4][3], bg_dot[4];
+  // behind[p] = colour accumulated behind the current list position, i.e. the reference's
+  // accum_rec AFTER its next update: alpha*c + (1-alpha)*accum is folded in right after a
+  // Gaussian is used instead of right before the next one (same operations, same values, no
+  // last_alpha / last_color registers).
+  float T[4], T_final[4], behind[4][3], dpix[4][3], bg_dot[4];
   uint32_t last[4];
   const float bg0 = __ldg(background), bg1 = __ldg(background + 1), bg2 = __ldg(background + 2);
   uint32_t tmax = 0;
@@ -54,11 +62,9 @@ __global__ void __launch_bounds__(BL_THREADS) render_backward_kernel(
 #pragma unroll
     for (int c = 0; c < 3; c++) {
       dpix[p][c] = inside ? dL_dpixels[c * HW + pix] : 0.0f;
-      accum[p][c] = 0.0f;
-      last_color[p][c] = 0.0f;
+      behind[p][c] = 0.0f;
     }
-    last_alpha[p] = 0.0f;
-    bg_dot[p] = bg0 * dpix[p][0] + bg1 * dpix[p][1] + bg2 * dpix[p][2];
+    bg_dot[p] = HAS_BG ? bg0 * dpix[p][0] + bg1 * dpix[p][1] + bg2 * dpix[p][2] : 0.0f;
   }
   const uint32_t wmax = __reduce_max_sync(0xFFFFFFFFu, tmax);
   if (lane == 0) s_max[warp] = wmax;
@@ -68,7 +74,6 @@ __global__ void __launch_bounds__(BL_THREADS) render_backward_kernel(
   for (int w = 0; w < BL_WARPS; w++) bmax = max(bmax, s_max[w]);
 
   const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
-  const bool has_bg = bg0 != 0.0f || bg1 != 0.0f || bg2 != 0.0f;  // CTA-uniform
 
   // positions hi-1 ... 0 of the tile list, back to front, in batches
   for (uint32_t hi = bmax; hi > 0; hi -= min(hi, (uint32_t)BL_BATCH)) {
@@ -118,14 +123,12 @@ __global__ void __launch_bounds__(BL_THREADS) render_backward_kernel(
           float dL_dalpha = 0.0f;
 #pragma unroll
           for (int c = 0; c < 3; c++) {
-            accum[p][c] = last_alpha[p] * last_color[p][c] + (1.0f - last_alpha[p]) * accum[p][c];
-            last_color[p][c] = col[c];
-            dL_dalpha += (col[c] - accum[p][c]) * dpix[p][c];
+            dL_dalpha += (col[c] - behind[p][c]) * dpix[p][c];
             g[ACC_R + c] += w * dpix[p][c];
+            behind[p][c] = alpha * col[c] + one_m * behind[p][c];
           }
           dL_dalpha *= T[p];
-          last_alpha[p] = alpha;
-          if (has_bg) dL_dalpha += __fdiv_rn(-T_final[p], one_m) * bg_dot[p];  // zero for DGE's black background
+          if (HAS_BG) dL_dalpha += __fdiv_rn(-T_final[p], one_m) * bg_dot[p];
           const float dL_dG = opacity * dL_dalpha;
           const float gdx = G * dx, gdy = G * dy;
           const float dG_ddelx = -gdx * a.z - gdy * a.w;
@@ -178,11 +181,17 @@ __global__ void __launch_bounds__(BL_THREADS) render_backward_kernel(
 
 cudaError_t launch_render_backward(const ViewParams& vp, const GeomState& g, const BinState& b,
                                    const ImgState& img, const float* background,
-                                   const float* dL_dpix, float* acc, cudaStream_t stream) {
+                                   const float* dL_dpix, float* acc, bool black_background,
+                                   cudaStream_t stream) {
   dim3 grid(vp.grid_x, vp.grid_y);
-  render_backward_kernel<<<grid, BL_THREADS, 0, stream>>>(
-      img.ranges, b.point_list, vp.W, vp.H, background, g.means2D, g.conic_opacity, g.rgb_depth,
-      img.final_T, img.n_contrib, dL_dpix, acc);
+  if (black_background)
+    render_backward_kernel<false><<<grid, BL_THREADS, 0, stream>>>(
+        img.ranges, b.point_list, vp.W, vp.H, background, g.means2D, g.conic_opacity, g.rgb_depth,
+        img.final_T, img.n_contrib, dL_dpix, acc);
+  else
+    render_backward_kernel<true><<<grid, BL_THREADS, 0, stream>>>(
+        img.ranges, b.point_list, vp.W, vp.H, background, g.means2D, g.conic_opacity, g.rgb_depth,
+        img.final_T, img.n_contrib, dL_dpix, acc);
   DGE_LAUNCHED(1);
   return cudaGetLastError();
 }

@@ -208,6 +208,9 @@ def _direct_views(model: FitModel, acts, cameras, targets, bg, scale, host_input
         with torch.cuda.stream(ln.stream):
             ln.reset()
     bgp = bg.data_ptr()
+    if getattr(model, "_bg_key", None) != bgp:  # one-time host copy of the (constant) background
+        model._bg_key, model._bg_black = bgp, int(not bool(bg.detach().cpu().any()))
+    bg_black = model._bg_black
     n_img = 3 * H * W
     for i, (cam, target) in enumerate(zip(cameras, targets)):
         ln = lanes[i % S]
@@ -230,7 +233,7 @@ def _direct_views(model: FitModel, acts, cameras, targets, bg, scale, host_input
             L.check(R, "fit forward")
             L.check(lib.dge_l1_loss_grad(ln.color.data_ptr(), target.data_ptr(), n_img, scale, ln.dL.data_ptr(),
                                          ln.loss.data_ptr(), ln.stream_ptr), "l1 loss")
-            L.check(lib.dge_fit_backward_blend(P, R, bgp, W, H, ln.geom.data_ptr(), ln.binning.data_ptr(),
+            L.check(lib.dge_fit_backward_blend(P, R, bgp, bg_black, W, H, ln.geom.data_ptr(), ln.binning.data_ptr(),
                                                ln.img.data_ptr(), ln.dL.data_ptr(), acc_ptr, ln.stream_ptr),
                     "fit backward blend")
             torch.maximum(ln.radii_max, ln.radii, out=ln.radii_max)

@@ -148,7 +148,9 @@ int dge_profile_read(float* ms_out, int* count_out);
  *
  * dge_fit_forward = dge_rasterize_forward (SH colours, scale/rotation covariances) that also
  * initialises `acc` (zeros + per-view visibility / clamp flags) from inside preprocess.
- * dge_fit_backward_blend = the blend backward of the view into `acc` (K7 only).
+ * dge_fit_backward_blend = the blend backward of the view into `acc` (K7 only);
+ * background_is_black != 0 is the caller's promise that background == (0,0,0) (DGE.py:87), which
+ * removes the background term of dL/dalpha at compile time.
  * dge_fit_backward_geom = K8 + K9 of rasterizer_impl.cu:324-340 for ALL V views of the step in one
  * pass over the Gaussians (acc of view v at acc + v*acc_stride_floats); with accumulate != 0 the six
  * outputs are added to, otherwise every row is written. */
@@ -158,9 +160,9 @@ int dge_fit_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge
                     const float* scales, float scale_modifier, const float* rotations,
                     const float* cam, float tan_fovx, float tan_fovy, float* out_color,
                     float* out_depth, int* radii, float* acc, void* stream);
-int dge_fit_backward_blend(int P, int R, const float* background, int width, int height,
-                           char* geom_buffer, char* binning_buffer, char* image_buffer,
-                           const float* dL_dpix, float* acc, void* stream);
+int dge_fit_backward_blend(int P, int R, const float* background, int background_is_black,
+                           int width, int height, char* geom_buffer, char* binning_buffer,
+                           char* image_buffer, const float* dL_dpix, float* acc, void* stream);
 int dge_fit_backward_geom(int P, int D, int M, int V, const float* cams, int width, int height,
                           float scale_modifier, const float* acc, size_t acc_stride_floats,
                           const float* means3D, const float* shs, const float* scales,

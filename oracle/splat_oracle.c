@@ -71,9 +71,15 @@ static void cov3d(const float* s3, float mod, const float* q4, float* cov) {
   const float R10 = xy_p_rz + xy_p_rz, R11 = 1.0f - (xx_p_zz + xx_p_zz), R12 = yz_m_rx + yz_m_rx;
   const float R20 = xz_m_ry + xz_m_ry, R21 = yz_p_rx + yz_p_rx, R22 = 1.0f - (xx_p_yy + xx_p_yy);
   const float s0 = s3[0] * mod, s1 = s3[1] * mod, s2 = s3[2] * mod;
-  const float M00 = s0 * R00, M01 = s1 * R01, M02 = s2 * R02;
-  const float M10 = s0 * R10, M11 = s1 * R11, M12 = s2 * R12;
-  const float M20 = s0 * R20, M21 = s1 * R21, M22 = s2 * R22;
+  /* M = S * R as GLM evaluates it, literal-zero products kept (they decide the sign of zeros) */
+  const volatile float Zv = 0.0f;
+  const float Z = Zv;
+  const float M00 = dot3_ref(s0, R00, Z, R01, Z, R02), M01 = dot3_ref(Z, R00, s1, R01, Z, R02),
+              M02 = dot3_ref(Z, R00, Z, R01, s2, R02);
+  const float M10 = dot3_ref(s0, R10, Z, R11, Z, R12), M11 = dot3_ref(Z, R10, s1, R11, Z, R12),
+              M12 = dot3_ref(Z, R10, Z, R11, s2, R12);
+  const float M20 = dot3_ref(s0, R20, Z, R21, Z, R22), M21 = dot3_ref(Z, R20, s1, R21, Z, R22),
+              M22 = dot3_ref(Z, R20, Z, R21, s2, R22);
   cov[0] = dot3_ref(M00, M00, M01, M01, M02, M02);
   cov[1] = dot3_ref(M10, M00, M11, M01, M12, M02);
   cov[2] = dot3_ref(M20, M00, M21, M01, M22, M02);
@@ -92,10 +98,13 @@ static void cov2d(float tx, float ty, float tz, const OView* v, float fx, float 
   const float tz2 = tz * tz;
   const float J00 = fx / tz, J02 = ((tz * -cx) * fx) / tz2;
   const float J11 = fy / tz, J12 = ((tz * -cy) * fy) / tz2;
-  const float T00 = fmaf(V[2], J02, V[0] * J00), T01 = fmaf(V[6], J02, V[4] * J00),
-              T02 = fmaf(V[10], J02, V[8] * J00);
-  const float T10 = fmaf(V[2], J12, V[1] * J11), T11 = fmaf(V[6], J12, V[5] * J11),
-              T12 = fmaf(V[10], J12, V[9] * J11);
+  /* T = W * J (GLM), J's literal zeros kept */
+  const volatile float Zv = 0.0f;
+  const float Z = Zv;
+  const float T00 = dot3_ref(V[0], J00, V[1], Z, V[2], J02), T01 = dot3_ref(V[4], J00, V[5], Z, V[6], J02),
+              T02 = dot3_ref(V[8], J00, V[9], Z, V[10], J02);
+  const float T10 = dot3_ref(V[0], Z, V[1], J11, V[2], J12), T11 = dot3_ref(V[4], Z, V[5], J11, V[6], J12),
+              T12 = dot3_ref(V[8], Z, V[9], J11, V[10], J12);
   const float A00 = dot3_ref(T00, c[0], T01, c[1], T02, c[2]);
   const float A10 = dot3_ref(T00, c[1], T01, c[3], T02, c[4]);
   const float A20 = dot3_ref(T00, c[2], T01, c[4], T02, c[5]);

@@ -20,10 +20,11 @@ def _setup(cuda, fused):
     return fit.FitModel(g, cuda, fused_adam=fused), cams, targets, torch.zeros(3, device=cuda)
 
 
-@pytest.mark.parametrize("streams", [1, 3])
-def test_direct_path_matches_autograd_path(cuda, streams):
+@pytest.mark.parametrize("streams,bgv", [(1, 0.0), (3, 0.0), (2, 0.4)])
+def test_direct_path_matches_autograd_path(cuda, streams, bgv):
     ref_model, cams, targets, bg = _setup(cuda, True)
     model, _, _, _ = _setup(cuda, True)
+    bg = bg + bgv
     for step in range(2):
         l_ref = fit.fit_step(ref_model, cams, targets, bg, global_batch=V, direct=False, num_streams=1)
         g_ref = ref_model.flat_grad.clone()
@@ -69,3 +70,35 @@ def test_fused_adam_matches_torch_adam(cuda):
         stock.adam_step()
     torch.cuda.synchronize()
     torch.testing.assert_close(fused.flat, stock.flat, rtol=2e-5, atol=2e-7)
+
+
+def test_local_edit_flow_mask_backprojection_then_masked_fit(cuda):
+    """BASELINE.json config 3 at small scale (DGE.update_mask, DGE.py:101-165 + masked fit):
+    apply_weights over the views with a binary mask -> weights/cnt -> selection at mask_thres ->
+    grad mask; after a fit step only selected Gaussians move (rotation is not masked,
+    gaussian_model.py:848)."""
+    from dge_b200 import diff_gaussian_rasterization as dgr
+    model, cams, targets, bg = _setup(cuda, True)
+    a = {k: v.detach() for k, v in model.activations().items()}
+    weights = torch.zeros(P, 1, device=cuda)
+    cnt = torch.zeros(P, 1, dtype=torch.int32, device=cuda)
+    mask_img = scene.disc_mask(W, H, radius=30).to(cuda)
+    for cam in cams:
+        rs = scene.raster_settings(cam, bg, 0, module=dgr)
+        dgr.GaussianRasterizer(rs).apply_weights(a["means3D"], None, a["opacities"], None, weights, a["scales"],
+                                                 a["rotations"], None, cnt, mask_img)
+    sel = ((weights / (cnt + 1e-7)) > 0.8).view(-1)          # DGE.py:149-152, dge.yaml mask_thres
+    assert 0 < int(sel.sum()) < P
+    model.set_grad_mask(sel)
+    before = model.flat.clone()
+    fit.fit_step(model, cams, targets, bg, global_batch=V, num_streams=2)
+    torch.cuda.synchronize()
+    moved = (model.flat != before)
+    for name in fit.MASKED_GROUPS:
+        sl = model.slices[name]
+        k = (sl.stop - sl.start) // P
+        m = moved[sl].view(P, k).any(1)
+        assert not m[~sel].any(), name
+        assert m[sel].any(), name
+    sl = model.slices["rotation"]
+    assert moved[sl].view(P, 4).any(1)[~sel].any()              # rotation is not masked in the reference

@@ -182,6 +182,28 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)) if b.size else 0.0
 
 
+def l2_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)) if b.size else 0.0
+
+
+def grad_ok(got, ref, oracle=None, tol=1e-4):
+    """Gradient parity (BASELINE.json north_star: 1e-4 relative, atomic ordering differs).
+    Per tensor: max|got-ref| <= tol*max|ref|. The reference sums float atomics in an arbitrary
+    order, so its own result is only known to within its distance from the exactly accumulated
+    value (the oracle sums in double): measured on a B200 it differs from itself by up to 4e-5 from
+    run to run and from the oracle by up to 3e-4 (dL_drotations at 1264x832, where ours is at
+    5e-5). When the oracle is available that distance is therefore granted as slack against the
+    reference, while `got` must still be within tol of the oracle and within tol of the reference
+    in the L2 sense."""
+    e_ref = rel_err(got, ref)
+    if oracle is None:
+        return e_ref <= tol, f"vs reference {e_ref:.2e}"
+    e_or, slack = rel_err(got, oracle), rel_err(ref, oracle)
+    ok = e_or <= tol and l2_err(got, ref) <= tol and e_ref <= tol + slack
+    return ok, f"vs oracle {e_or:.2e}, vs reference {e_ref:.2e} (max) {l2_err(got, ref):.2e} (L2), reference vs oracle {slack:.2e}"
+
+
 BIT_EXACT = ("radii", "tiles_touched", "means2D", "depths", "conic_opacity", "rgb", "clamped", "keys", "point_list",
              "ranges", "n_contrib", "final_T", "out_color", "out_depth")
 
