@@ -10,7 +10,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_build", "libdge_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
@@ -45,6 +45,9 @@ _SIGNATURES = {
     "dge_fit_backward_blend": (_i, [_i, _i, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "dge_fit_backward_geom": (_i, [_i, _i, _i, _i, _p, _i, _i, _f, _p, C.c_size_t, _p, _p, _p, _p, _p, _p, _p, _p,
                                    _p, _p, _i, _p]),
+    "dge_fit_activate": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "dge_fit_backward_geom_raw": (_i, [_i, _i, _i, _p, _i, _i, _f, _p, C.c_size_t, _p, _p, _p, _p, _p, _p, _p, _p, _p,
+                                       _p, _p, _p, _p, _p]),
     "dge_l1_loss_grad": (_i, [_p, _p, C.c_size_t, _f, _p, _p, _p]),
     "dge_fused_adam": (_i, [_p, _p, _p, _p, C.c_size_t, _f, _f, _f, _f, _i, _p, _i, _p]),
 }

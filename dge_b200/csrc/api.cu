@@ -195,7 +195,7 @@ using namespace dge;
 extern "C" {
 
 const char* dge_last_error(void) { return g_err; }
-int dge_abi_version(void) { return 4; }
+int dge_abi_version(void) { return 5; }
 unsigned long long dge_launch_count(void) { return g_kernel_launches; }
 
 void dge_profile_enable(unsigned stage_mask) { g_profile_mask = stage_mask; }
@@ -311,6 +311,34 @@ int dge_fit_backward_geom(int P, int D, int M, int V, const float* cams, int wid
         launch_geom_backward_batched(P, D, M, V, cams, width, height, scale_modifier, acc, acc_stride_floats,
                                      means3D, shs, scales, rotations, dL_dmean3D, dL_dmean2D, dL_dsh,
                                      dL_dopacity, dL_dscale, dL_drot, accumulate != 0, stream));
+  return 0;
+}
+
+int dge_fit_activate(int P, const float* f_dc, const float* f_rest, const float* opacity_raw,
+                     const float* scaling_raw, const float* rotation_raw, float* shs, float* opacities,
+                     float* scales, float* rotations, void* stream_) {
+  if (P == 0) return 0;
+  CK("activate", launch_activate(P, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, shs, opacities, scales,
+                                 rotations, (cudaStream_t)stream_));
+  return 0;
+}
+
+int dge_fit_backward_geom_raw(int P, int D, int V, const float* cams, int width, int height,
+                              float scale_modifier, const float* acc, size_t acc_stride_floats,
+                              const float* means3D, const float* shs, const float* opacities,
+                              const float* scales, const float* rotations, const float* rotation_raw,
+                              float* d_xyz, float* d_means2D, float* d_f_dc, float* d_f_rest,
+                              float* d_opacity_raw, float* d_scaling_raw, float* d_rotation_raw,
+                              void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool debug = false;
+  if (P == 0) return 0;
+  if (rotation_raw == nullptr) return fail_msg("rotation_raw is required");
+  STAGE(ST_GEOM_BWD, "batched geometry backward (raw)",
+        launch_geom_backward_batched(P, D, 16, V, cams, width, height, scale_modifier, acc, acc_stride_floats,
+                                     means3D, shs, scales, rotations, d_xyz, d_means2D, d_f_dc, d_opacity_raw,
+                                     d_scaling_raw, d_rotation_raw, false, stream, opacities, rotation_raw,
+                                     d_f_rest));
   return 0;
 }
 

@@ -84,7 +84,12 @@ cudaError_t launch_geom_backward_batched(int P, int D, int M, int V, const float
                                          const float* means3D, const float* shs, const float* scales,
                                          const float* rotations, float* dL_dmean3D, float* dL_dmean2D,
                                          float* dL_dsh, float* dL_dopacity, float* dL_dscale,
-                                         float* dL_drot, bool accumulate, cudaStream_t stream);
+                                         float* dL_drot, bool accumulate, cudaStream_t stream,
+                                         const float* opacities = nullptr,
+                                         const float* rotation_raw = nullptr, float* dL_drest = nullptr);
+cudaError_t launch_activate(int P, const float* f_dc, const float* f_rest, const float* opacity_raw,
+                            const float* scaling_raw, const float* rotation_raw, float* shs,
+                            float* opacities, float* scales, float* rotations, cudaStream_t stream);
 cudaError_t launch_mark_visible(int P, const float* means3D, const float* view, const float* proj,
                                 uint8_t* present, cudaStream_t stream);
 // depth sort -> scan -> expand -> tile sort -> ranges. R already known on host.

@@ -406,13 +406,19 @@ __global__ void __launch_bounds__(256) geom_backward_kernel(
 constexpr int CAM_FLOATS = 40;   // view[16] | proj[16] | campos[3] | tan_fovx | tan_fovy | pad[3]
 constexpr int MAX_BATCH_VIEWS = 64;
 
+// RAW: the outputs are gradients w.r.t. GaussianModel's raw parameters (gaussian_model.py:221-258:
+// scaling = exp(raw), opacity = sigmoid(raw), rotation = normalize(raw), features = cat(f_dc, f_rest)),
+// i.e. the activations' backward is applied in the epilogue and dL/dsh is split into f_dc / f_rest
+// rows (dL_dsh -> f_dc [P,1,3], dL_drest -> f_rest [P,15,3]); every row is written (no accumulate).
+template <bool RAW>
 __global__ void __launch_bounds__(128, 4) geom_backward_batched_kernel(
     int P, int D, int M, int V, const float* __restrict__ cams, int W, int H, float scale_modifier,
     const float* __restrict__ acc, size_t acc_stride, const float* __restrict__ means3D,
     const float* __restrict__ shs, const float* __restrict__ scales, const float* __restrict__ rotations,
+    const float* __restrict__ opacities, const float* __restrict__ rotation_raw,
     float* __restrict__ dL_dmean3D, float* __restrict__ dL_dmean2D, float* __restrict__ dL_dsh,
-    float* __restrict__ dL_dopacity, float* __restrict__ dL_dscale, float* __restrict__ dL_drot,
-    bool accumulate) {
+    float* __restrict__ dL_drest, float* __restrict__ dL_dopacity, float* __restrict__ dL_dscale,
+    float* __restrict__ dL_drot, bool accumulate) {
   extern __shared__ float s_cam[];
   for (int k = threadIdx.x; k < V * CAM_FLOATS; k += blockDim.x) s_cam[k] = cams[k];
   __syncthreads();
@@ -502,6 +508,24 @@ __global__ void __launch_bounds__(128, 4) geom_backward_batched_kernel(
   float dscale[3] = {0.f, 0.f, 0.f};
   float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
   if (any) cov3d_backward(q, sc, scale_modifier, dcov, dscale, dq);
+  if (RAW) {
+    out3<false>(dL_dmean3D, i, dmean[0], dmean[1], dmean[2]);
+    out3<false>(dL_dmean2D, i, dm2x, dm2y, 0.f);
+    const float o = __ldg(opacities + i);
+    dL_dopacity[i] = dop * o * (1.0f - o);                                   // sigmoid
+    out3<false>(dL_dscale, i, dscale[0] * sc[0], dscale[1] * sc[1], dscale[2] * sc[2]);  // exp
+    const float4 qr = __ldg(reinterpret_cast<const float4*>(rotation_raw) + i);  // normalize
+    const float nrm = fmaxf(sqrtf(qr.x * qr.x + qr.y * qr.y + qr.z * qr.z + qr.w * qr.w), 1e-12f);
+    const float qd = q.x * dq.x + q.y * dq.y + q.z * dq.z + q.w * dq.w;
+    const float inv = 1.0f / nrm;
+    out4<false>(dL_drot, i, make_float4((dq.x - q.x * qd) * inv, (dq.y - q.y * qd) * inv,
+                                        (dq.z - q.z * qd) * inv, (dq.w - q.w * qd) * inv));
+    out3<false>(dL_dsh, i, dsh[0], dsh[1], dsh[2]);                          // f_dc
+    float* r = dL_drest + 45 * i;                                            // f_rest
+#pragma unroll
+    for (int k = 0; k < 45; k++) r[k] = dsh[3 + k];
+    return;
+  }
   if (accumulate) {
     out3<true>(dL_dmean3D, i, dmean[0], dmean[1], dmean[2]);
     out3<true>(dL_dmean2D, i, dm2x, dm2y, 0.f);
@@ -533,16 +557,63 @@ __global__ void __launch_bounds__(128, 4) geom_backward_batched_kernel(
   }
 }
 
+// GaussianModel's activations (gaussian_model.py:221-258) for the whole model in one pass:
+// shs = cat(f_dc, f_rest), opacity = sigmoid, scaling = exp, rotation = normalize (eps 1e-12).
+__global__ void __launch_bounds__(256) activate_kernel(int P, const float* __restrict__ f_dc,
+                                                       const float* __restrict__ f_rest,
+                                                       const float* __restrict__ opacity_raw,
+                                                       const float* __restrict__ scaling_raw,
+                                                       const float* __restrict__ rotation_raw,
+                                                       float* __restrict__ shs, float* __restrict__ opacities,
+                                                       float* __restrict__ scales, float* __restrict__ rotations) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  const size_t i = (size_t)idx;
+  float v[48];
+#pragma unroll
+  for (int k = 0; k < 3; k++) v[k] = __ldg(f_dc + 3 * i + k);
+#pragma unroll
+  for (int k = 0; k < 45; k++) v[3 + k] = __ldg(f_rest + 45 * i + k);
+#pragma unroll
+  for (int j = 0; j < 12; j++)
+    reinterpret_cast<float4*>(shs + 48 * i)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  opacities[i] = 1.0f / (1.0f + expf(-__ldg(opacity_raw + i)));
+#pragma unroll
+  for (int k = 0; k < 3; k++) scales[3 * i + k] = expf(__ldg(scaling_raw + 3 * i + k));
+  const float4 q = __ldg(reinterpret_cast<const float4*>(rotation_raw) + i);
+  const float inv = 1.0f / fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
+  reinterpret_cast<float4*>(rotations)[i] = make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);
+}
+
+cudaError_t launch_activate(int P, const float* f_dc, const float* f_rest, const float* opacity_raw,
+                            const float* scaling_raw, const float* rotation_raw, float* shs,
+                            float* opacities, float* scales, float* rotations, cudaStream_t stream) {
+  activate_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw,
+                                                       shs, opacities, scales, rotations);
+  DGE_LAUNCHED(1);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_geom_backward_batched(int P, int D, int M, int V, const float* cams, int W, int H,
                                          float scale_modifier, const float* acc, size_t acc_stride,
                                          const float* means3D, const float* shs, const float* scales,
                                          const float* rotations, float* dL_dmean3D, float* dL_dmean2D,
                                          float* dL_dsh, float* dL_dopacity, float* dL_dscale,
-                                         float* dL_drot, bool accumulate, cudaStream_t stream) {
+                                         float* dL_drot, bool accumulate, cudaStream_t stream,
+                                         const float* opacities, const float* rotation_raw,
+                                         float* dL_drest) {
   if (V < 1 || V > MAX_BATCH_VIEWS) return cudaErrorInvalidValue;
-  geom_backward_batched_kernel<<<(P + 127) / 128, 128, V * CAM_FLOATS * sizeof(float), stream>>>(
-      P, D, M, V, cams, W, H, scale_modifier, acc, acc_stride, means3D, shs, scales, rotations,
-      dL_dmean3D, dL_dmean2D, dL_dsh, dL_dopacity, dL_dscale, dL_drot, accumulate);
+  const size_t smem = V * CAM_FLOATS * sizeof(float);
+  if (rotation_raw != nullptr) {
+    if (M != 16) return cudaErrorInvalidValue;
+    geom_backward_batched_kernel<true><<<(P + 127) / 128, 128, smem, stream>>>(
+        P, D, M, V, cams, W, H, scale_modifier, acc, acc_stride, means3D, shs, scales, rotations, opacities,
+        rotation_raw, dL_dmean3D, dL_dmean2D, dL_dsh, dL_drest, dL_dopacity, dL_dscale, dL_drot, false);
+  } else {
+    geom_backward_batched_kernel<false><<<(P + 127) / 128, 128, smem, stream>>>(
+        P, D, M, V, cams, W, H, scale_modifier, acc, acc_stride, means3D, shs, scales, rotations, nullptr,
+        nullptr, dL_dmean3D, dL_dmean2D, dL_dsh, nullptr, dL_dopacity, dL_dscale, dL_drot, accumulate);
+  }
   DGE_LAUNCHED(1);
   return cudaGetLastError();
 }

@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(
   __shared__ uint32_t s_tile;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int digit_bits = __popc(digit_mask);
   if (tid == 0) s_tile = atomicAdd(ticket, 1u);
   for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&s_cnt[0][0])[i] = 0;
   __syncthreads();
@@ -119,9 +120,10 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(
     if (!valid) peers = ~peers;
 #pragma unroll
     for (int b = 0; b < RADIX_BITS; b++) {
-      const bool bit = (d >> b) & 1u;
-      const uint32_t vote = __ballot_sync(0xFFFFFFFFu, bit);
-      peers &= bit ? vote : ~vote;
+      if (b >= digit_bits) break;  // warp-uniform: 5-bit tile digits need 5 ballots, not 8
+      const uint32_t m = 0u - ((d >> b) & 1u);  // all ones if this lane's bit is set
+      const uint32_t vote = __ballot_sync(0xFFFFFFFFu, m != 0u);
+      peers &= ~(vote ^ m);
     }
     const int leader = __ffs(peers) - 1;
     uint32_t prev = 0;

@@ -95,6 +95,20 @@ class FitModel:
             "rotations": torch.nn.functional.normalize(p["rotation"]),
         }
 
+    def activations_fused(self):
+        """The same activations from ONE kernel into persistent buffers (no autograd graph): their
+        backward is applied by dge_fit_backward_geom_raw's epilogue."""
+        if getattr(self, "_acts", None) is None:
+            f32 = dict(dtype=torch.float32, device=self.device)
+            self._acts = {"shs": torch.empty(self.P, 16, 3, **f32), "opacities": torch.empty(self.P, 1, **f32),
+                          "scales": torch.empty(self.P, 3, **f32), "rotations": torch.empty(self.P, 4, **f32)}
+        a, p = self._acts, self.params
+        L.check(L.load().dge_fit_activate(self.P, p["f_dc"].data_ptr(), p["f_rest"].data_ptr(),
+                                          p["opacity"].data_ptr(), p["scaling"].data_ptr(), p["rotation"].data_ptr(),
+                                          a["shs"].data_ptr(), a["opacities"].data_ptr(), a["scales"].data_ptr(),
+                                          a["rotations"].data_ptr(), L.stream_ptr(self.device)), "activate")
+        return {"means3D": p["xyz"].detach(), **a}
+
     def set_grad_mask(self, mask: Optional[torch.Tensor]):
         self.grad_mask = None if mask is None else mask.to(self.device).to(torch.uint8).contiguous()
 
@@ -181,7 +195,7 @@ def _direct_views(model: FitModel, acts, cameras, targets, bg, scale, host_input
     """The step's views through the C-ABI, round-robin over `num_streams` lanes (no autograd):
     per view forward -> fused L1 loss+gradient -> blend backward into that view's acc rows; then ONE
     batched per-Gaussian backward over all views. Returns (grads w.r.t. the activated tensors and the
-    screen-space tap, loss, max radii)."""
+    screen-space tap, loss, max radii). Leaves the step's gradients in model.flat_grad."""
     lib = L.load()
     dev = model.device
     H, W = cameras[0].image_height, cameras[0].image_width
@@ -195,8 +209,6 @@ def _direct_views(model: FitModel, acts, cameras, targets, bg, scale, host_input
         f32 = dict(dtype=torch.float32, device=dev)
         model._acc = torch.empty(V, P, 12, **f32)          # blend-stage sums of every view of the step
         model._cams = torch.empty(V, CAM_FLOATS, **f32)
-        model._act_grads = {"shs": torch.empty(P, 16, 3, **f32), "opacities": torch.empty(P, 1, **f32),
-                            "scales": torch.empty(P, 3, **f32), "rotations": torch.empty(P, 4, **f32)}
         model._cam_cache = {}
         model._lane_key = key
     lanes, acc, cams_dev = model._lanes, model._acc, model._cams
@@ -239,19 +251,20 @@ def _direct_views(model: FitModel, acts, cameras, targets, bg, scale, host_input
             torch.maximum(ln.radii_max, ln.radii, out=ln.radii_max)
     for ln in lanes:
         main.wait_stream(ln.stream)
-    g = dict(model._act_grads)
-    g["means3D"] = model.params["xyz"].grad      # xyz has no activation: straight into the flat buffer
-    g["means2D"] = model.means2D.grad
-    L.check(lib.dge_fit_backward_geom(
-        P, model.sh_degree, M, V, cams_dev.data_ptr(), W, H, 1.0, acc.data_ptr(), P * 12, ptrs["means3D"],
-        ptrs["shs"], ptrs["scales"], ptrs["rotations"], g["means3D"].data_ptr(), g["means2D"].data_ptr(),
-        g["shs"].data_ptr(), g["opacities"].data_ptr(), g["scales"].data_ptr(), g["rotations"].data_ptr(), 0,
+    # ONE per-Gaussian backward for all views, activations' backward in its epilogue: gradients
+    # w.r.t. the raw parameters go straight into the flat buffer the collective reduces (every
+    # row is written, so the buffer needs no zero fill either)
+    gp = {k: v.grad.data_ptr() for k, v in model.params.items()}
+    L.check(lib.dge_fit_backward_geom_raw(
+        P, model.sh_degree, V, cams_dev.data_ptr(), W, H, 1.0, acc.data_ptr(), P * 12, ptrs["means3D"], ptrs["shs"],
+        ptrs["opacities"], ptrs["scales"], ptrs["rotations"], model.params["rotation"].data_ptr(), gp["xyz"],
+        model.means2D.grad.data_ptr(), gp["f_dc"], gp["f_rest"], gp["opacity"], gp["scaling"], gp["rotation"],
         L.stream_ptr(dev)), "fit backward geom")
     loss, radii_max = lanes[0].loss.clone(), lanes[0].radii_max
     for ln in lanes[1:]:
         loss += ln.loss
         radii_max = torch.maximum(radii_max, ln.radii_max)
-    return g, loss, radii_max
+    return loss, radii_max
 
 
 def shard_views(num_views: int, rank: int, world: int) -> List[int]:
@@ -283,17 +296,16 @@ def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence
     stream's running sums. The autograd path below is the reference-shaped one (per-view tensors,
     torch ops for the loss, AccumulateGrad) and is what `rasterize` overrides go through."""
     dev = model.device
-    model.zero_grad()
-    acts_graph = model.activations()
     H, W = cameras[0].image_height, cameras[0].image_width
     scale = lambda_l1 / float(global_batch * 3 * H * W)
     if direct is None:
-        direct = dev.type == "cuda" and rasterize is default_rasterize
+        direct = dev.type == "cuda" and rasterize is default_rasterize and model.sh_degree == 3
     if direct:
-        grads, loss, radii_max = _direct_views(model, acts_graph, cameras, targets, bg, scale, host_inputs, num_streams)
-        through = [k for k in acts_graph if acts_graph[k].grad_fn is not None]
-        torch.autograd.backward([acts_graph[k] for k in through], [grads[k] for k in through])
+        loss, radii_max = _direct_views(model, model.activations_fused(), cameras, targets, bg, scale, host_inputs,
+                                        num_streams)
         return _finish_step(model, loss, radii_max, process_group, update_stats)
+    model.zero_grad()
+    acts_graph = model.activations()
     S = max(1, min(num_streams, len(cameras)))
     main = torch.cuda.current_stream(dev) if dev.type == "cuda" else None
     if S > 1:

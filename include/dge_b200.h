@@ -170,6 +170,21 @@ int dge_fit_backward_geom(int P, int D, int M, int V, const float* cams, int wid
                           float* dL_dsh, float* dL_dopacity, float* dL_dscale, float* dL_drot,
                           int accumulate, void* stream);
 
+/* GaussianModel's activations (gaussiansplatting/scene/gaussian_model.py:221-258)
+ * for the whole model in one pass — shs[P,16,3] = cat(f_dc[P,1,3], f_rest[P,15,3]), opacities =
+ * sigmoid, scales = exp, rotations = normalize — and dge_fit_backward_geom with their backward in
+ * its epilogue: the seven outputs are gradients w.r.t. the RAW parameters, every row written. */
+int dge_fit_activate(int P, const float* f_dc, const float* f_rest, const float* opacity_raw,
+                     const float* scaling_raw, const float* rotation_raw, float* shs,
+                     float* opacities, float* scales, float* rotations, void* stream);
+int dge_fit_backward_geom_raw(int P, int D, int V, const float* cams, int width, int height,
+                              float scale_modifier, const float* acc, size_t acc_stride_floats,
+                              const float* means3D, const float* shs, const float* opacities,
+                              const float* scales, const float* rotations,
+                              const float* rotation_raw, float* d_xyz, float* d_means2D,
+                              float* d_f_dc, float* d_f_rest, float* d_opacity_raw,
+                              float* d_scaling_raw, float* d_rotation_raw, void* stream);
+
 /* ---- fit-step helpers ----
  * L1 loss of one rendered view and its gradient (threestudio/systems/DGE.py:672):
  * grad[i] = scale * sign(image[i] - target[i]); *loss_accum += scale * sum |image - target|. */

