@@ -437,19 +437,29 @@ __global__ void __launch_bounds__(128, 4) geom_backward_batched_kernel(
   float dsh[48];
 #pragma unroll
   for (int k = 0; k < 48; k++) dsh[k] = 0.f;
+  // Pass 1: which views gave this Gaussian anything? A row is all zeros when the Gaussian was
+  // culled, occluded or below alpha 1/255 everywhere in that view — the common case (ncu: 2 of 32
+  // lanes had work per view when the views were walked in lock-step). Every term below is
+  // linear in the nine sums, so such views are skipped; each lane then walks ITS OWN list of
+  // non-empty views, and a warp iterates max-over-lanes(#non-empty) times instead of V times.
   bool any = false;
+  unsigned long long todo = 0ull;
   for (int v = 0; v < V; v++) {
     const float4* row = reinterpret_cast<const float4*>(acc + (size_t)v * acc_stride) + 3 * i;
     const float4 a2 = __ldg(row + 2);
-    const uint32_t flags = __float_as_uint(a2.w);
-    if (!(flags & 1u)) continue;
-    const float4 a0 = __ldg(row), a1 = __ldg(row + 1);
+    if (!(__float_as_uint(a2.w) & 1u)) continue;
     any = true;
-    // visible but untouched by any pixel of this view (occluded, or alpha < 1/255 everywhere):
-    // every term below is linear in these nine sums
-    if (a0.x == 0.f && a0.y == 0.f && a0.z == 0.f && a0.w == 0.f && a1.x == 0.f && a1.y == 0.f && a1.z == 0.f &&
-        a1.w == 0.f && a2.x == 0.f)
-      continue;
+    const float4 a0 = __ldg(row), a1 = __ldg(row + 1);
+    if (a0.x != 0.f || a0.y != 0.f || a0.z != 0.f || a0.w != 0.f || a1.x != 0.f || a1.y != 0.f || a1.z != 0.f ||
+        a1.w != 0.f || a2.x != 0.f)
+      todo |= 1ull << v;
+  }
+  while (todo) {
+    const int v = __ffsll((long long)todo) - 1;
+    todo &= todo - 1ull;
+    const float4* row = reinterpret_cast<const float4*>(acc + (size_t)v * acc_stride) + 3 * i;
+    const float4 a0 = __ldg(row), a1 = __ldg(row + 1), a2 = __ldg(row + 2);
+    const uint32_t flags = __float_as_uint(a2.w);
     const float* cam = s_cam + v * CAM_FLOATS;
     const float tan_fovx = cam[35], tan_fovy = cam[36];
     const float focal_y = H / (2.0f * tan_fovy), focal_x = W / (2.0f * tan_fovx);
