@@ -162,7 +162,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="config2", choices=list(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=3, help="CUDA streams the views of a step are pipelined on (ours)")
+    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the views of a step are pipelined on (ours)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
 

@@ -1,0 +1,54 @@
+"""Profiling driver (not a pytest file): kernel timeline of fit steps of BASELINE.json config 2 with the
+multi-stream pipeline ON, captured with torch.profiler (CUPTI activity records cover the kernels this
+library launches through ctypes as well). Prints, per kernel name, launches / total / mean duration,
+and the step's concurrency figures: wall span, union of busy time, sum of kernel time."""
+import argparse, collections, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from torch.profiler import profile, ProfilerActivity
+from dge_b200 import fit, scene
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--views", type=int, default=20)
+ap.add_argument("--P", type=int, default=1_000_000)
+ap.add_argument("--res", type=int, default=512)
+ap.add_argument("--streams", type=int, default=4)
+ap.add_argument("--out", default="")
+args = ap.parse_args()
+dev = torch.device("cuda:0")
+g = scene.make_gaussians(args.P, seed=1236)
+cams = [scene.camera_to(c, dev) for c in scene.ring_cameras(20, args.res, args.res)[:args.views]]
+gen = torch.Generator().manual_seed(3)
+targets = [torch.rand(3, args.res, args.res, generator=gen).to(dev) for _ in range(args.views)]
+model = fit.FitModel(g, dev, fused_adam=True)
+bg = torch.zeros(3, device=dev)
+for _ in range(3):
+    fit.fit_step(model, cams, targets, bg, global_batch=args.views, num_streams=args.streams)
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    fit.fit_step(model, cams, targets, bg, global_batch=args.views, num_streams=args.streams)
+    torch.cuda.synchronize()
+ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+iv = sorted((e.time_range.start, e.time_range.end, e.name) for e in ev)
+agg = collections.OrderedDict()
+for s, e, n in iv:
+    a = agg.setdefault(n.split("(")[0][:60], [0, 0.0])
+    a[0] += 1
+    a[1] += e - s
+span = iv[-1][1] - iv[0][0]
+busy, cur_s, cur_e = 0.0, None, None
+for s, e, _ in iv:
+    if cur_e is None or s > cur_e:
+        if cur_e is not None:
+            busy += cur_e - cur_s
+        cur_s, cur_e = s, e
+    else:
+        cur_e = max(cur_e, e)
+busy += cur_e - cur_s
+total = sum(a[1] for a in agg.values())
+print(f"span {span / 1e3:.3f} ms, busy(union) {busy / 1e3:.3f} ms, sum of kernel time {total / 1e3:.3f} ms, "
+      f"{len(iv)} device activities, streams={args.streams}")
+for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    print(f"{n:60s} {c:5d} {t / 1e3:9.3f} ms {t / c:9.1f} us")
+if args.out:
+    json.dump([(s - iv[0][0], e - iv[0][0], n.split("(")[0][:40]) for s, e, n in iv], open(args.out, "w"))
