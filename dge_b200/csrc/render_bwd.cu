@@ -37,8 +37,8 @@ __global__ void __launch_bounds__(BL_THREADS, 9) render_backward_kernel(
   // quadrant of the warp's 16x8 half-tile (see blend.cuh)
   const int px0 = blockIdx.x * DGE_TILE + (lane & 7), py0 = blockIdx.y * DGE_TILE + 8 * warp + (lane >> 3);
   const float fx0 = (float)px0, fx1 = (float)(px0 + PX_STEP), fy0 = (float)py0, fy1 = (float)(py0 + PY_STEP);
-  const float X0 = (float)(blockIdx.x * DGE_TILE), X1 = X0 + 15.0f;
-  const float Y0 = (float)(blockIdx.y * DGE_TILE + 8 * warp), Y1 = Y0 + 7.0f;
+  const float X0 = (float)(blockIdx.x * DGE_TILE);
+  const float Y0 = (float)(blockIdx.y * DGE_TILE + 8 * warp);
   const size_t HW = (size_t)H * W;
   const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
 
@@ -67,6 +67,9 @@ __global__ void __launch_bounds__(BL_THREADS, 9) render_backward_kernel(
     bg_dot[p] = HAS_BG ? bg0 * dpix[p][0] + bg1 * dpix[p][1] + bg2 * dpix[p][2] : 0.0f;
   }
   const uint32_t wmax = __reduce_max_sync(0xFFFFFFFFu, tmax);
+  uint32_t qmax[4];  // last contributor of each 8x4 quadrant (warp-uniform)
+#pragma unroll
+  for (int p = 0; p < 4; p++) qmax[p] = __reduce_max_sync(0xFFFFFFFFu, last[p]);
   if (lane == 0) s_max[warp] = wmax;
   __syncthreads();
   uint32_t bmax = 0;
@@ -83,63 +86,57 @@ __global__ void __launch_bounds__(BL_THREADS, 9) render_backward_kernel(
                       means2D, conic_opacity, rgb_depth);
     __syncthreads();
     if (hi - count >= wmax) continue;  // nothing in this batch reaches this warp (warp-uniform)
-    const int n = compact_batch(s, warp, lane, count, X0, X1, Y0, Y1,
-                                [&](int k) { return hi - 1 - k < wmax; });
+    const int n = compact_batch(s, warp, lane, count, X0, Y0, [&](int k) {
+      const uint32_t pos = hi - 1 - k;
+      return (pos < qmax[0] ? 1u : 0u) | (pos < qmax[1] ? 2u : 0u) | (pos < qmax[2] ? 4u : 0u) |
+             (pos < qmax[3] ? 8u : 0u);
+    });
     for (int i = 0; i < n; i++) {
-      const int j = s.list[warp][i];
+      const uint32_t e = s.list[warp][i];  // warp-uniform
+      const int j = e & 0xFF;
       const uint32_t pos = hi - 1 - j;  // 0-based list position
       const float4 a = s.a[j];
       const float4 b = s.b[j];
-      const Quad q = quad_power(a, b.x, fx0, fx1, fy0, fy1);
-      const float dx0 = q.dx0, dx1 = q.dx1, dy0 = q.dy0, dy1 = q.dy1;
-      bool cand[4];
-      bool any = false;
-#pragma unroll
-      for (int p = 0; p < 4; p++) {
-        cand[p] = pos < last[p] && !(q.power[p] > 0.0f) && !(q.power[p] < b.y);
-        any |= cand[p];
-      }
-      if (!__any_sync(0xFFFFFFFFu, any)) continue;
+      const float4 cd = s.c[j];
+      const float opacity = b.z;
+      const float col[3] = {cd.x, cd.y, cd.z};
 
       float g[9];
 #pragma unroll
       for (int i = 0; i < 9; i++) g[i] = 0.0f;
       bool touched = false;
-      if (any) {
-        const float opacity = b.z;
-        const float4 cd = s.c[j];
-        const float col[3] = {cd.x, cd.y, cd.z};
 #pragma unroll
-        for (int p = 0; p < 4; p++) {
-          if (!cand[p]) continue;
-          const float G = expf(q.power[p]);
-          const float alpha = fminf(0.99f, BMUL(opacity, G));
-          if (alpha < 1.0f / 255.0f) continue;
-          touched = true;
-          const float dx = (p & 1) ? dx1 : dx0, dy = (p >> 1) ? dy1 : dy0;
-          const float one_m = 1.0f - alpha;
-          T[p] = __fdiv_rn(T[p], one_m);  // same recurrence as the reference (backward.cu:505)
-          const float w = alpha * T[p];
-          float dL_dalpha = 0.0f;
+      for (int p = 0; p < 4; p++) {
+        if (!(e & (0x100u << p))) continue;  // warp-uniform branch
+        const float dx = BADD(a.x, (p & 1) ? -fx1 : -fx0), dy = BADD(a.y, (p >> 1) ? -fy1 : -fy0);
+        const float power = pixel_power(a, b.x, dx, dy);
+        if (pos >= last[p] || power > 0.0f || power < b.y) continue;
+        const float G = expf(power);
+        const float alpha = fminf(0.99f, BMUL(opacity, G));
+        if (alpha < 1.0f / 255.0f) continue;
+        touched = true;
+        const float one_m = 1.0f - alpha;
+        T[p] = __fdiv_rn(T[p], one_m);  // same recurrence as the reference (backward.cu:505)
+        const float w = alpha * T[p];
+        float dL_dalpha = 0.0f;
 #pragma unroll
-          for (int c = 0; c < 3; c++) {
-            dL_dalpha += (col[c] - behind[p][c]) * dpix[p][c];
-            g[ACC_R + c] += w * dpix[p][c];
-            behind[p][c] = alpha * col[c] + one_m * behind[p][c];
-          }
-          dL_dalpha *= T[p];
-          if (HAS_BG) dL_dalpha += __fdiv_rn(-T_final[p], one_m) * bg_dot[p];
-          const float dL_dG = opacity * dL_dalpha;
-          const float gdx = G * dx, gdy = G * dy;
-          const float dG_ddelx = -gdx * a.z - gdy * a.w;
-          const float dG_ddely = -gdy * b.x - gdx * a.w;
-          g[ACC_MEAN_X] += dL_dG * dG_ddelx * ddelx_dx;
-          g[ACC_MEAN_Y] += dL_dG * dG_ddely * ddely_dy;
-          g[ACC_CONIC_X] += -0.5f * gdx * dx * dL_dG;
-          g[ACC_CONIC_Y] += -0.5f * gdx * dy * dL_dG;
-          g[ACC_CONIC_W] += -0.5f * gdy * dy * dL_dG;
-          g[ACC_OPACITY] += G * dL_dalpha;
+        for (int c = 0; c < 3; c++) {
+          dL_dalpha += (col[c] - behind[p][c]) * dpix[p][c];
+          g[ACC_R + c] += w * dpix[p][c];
+          behind[p][c] = alpha * col[c] + one_m * behind[p][c];
         }
+        dL_dalpha *= T[p];
+        if (HAS_BG) dL_dalpha += __fdiv_rn(-T_final[p], one_m) * bg_dot[p];
+        const float dL_dG = opacity * dL_dalpha;
+        const float gdx = G * dx, gdy = G * dy;
+        const float dG_ddelx = -gdx * a.z - gdy * a.w;
+        const float dG_ddely = -gdy * b.x - gdx * a.w;
+        g[ACC_MEAN_X] += dL_dG * dG_ddelx * ddelx_dx;
+        g[ACC_MEAN_Y] += dL_dG * dG_ddely * ddely_dy;
+        g[ACC_CONIC_X] += -0.5f * gdx * dx * dL_dG;
+        g[ACC_CONIC_Y] += -0.5f * gdx * dy * dL_dG;
+        g[ACC_CONIC_W] += -0.5f * gdy * dy * dL_dG;
+        g[ACC_OPACITY] += G * dL_dalpha;
       }
       if (!__any_sync(0xFFFFFFFFu, touched)) continue;
 

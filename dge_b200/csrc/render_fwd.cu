@@ -31,8 +31,8 @@ __global__ void __launch_bounds__(BL_THREADS) render_forward_kernel(
   const int px0 = blockIdx.x * DGE_TILE + (lane & 7), py0 = blockIdx.y * DGE_TILE + 8 * warp + (lane >> 3);
   const float fx0 = (float)px0, fx1 = (float)(px0 + PX_STEP), fy0 = (float)py0, fy1 = (float)(py0 + PY_STEP);
   // the warp's half-tile, in pixel-centre coordinates
-  const float X0 = (float)(blockIdx.x * DGE_TILE), X1 = X0 + 15.0f;
-  const float Y0 = (float)(blockIdx.y * DGE_TILE + 8 * warp), Y1 = Y0 + 7.0f;
+  const float X0 = (float)(blockIdx.x * DGE_TILE);
+  const float Y0 = (float)(blockIdx.y * DGE_TILE + 8 * warp);
   // pixel p = 2*row + col inside the quad
   bool inside[4];
 #pragma unroll
@@ -59,26 +59,23 @@ __global__ void __launch_bounds__(BL_THREADS) render_forward_kernel(
                       conic_opacity, rgb_depth);
     __syncthreads();
     if (__all_sync(0xFFFFFFFFu, all_done)) continue;  // this half-tile is saturated
-    const int n = compact_batch(s, warp, lane, count, X0, X1, Y0, Y1, [](int) { return true; });
-    for (int i = 0; i < n; i++) {
-      const int j = s.list[warp][i];
-      const float4 a = s.a[j];
-      const float2 b = *reinterpret_cast<const float2*>(&s.b[j]);
-      const Quad q = quad_power(a, b.x, fx0, fx1, fy0, fy1);
-      bool cand[4];
-      bool any = false;
+    // quadrants in which every pixel has terminated need no further visits
+    uint32_t live = 0;
 #pragma unroll
-      for (int p = 0; p < 4; p++) {
-        cand[p] = !done[p] && !(q.power[p] > 0.0f) && !(q.power[p] < b.y);
-        any |= cand[p];
-      }
-      if (!any) continue;
-      const float opacity = s.b[j].z;
+    for (int p = 0; p < 4; p++) live |= __all_sync(0xFFFFFFFFu, done[p]) ? 0u : (1u << p);
+    const int n = compact_batch(s, warp, lane, count, X0, Y0, [&](int) { return live; });
+    for (int i = 0; i < n; i++) {
+      const uint32_t e = s.list[warp][i];  // warp-uniform
+      const int j = e & 0xFF;
+      const float4 a = s.a[j];
+      const float4 b = s.b[j];
       const float4 cd = s.c[j];
 #pragma unroll
       for (int p = 0; p < 4; p++) {
-        if (!cand[p]) continue;
-        const float alpha = fminf(0.99f, BMUL(opacity, expf(q.power[p])));
+        if (!(e & (0x100u << p))) continue;  // warp-uniform branch
+        const float power = pixel_power(a, b.x, BADD(a.x, (p & 1) ? -fx1 : -fx0), BADD(a.y, (p >> 1) ? -fy1 : -fy0));
+        if (done[p] || power > 0.0f || power < b.y) continue;
+        const float alpha = fminf(0.99f, BMUL(b.z, expf(power)));
         if (alpha < 1.0f / 255.0f) continue;
         const float test_T = BMUL(T[p], BADD(1.0f, -alpha));
         if (test_T < 0.0001f) {

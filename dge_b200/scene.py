@@ -32,12 +32,12 @@ class Camera(NamedTuple):
     camera_center: torch.Tensor         # [3]
 
 
-def make_gaussians(P, seed=1234, sh_degree=3, scale_median=0.012):
+def make_gaussians(P, seed=1234, sh_degree=3, scale_median=0.012, scale_sigma=0.6):
     g = torch.Generator(device="cpu").manual_seed(seed)
     means = torch.randn(P, 3, generator=g)
     norm = means.norm(dim=1, keepdim=True).clamp_min(1e-12)
     means = means * torch.clamp(3.0 / norm, max=1.0)  # clip to ||x|| <= 3
-    scales = torch.exp(math.log(scale_median) + 0.6 * torch.randn(P, 3, generator=g))
+    scales = torch.exp(math.log(scale_median) + scale_sigma * torch.randn(P, 3, generator=g))
     q = torch.randn(P, 4, generator=g)
     q = q / q.norm(dim=1, keepdim=True).clamp_min(1e-12)
     opac = 0.02 + 0.96 * torch.rand(P, 1, generator=g)

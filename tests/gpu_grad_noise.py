@@ -9,8 +9,11 @@ from tests import util
 dev = torch.device("cuda:0")
 PAIRS = [("means3D", "dL_dmeans3D"), ("means2D", "dL_dmeans2D"), ("shs", "dL_dsh"), ("opacities", "dL_dopacity"),
          ("scales", "dL_dscales"), ("rotations", "dL_drotations")]
-for (P, W, H, seed, sm) in [(200000, 1264, 832, 77, 0.02), (300000, 512, 512, 1236, 0.012), (200000, 512, 512, 1236, 0.012)]:
-    g = scene.make_gaussians(P, seed=seed, scale_median=sm)
+CASES = [(200000, 1264, 832, 77, 0.02, 0.6), (300000, 512, 512, 1236, 0.012, 0.6), (200000, 512, 512, 1236, 0.012, 0.6)]
+if len(sys.argv) > 1 and sys.argv[1] == "aniso":  # the needle scenes of test_anisotropic_needles_images_bit_exact
+    CASES = [(12000, 256, 192, 31, 0.03, 1.6), (12000, 200, 120, 32, 0.15, 1.2), (12000, 320, 256, 33, 0.006, 2.2)]
+for (P, W, H, seed, sm, ss) in CASES:
+    g = scene.make_gaussians(P, seed=seed, scale_median=sm, scale_sigma=ss)
     cam = scene.ring_cameras(5, W, H)[2]
     bg = torch.zeros(3)
     dL = (scene.upstream_grad(W, H, 5) * 50).to(dev)
