@@ -162,7 +162,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="config2", choices=list(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the views of a step are pipelined on (ours)")
+    ap.add_argument("--chunks", type=int, default=1, help="batched path: split the step's views into this many "
+                    "chunks, each on its own stream")
+    ap.add_argument("--streams", type=int, default=0,
+                    help="0 (default): all views of a step per launch (batched path); N>0: views one by one, "
+                         "round-robin on N CUDA streams")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
 
@@ -195,6 +199,7 @@ def main():
     targets_host = [targets_all[i].pin_memory() for i in mine]
     cams_dev = [scene.camera_to(c, dev) for c in cams_host]
     targets_dev = [t.to(dev) for t in targets_host]
+    targets_stacked = torch.stack(targets_dev)  # resident [V,3,H,W] block (what the batched path consumes as is)
     bg = torch.zeros(3, device=dev)
 
     if args.impl == "ours":
@@ -205,10 +210,14 @@ def main():
         rasterize, module = make_reference_rasterize(), dgr
     lib = L.load()
 
+    batched = args.impl == "ours" and args.streams == 0
+
     def step(host):
-        return fit.fit_step(model, cams_host if host else cams_dev, targets_host if host else targets_dev, bg,
+        tg = targets_host if host else (targets_stacked if batched else targets_dev)
+        return fit.fit_step(model, cams_host if host else cams_dev, tg, bg,
                             global_batch=V * n_gpus, rasterize=rasterize, settings_module=module, host_inputs=host,
-                            num_streams=args.streams if args.impl == "ours" else 1)
+                            num_streams=max(args.streams, 1) if args.impl == "ours" else 1, batched=batched,
+                            num_chunks=args.chunks)
 
     def barrier():
         if world > 1 and args.impl == "ours":
@@ -278,16 +287,20 @@ def main():
             pass
         peak, which = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
         T = ((W + 15) // 16) * ((H + 15) // 16)
-        abytes = algorithmic_bytes(dominant, P, stats["P_visible"], stats["R"], W * H, T)
+        # SURVEY.md §8d per-view figure x the views one launch of the stage processes
+        units = V if dominant == "geom_bwd" else (-(-V // args.chunks) if batched else 1)
+        abytes = units * algorithmic_bytes(dominant, P, stats["P_visible"], stats["R"], W * H, T)
         achieved = abytes / (avg_ms * 1e-3) / 1e9
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(KERNEL_OF_STAGE[dominant])
+            traffic = traffic * units if traffic is not None else None  # the capture is of ONE view
         except Exception:
             pass
         roof = {"bound": "hbm", "kernel": KERNEL_OF_STAGE[dominant], "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": which,
                 "avg_launch_ms": avg_ms, "launches_timed": int(cnt[i]), "algorithmic_bytes_per_launch": abytes,
+                "views_per_launch": units,
                 "note": "blend kernels are issue/atomic bound, not HBM bound (SURVEY.md §8d); see DESIGN.md"}
 
     # ---- timed region 2: K steps end to end (pinned host inputs copied inside, loss read back)
@@ -334,7 +347,8 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.config}: {cfg['desc']}", "gaussians": P, "resolution": [W, H],
                    "views_per_step_per_gpu": V, "global_batch": V * n_gpus, "sh_degree": 3, "parallelism": f"dp{n_gpus} (views)",
-                   "streams_per_gpu": args.streams if args.impl == "ours" else 1,
+                   "views_per_launch": -(-V // args.chunks) if batched else 1, "chunks": args.chunks if batched else None,
+                   "streams_per_gpu": max(args.streams, 1) if args.impl == "ours" else 1,
                    "l2": "per-view working set (inputs 236 MB + scratch) exceeds the 126 MB L2; no explicit flush",
                    "scene": "randgauss-v1", **stats},
         "clocks": clocks,

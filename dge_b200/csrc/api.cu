@@ -83,7 +83,7 @@ size_t carve_geom(char* base, int P, GeomState* st) {
   take(p, s.sort_val[1], n);
   take(p, s.offsets, n);
   take(p, s.block_sums, (n + 255) / 256 + 1);
-  take(p, s.counters, 64);
+  take(p, s.counters, 256);  // [0] num_rendered; view 0 of a batch: [64 .. 64+V] = seg_off
   s.sort_ws_bytes = sort_workspace_bytes((uint32_t)P);
   take(p, s.sort_ws, s.sort_ws_bytes / sizeof(uint32_t));
   if (st) *st = s;
@@ -101,6 +101,21 @@ size_t carve_binning(char* base, int R, int width, int height, BinState* st) {
   take(p, s.key_alt, n);
   take(p, s.val_alt, n);
   s.sort_ws_bytes = sort_workspace_bytes((uint32_t)n);
+  take(p, s.sort_ws, s.sort_ws_bytes / sizeof(uint32_t));
+  if (st) *st = s;
+  return (size_t)(p - base) + 256;
+}
+
+// Instance lists of all V views of a fit step, back to back (view v at seg_off[v]).
+size_t carve_binning_batched(char* base, uint32_t R_total, int V, BinState* st) {
+  BinState s;
+  char* p = base;
+  const size_t n = (size_t)(R_total > 0 ? R_total : 1);
+  take(p, s.point_list, n);
+  take(p, s.tile_ids, n);
+  take(p, s.key_alt, n);
+  take(p, s.val_alt, n);
+  s.sort_ws_bytes = sort_workspace_bytes_segmented((uint32_t)n, V);
   take(p, s.sort_ws, s.sort_ws_bytes / sizeof(uint32_t));
   if (st) *st = s;
   return (size_t)(p - base) + 256;
@@ -128,7 +143,7 @@ static thread_local HostSlot g_slot;
 
 static cudaError_t ensure_slot() {
   if (g_slot.pinned) return cudaSuccess;
-  cudaError_t e = cudaHostAlloc((void**)&g_slot.pinned, 64, cudaHostAllocDefault);
+  cudaError_t e = cudaHostAlloc((void**)&g_slot.pinned, 1024, cudaHostAllocDefault);
   if (e != cudaSuccess) return e;
   return cudaEventCreateWithFlags(&g_slot.ev, cudaEventDisableTiming);
 }
@@ -195,7 +210,7 @@ using namespace dge;
 extern "C" {
 
 const char* dge_last_error(void) { return g_err; }
-int dge_abi_version(void) { return 5; }
+int dge_abi_version(void) { return 6; }
 unsigned long long dge_launch_count(void) { return g_kernel_launches; }
 
 void dge_profile_enable(unsigned stage_mask) { g_profile_mask = stage_mask; }
@@ -279,6 +294,98 @@ int dge_fit_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge
   STAGE(ST_RENDER_FWD, "render forward",
         launch_render_forward(vp, g, b, img, background, out_color, out_depth, stream));
   return R;
+}
+
+// ---- all V views of a step, one launch per stage ----
+#define DGE_MAX_BATCH_VIEWS 64
+static uint32_t* batch_seg_off(const GeomState& g0) { return g0.counters + 64; }
+// per-view blobs of a batch: the single-view layout repeated at a 256-byte-aligned stride
+static size_t batch_stride(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+
+size_t dge_fit_binning_bytes(int R_total, int V) {
+  return carve_binning_batched(nullptr, (uint32_t)(R_total > 0 ? R_total : 0), V, nullptr);
+}
+
+int dge_fit_views_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge_alloc_fn imageBuffer,
+                          void* alloc_ctx, int P, int D, int M, int V, const float* background, int width,
+                          int height, const float* means3D, const float* shs, const float* opacities,
+                          const float* scales, float scale_modifier, const float* rotations,
+                          const float* cams, float* out_color, float* out_depth, int* radii_max, float* acc,
+                          size_t acc_stride_floats, int* num_rendered_host, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool debug = false;
+  if (P == 0 || width <= 0 || height <= 0) return fail_msg("empty problem");
+  if (V < 1 || V > DGE_MAX_BATCH_VIEWS) return fail_msg("a batch holds 1..64 views");
+  if (M != 16) return fail_msg("the batched fit path needs SH degree-3 storage (M == 16)");
+  // tan_fov / focal are per view and filled in by the batched preprocess from the camera records
+  const ViewParams vp = make_view(P, D, M, width, height, nullptr, nullptr, nullptr, 1.f, 1.f, scale_modifier);
+  if (vp.grid_x > 65535 || vp.grid_y > 65535) return fail_msg("image too large (tile grid > 65535)");
+  CK("pinned slot", ensure_slot());
+  const size_t gstride = batch_stride(carve_geom(nullptr, P, nullptr));
+  const size_t istride = batch_stride(carve_image(nullptr, width, height, nullptr));
+  char* gp = geometryBuffer(alloc_ctx, gstride * V);
+  char* ip = imageBuffer(alloc_ctx, istride * V);
+  if (!gp || !ip) return fail_msg("scratch allocator returned NULL");
+  GeomState g0;
+  ImgState img0;
+  BinState b;
+  carve_geom(gp, P, &g0);
+  carve_image(ip, width, height, &img0);
+  ViewBatch vb;
+  vb.V = V;
+  vb.geom_stride = gstride;
+  vb.img_stride = istride;
+  vb.seg_off = batch_seg_off(g0);
+  vb.cams = cams;
+  STAGE(ST_PREPROCESS, "preprocess (batched)",
+        launch_preprocess_batched(vp, vb, means3D, scales, rotations, opacities, shs, g0, acc, acc_stride_floats,
+                                  radii_max, stream));
+  CK("segment offsets", launch_seg_offsets(vb, g0, batch_seg_off(g0), stream));
+  CK("num_rendered copy", cudaMemcpyAsync(g_slot.pinned, batch_seg_off(g0), sizeof(uint32_t) * (V + 1),
+                                          cudaMemcpyDeviceToHost, stream));
+  CK("event record", cudaEventRecord(g_slot.ev, stream));
+  STAGE(ST_DEPTH_SORT, "depth sort (batched)", launch_depth_sort_batched(P, vb, g0, stream));
+  CK("num_rendered wait", cudaEventSynchronize(g_slot.ev));
+  const uint32_t R_total = g_slot.pinned[V];
+  uint32_t R_max = 0;
+  for (int v = 0; v < V; v++) {
+    const uint32_t r = g_slot.pinned[v + 1] - g_slot.pinned[v];
+    if (r > R_max) R_max = r;
+    if (num_rendered_host) num_rendered_host[v] = (int)r;
+  }
+  if (R_total >= (1u << 30)) return fail_msg("the step's views exceed 2^30 instances: use smaller batches");
+  char* bp = binningBuffer(alloc_ctx, carve_binning_batched(nullptr, R_total, V, nullptr));
+  if (!bp) return fail_msg("scratch allocator returned NULL");
+  carve_binning_batched(bp, R_total, V, &b);
+  STAGE(ST_BINNING, "binning (batched)", launch_binning_batched(vp, vb, R_total, R_max, g0, b, img0, stream));
+  STAGE(ST_RENDER_FWD, "render forward (batched)",
+        launch_render_forward_batched(vp, vb, g0, b, img0, background, out_color, out_depth, stream));
+  return (int)R_total;
+}
+
+int dge_fit_views_backward_blend(int P, int V, int R_total, const float* background, int background_is_black,
+                                 int width, int height, char* geom_buffer, char* binning_buffer,
+                                 char* image_buffer, const float* dL_dpix, float* acc, size_t acc_stride_floats,
+                                 void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool debug = false;
+  if (P == 0 || R_total == 0) return 0;
+  if (V < 1 || V > DGE_MAX_BATCH_VIEWS) return fail_msg("a batch holds 1..64 views");
+  const ViewParams vp = make_view(P, 0, 0, width, height, nullptr, nullptr, nullptr, 1.f, 1.f, 1.f);
+  GeomState g0;
+  BinState b;
+  ImgState img0;
+  ViewBatch vb;
+  vb.V = V;
+  vb.geom_stride = batch_stride(carve_geom(geom_buffer, P, &g0));
+  vb.img_stride = batch_stride(carve_image(image_buffer, width, height, &img0));
+  carve_binning_batched(binning_buffer, (uint32_t)R_total, V, &b);
+  vb.seg_off = batch_seg_off(g0);
+  vb.cams = nullptr;
+  STAGE(ST_RENDER_BWD, "render backward (batched)",
+        launch_render_backward_batched(vp, vb, g0, b, img0, background, dL_dpix, acc, acc_stride_floats,
+                                       background_is_black != 0, stream));
+  return 0;
 }
 
 int dge_fit_backward_blend(int P, int R, const float* background, int background_is_black, int width,

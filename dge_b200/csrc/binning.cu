@@ -23,7 +23,13 @@ __device__ __forceinline__ uint32_t rect_count(ushort4 r) {
 // block sums of tiles_touched taken in depth order
 __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(
     int P, const uint32_t* __restrict__ order, const ushort4* __restrict__ rect,
-    uint32_t* __restrict__ block_sums) {
+    uint32_t* __restrict__ block_sums, size_t view_stride) {
+  if (blockIdx.y) {  // view of a batch (fit step): same arrays, view_stride bytes per view further on
+    const size_t sh = blockIdx.y * view_stride;
+    order = shift_ptr(order, sh);
+    rect = shift_ptr(rect, sh);
+    block_sums = shift_ptr(block_sums, sh);
+  }
   const int r = blockIdx.x * SCAN_THREADS + threadIdx.x;
   uint32_t c = 0;
   if (r < P) c = rect_count(rect[order[r]]);
@@ -40,7 +46,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(
 }
 
 // in-place exclusive scan of the block sums (single CTA, 1024 threads, carried chunks)
-__global__ void __launch_bounds__(1024) scan_block_sums_kernel(int n, uint32_t* __restrict__ sums) {
+__global__ void __launch_bounds__(1024) scan_block_sums_kernel(int n, uint32_t* __restrict__ sums,
+                                                              size_t view_stride) {
+  sums = shift_ptr(sums, blockIdx.x * view_stride);  // one CTA per view
   __shared__ uint32_t ws[32];
   __shared__ uint32_t carry_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -84,7 +92,17 @@ __global__ void __launch_bounds__(1024) scan_block_sums_kernel(int n, uint32_t* 
 __global__ void __launch_bounds__(SCAN_THREADS) expand_kernel(
     int P, int grid_x, const uint32_t* __restrict__ order, const ushort4* __restrict__ rect,
     const uint32_t* __restrict__ block_prefix, uint32_t* __restrict__ offsets,
-    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, size_t view_stride,
+    const uint32_t* __restrict__ seg_off) {
+  if (seg_off) {  // view of a batch: geometry arrays at a uniform stride, instances at seg_off[view]
+    const size_t sh = blockIdx.y * view_stride;
+    order = shift_ptr(order, sh);
+    rect = shift_ptr(rect, sh);
+    block_prefix = shift_ptr(block_prefix, sh);
+    offsets = shift_ptr(offsets, sh);
+    keys_out += seg_off[blockIdx.y];
+    vals_out += seg_off[blockIdx.y];
+  }
   __shared__ uint32_t ws[SCAN_THREADS / 32];
   __shared__ uint32_t s_off[SCAN_THREADS / 32][33];
   __shared__ uint32_t s_gid[SCAN_THREADS / 32][32];
@@ -137,7 +155,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) expand_kernel(
 // identifyTileRanges (DGR/cuda_rasterizer/rasterizer_impl.cu:105-125) on 32-bit tile ids
 __global__ void __launch_bounds__(256) tile_ranges_kernel(uint32_t R,
                                                          const uint32_t* __restrict__ tile_ids,
-                                                         uint2* __restrict__ ranges) {
+                                                         uint2* __restrict__ ranges, size_t img_stride,
+                                                         const uint32_t* __restrict__ seg_off) {
+  if (seg_off) {  // view of a batch; ranges stay relative to the view's own segment
+    const uint32_t o = seg_off[blockIdx.y];
+    R = seg_off[blockIdx.y + 1] - o;
+    tile_ids += o;
+    ranges = shift_ptr(ranges, blockIdx.y * img_stride);
+  }
   const uint32_t i = blockIdx.x * 256u + threadIdx.x;
   if (i >= R) return;
   const uint32_t cur = tile_ids[i];
@@ -182,21 +207,78 @@ cudaError_t launch_binning(const ViewParams& vp, int R, GeomState& g, BinState& 
   const int P = vp.P;
   const int blocks = (P + SCAN_THREADS - 1) / SCAN_THREADS;
   const uint32_t* order = g.sort_val[0];
-  scan_reduce_kernel<<<blocks, SCAN_THREADS, 0, stream>>>(P, order, g.rect, g.block_sums);
-  scan_block_sums_kernel<<<1, 1024, 0, stream>>>(blocks, g.block_sums);
+  scan_reduce_kernel<<<blocks, SCAN_THREADS, 0, stream>>>(P, order, g.rect, g.block_sums, 0);
+  scan_block_sums_kernel<<<1, 1024, 0, stream>>>(blocks, g.block_sums, 0);
   const int bits = tile_bits(T);
   const int passes = sort_num_passes(bits);
   uint32_t* keys[2] = {b.tile_ids, b.key_alt};
   uint32_t* vals[2] = {b.point_list, b.val_alt};
   expand_kernel<<<blocks, SCAN_THREADS, 0, stream>>>(P, vp.grid_x, order, g.rect, g.block_sums,
-                                                     g.offsets, keys[passes & 1], vals[passes & 1]);
+                                                     g.offsets, keys[passes & 1], vals[passes & 1], 0,
+                                                     nullptr);
   DGE_LAUNCHED(3);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (passes > 0) {
     e = sort_pairs(keys, vals, (uint32_t)R, bits, /*iota=*/false, b.sort_ws, b.sort_ws_bytes, stream);
     if (e != cudaSuccess) return e;
   }
-  tile_ranges_kernel<<<(R + 255) / 256, 256, 0, stream>>>((uint32_t)R, b.tile_ids, img.ranges);
+  tile_ranges_kernel<<<(R + 255) / 256, 256, 0, stream>>>((uint32_t)R, b.tile_ids, img.ranges, 0, nullptr);
+  DGE_LAUNCHED(1);
+  return cudaGetLastError();
+}
+
+// ---- fit step: the same stages for all V views of a step, one launch each (grid.y = view) ----
+// seg_off[v] = sum of num_rendered of the views before v (num_rendered of view v = counters[0] of its
+// geometry blob, written by the batched preprocess); lives in view 0's counters[64 .. 64+V].
+__global__ void seg_offsets_kernel(int V, const uint32_t* __restrict__ counters0, size_t geom_stride,
+                                   uint32_t* __restrict__ seg_off) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  uint32_t run = 0;
+  for (int v = 0; v < V; v++) {
+    seg_off[v] = run;
+    run += *shift_ptr(counters0, v * geom_stride);
+  }
+  seg_off[V] = run;
+}
+
+cudaError_t launch_seg_offsets(const ViewBatch& vb, const GeomState& g0, uint32_t* seg_off, cudaStream_t stream) {
+  seg_offsets_kernel<<<1, 32, 0, stream>>>(vb.V, g0.counters, vb.geom_stride, seg_off);
+  DGE_LAUNCHED(1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_depth_sort_batched(int P, const ViewBatch& vb, GeomState& g0, cudaStream_t stream) {
+  return sort_pairs_segmented(g0.sort_key, g0.sort_val, (uint32_t)P, 32, /*iota=*/true, g0.sort_ws,
+                              g0.sort_ws_bytes, vb.V, vb.geom_stride, nullptr, 0, stream);
+}
+
+cudaError_t launch_binning_batched(const ViewParams& vp, const ViewBatch& vb, uint32_t R_total, uint32_t R_max,
+                                   GeomState& g0, BinState& b, ImgState& img0, cudaStream_t stream) {
+  const int T = vp.grid_x * vp.grid_y;
+  cudaError_t e = cudaMemset2DAsync(img0.ranges, vb.img_stride, 0, sizeof(uint2) * (size_t)T, (size_t)vb.V, stream);
+  if (e != cudaSuccess || R_total == 0) return e;
+  const int P = vp.P;
+  const int blocks = (P + SCAN_THREADS - 1) / SCAN_THREADS;
+  const uint32_t* order = g0.sort_val[0];
+  scan_reduce_kernel<<<dim3(blocks, vb.V), SCAN_THREADS, 0, stream>>>(P, order, g0.rect, g0.block_sums,
+                                                                      vb.geom_stride);
+  scan_block_sums_kernel<<<vb.V, 1024, 0, stream>>>(blocks, g0.block_sums, vb.geom_stride);
+  const int bits = tile_bits(T);
+  const int passes = sort_num_passes(bits);
+  uint32_t* keys[2] = {b.tile_ids, b.key_alt};
+  uint32_t* vals[2] = {b.point_list, b.val_alt};
+  expand_kernel<<<dim3(blocks, vb.V), SCAN_THREADS, 0, stream>>>(P, vp.grid_x, order, g0.rect, g0.block_sums,
+                                                                 g0.offsets, keys[passes & 1], vals[passes & 1],
+                                                                 vb.geom_stride, vb.seg_off);
+  DGE_LAUNCHED(3);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (passes > 0) {
+    e = sort_pairs_segmented(keys, vals, R_max, bits, /*iota=*/false, b.sort_ws, b.sort_ws_bytes, vb.V, 0,
+                             vb.seg_off, R_total, stream);
+    if (e != cudaSuccess) return e;
+  }
+  tile_ranges_kernel<<<dim3((R_max + 255) / 256, vb.V), 256, 0, stream>>>(R_max, b.tile_ids, img0.ranges,
+                                                                          vb.img_stride, vb.seg_off);
   DGE_LAUNCHED(1);
   return cudaGetLastError();
 }

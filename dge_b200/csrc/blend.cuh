@@ -29,6 +29,15 @@ constexpr int BL_BATCH = 128;
 #define BADD(a, b) __fadd_rn((a), (b))
 #define BFMA(a, b, c) __fmaf_rn((a), (b), (c))
 
+// Fit-step batch: blockIdx.z = view; per-view geometry / image arrays at uniform byte strides, the
+// view's instance list at point_list + seg_off[view], its acc rows acc_stride floats apart.
+// seg_off == nullptr <=> a single view (the per-view API).
+struct BlendBatch {
+  size_t geom_stride, img_stride;
+  const uint32_t* seg_off;
+  size_t acc_stride;
+};
+
 struct BlendSmem {
   float4 a[BL_BATCH];    // x, y, conic.x, conic.y
   float4 b[BL_BATCH];    // conic.z, power threshold, opacity, gid (bits)

@@ -47,6 +47,46 @@ struct ImgState {
   uint2* ranges;          // [T]
 };
 
+// The same arrays `bytes` further on: view v of a batch whose per-view blobs are laid out with a
+// uniform stride (fit step, all views of a step in one launch).
+template <typename T>
+__host__ __device__ __forceinline__ T* shift_ptr(T* p, size_t bytes) {
+  return (T*)((const char*)p + bytes);
+}
+__host__ __device__ __forceinline__ GeomState shift_geom(GeomState g, size_t bytes) {
+  g.means2D = shift_ptr(g.means2D, bytes);
+  g.conic_opacity = shift_ptr(g.conic_opacity, bytes);
+  g.rgb_depth = shift_ptr(g.rgb_depth, bytes);
+  g.rect = shift_ptr(g.rect, bytes);
+  g.clamped = shift_ptr(g.clamped, bytes);
+  g.sort_key[0] = shift_ptr(g.sort_key[0], bytes);
+  g.sort_key[1] = shift_ptr(g.sort_key[1], bytes);
+  g.sort_val[0] = shift_ptr(g.sort_val[0], bytes);
+  g.sort_val[1] = shift_ptr(g.sort_val[1], bytes);
+  g.offsets = shift_ptr(g.offsets, bytes);
+  g.block_sums = shift_ptr(g.block_sums, bytes);
+  g.counters = shift_ptr(g.counters, bytes);
+  g.sort_ws = shift_ptr(g.sort_ws, bytes);
+  return g;
+}
+__host__ __device__ __forceinline__ ImgState shift_img(ImgState s, size_t bytes) {
+  s.final_T = shift_ptr(s.final_T, bytes);
+  s.n_contrib = shift_ptr(s.n_contrib, bytes);
+  s.ranges = shift_ptr(s.ranges, bytes);
+  return s;
+}
+
+// Views of one fit step processed by single launches (grid dimension = view). Per-view geometry and
+// image blobs have uniform strides; the instance lists of the views lie back to back in ONE binning
+// arena, view v at element offset seg_off[v] (seg_off[V] = total number of instances).
+struct ViewBatch {
+  int V;
+  size_t geom_stride;       // bytes between the geometry blobs of consecutive views
+  size_t img_stride;        // bytes between the image blobs
+  const uint32_t* seg_off;  // device, [V+1]
+  const float* cams;        // device, V records of 40 floats (include/dge_b200.h "fit step")
+};
+
 size_t carve_geom(char* base, int P, GeomState* st);
 size_t carve_binning(char* base, int R, int width, int height, BinState* st);
 size_t carve_image(char* base, int width, int height, ImgState* st);
@@ -60,6 +100,17 @@ size_t sort_workspace_bytes(uint32_t n);
 cudaError_t sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int num_bits,
                        bool iota_values, uint32_t* ws, size_t ws_bytes, cudaStream_t stream);
 int sort_num_passes(int num_bits);
+// The same sort over `segs` independent segments in ONE launch per pass (grid.y = segment).
+//  * seg_off == nullptr: uniform segments of n items; segment s of every array (keys, vals, ws) lies
+//    s * seg_stride_bytes after segment 0 (the per-view geometry blobs of a fit step);
+//  * seg_off != nullptr: segment s is elements [seg_off[s], seg_off[s+1]) of the arrays (the views'
+//    instance lists inside one binning arena); n = the largest segment, n_total = seg_off[segs]; the
+//    workspace is shared: sort_workspace_bytes_segmented(n_total, segs).
+size_t sort_workspace_bytes_segmented(uint32_t n_total, int segs);
+cudaError_t sort_pairs_segmented(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int num_bits,
+                                 bool iota_values, uint32_t* ws, size_t ws_bytes, int segs,
+                                 size_t seg_stride_bytes, const uint32_t* seg_off, uint32_t n_total,
+                                 cudaStream_t stream);
 
 // ----------------------------------------------------------------- stages ---
 struct ViewParams {
@@ -110,6 +161,23 @@ cudaError_t launch_geom_backward(const ViewParams& vp, const float* means3D, con
                                  float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
                                  float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
                                  float* dL_dscale, float* dL_drot, bool accumulate, cudaStream_t stream);
+// fit step: all V views of a step per launch (preprocess.cu, binning.cu, render_fwd.cu, render_bwd.cu)
+cudaError_t launch_preprocess_batched(const ViewParams& vp, const ViewBatch& vb, const float* means3D,
+                                      const float* scales, const float* rotations, const float* opacities,
+                                      const float* shs, GeomState& g0, float* acc, size_t acc_stride_floats,
+                                      int* radii_max, cudaStream_t stream);
+cudaError_t launch_seg_offsets(const ViewBatch& vb, const GeomState& g0, uint32_t* seg_off, cudaStream_t stream);
+cudaError_t launch_depth_sort_batched(int P, const ViewBatch& vb, GeomState& g0, cudaStream_t stream);
+cudaError_t launch_binning_batched(const ViewParams& vp, const ViewBatch& vb, uint32_t R_total, uint32_t R_max,
+                                   GeomState& g0, BinState& b, ImgState& img0, cudaStream_t stream);
+cudaError_t launch_render_forward_batched(const ViewParams& vp, const ViewBatch& vb, const GeomState& g0,
+                                          const BinState& b, ImgState& img0, const float* background,
+                                          float* out_color, float* out_depth, cudaStream_t stream);
+cudaError_t launch_render_backward_batched(const ViewParams& vp, const ViewBatch& vb, const GeomState& g0,
+                                           const BinState& b, const ImgState& img0, const float* background,
+                                           const float* dL_dpix, float* acc, size_t acc_stride_floats,
+                                           bool black_background, cudaStream_t stream);
+size_t carve_binning_batched(char* base, uint32_t R_total, int V, BinState* st);
 cudaError_t launch_l1_loss_grad(const float* image, const float* target, size_t n, float scale,
                                 float* grad, float* loss_accum, cudaStream_t stream);
 cudaError_t launch_apply_weights_render(const ViewParams& vp, const GeomState& g, const BinState& b,

@@ -112,6 +112,109 @@ __device__ __forceinline__ void sh_to_rgb_ref(int deg, float dx, float dy, float
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg((const float4*)p); }
 
+// What one view's projection of one Gaussian produces (radius == 0 <=> culled).
+struct PreOut {
+  int radius;
+  uint32_t tiles, key;
+  uint8_t clamp_bits;
+  ushort4 rect;
+  float4 m2d, co, rgbd;
+};
+
+// The per-Gaussian forward of ONE view (forward.cu:186-255), shared by the per-view kernel and the
+// batched one. cov3(c) fills the world-space covariance, color(rgb) the colour BEFORE clamping
+// flags are taken (returns the clamp mask), opacity() loads the opacity; all three are only
+// called for Gaussians that survive the culls, as in the reference.
+template <typename COV3, typename COLOR, typename OPAC>
+__device__ __forceinline__ PreOut preprocess_view(const ViewParams& vp, const float* V, const float* Pm,
+                                                  float px, float py, float pz, bool prefiltered,
+                                                  COV3 cov3f, COLOR colorf, OPAC opacf) {
+  PreOut o;
+  o.radius = 0;
+  o.tiles = 0;
+  o.key = 0xFFFFFFFFu;
+  o.clamp_bits = 0;
+  o.rect = make_ushort4(0, 0, 0, 0);
+  // in_frustum (auxiliary.h:139-164): near-plane test only
+  const float depth = xform_row(V, 2, px, py, pz);
+  if (depth > 0.2f) {
+    const float hw = ADD(xform_row(Pm, 3, px, py, pz), 0.0000001f);
+    const float p_w = __frcp_rn(hw);
+    const float projx = MUL(xform_row(Pm, 0, px, py, pz), p_w);
+    const float projy = MUL(xform_row(Pm, 1, px, py, pz), p_w);
+    float cov3[6];
+    cov3f(cov3);
+    const float tx = xform_row(V, 0, px, py, pz), ty = xform_row(V, 1, px, py, pz);
+    const float3 cov = cov2d_ref(tx, ty, depth, vp, V, cov3);
+    const float det = FMA(cov.x, cov.z, -MUL(cov.y, cov.y));
+    if (det != 0.0f) {
+      const float inv = __frcp_rn(det);
+      const float mid = MUL(ADD(cov.x, cov.z), 0.5f);
+      const float s = __fsqrt_rn(fmaxf(FMA(mid, mid, -det), 0.1f));
+      const float lam = fmaxf(ADD(mid, s), ADD(mid, -s));
+      const int rad = (int)ceilf(MUL(__fsqrt_rn(lam), 3.0f));
+      // ndc2Pix in FP64 (auxiliary.h:41-44): ((v + 1.0) * S - 1.0) * 0.5 with one DFMA
+      const float pix_x =
+          (float)__dmul_rn(__fma_rn(__dadd_rn((double)projx, 1.0), (double)vp.W, -1.0), 0.5);
+      const float pix_y =
+          (float)__dmul_rn(__fma_rn(__dadd_rn((double)projy, 1.0), (double)vp.H, -1.0), 0.5);
+      int x0, y0, x1, y1;
+      tile_rect(pix_x, pix_y, rad, vp.grid_x, vp.grid_y, x0, y0, x1, y1);
+      const uint32_t cnt = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
+      if (cnt != 0) {
+        float rgb[3];
+        o.clamp_bits = colorf(rgb);
+        const float con_x = MUL(cov.z, inv), con_y = MUL(cov.y, -inv), con_z = MUL(cov.x, inv);
+        const float opac = opacf();
+        // Conservative screen-space box of {alpha >= 1/255}: power >= -ln(255 o) bounds the
+        // quadratic form, whose extreme |dx|, |dy| are sqrt(2t cz/det), sqrt(2t cx/det). Used by
+        // the blend kernels only to SKIP work; every skipped pair fails the exact test too.
+        float hx = __int_as_float(0xff800000), hy = hx;  // -inf: never visible
+        if (opac > 0.0f) {
+          const float k2 = 2.0f * (logf(255.0f * opac) + 0.02f);
+          const float dc = con_x * con_z - con_y * con_y;
+          if (k2 > 0.0f) {
+            if (dc > 0.0f) {
+              hx = sqrtf(k2 * con_z / dc) * 1.0001f + 0.01f;
+              hy = sqrtf(k2 * con_x / dc) * 1.0001f + 0.01f;
+            } else {
+              hx = hy = __int_as_float(0x7f800000);
+            }
+          }
+        }
+        o.m2d = make_float4(pix_x, pix_y, hx, hy);
+        o.co = make_float4(con_x, con_y, con_z, opac);
+        o.rgbd = make_float4(rgb[0], rgb[1], rgb[2], depth);
+        o.radius = rad;
+        o.rect = make_ushort4(x0, y0, x1, y1);
+        o.key = __float_as_uint(depth);
+        o.tiles = cnt;
+      }
+    }
+  } else if (prefiltered) {
+    // auxiliary.h:156-160: the reference traps here
+    printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+    __trap();
+  }
+  return o;
+}
+
+// SH colour of one Gaussian for one camera position + clamp mask (forward.cu:20-71, :241-247)
+template <typename SHF>
+__device__ __forceinline__ uint8_t sh_color(int D, float px, float py, float pz, float cx, float cy, float cz,
+                                            SHF sh, float rgb[3]) {
+  const float ddx = ADD(px, -cx), ddy = ADD(py, -cy), ddz = ADD(pz, -cz);
+  sh_to_rgb_ref(D, ddx, ddy, ddz, sh, rgb);
+  uint8_t cl = 0;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    rgb[c] = ADD(rgb[c], 0.5f);
+    if (rgb[c] < 0.0f) cl |= (1u << c);
+    rgb[c] = fmaxf(rgb[c], 0.0f);
+  }
+  return cl;
+}
+
 // One thread per Gaussian, 256 per CTA. Loads: xyz/scale 3 coalesced scalar streams,
 // quaternion one float4, SH 12 float4 (M==16) issued together only by surviving lanes.
 __global__ void __launch_bounds__(256) preprocess_kernel(
@@ -129,71 +232,37 @@ __global__ void __launch_bounds__(256) preprocess_kernel(
       V[i] = __ldg(vp.view + i);
       Pm[i] = __ldg(vp.proj + i);
     }
-    int radius = 0;
-    uint8_t clamp_bits = 0;
-    ushort4 rect = make_ushort4(0, 0, 0, 0);
-    uint32_t key = 0xFFFFFFFFu;
     const float px = __ldg(means3D + 3 * idx), py = __ldg(means3D + 3 * idx + 1),
                 pz = __ldg(means3D + 3 * idx + 2);
-    // in_frustum (auxiliary.h:139-164): near-plane test only
-    const float depth = xform_row(V, 2, px, py, pz);
-    if (depth > 0.2f) {
-      const float hw = ADD(xform_row(Pm, 3, px, py, pz), 0.0000001f);
-      const float p_w = __frcp_rn(hw);
-      const float projx = MUL(xform_row(Pm, 0, px, py, pz), p_w);
-      const float projy = MUL(xform_row(Pm, 1, px, py, pz), p_w);
-      float cov3[6];
-      if (cov3D_precomp != nullptr) {
+    const PreOut o = preprocess_view(
+        vp, V, Pm, px, py, pz, prefiltered,
+        [&](float* cov3) {
+          if (cov3D_precomp != nullptr) {
 #pragma unroll
-        for (int i = 0; i < 6; i++) cov3[i] = __ldg(cov3D_precomp + 6 * (size_t)idx + i);
-      } else {
-        const float4 q = ldg4(rotations + 4 * (size_t)idx);
-        cov3d_from_scale_rot(__ldg(scales + 3 * idx), __ldg(scales + 3 * idx + 1),
-                             __ldg(scales + 3 * idx + 2), vp.scale_modifier, q, cov3);
-      }
-      const float tx = xform_row(V, 0, px, py, pz), ty = xform_row(V, 1, px, py, pz);
-      const float3 cov = cov2d_ref(tx, ty, depth, vp, V, cov3);
-      const float det = FMA(cov.x, cov.z, -MUL(cov.y, cov.y));
-      if (det != 0.0f) {
-        const float inv = __frcp_rn(det);
-        const float mid = MUL(ADD(cov.x, cov.z), 0.5f);
-        const float s = __fsqrt_rn(fmaxf(FMA(mid, mid, -det), 0.1f));
-        const float lam = fmaxf(ADD(mid, s), ADD(mid, -s));
-        const int rad = (int)ceilf(MUL(__fsqrt_rn(lam), 3.0f));
-        // ndc2Pix in FP64 (auxiliary.h:41-44): ((v + 1.0) * S - 1.0) * 0.5 with one DFMA
-        const float pix_x =
-            (float)__dmul_rn(__fma_rn(__dadd_rn((double)projx, 1.0), (double)vp.W, -1.0), 0.5);
-        const float pix_y =
-            (float)__dmul_rn(__fma_rn(__dadd_rn((double)projy, 1.0), (double)vp.H, -1.0), 0.5);
-        int x0, y0, x1, y1;
-        tile_rect(pix_x, pix_y, rad, vp.grid_x, vp.grid_y, x0, y0, x1, y1);
-        const uint32_t cnt = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
-        if (cnt != 0) {
-          float rgb[3];
+            for (int i = 0; i < 6; i++) cov3[i] = __ldg(cov3D_precomp + 6 * (size_t)idx + i);
+          } else {
+            const float4 q = ldg4(rotations + 4 * (size_t)idx);
+            cov3d_from_scale_rot(__ldg(scales + 3 * idx), __ldg(scales + 3 * idx + 1),
+                                 __ldg(scales + 3 * idx + 2), vp.scale_modifier, q, cov3);
+          }
+        },
+        [&](float* rgb) -> uint8_t {
           if (colors_mode == 0) {
-            const float ddx = ADD(px, -__ldg(vp.campos)), ddy = ADD(py, -__ldg(vp.campos + 1)),
-                        ddz = ADD(pz, -__ldg(vp.campos + 2));
+            const float cx = __ldg(vp.campos), cy = __ldg(vp.campos + 1), cz = __ldg(vp.campos + 2);
+            uint8_t cl;
             if (vp.M == 16) {
               float4 v[12];
               const float* base = shs + 48 * (size_t)idx;
 #pragma unroll
               for (int i = 0; i < 12; i++) v[i] = ldg4(base + 4 * i);
               const float* f = reinterpret_cast<const float*>(v);
-              sh_to_rgb_ref(vp.D, ddx, ddy, ddz, [&](int k, int c) { return f[3 * k + c]; }, rgb);
+              cl = sh_color(vp.D, px, py, pz, cx, cy, cz, [&](int k, int c) { return f[3 * k + c]; }, rgb);
             } else {
               const float* base = shs + 3 * (size_t)vp.M * idx;
-              sh_to_rgb_ref(vp.D, ddx, ddy, ddz,
-                            [&](int k, int c) { return __ldg(base + 3 * k + c); }, rgb);
-            }
-            uint8_t cl = 0;
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-              rgb[c] = ADD(rgb[c], 0.5f);
-              if (rgb[c] < 0.0f) cl |= (1u << c);
-              rgb[c] = fmaxf(rgb[c], 0.0f);
+              cl = sh_color(vp.D, px, py, pz, cx, cy, cz, [&](int k, int c) { return __ldg(base + 3 * k + c); }, rgb);
             }
             g.clamped[idx] = cl;
-            clamp_bits = cl;
+            return cl;
           } else if (colors_mode == 1) {
             // forward.cu:241-247 / rasterizer_impl.cu:274-275: precomputed colours are blended
             // as given; staged into the same record the blend kernels read.
@@ -202,46 +271,23 @@ __global__ void __launch_bounds__(256) preprocess_kernel(
           } else {
             rgb[0] = rgb[1] = rgb[2] = 0.0f;  // apply_weights blends no colour
           }
-          const float con_x = MUL(cov.z, inv), con_y = MUL(cov.y, -inv), con_z = MUL(cov.x, inv);
-          const float opac = __ldg(opacities + idx);
-          // Conservative screen-space box of {alpha >= 1/255}: power >= -ln(255 o) bounds the
-          // quadratic form, whose extreme |dx|, |dy| are sqrt(2t cz/det), sqrt(2t cx/det). Used by
-          // the blend kernels only to SKIP work; every skipped pair fails the exact test too.
-          float hx = __int_as_float(0xff800000), hy = hx;  // -inf: never visible
-          if (opac > 0.0f) {
-            const float k2 = 2.0f * (logf(255.0f * opac) + 0.02f);
-            const float dc = con_x * con_z - con_y * con_y;
-            if (k2 > 0.0f) {
-              if (dc > 0.0f) {
-                hx = sqrtf(k2 * con_z / dc) * 1.0001f + 0.01f;
-                hy = sqrtf(k2 * con_x / dc) * 1.0001f + 0.01f;
-              } else {
-                hx = hy = __int_as_float(0x7f800000);
-              }
-            }
-          }
-          g.means2D[idx] = make_float4(pix_x, pix_y, hx, hy);
-          g.conic_opacity[idx] = make_float4(con_x, con_y, con_z, opac);
-          g.rgb_depth[idx] = make_float4(rgb[0], rgb[1], rgb[2], depth);
-          radius = rad;
-          rect = make_ushort4(x0, y0, x1, y1);
-          key = __float_as_uint(depth);
-          tiles = cnt;
-        }
-      }
-    } else if (prefiltered) {
-      // auxiliary.h:156-160: the reference traps here
-      printf("Point is filtered although prefiltered is set. This shouldn't happen!");
-      __trap();
+          return 0;
+        },
+        [&]() { return __ldg(opacities + idx); });
+    if (o.radius > 0) {
+      g.means2D[idx] = o.m2d;
+      g.conic_opacity[idx] = o.co;
+      g.rgb_depth[idx] = o.rgbd;
     }
-    radii[idx] = radius;
-    g.rect[idx] = rect;
-    g.sort_key[0][idx] = key;
+    tiles = o.tiles;
+    radii[idx] = o.radius;
+    g.rect[idx] = o.rect;
+    g.sort_key[0][idx] = o.key;
     if (acc_init != nullptr) {
       // fit step: this view's row of blend-stage sums starts at zero and carries, in slot 11, what
       // the batched per-Gaussian backward needs to know about this view: bit 0 visible, bits 1-3
       // the SH clamp mask (instead of a separate memset and per-view radii / clamped arrays).
-      const uint32_t flags = radius > 0 ? (1u | ((uint32_t)clamp_bits << 1)) : 0u;
+      const uint32_t flags = o.radius > 0 ? (1u | ((uint32_t)o.clamp_bits << 1)) : 0u;
       acc_init[3 * (size_t)idx] = make_float4(0.f, 0.f, 0.f, 0.f);
       acc_init[3 * (size_t)idx + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
       acc_init[3 * (size_t)idx + 2] = make_float4(0.f, 0.f, 0.f, __uint_as_float(flags));
@@ -271,6 +317,102 @@ cudaError_t launch_preprocess(const ViewParams& vp, const float* means3D, const 
   preprocess_kernel<<<blocks, 256, 0, stream>>>(vp, means3D, scales, rotations, opacities, shs,
                                                 cov3D_precomp, colors_precomp, colors_mode, prefiltered,
                                                 radii, g, reinterpret_cast<float4*>(acc_init));
+  DGE_LAUNCHED(1);
+  return cudaGetLastError();
+}
+
+// ---- fit step: all V views of a step in ONE pass over the Gaussians -------------------------------
+// The 236 B of per-Gaussian inputs (192 B of them SH) and cov3D are view-independent: a thread loads
+// them once, then projects its Gaussian into every view of the step (cameras in shared memory) and
+// writes the per-view records: ~20x less input traffic than V per-view launches. Also produces the
+// running max of the radii over the views (max_radii2D statistics) instead of V radii arrays.
+constexpr int PRE_B_THREADS = 128;
+__global__ void __launch_bounds__(PRE_B_THREADS) preprocess_batched_kernel(
+    ViewParams vp, int V, const float* __restrict__ cams, const float* __restrict__ means3D,
+    const float* __restrict__ scales, const float* __restrict__ rotations,
+    const float* __restrict__ opacities, const float* __restrict__ shs, GeomState g0, size_t geom_stride,
+    float4* __restrict__ acc0, size_t acc_stride_floats, int* __restrict__ radii_max) {
+  extern __shared__ float s_cam[];  // V * 40 floats, then V warp-sum rows
+  uint32_t* s_tiles = reinterpret_cast<uint32_t*>(s_cam + V * 40);  // [V]
+  for (int k = threadIdx.x; k < V * 40; k += blockDim.x) s_cam[k] = cams[k];
+  for (int k = threadIdx.x; k < V; k += blockDim.x) s_tiles[k] = 0;
+  __syncthreads();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = idx < vp.P;
+  float px = 0.f, py = 0.f, pz = 0.f, opac = 0.f;
+  float cov3[6];
+  float4 v[12];
+  if (live) {
+    px = __ldg(means3D + 3 * idx);
+    py = __ldg(means3D + 3 * idx + 1);
+    pz = __ldg(means3D + 3 * idx + 2);
+    const float4 q = ldg4(rotations + 4 * (size_t)idx);
+    cov3d_from_scale_rot(__ldg(scales + 3 * idx), __ldg(scales + 3 * idx + 1), __ldg(scales + 3 * idx + 2),
+                         vp.scale_modifier, q, cov3);
+    opac = __ldg(opacities + idx);
+    const float* base = shs + 48 * (size_t)idx;
+#pragma unroll
+    for (int i = 0; i < 12; i++) v[i] = ldg4(base + 4 * i);
+  }
+  const float* f = reinterpret_cast<const float*>(v);
+  int rmax = 0;
+  for (int view = 0; view < V; view++) {
+    const float* cam = s_cam + view * 40;
+    uint32_t tiles = 0;
+    if (live) {
+      ViewParams w = vp;
+      w.tan_fovx = cam[35];
+      w.tan_fovy = cam[36];
+      // rasterizer_impl.cu:190-191 (host float arithmetic in the reference; same operations here)
+      w.focal_y = __fdiv_rn((float)vp.H, MUL(2.0f, w.tan_fovy));
+      w.focal_x = __fdiv_rn((float)vp.W, MUL(2.0f, w.tan_fovx));
+      const PreOut o = preprocess_view(
+          w, cam, cam + 16, px, py, pz, false,
+          [&](float* c) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) c[i] = cov3[i];
+          },
+          [&](float* rgb) -> uint8_t {
+            return sh_color(vp.D, px, py, pz, cam[32], cam[33], cam[34], [&](int k, int c) { return f[3 * k + c]; }, rgb);
+          },
+          [&]() { return opac; });
+      const size_t sh_ = (size_t)view * geom_stride;
+      if (o.radius > 0) {
+        shift_ptr(g0.means2D, sh_)[idx] = o.m2d;
+        shift_ptr(g0.conic_opacity, sh_)[idx] = o.co;
+        shift_ptr(g0.rgb_depth, sh_)[idx] = o.rgbd;
+      }
+      shift_ptr(g0.rect, sh_)[idx] = o.rect;
+      shift_ptr(g0.sort_key[0], sh_)[idx] = o.key;
+      const uint32_t flags = o.radius > 0 ? (1u | ((uint32_t)o.clamp_bits << 1)) : 0u;
+      float4* row = acc0 + (size_t)view * (acc_stride_floats / 4) + 3 * (size_t)idx;
+      row[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      row[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      row[2] = make_float4(0.f, 0.f, 0.f, __uint_as_float(flags));
+      rmax = max(rmax, o.radius);
+      tiles = o.tiles;
+    }
+    const uint32_t s = __reduce_add_sync(0xFFFFFFFFu, tiles);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(&s_tiles[view], s);
+  }
+  if (live) radii_max[idx] = rmax;
+  __syncthreads();
+  for (int k = threadIdx.x; k < V; k += blockDim.x)
+    if (s_tiles[k]) atomicAdd(shift_ptr(g0.counters, (size_t)k * geom_stride), s_tiles[k]);
+}
+
+cudaError_t launch_preprocess_batched(const ViewParams& vp, const ViewBatch& vb, const float* means3D,
+                                      const float* scales, const float* rotations, const float* opacities,
+                                      const float* shs, GeomState& g0, float* acc, size_t acc_stride_floats,
+                                      int* radii_max, cudaStream_t stream) {
+  if (vp.M != 16 || (acc_stride_floats & 3)) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemset2DAsync(g0.counters, vb.geom_stride, 0, 64 * sizeof(uint32_t), (size_t)vb.V, stream);
+  if (e != cudaSuccess) return e;
+  const int blocks = (vp.P + PRE_B_THREADS - 1) / PRE_B_THREADS;
+  const size_t smem = (size_t)vb.V * (40 * sizeof(float) + sizeof(uint32_t));
+  preprocess_batched_kernel<<<blocks, PRE_B_THREADS, smem, stream>>>(
+      vp, vb.V, vb.cams, means3D, scales, rotations, opacities, shs, g0, vb.geom_stride,
+      reinterpret_cast<float4*>(acc), acc_stride_floats, radii_max);
   DGE_LAUNCHED(1);
   return cudaGetLastError();
 }

@@ -28,8 +28,20 @@ __global__ void __launch_bounds__(BL_THREADS, 9) render_backward_kernel(
     const float* __restrict__ background, const float4* __restrict__ means2D,
     const float4* __restrict__ conic_opacity, const float4* __restrict__ rgb_depth,
     const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
-    const float* __restrict__ dL_dpixels, float* __restrict__ acc) {
+    const float* __restrict__ dL_dpixels, float* __restrict__ acc, BlendBatch bb) {
   __shared__ BlendSmem s;
+  if (bb.seg_off) {  // view blockIdx.z of a fit-step batch (blend.cuh)
+    const size_t gs = blockIdx.z * bb.geom_stride, is = blockIdx.z * bb.img_stride;
+    ranges = shift_ptr(ranges, is);
+    final_Ts = shift_ptr(final_Ts, is);
+    n_contrib = shift_ptr(n_contrib, is);
+    means2D = shift_ptr(means2D, gs);
+    conic_opacity = shift_ptr(conic_opacity, gs);
+    rgb_depth = shift_ptr(rgb_depth, gs);
+    point_list += bb.seg_off[blockIdx.z];
+    dL_dpixels += (size_t)blockIdx.z * 3 * H * W;
+    acc += blockIdx.z * bb.acc_stride;
+  }
   __shared__ uint32_t s_max[BL_WARPS];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -176,21 +188,36 @@ __global__ void __launch_bounds__(BL_THREADS, 9) render_backward_kernel(
   }
 }
 
+static cudaError_t launch_bwd(dim3 grid, const GeomState& g, const BinState& b, const ImgState& img, int W, int H,
+                              const float* background, const float* dL_dpix, float* acc,
+                              bool black_background, BlendBatch bb, cudaStream_t stream) {
+  if (black_background)
+    render_backward_kernel<false><<<grid, BL_THREADS, 0, stream>>>(
+        img.ranges, b.point_list, W, H, background, g.means2D, g.conic_opacity, g.rgb_depth, img.final_T,
+        img.n_contrib, dL_dpix, acc, bb);
+  else
+    render_backward_kernel<true><<<grid, BL_THREADS, 0, stream>>>(
+        img.ranges, b.point_list, W, H, background, g.means2D, g.conic_opacity, g.rgb_depth, img.final_T,
+        img.n_contrib, dL_dpix, acc, bb);
+  DGE_LAUNCHED(1);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_render_backward(const ViewParams& vp, const GeomState& g, const BinState& b,
                                    const ImgState& img, const float* background,
                                    const float* dL_dpix, float* acc, bool black_background,
                                    cudaStream_t stream) {
-  dim3 grid(vp.grid_x, vp.grid_y);
-  if (black_background)
-    render_backward_kernel<false><<<grid, BL_THREADS, 0, stream>>>(
-        img.ranges, b.point_list, vp.W, vp.H, background, g.means2D, g.conic_opacity, g.rgb_depth,
-        img.final_T, img.n_contrib, dL_dpix, acc);
-  else
-    render_backward_kernel<true><<<grid, BL_THREADS, 0, stream>>>(
-        img.ranges, b.point_list, vp.W, vp.H, background, g.means2D, g.conic_opacity, g.rgb_depth,
-        img.final_T, img.n_contrib, dL_dpix, acc);
-  DGE_LAUNCHED(1);
-  return cudaGetLastError();
+  return launch_bwd(dim3(vp.grid_x, vp.grid_y), g, b, img, vp.W, vp.H, background, dL_dpix, acc, black_background,
+                    BlendBatch{0, 0, nullptr, 0}, stream);
+}
+
+cudaError_t launch_render_backward_batched(const ViewParams& vp, const ViewBatch& vb, const GeomState& g0,
+                                           const BinState& b, const ImgState& img0, const float* background,
+                                           const float* dL_dpix, float* acc, size_t acc_stride_floats,
+                                           bool black_background, cudaStream_t stream) {
+  return launch_bwd(dim3(vp.grid_x, vp.grid_y, vb.V), g0, b, img0, vp.W, vp.H, background, dL_dpix, acc,
+                    black_background, BlendBatch{vb.geom_stride, vb.img_stride, vb.seg_off, acc_stride_floats},
+                    stream);
 }
 
 }  // namespace dge

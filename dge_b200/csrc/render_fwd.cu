@@ -23,8 +23,20 @@ __global__ void __launch_bounds__(BL_THREADS) render_forward_kernel(
     const float4* __restrict__ means2D, const float4* __restrict__ conic_opacity,
     const float4* __restrict__ rgb_depth, const float* __restrict__ background,
     float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
-    float* __restrict__ out_depth) {
+    float* __restrict__ out_depth, BlendBatch bb) {
   __shared__ BlendSmem s;
+  if (bb.seg_off) {  // view blockIdx.z of a fit-step batch (blend.cuh)
+    const size_t gs = blockIdx.z * bb.geom_stride, is = blockIdx.z * bb.img_stride;
+    ranges = shift_ptr(ranges, is);
+    final_T = shift_ptr(final_T, is);
+    n_contrib = shift_ptr(n_contrib, is);
+    means2D = shift_ptr(means2D, gs);
+    conic_opacity = shift_ptr(conic_opacity, gs);
+    rgb_depth = shift_ptr(rgb_depth, gs);
+    point_list += bb.seg_off[blockIdx.z];
+    out_color += (size_t)blockIdx.z * 3 * H * W;
+    out_depth += (size_t)blockIdx.z * H * W;
+  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // pixel p of this thread = (px0 + PX_STEP*(p&1), py0 + PY_STEP*(p>>1)): one pixel in each 8x4
   // quadrant of the warp's 16x8 half-tile (see blend.cuh)
@@ -113,7 +125,18 @@ cudaError_t launch_render_forward(const ViewParams& vp, const GeomState& g, cons
   dim3 grid(vp.grid_x, vp.grid_y);
   render_forward_kernel<<<grid, BL_THREADS, 0, stream>>>(
       img.ranges, b.point_list, vp.W, vp.H, g.means2D, g.conic_opacity, g.rgb_depth, background,
-      img.final_T, img.n_contrib, out_color, out_depth);
+      img.final_T, img.n_contrib, out_color, out_depth, BlendBatch{0, 0, nullptr, 0});
+  DGE_LAUNCHED(1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_render_forward_batched(const ViewParams& vp, const ViewBatch& vb, const GeomState& g0,
+                                          const BinState& b, ImgState& img0, const float* background,
+                                          float* out_color, float* out_depth, cudaStream_t stream) {
+  dim3 grid(vp.grid_x, vp.grid_y, vb.V);
+  render_forward_kernel<<<grid, BL_THREADS, 0, stream>>>(
+      img0.ranges, b.point_list, vp.W, vp.H, g0.means2D, g0.conic_opacity, g0.rgb_depth, background,
+      img0.final_T, img0.n_contrib, out_color, out_depth, BlendBatch{vb.geom_stride, vb.img_stride, vb.seg_off, 0});
   DGE_LAUNCHED(1);
   return cudaGetLastError();
 }

@@ -43,12 +43,41 @@ __device__ __forceinline__ void st_relaxed(uint32_t* p, uint32_t v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// shared workspace of a variable-length segmented sort:
+// [tickets: segs*64][hist: segs*MAX_PASSES*RADIX][status: MAX_PASSES * total_tiles * RADIX],
+// segment s owning status tiles [seg_off[s]/TILE + s, ...) (disjoint: ceil(n_s/TILE) <= floor(n_s/TILE) + 1)
+static inline uint32_t seg_total_tiles(uint32_t n_total, int segs) {
+  return n_total / (SORT_THREADS * SORT_IPT_MIN) + (uint32_t)segs + 1u;
+}
+size_t sort_workspace_bytes_segmented(uint32_t n_total, int segs) {
+  return sizeof(uint32_t) * ((size_t)segs * 64 + (size_t)segs * MAX_PASSES * RADIX +
+                             (size_t)MAX_PASSES * seg_total_tiles(n_total, segs) * RADIX);
+}
+
+// How a launch finds its segment (grid.y): uniform byte stride, or element offsets seg_off[].
+struct SegArgs {
+  size_t stride_bytes;
+  const uint32_t* seg_off;
+};
+
 // Digit histograms of every pass in one read of the keys.
 __global__ void __launch_bounds__(256) sort_histogram_kernel(const uint32_t* __restrict__ keys,
                                                              uint32_t n, int num_passes,
                                                              int num_bits,
-                                                             uint32_t* __restrict__ hist) {
+                                                             uint32_t* __restrict__ hist, SegArgs sa) {
   __shared__ uint32_t sh[MAX_PASSES * RADIX];
+  {
+    const uint32_t seg = blockIdx.y;
+    if (sa.seg_off) {
+      const uint32_t o = sa.seg_off[seg];
+      n = sa.seg_off[seg + 1] - o;
+      keys += o;
+      hist += (size_t)seg * MAX_PASSES * RADIX;
+    } else {
+      keys = shift_ptr(keys, seg * sa.stride_bytes);
+      hist = shift_ptr(hist, seg * sa.stride_bytes);
+    }
+  }
   for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += blockDim.x) sh[i] = 0;
   __syncthreads();
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -71,8 +100,32 @@ template <int SORT_IPT>
 __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(
     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
-    uint32_t digit_mask, const uint32_t* __restrict__ hist, uint32_t* status, uint32_t* ticket) {
+    uint32_t digit_mask, const uint32_t* __restrict__ hist, uint32_t* status, uint32_t* ticket,
+    SegArgs sa) {
   constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;
+  {
+    const uint32_t seg = blockIdx.y;
+    if (sa.seg_off) {
+      const uint32_t o = sa.seg_off[seg];
+      n = sa.seg_off[seg + 1] - o;
+      keys_in += o;
+      if (vals_in) vals_in += o;
+      keys_out += o;
+      vals_out += o;
+      hist += (size_t)seg * MAX_PASSES * RADIX;
+      ticket += seg * 64;
+      status += ((size_t)(o / SORT_TILE) + seg) * RADIX;
+    } else if (seg) {
+      const size_t sh_ = seg * sa.stride_bytes;
+      keys_in = shift_ptr(keys_in, sh_);
+      if (vals_in) vals_in = shift_ptr(vals_in, sh_);
+      keys_out = shift_ptr(keys_out, sh_);
+      vals_out = shift_ptr(vals_out, sh_);
+      hist = shift_ptr(hist, sh_);
+      ticket = shift_ptr(ticket, sh_);
+      status = shift_ptr(status, sh_);
+    }
+  }
   __shared__ uint32_t s_cnt[SORT_WARPS][RADIX];  // per-warp digit counters -> warp bases
   __shared__ uint32_t s_excl[RADIX];             // CTA-local exclusive digit prefix
   __shared__ uint32_t s_base[RADIX];             // global base of each digit for this CTA, minus s_excl
@@ -87,6 +140,7 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(
   for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&s_cnt[0][0])[i] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
+  if ((uint64_t)tile * SORT_TILE >= n) return;  // a shorter segment of a segmented launch (block-uniform)
   const uint32_t tile_base = tile * SORT_TILE;
   const uint32_t tile_n = min((uint32_t)SORT_TILE, n - tile_base);
 
@@ -237,25 +291,41 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(
 }
 
 // Input in (keys[passes&1], vals[passes&1]); output in (keys[0], vals[0]).
-cudaError_t sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int num_bits,
-                       bool iota_values, uint32_t* ws, size_t ws_bytes, cudaStream_t stream) {
-  if (n == 0) return cudaSuccess;
-  if (n >= (1u << 30)) return cudaErrorInvalidValue;
+cudaError_t sort_pairs_segmented(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int num_bits,
+                                 bool iota_values, uint32_t* ws, size_t ws_bytes, int segs,
+                                 size_t seg_stride_bytes, const uint32_t* seg_off, uint32_t n_total,
+                                 cudaStream_t stream) {
+  if (n == 0 || segs <= 0) return cudaSuccess;
+  if (n >= (1u << 30) || segs > 65535) return cudaErrorInvalidValue;
   const int passes = sort_num_passes(num_bits);
   if (passes < 1 || passes > MAX_PASSES) return cudaErrorInvalidValue;
   static const int env_ipt = getenv("DGE_SORT_IPT") ? atoi(getenv("DGE_SORT_IPT")) : 0;
   const int ipt = env_ipt == 8 || env_ipt == 16 ? env_ipt : (n <= (2u << 20) ? 8 : 16);
   const uint32_t tiles = sort_num_tiles(n, ipt);
-  const size_t need = sizeof(uint32_t) * (64 + (size_t)MAX_PASSES * RADIX + (size_t)passes * tiles * RADIX);
-  if (need > ws_bytes) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemsetAsync(ws, 0, need, stream);
+  uint32_t *tickets = ws, *hist, *status;
+  size_t pass_stride;  // words between the status tables of consecutive passes
+  cudaError_t e;
+  if (seg_off == nullptr) {
+    const size_t need = sizeof(uint32_t) * (64 + (size_t)MAX_PASSES * RADIX + (size_t)passes * tiles * RADIX);
+    if (need > ws_bytes || (segs > 1 && need > seg_stride_bytes)) return cudaErrorInvalidValue;
+    e = segs == 1 ? cudaMemsetAsync(ws, 0, need, stream)
+                  : cudaMemset2DAsync(ws, seg_stride_bytes, 0, need, (size_t)segs, stream);
+    hist = ws + 64;
+    status = hist + MAX_PASSES * RADIX;
+    pass_stride = (size_t)tiles * RADIX;
+  } else {
+    const size_t need = sort_workspace_bytes_segmented(n_total, segs);
+    if (need > ws_bytes) return cudaErrorInvalidValue;
+    e = cudaMemsetAsync(ws, 0, need, stream);
+    hist = ws + (size_t)segs * 64;
+    status = hist + (size_t)segs * MAX_PASSES * RADIX;
+    pass_stride = (size_t)seg_total_tiles(n_total, segs) * RADIX;
+  }
   if (e != cudaSuccess) return e;
-  uint32_t* tickets = ws;
-  uint32_t* hist = ws + 64;
-  uint32_t* status = hist + MAX_PASSES * RADIX;
+  const SegArgs sa = {seg_stride_bytes, seg_off};
   int cur = passes & 1;
   const int hist_blocks = (int)min((uint32_t)(DGE_NUM_SMS * 4), (n + 2047) / 2048);
-  sort_histogram_kernel<<<hist_blocks, 256, 0, stream>>>(keys[cur], n, passes, num_bits, hist);
+  sort_histogram_kernel<<<dim3(hist_blocks, segs), 256, 0, stream>>>(keys[cur], n, passes, num_bits, hist, sa);
   for (int p = 0; p < passes; p++) {
     // Digits of equal width (10 tile-id bits -> 5+5, not 8+2): a pass over few, long digit runs
     // writes whole lines and ranks without bank conflicts (measured 30 us vs 59 us per pass).
@@ -263,18 +333,24 @@ cudaError_t sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int num
     const int shift = p * per;
     const int bits = (num_bits - shift) < per ? (num_bits - shift) : per;
     const uint32_t* vin = (p == 0 && iota_values) ? nullptr : vals[cur];
+    const dim3 grid(tiles, segs);
     if (ipt == 8)
-      onesweep_kernel<8><<<tiles, SORT_THREADS, 0, stream>>>(
+      onesweep_kernel<8><<<grid, SORT_THREADS, 0, stream>>>(
           keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift, (1u << bits) - 1u,
-          hist + p * RADIX, status + (size_t)p * tiles * RADIX, tickets + p);
+          hist + p * RADIX, status + (size_t)p * pass_stride, tickets + p, sa);
     else
-      onesweep_kernel<16><<<tiles, SORT_THREADS, 0, stream>>>(
+      onesweep_kernel<16><<<grid, SORT_THREADS, 0, stream>>>(
           keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift, (1u << bits) - 1u,
-          hist + p * RADIX, status + (size_t)p * tiles * RADIX, tickets + p);
+          hist + p * RADIX, status + (size_t)p * pass_stride, tickets + p, sa);
     cur ^= 1;
   }
   DGE_LAUNCHED(1 + passes);
   return cudaGetLastError();
+}
+
+cudaError_t sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int num_bits,
+                       bool iota_values, uint32_t* ws, size_t ws_bytes, cudaStream_t stream) {
+  return sort_pairs_segmented(keys, vals, n, num_bits, iota_values, ws, ws_bytes, 1, 0, nullptr, n, stream);
 }
 
 }  // namespace dge

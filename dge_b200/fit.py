@@ -267,6 +267,147 @@ def _direct_views(model: FitModel, acts, cameras, targets, bg, scale, host_input
     return loss, radii_max
 
 
+class ViewBatch:
+    """Buffers for pushing a CHUNK of the step's views through the batched C-ABI entry points
+    (dge_fit_views_forward / _backward_blend): one launch per stage with the view as a grid dimension.
+    Geometry / image blobs hold V views at a uniform stride, the binning arena only grows. Each chunk
+    has its own stream; `acc` and `cams` are this chunk's rows of the step-wide buffers."""
+
+    def __init__(self, model: "FitModel", W: int, H: int, V: int, acc, cams, cams_host):
+        lib = L.load()
+        dev, P = model.device, model.P
+        self.W, self.H, self.V, self.P = W, H, V, P
+        f32 = dict(dtype=torch.float32, device=dev)
+        u8 = dict(dtype=torch.uint8, device=dev)
+        self.stream = torch.cuda.Stream(dev)
+        self.color = torch.empty(V, 3, H, W, **f32)
+        self.depth = torch.empty(V, 1, H, W, **f32)
+        self.dL = torch.empty(V, 3, H, W, **f32)
+        self.targets = torch.empty(V, 3, H, W, **f32)       # staging for host / listed targets
+        self.radii_max = torch.zeros(P, dtype=torch.int32, device=dev)
+        self.loss = torch.zeros((), **f32)
+        self.acc, self.cams, self.cams_host = acc, cams, cams_host
+        self.geom = torch.empty((lib.dge_geom_bytes(P) + 255) // 256 * 256 * V, **u8)
+        self.img = torch.empty((lib.dge_image_bytes(W, H) + 255) // 256 * 256 * V, **u8)
+        self.binning = torch.empty(0, **u8)
+        self.num_rendered = (L.C.c_int * V)()
+        self.R = 0
+        self.copy_stream = torch.cuda.Stream(dev)
+        self.copied = torch.cuda.Event()
+        self.stream_ptr = L.C.c_void_p(self.stream.cuda_stream)
+
+        def fixed(t):
+            ptr = t.data_ptr()
+            return L.ALLOC_FN(lambda _ctx, nbytes: ptr if nbytes <= t.numel() else 0)
+
+        def growing(_ctx, nbytes):
+            if nbytes > self.binning.numel():
+                with torch.cuda.stream(self.stream):
+                    self.binning = torch.empty(int(nbytes * 1.25) + 256, **u8)
+            return self.binning.data_ptr()
+
+        self.cb_geom, self.cb_img = fixed(self.geom), fixed(self.img)
+        self.cb_binning = L.ALLOC_FN(growing)
+
+
+def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inputs, num_chunks=1):
+    """The step's views through the batched C-ABI: ONE launch per stage for all views of a chunk
+    (preprocess that reads the Gaussians once for all its cameras, segmented depth sort / binning, forward
+    blend, fused L1 loss+gradient, backward blend), then ONE batched per-Gaussian backward over all
+    views. With num_chunks > 1 the views are split into that many chunks, each on its own stream, so
+    one chunk's bandwidth-bound stages (preprocess, sorts) overlap another's issue-bound blends.
+    Returns (loss, max radii); leaves the step's raw-parameter gradients in model.flat_grad."""
+    lib = L.load()
+    dev = model.device
+    H, W = cameras[0].image_height, cameras[0].image_width
+    V, P = len(cameras), model.P
+    if V > 64:
+        raise ValueError("a step holds at most 64 views per rank (dge_fit_backward_geom_raw)")
+    C = max(1, min(num_chunks, V))
+    key = (W, H, V, C)
+    if getattr(model, "_batch_key", None) != key:
+        f32 = dict(dtype=torch.float32, device=dev)
+        model._acc = torch.empty(V, P, 12, **f32)          # blend-stage sums of every view of the step
+        model._cams = torch.empty(V, CAM_FLOATS, **f32)
+        model._cams_host = torch.empty(V, CAM_FLOATS, dtype=torch.float32).pin_memory()
+        bounds = [V * c // C for c in range(C + 1)]
+        model._chunk_bounds = bounds
+        model._batches = [ViewBatch(model, W, H, bounds[c + 1] - bounds[c], model._acc[bounds[c]:bounds[c + 1]],
+                                    model._cams[bounds[c]:bounds[c + 1]], model._cams_host[bounds[c]:bounds[c + 1]])
+                          for c in range(C)]
+        model._cam_cache = {}
+        model._batch_key = key
+    batches, bounds = model._batches, model._chunk_bounds
+    main = torch.cuda.current_stream(dev)
+    a = {k: v.detach() for k, v in acts.items()}
+    ptrs = {k: v.data_ptr() for k, v in a.items()}
+    M = a["shs"].shape[1]
+    bgp = bg.data_ptr()
+    if getattr(model, "_bg_key", None) != bgp:  # one-time host copy of the (constant) background
+        model._bg_key, model._bg_black = bgp, int(not bool(bg.detach().cpu().any()))
+    # cameras: one pinned [V,40] block, one H2D copy
+    for i, cam in enumerate(cameras):
+        ck = cam.world_view_transform.data_ptr()
+        rec = model._cam_cache.get(ck)
+        if rec is None:
+            rec = model._cam_cache[ck] = pack_camera(cam)
+        model._cams_host[i].copy_(rec)
+    model._cams.copy_(model._cams_host, non_blocking=True)
+    resident = isinstance(targets, torch.Tensor) and targets.is_cuda
+    acc_stride = P * 12
+    n_img = 3 * H * W
+    for vb in batches:
+        vb.stream.wait_stream(main)
+    # forward of every chunk first (each call waits once for its instance counts), then loss + backward
+    for c, vb in enumerate(batches):
+        lo, hi = bounds[c], bounds[c + 1]
+        # targets: a resident [V,3,H,W] tensor is used as is; host tensors are copied on a side stream
+        # (overlapping preprocess / sorts / the forward blend), device lists are gathered once
+        if resident:
+            vb.tgt = targets[lo:hi]
+        elif host_inputs:
+            vb.copy_stream.wait_stream(main)
+            with torch.cuda.stream(vb.copy_stream):
+                for i in range(lo, hi):
+                    vb.targets[i - lo].copy_(targets[i], non_blocking=True)
+                vb.copied.record(vb.copy_stream)
+            vb.tgt = vb.targets
+        else:
+            with torch.cuda.stream(vb.stream):
+                torch.stack(list(targets[lo:hi]), out=vb.targets)
+            vb.tgt = vb.targets
+        with torch.cuda.stream(vb.stream):
+            vb.loss.zero_()
+            vb.R = L.check(lib.dge_fit_views_forward(
+                vb.cb_geom, vb.cb_binning, vb.cb_img, None, P, model.sh_degree, M, vb.V, bgp, W, H, ptrs["means3D"],
+                ptrs["shs"], ptrs["opacities"], ptrs["scales"], 1.0, ptrs["rotations"], vb.cams.data_ptr(),
+                vb.color.data_ptr(), vb.depth.data_ptr(), vb.radii_max.data_ptr(), vb.acc.data_ptr(), acc_stride,
+                vb.num_rendered, vb.stream_ptr), "fit views forward")
+    for vb in batches:
+        with torch.cuda.stream(vb.stream):
+            if host_inputs and not resident:
+                vb.stream.wait_event(vb.copied)
+            L.check(lib.dge_l1_loss_grad(vb.color.data_ptr(), vb.tgt.data_ptr(), vb.V * n_img, scale, vb.dL.data_ptr(),
+                                         vb.loss.data_ptr(), vb.stream_ptr), "l1 loss")
+            L.check(lib.dge_fit_views_backward_blend(P, vb.V, vb.R, bgp, model._bg_black, W, H, vb.geom.data_ptr(),
+                                                     vb.binning.data_ptr(), vb.img.data_ptr(), vb.dL.data_ptr(),
+                                                     vb.acc.data_ptr(), acc_stride, vb.stream_ptr),
+                    "fit views backward blend")
+    for vb in batches:
+        main.wait_stream(vb.stream)
+    gp = {k: v.grad.data_ptr() for k, v in model.params.items()}
+    L.check(lib.dge_fit_backward_geom_raw(
+        P, model.sh_degree, V, model._cams.data_ptr(), W, H, 1.0, model._acc.data_ptr(), acc_stride, ptrs["means3D"],
+        ptrs["shs"], ptrs["opacities"], ptrs["scales"], ptrs["rotations"], model.params["rotation"].data_ptr(),
+        gp["xyz"], model.means2D.grad.data_ptr(), gp["f_dc"], gp["f_rest"], gp["opacity"], gp["scaling"],
+        gp["rotation"], L.stream_ptr(dev)), "fit backward geom")
+    loss, radii_max = batches[0].loss.clone(), batches[0].radii_max
+    for vb in batches[1:]:
+        loss += vb.loss
+        radii_max = torch.maximum(radii_max, vb.radii_max)
+    return loss, radii_max
+
+
 def shard_views(num_views: int, rank: int, world: int) -> List[int]:
     """View i of the step's batch goes to rank i mod world."""
     return list(range(rank, num_views, world))
@@ -280,7 +421,8 @@ def default_rasterize(rs, means3D, means2D, shs, opacities, scales, rotations):
 def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence[torch.Tensor], bg: torch.Tensor,
              global_batch: int, rasterize: Callable = default_rasterize, settings_module=dgr,
              process_group=None, lambda_l1: float = 10.0, host_inputs: bool = False, update_stats: bool = True,
-             num_streams: int = 1, direct: Optional[bool] = None):
+             num_streams: int = 1, direct: Optional[bool] = None, batched: Optional[bool] = None,
+             num_chunks: int = 1):
     """One optimisation step over this rank's views. `cameras`/`targets` are this rank's share;
     `global_batch` the number of views in the whole step (L1 is a mean over the global batch,
     DGE.py:672). With host_inputs the cameras/targets live in pinned host memory and are copied
@@ -291,9 +433,10 @@ def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence
     the blend over the densest tiles) overlap another view's kernels. Each stream accumulates
     into its own gradient leaves; the partial sums are added on the main stream afterwards.
 
-    direct (default: on CUDA with the stock rasterizer) drives the C-ABI without autograd: fixed
-    per-stream buffers, one fused L1 loss+gradient kernel per view and a backward that adds into the
-    stream's running sums. The autograd path below is the reference-shaped one (per-view tensors,
+    direct (default: on CUDA with the stock rasterizer) drives the C-ABI without autograd. batched
+    (default) pushes ALL views of the step through each stage in one launch (_batched_views: the view
+    is a grid dimension, the Gaussians are read once per step, one host wait per step); batched=False
+    issues the views one by one round-robin on num_streams CUDA streams (_direct_views). The autograd path below is the reference-shaped one (per-view tensors,
     torch ops for the loss, AccumulateGrad) and is what `rasterize` overrides go through."""
     dev = model.device
     H, W = cameras[0].image_height, cameras[0].image_width
@@ -301,8 +444,14 @@ def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence
     if direct is None:
         direct = dev.type == "cuda" and rasterize is default_rasterize and model.sh_degree == 3
     if direct:
-        loss, radii_max = _direct_views(model, model.activations_fused(), cameras, targets, bg, scale, host_inputs,
-                                        num_streams)
+        if batched is None:
+            batched = len(cameras) <= 64
+        if batched:
+            loss, radii_max = _batched_views(model, model.activations_fused(), cameras, targets, bg, scale, host_inputs,
+                                             num_chunks)
+        else:
+            loss, radii_max = _direct_views(model, model.activations_fused(), cameras, targets, bg, scale, host_inputs,
+                                            num_streams)
         return _finish_step(model, loss, radii_max, process_group, update_stats)
     model.zero_grad()
     acts_graph = model.activations()

@@ -170,6 +170,28 @@ int dge_fit_backward_geom(int P, int D, int M, int V, const float* cams, int wid
                           float* dL_dsh, float* dL_dopacity, float* dL_dscale, float* dL_drot,
                           int accumulate, void* stream);
 
+/* The same three stages for ALL V views of the step at once (1 <= V <= 64): every stage is ONE launch
+ * whose grid carries the view as a dimension, so a 512x512 view's 1024 tiles no longer leave most of
+ * the 148 SMs idle, the 236 B of per-Gaussian inputs are read once per step instead of once per
+ * view, and the host waits for the instance counts once per step. `cams` is [V][40], out_color
+ * [V,3,H,W], out_depth [V,1,H,W], acc [V][acc_stride_floats] (acc_stride_floats >= 12*P, multiple
+ * of 4), radii_max [P] = max over the views of the reference's per-view radii. geometryBuffer is
+ * asked for V*dge_geom_bytes(P) bytes, imageBuffer for V*dge_image_bytes(W,H), binningBuffer for
+ * dge_fit_binning_bytes(R_total, V) once the counts are known. num_rendered_host (host, [V], may be
+ * NULL) receives the per-view num_rendered. Returns R_total = their sum. */
+int dge_fit_views_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge_alloc_fn imageBuffer,
+                          void* alloc_ctx, int P, int D, int M, int V, const float* background, int width,
+                          int height, const float* means3D, const float* shs, const float* opacities,
+                          const float* scales, float scale_modifier, const float* rotations,
+                          const float* cams, float* out_color, float* out_depth, int* radii_max, float* acc,
+                          size_t acc_stride_floats, int* num_rendered_host, void* stream);
+/* dL_dpix is [V,3,H,W]; the three blobs are the ones dge_fit_views_forward filled. */
+int dge_fit_views_backward_blend(int P, int V, int R_total, const float* background, int background_is_black,
+                                 int width, int height, char* geom_buffer, char* binning_buffer,
+                                 char* image_buffer, const float* dL_dpix, float* acc, size_t acc_stride_floats,
+                                 void* stream);
+size_t dge_fit_binning_bytes(int R_total, int V);
+
 /* GaussianModel's activations (gaussiansplatting/scene/gaussian_model.py:221-258)
  * for the whole model in one pass — shs[P,16,3] = cat(f_dc[P,1,3], f_rest[P,15,3]), opacities =
  * sigmoid, scales = exp, rotations = normalize — and dge_fit_backward_geom with their backward in

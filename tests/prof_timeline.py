@@ -12,7 +12,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--views", type=int, default=20)
 ap.add_argument("--P", type=int, default=1_000_000)
 ap.add_argument("--res", type=int, default=512)
-ap.add_argument("--streams", type=int, default=4)
+ap.add_argument("--streams", type=int, default=0, help="0 = batched path")
 ap.add_argument("--out", default="")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
@@ -20,13 +20,15 @@ g = scene.make_gaussians(args.P, seed=1236)
 cams = [scene.camera_to(c, dev) for c in scene.ring_cameras(20, args.res, args.res)[:args.views]]
 gen = torch.Generator().manual_seed(3)
 targets = [torch.rand(3, args.res, args.res, generator=gen).to(dev) for _ in range(args.views)]
+if args.streams == 0:
+    targets = torch.stack(targets)
 model = fit.FitModel(g, dev, fused_adam=True)
 bg = torch.zeros(3, device=dev)
 for _ in range(3):
-    fit.fit_step(model, cams, targets, bg, global_batch=args.views, num_streams=args.streams)
+    fit.fit_step(model, cams, targets, bg, global_batch=args.views, num_streams=max(args.streams, 1), batched=args.streams == 0)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    fit.fit_step(model, cams, targets, bg, global_batch=args.views, num_streams=args.streams)
+    fit.fit_step(model, cams, targets, bg, global_batch=args.views, num_streams=max(args.streams, 1), batched=args.streams == 0)
     torch.cuda.synchronize()
 ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 iv = sorted((e.time_range.start, e.time_range.end, e.name) for e in ev)

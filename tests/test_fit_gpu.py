@@ -21,15 +21,17 @@ def _setup(cuda, fused):
     return fit.FitModel(g, cuda, fused_adam=fused), cams, targets, torch.zeros(3, device=cuda)
 
 
-@pytest.mark.parametrize("streams,bgv", [(1, 0.0), (3, 0.0), (2, 0.4)])
-def test_direct_path_matches_autograd_path(cuda, streams, bgv):
+@pytest.mark.parametrize("streams,bgv,batched", [(1, 0.0, False), (3, 0.0, False), (2, 0.4, False), (1, 0.0, True),
+                                                 (1, 0.4, True), (2, 0.0, True)])
+def test_direct_path_matches_autograd_path(cuda, streams, bgv, batched):
     ref_model, cams, targets, bg = _setup(cuda, True)
     model, _, _, _ = _setup(cuda, True)
     bg = bg + bgv
     for step in range(2):
         l_ref = fit.fit_step(ref_model, cams, targets, bg, global_batch=V, direct=False, num_streams=1)
         g_ref = ref_model.flat_grad.clone()
-        l = fit.fit_step(model, cams, targets, bg, global_batch=V, direct=True, num_streams=streams)
+        l = fit.fit_step(model, cams, targets, bg, global_batch=V, direct=True, num_streams=streams, batched=batched,
+                         num_chunks=streams)
         torch.cuda.synchronize()
         assert abs(float(l) - float(l_ref)) <= 1e-5 * abs(float(l_ref))
         n59 = fit.FLOATS_PER_GAUSSIAN * P
@@ -47,18 +49,46 @@ def test_direct_path_matches_autograd_path(cuda, streams, bgv):
         model.exp_avg_sq.copy_(ref_model.exp_avg_sq)
 
 
+def test_batched_views_bit_identical_to_per_view(cuda):
+    """dge_fit_views_forward (all views of the step per launch: batched preprocess, segmented sorts,
+    grid.z = view) must reproduce the per-view API bit for bit: images, depth, and the max of the radii."""
+    from dge_b200 import diff_gaussian_rasterization as dgr
+    model, cams, targets, bg = _setup(cuda, True)
+    bg = bg + 0.25
+    fit.fit_step(model, cams, targets, bg, global_batch=V, batched=True, update_stats=False)
+    vb = model._batches[0]
+    # the step above moved the parameters (Adam): the per-view API renders an untouched twin
+    model2, _, _, _ = _setup(cuda, True)
+    a2 = model2.activations_fused()
+    radii_max = torch.zeros(P, dtype=torch.int32, device=cuda)
+    total_R = 0
+    for v, cam in enumerate(cams):
+        rs = scene.raster_settings(cam, bg, 3, module=dgr)
+        e = torch.empty(0, device=cuda)
+        R, color, depth, radii, *_ = dgr._forward_call(rs, a2["means3D"], e, a2["opacities"], a2["scales"],
+                                                       a2["rotations"], e, a2["shs"])
+        assert torch.equal(color, vb.color[v]), v
+        assert torch.equal(depth, vb.depth[v]), v
+        assert R == vb.num_rendered[v], v
+        radii_max = torch.maximum(radii_max, radii)
+        total_R += R
+    assert torch.equal(radii_max, vb.radii_max)
+
+
 def test_host_inputs_equal_resident(cuda):
     a, cams, targets, bg = _setup(cuda, True)
     b, _, _, _ = _setup(cuda, True)
     cams_h = [scene.Camera(*[t.cpu().pin_memory() if isinstance(t, torch.Tensor) else t for t in c]) for c in cams]
     targets_h = [t.cpu().pin_memory() for t in targets]
-    la = fit.fit_step(a, cams, targets, bg, global_batch=V, num_streams=2)
-    lb = fit.fit_step(b, cams_h, targets_h, bg, global_batch=V, num_streams=2, host_inputs=True)
-    torch.cuda.synchronize()
-    assert abs(float(la) - float(lb)) <= 1e-6 * abs(float(la))
-    for name, sl in a.slices.items():
-        ok, msg = util.grad_ok(b.flat_grad[sl].cpu().numpy(), a.flat_grad[sl].cpu().numpy())
-        assert ok, (name, msg)
+    for batched in (True, False):
+        la = fit.fit_step(a, cams, targets, bg, global_batch=V, num_streams=2, batched=batched)
+        lb = fit.fit_step(b, cams_h, targets_h, bg, global_batch=V, num_streams=2, host_inputs=True, batched=batched)
+        torch.cuda.synchronize()
+        assert abs(float(la) - float(lb)) <= 1e-6 * abs(float(la))
+        for name, sl in a.slices.items():
+            ok, msg = util.grad_ok(b.flat_grad[sl].cpu().numpy(), a.flat_grad[sl].cpu().numpy())
+            assert ok, (name, msg)
+        b.flat.copy_(a.flat), b.exp_avg.copy_(a.exp_avg), b.exp_avg_sq.copy_(a.exp_avg_sq)
 
 
 def test_fused_adam_matches_torch_adam(cuda):
