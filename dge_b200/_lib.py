@@ -46,7 +46,7 @@ _SIGNATURES = {
     "dge_fit_views_forward": (_i, [ALLOC_FN, ALLOC_FN, ALLOC_FN, _p, _i, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _f, _p,
                                    _p, _p, _p, _p, _p, C.c_size_t, _p, _p]),
     "dge_fit_views_backward_blend": (_i, [_i, _i, _i, _p, _i, _i, _i, _p, _p, _p, _p, _p, C.c_size_t, _p]),
-    "dge_fit_binning_bytes": (C.c_size_t, [_i, _i]),
+    "dge_fit_binning_bytes": (C.c_size_t, [_i, _i, _i, _i]),
     "dge_fit_backward_geom": (_i, [_i, _i, _i, _i, _p, _i, _i, _f, _p, C.c_size_t, _p, _p, _p, _p, _p, _p, _p, _p,
                                    _p, _p, _i, _p]),
     "dge_fit_activate": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),

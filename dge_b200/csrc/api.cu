@@ -107,7 +107,7 @@ size_t carve_binning(char* base, int R, int width, int height, BinState* st) {
 }
 
 // Instance lists of all V views of a fit step, back to back (view v at seg_off[v]).
-size_t carve_binning_batched(char* base, uint32_t R_total, int V, BinState* st) {
+size_t carve_binning_batched(char* base, uint32_t R_total, int V, int T, BinState* st) {
   BinState s;
   char* p = base;
   const size_t n = (size_t)(R_total > 0 ? R_total : 1);
@@ -115,7 +115,7 @@ size_t carve_binning_batched(char* base, uint32_t R_total, int V, BinState* st) 
   take(p, s.tile_ids, n);
   take(p, s.key_alt, n);
   take(p, s.val_alt, n);
-  s.sort_ws_bytes = sort_workspace_bytes_segmented((uint32_t)n, V);
+  s.sort_ws_bytes = binning_batched_workspace_bytes((uint32_t)n, V, T);
   take(p, s.sort_ws, s.sort_ws_bytes / sizeof(uint32_t));
   if (st) *st = s;
   return (size_t)(p - base) + 256;
@@ -302,8 +302,9 @@ static uint32_t* batch_seg_off(const GeomState& g0) { return g0.counters + 64; }
 // per-view blobs of a batch: the single-view layout repeated at a 256-byte-aligned stride
 static size_t batch_stride(size_t bytes) { return (bytes + 255) & ~size_t(255); }
 
-size_t dge_fit_binning_bytes(int R_total, int V) {
-  return carve_binning_batched(nullptr, (uint32_t)(R_total > 0 ? R_total : 0), V, nullptr);
+size_t dge_fit_binning_bytes(int R_total, int V, int width, int height) {
+  const int T = ((width + DGE_TILE - 1) / DGE_TILE) * ((height + DGE_TILE - 1) / DGE_TILE);
+  return carve_binning_batched(nullptr, (uint32_t)(R_total > 0 ? R_total : 0), V, T, nullptr);
 }
 
 int dge_fit_views_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge_alloc_fn imageBuffer,
@@ -354,9 +355,10 @@ int dge_fit_views_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffe
     if (num_rendered_host) num_rendered_host[v] = (int)r;
   }
   if (R_total >= (1u << 30)) return fail_msg("the step's views exceed 2^30 instances: use smaller batches");
-  char* bp = binningBuffer(alloc_ctx, carve_binning_batched(nullptr, R_total, V, nullptr));
+  const int T = vp.grid_x * vp.grid_y;
+  char* bp = binningBuffer(alloc_ctx, carve_binning_batched(nullptr, R_total, V, T, nullptr));
   if (!bp) return fail_msg("scratch allocator returned NULL");
-  carve_binning_batched(bp, R_total, V, &b);
+  carve_binning_batched(bp, R_total, V, T, &b);
   STAGE(ST_BINNING, "binning (batched)", launch_binning_batched(vp, vb, R_total, R_max, g0, b, img0, stream));
   STAGE(ST_RENDER_FWD, "render forward (batched)",
         launch_render_forward_batched(vp, vb, g0, b, img0, background, out_color, out_depth, stream));
@@ -379,7 +381,7 @@ int dge_fit_views_backward_blend(int P, int V, int R_total, const float* backgro
   vb.V = V;
   vb.geom_stride = batch_stride(carve_geom(geom_buffer, P, &g0));
   vb.img_stride = batch_stride(carve_image(image_buffer, width, height, &img0));
-  carve_binning_batched(binning_buffer, (uint32_t)R_total, V, &b);
+  carve_binning_batched(binning_buffer, (uint32_t)R_total, V, vp.grid_x * vp.grid_y, &b);
   vb.seg_off = batch_seg_off(g0);
   vb.cams = nullptr;
   STAGE(ST_RENDER_BWD, "render backward (batched)",

@@ -10,6 +10,7 @@
 // Stability of both sorts makes the resulting point_list / ranges bit-identical
 // to the reference's (ties in depth keep Gaussian-id order, exactly as CUB's
 // stable sort of the id-ordered unsorted list does).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace dge {
@@ -252,6 +253,254 @@ cudaError_t launch_depth_sort_batched(int P, const ViewBatch& vb, GeomState& g0,
                               g0.sort_ws_bytes, vb.V, vb.geom_stride, nullptr, 0, stream);
 }
 
+// ---- single-pass stable partition by tile id (fit step, T <= PART_MAX_TILES) ----------------------
+// The generic path sorts the (tile id, Gaussian id) pairs with ceil(log2 T / 8) onesweep passes, each
+// with a decoupled look-back whose chains are as long as a view has sort tiles. For the batched fit
+// step the partition is done in ONE deterministic pass without any look-back:
+//   part_count    every CTA counts, per tile id, the instances of its run of PART_RUN consecutive
+//                 instances (instances are in depth order) -> table[run][tile]
+//   part_scan_*   per tile: exclusive prefix over the runs, on top of the tile's start in the view's
+//                 list (exclusive scan of the per-tile totals, which also IS the `ranges` array, so
+//                 identifyTileRanges and the sorted tile-id array disappear) -> table[run][tile] =
+//                 position of the run's first instance of that tile
+//   part_scatter  every CTA ranks its run stably (warp w owns the w-th eighth of the run; ballot
+//                 ranking inside a warp, per-warp running positions in shared memory) and writes the
+//                 Gaussian ids straight to their final position.
+// Traffic per instance: 8 B written by expand, 4 + 8 B read, 4 B written (was 8 + 2 x 16 + 4 + 4).
+constexpr int PART_THREADS = 256;
+constexpr int PART_WARPS = PART_THREADS / 32;
+constexpr int PART_WARP_ITEMS = 512;
+constexpr int PART_IPL = PART_WARP_ITEMS / 32;          // instances per lane, register resident
+constexpr int PART_RUN = PART_WARPS * PART_WARP_ITEMS;  // instances per CTA
+constexpr int PART_GROUPS = 16;                         // run groups of the two-level scan over runs
+constexpr int PART_MAX_TILES = 2048;
+
+// rows of the count table owned by view v start at row (seg_off[v] / PART_RUN + v): disjoint, since a
+// view of n instances has ceil(n / PART_RUN) <= floor(n / PART_RUN) + 1 runs
+__device__ __forceinline__ size_t part_row0(const uint32_t* seg_off, int v) {
+  return (size_t)(seg_off[v] / PART_RUN) + (size_t)v;
+}
+size_t part_table_rows(uint32_t R_total, int V) { return (size_t)(R_total / PART_RUN) + (size_t)V + 1; }
+size_t part_workspace_bytes(uint32_t R_total, int V, int T) {
+  // count table + per-(view, group, tile) partial sums
+  return sizeof(uint32_t) * (part_table_rows(R_total, V) * (size_t)T + (size_t)V * PART_GROUPS * T) + 256;
+}
+
+__global__ void __launch_bounds__(PART_THREADS) part_count_kernel(const uint32_t* __restrict__ tile_ids,
+                                                                  const uint32_t* __restrict__ seg_off,
+                                                                  int T, uint32_t* __restrict__ table) {
+  extern __shared__ uint32_t s_cnt[];  // [T]
+  const int v = blockIdx.y;
+  const uint32_t o = seg_off[v], n = seg_off[v + 1] - o;
+  const uint32_t lo = blockIdx.x * (uint32_t)PART_RUN;
+  if (lo >= n) return;
+  const uint32_t hi = min(n, lo + (uint32_t)PART_RUN);
+  for (int t = threadIdx.x; t < T; t += PART_THREADS) s_cnt[t] = 0;
+  __syncthreads();
+  const uint32_t* keys = tile_ids + o;
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += PART_THREADS) atomicAdd(&s_cnt[keys[i]], 1u);
+  __syncthreads();
+  uint32_t* row = table + (part_row0(seg_off, v) + blockIdx.x) * (size_t)T;
+  for (int t = threadIdx.x; t < T; t += PART_THREADS) row[t] = s_cnt[t];
+}
+
+// partial[v][g][t] = sum over the runs of group g of table[run][t]
+__global__ void __launch_bounds__(256) part_scan_partial_kernel(const uint32_t* __restrict__ seg_off, int T,
+                                                                const uint32_t* __restrict__ table,
+                                                                uint32_t* __restrict__ partial) {
+  const int v = blockIdx.z, g = blockIdx.y;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= T) return;
+  const uint32_t n = seg_off[v + 1] - seg_off[v];
+  const uint32_t runs = (n + PART_RUN - 1) / PART_RUN, per = (runs + PART_GROUPS - 1) / PART_GROUPS;
+  const uint32_t r0 = min(runs, g * per), r1 = min(runs, r0 + per);
+  const uint32_t* col = table + part_row0(seg_off, v) * (size_t)T + t;
+  uint32_t sum = 0;
+#pragma unroll 4
+  for (uint32_t r = r0; r < r1; r++) sum += col[(size_t)r * T];
+  partial[((size_t)v * PART_GROUPS + g) * T + t] = sum;
+}
+
+// per view: totals per tile -> exclusive scan over tiles = ranges; partial[v][g][t] becomes the position
+// of group g's first instance of tile t
+__global__ void __launch_bounds__(1024) part_scan_tiles_kernel(int T, uint32_t* __restrict__ partial,
+                                                               uint2* __restrict__ ranges, size_t img_stride) {
+  __shared__ uint32_t ws[32];
+  __shared__ uint32_t carry_s;
+  const int v = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* part = partial + (size_t)v * PART_GROUPS * T;
+  uint2* rg = shift_ptr(ranges, v * img_stride);
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < T; base += 1024) {
+    const int t = base + threadIdx.x;
+    uint32_t total = 0;
+    if (t < T)
+#pragma unroll
+      for (int g = 0; g < PART_GROUPS; g++) total += part[(size_t)g * T + t];
+    uint32_t x = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) ws[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = ws[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, o);
+        if (lane >= o) w += y;
+      }
+      ws[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t excl = carry_s + (warp ? ws[warp - 1] : 0) + x - total;
+    if (t < T) {
+      // identifyTileRanges leaves (0, 0) for tiles without instances (rasterizer_impl.cu:263-271)
+      rg[t] = total ? make_uint2(excl, excl + total) : make_uint2(0u, 0u);
+      uint32_t run = excl;
+#pragma unroll
+      for (int g = 0; g < PART_GROUPS; g++) {
+        const uint32_t c = part[(size_t)g * T + t];
+        part[(size_t)g * T + t] = run;
+        run += c;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = excl + total;
+    __syncthreads();
+  }
+}
+
+// table[run][t]: count -> position of the run's first instance of tile t in the view's list
+__global__ void __launch_bounds__(256) part_scan_runs_kernel(const uint32_t* __restrict__ seg_off, int T,
+                                                             uint32_t* __restrict__ table,
+                                                             const uint32_t* __restrict__ partial) {
+  const int v = blockIdx.z, g = blockIdx.y;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= T) return;
+  const uint32_t n = seg_off[v + 1] - seg_off[v];
+  const uint32_t runs = (n + PART_RUN - 1) / PART_RUN, per = (runs + PART_GROUPS - 1) / PART_GROUPS;
+  const uint32_t r0 = min(runs, g * per), r1 = min(runs, r0 + per);
+  uint32_t* col = table + part_row0(seg_off, v) * (size_t)T + t;
+  uint32_t run = partial[((size_t)v * PART_GROUPS + g) * T + t];
+  for (uint32_t r = r0; r < r1; r++) {
+    const uint32_t c = col[(size_t)r * T];
+    col[(size_t)r * T] = run;
+    run += c;
+  }
+}
+
+__global__ void __launch_bounds__(PART_THREADS) part_scatter_kernel(
+    const uint32_t* __restrict__ tile_ids, const uint32_t* __restrict__ gids,
+    const uint32_t* __restrict__ seg_off, int T, int tile_bits, const uint32_t* __restrict__ table,
+    uint32_t* __restrict__ point_list) {
+  extern __shared__ uint32_t s_part[];
+  const int TP = (T + 1) >> 1;                      // packed u16 pairs per warp row
+  uint32_t* s_cnt = s_part;                         // [PART_WARPS][TP]  two 16-bit counters per word
+  uint32_t* s_base = s_part + PART_WARPS * TP;      // [PART_WARPS][T]
+  const int v = blockIdx.y;
+  const uint32_t o = seg_off[v], n = seg_off[v + 1] - o;
+  const uint32_t lo = blockIdx.x * (uint32_t)PART_RUN;
+  if (lo >= n) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t* keys = tile_ids + o;
+  const uint32_t* vals = gids + o;
+  uint32_t* out = point_list + o;
+  for (int i = threadIdx.x; i < PART_WARPS * TP; i += PART_THREADS) s_cnt[i] = 0;
+  __syncthreads();
+  // A: per-warp counts of the warp's own PART_WARP_ITEMS consecutive instances. Keys and Gaussian ids
+  // are loaded ONCE, all loads in flight together, and stay in registers for the ranking below.
+  const uint32_t wlo = lo + warp * (uint32_t)PART_WARP_ITEMS;
+  const uint32_t whi = min(n, wlo + (uint32_t)PART_WARP_ITEMS);
+  uint32_t key[PART_IPL], val[PART_IPL];
+#pragma unroll
+  for (int k = 0; k < PART_IPL; k++) {
+    const uint32_t i = wlo + k * 32 + lane;
+    key[k] = i < whi ? keys[i] : 0xFFFFFFFFu;
+  }
+#pragma unroll
+  for (int k = 0; k < PART_IPL; k++) {
+    const uint32_t i = wlo + k * 32 + lane;
+    val[k] = i < whi ? vals[i] : 0u;
+  }
+#pragma unroll
+  for (int k = 0; k < PART_IPL; k++)
+    if (key[k] != 0xFFFFFFFFu) atomicAdd(&s_cnt[warp * TP + (key[k] >> 1)], 1u << (16 * (key[k] & 1)));
+  __syncthreads();
+  // B: position of each warp's first instance of every tile
+  const uint32_t* row = table + (part_row0(seg_off, v) + blockIdx.x) * (size_t)T;
+  for (int t = threadIdx.x; t < T; t += PART_THREADS) {
+    uint32_t run = row[t];
+#pragma unroll
+    for (int w = 0; w < PART_WARPS; w++) {
+      s_base[w * T + t] = run;
+      run += (s_cnt[w * TP + (t >> 1)] >> (16 * (t & 1))) & 0xFFFFu;
+    }
+  }
+  __syncthreads();
+  // C: stable ranking, 32 instances at a time in list order
+  uint32_t* my_base = s_base + warp * T;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int k = 0; k < PART_IPL; k++) {
+    if (wlo + k * 32 >= whi) break;  // warp-uniform
+    const uint32_t t = key[k];
+    const bool valid = t != 0xFFFFFFFFu;
+    uint32_t peers = __ballot_sync(0xFFFFFFFFu, valid);
+    if (!valid) peers = ~peers;
+    for (int bit = 0; bit < tile_bits; bit++) {
+      const uint32_t m = 0u - ((t >> bit) & 1u);
+      const uint32_t vote = __ballot_sync(0xFFFFFFFFu, m != 0u);
+      peers &= ~(vote ^ m);
+    }
+    const int leader = __ffs(peers) - 1;
+    uint32_t prev = 0;
+    if (valid && lane == leader) {
+      prev = my_base[t];
+      my_base[t] = prev + __popc(peers);
+    }
+    prev = __shfl_sync(0xFFFFFFFFu, prev, leader);
+    if (valid) out[prev + __popc(peers & lt_mask)] = val[k];
+    __syncwarp();
+  }
+}
+
+static cudaError_t partition_by_tile(const ViewBatch& vb, int T, int bits, uint32_t R_total, uint32_t R_max,
+                                     const uint32_t* keys, const uint32_t* vals, uint32_t* point_list,
+                                     uint32_t* ws, size_t ws_bytes, ImgState& img0, cudaStream_t stream) {
+  if (part_workspace_bytes(R_total, vb.V, T) > ws_bytes) return cudaErrorInvalidValue;
+  uint32_t* table = ws;
+  uint32_t* partial = ws + part_table_rows(R_total, vb.V) * (size_t)T;
+  const int runs = (int)((R_max + PART_RUN - 1) / PART_RUN);
+  const int tb = (T + 255) / 256;
+  static bool attr_set = false;
+  const size_t scatter_smem = sizeof(uint32_t) * PART_WARPS * (size_t)(((T + 1) >> 1) + T);
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(part_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(sizeof(uint32_t) * PART_WARPS * (size_t)(PART_MAX_TILES / 2 + PART_MAX_TILES)));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  part_count_kernel<<<dim3(runs, vb.V), PART_THREADS, sizeof(uint32_t) * T, stream>>>(keys, vb.seg_off, T, table);
+  part_scan_partial_kernel<<<dim3(tb, PART_GROUPS, vb.V), 256, 0, stream>>>(vb.seg_off, T, table, partial);
+  part_scan_tiles_kernel<<<vb.V, 1024, 0, stream>>>(T, partial, img0.ranges, vb.img_stride);
+  part_scan_runs_kernel<<<dim3(tb, PART_GROUPS, vb.V), 256, 0, stream>>>(vb.seg_off, T, table, partial);
+  part_scatter_kernel<<<dim3(runs, vb.V), PART_THREADS, scatter_smem, stream>>>(keys, vals, vb.seg_off, T, bits,
+                                                                              table, point_list);
+  DGE_LAUNCHED(5);
+  return cudaGetLastError();
+}
+
+size_t binning_batched_workspace_bytes(uint32_t R_total, int V, int T) {
+  const size_t a = sort_workspace_bytes_segmented(R_total, V);
+  const size_t b = T <= PART_MAX_TILES ? part_workspace_bytes(R_total, V, T) : 0;
+  return a > b ? a : b;
+}
+
 cudaError_t launch_binning_batched(const ViewParams& vp, const ViewBatch& vb, uint32_t R_total, uint32_t R_max,
                                    GeomState& g0, BinState& b, ImgState& img0, cudaStream_t stream) {
   const int T = vp.grid_x * vp.grid_y;
@@ -272,6 +521,10 @@ cudaError_t launch_binning_batched(const ViewParams& vp, const ViewBatch& vb, ui
                                                                  vb.geom_stride, vb.seg_off);
   DGE_LAUNCHED(3);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  static const bool no_part = getenv("DGE_NO_PARTITION") != nullptr;
+  if (passes > 0 && T <= PART_MAX_TILES && !no_part)  // one deterministic pass; writes point_list and ranges
+    return partition_by_tile(vb, T, bits, R_total, R_max, keys[passes & 1], vals[passes & 1], b.point_list,
+                             b.sort_ws, b.sort_ws_bytes, img0, stream);
   if (passes > 0) {
     e = sort_pairs_segmented(keys, vals, R_max, bits, /*iota=*/false, b.sort_ws, b.sort_ws_bytes, vb.V, 0,
                              vb.seg_off, R_total, stream);

@@ -177,7 +177,8 @@ cudaError_t launch_render_backward_batched(const ViewParams& vp, const ViewBatch
                                            const BinState& b, const ImgState& img0, const float* background,
                                            const float* dL_dpix, float* acc, size_t acc_stride_floats,
                                            bool black_background, cudaStream_t stream);
-size_t carve_binning_batched(char* base, uint32_t R_total, int V, BinState* st);
+size_t carve_binning_batched(char* base, uint32_t R_total, int V, int T, BinState* st);
+size_t binning_batched_workspace_bytes(uint32_t R_total, int V, int T);
 cudaError_t launch_l1_loss_grad(const float* image, const float* target, size_t n, float scale,
                                 float* grad, float* loss_accum, cudaStream_t stream);
 cudaError_t launch_apply_weights_render(const ViewParams& vp, const GeomState& g, const BinState& b,

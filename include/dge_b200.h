@@ -177,7 +177,7 @@ int dge_fit_backward_geom(int P, int D, int M, int V, const float* cams, int wid
  * [V,3,H,W], out_depth [V,1,H,W], acc [V][acc_stride_floats] (acc_stride_floats >= 12*P, multiple
  * of 4), radii_max [P] = max over the views of the reference's per-view radii. geometryBuffer is
  * asked for V*dge_geom_bytes(P) bytes, imageBuffer for V*dge_image_bytes(W,H), binningBuffer for
- * dge_fit_binning_bytes(R_total, V) once the counts are known. num_rendered_host (host, [V], may be
+ * dge_fit_binning_bytes(R_total, V, W, H) once the counts are known. num_rendered_host (host, [V], may be
  * NULL) receives the per-view num_rendered. Returns R_total = their sum. */
 int dge_fit_views_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge_alloc_fn imageBuffer,
                           void* alloc_ctx, int P, int D, int M, int V, const float* background, int width,
@@ -190,7 +190,7 @@ int dge_fit_views_backward_blend(int P, int V, int R_total, const float* backgro
                                  int width, int height, char* geom_buffer, char* binning_buffer,
                                  char* image_buffer, const float* dL_dpix, float* acc, size_t acc_stride_floats,
                                  void* stream);
-size_t dge_fit_binning_bytes(int R_total, int V);
+size_t dge_fit_binning_bytes(int R_total, int V, int width, int height);
 
 /* GaussianModel's activations (gaussiansplatting/scene/gaussian_model.py:221-258)
  * for the whole model in one pass — shs[P,16,3] = cat(f_dc[P,1,3], f_rest[P,15,3]), opacities =

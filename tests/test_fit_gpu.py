@@ -52,7 +52,10 @@ def test_direct_path_matches_autograd_path(cuda, streams, bgv, batched):
 def test_batched_views_bit_identical_to_per_view(cuda):
     """dge_fit_views_forward (all views of the step per launch: batched preprocess, segmented sorts,
     grid.z = view) must reproduce the per-view API bit for bit: images, depth, and the max of the radii."""
+    import ctypes as C
+    from dge_b200 import _lib as L
     from dge_b200 import diff_gaussian_rasterization as dgr
+    lib = L.load()
     model, cams, targets, bg = _setup(cuda, True)
     bg = bg + 0.25
     fit.fit_step(model, cams, targets, bg, global_batch=V, batched=True, update_stats=False)
@@ -65,11 +68,21 @@ def test_batched_views_bit_identical_to_per_view(cuda):
     for v, cam in enumerate(cams):
         rs = scene.raster_settings(cam, bg, 3, module=dgr)
         e = torch.empty(0, device=cuda)
-        R, color, depth, radii, *_ = dgr._forward_call(rs, a2["means3D"], e, a2["opacities"], a2["scales"],
-                                                       a2["rotations"], e, a2["shs"])
+        R, color, depth, radii, geom, binning, img = dgr._forward_call(rs, a2["means3D"], e, a2["opacities"],
+                                                                       a2["scales"], a2["rotations"], e, a2["shs"])
         assert torch.equal(color, vb.color[v]), v
         assert torch.equal(depth, vb.depth[v]), v
         assert R == vb.num_rendered[v], v
+        # the instance list and the tile ranges of the view inside the batch's arenas
+        bp, ip = (C.c_void_p * 2)(), (C.c_void_p * 3)()
+        lib.dge_binning_pointers(binning.data_ptr(), R, W, H, bp)
+        lib.dge_image_pointers(img.data_ptr(), W, H, ip)
+        pl = binning[bp[0] - binning.data_ptr():][:4 * R].view(torch.int32)
+        T = ((W + 15) // 16) * ((H + 15) // 16)
+        rg = img[ip[2] - img.data_ptr():][:8 * T].view(torch.int32)
+        assert torch.equal(pl, vb.binning[:4 * (total_R + R)].view(torch.int32)[total_R:]), v
+        istride = (lib.dge_image_bytes(W, H) + 255) // 256 * 256
+        assert torch.equal(rg, vb.img[v * istride + (ip[2] - img.data_ptr()):][:8 * T].view(torch.int32)), v
         radii_max = torch.maximum(radii_max, radii)
         total_R += R
     assert torch.equal(radii_max, vb.radii_max)
