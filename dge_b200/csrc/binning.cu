@@ -514,17 +514,21 @@ cudaError_t launch_binning_batched(const ViewParams& vp, const ViewBatch& vb, ui
   scan_block_sums_kernel<<<vb.V, 1024, 0, stream>>>(blocks, g0.block_sums, vb.geom_stride);
   const int bits = tile_bits(T);
   const int passes = sort_num_passes(bits);
+  static const bool no_part = getenv("DGE_NO_PARTITION") != nullptr;
+  const bool one_pass = passes > 0 && T <= PART_MAX_TILES && !no_part;
   uint32_t* keys[2] = {b.tile_ids, b.key_alt};
   uint32_t* vals[2] = {b.point_list, b.val_alt};
+  // the single-pass partition reads (key_alt, val_alt) and writes point_list; the generic sort
+  // ping-pongs and must END in (tile_ids, point_list)
+  const int src = one_pass ? 1 : (passes & 1);
   expand_kernel<<<dim3(blocks, vb.V), SCAN_THREADS, 0, stream>>>(P, vp.grid_x, order, g0.rect, g0.block_sums,
-                                                                 g0.offsets, keys[passes & 1], vals[passes & 1],
+                                                                 g0.offsets, keys[src], vals[src],
                                                                  vb.geom_stride, vb.seg_off);
   DGE_LAUNCHED(3);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  static const bool no_part = getenv("DGE_NO_PARTITION") != nullptr;
-  if (passes > 0 && T <= PART_MAX_TILES && !no_part)  // one deterministic pass; writes point_list and ranges
-    return partition_by_tile(vb, T, bits, R_total, R_max, keys[passes & 1], vals[passes & 1], b.point_list,
-                             b.sort_ws, b.sort_ws_bytes, img0, stream);
+  if (one_pass)  // one deterministic pass; writes point_list and ranges
+    return partition_by_tile(vb, T, bits, R_total, R_max, keys[1], vals[1], b.point_list, b.sort_ws,
+                             b.sort_ws_bytes, img0, stream);
   if (passes > 0) {
     e = sort_pairs_segmented(keys, vals, R_max, bits, /*iota=*/false, b.sort_ws, b.sort_ws_bytes, vb.V, 0,
                              vb.seg_off, R_total, stream);

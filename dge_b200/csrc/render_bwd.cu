@@ -128,7 +128,10 @@ __global__ void __launch_bounds__(BL_THREADS, 9) render_backward_kernel(
         if (alpha < 1.0f / 255.0f) continue;
         touched = true;
         const float one_m = 1.0f - alpha;
-        T[p] = __fdiv_rn(T[p], one_m);  // same recurrence as the reference (backward.cu:505)
+        // the reference's recurrence T /= (1 - alpha) (backward.cu:505); the quotient only feeds
+        // gradients (tolerance 1e-4), so the 2-instruction reciprocal-multiply replaces the IEEE
+        // division sequence (its error, ~1 ulp per step, stays below 1e-5 over a whole list)
+        T[p] = __fdividef(T[p], one_m);
         const float w = alpha * T[p];
         float dL_dalpha = 0.0f;
 #pragma unroll
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(BL_THREADS, 9) render_backward_kernel(
           behind[p][c] = alpha * col[c] + one_m * behind[p][c];
         }
         dL_dalpha *= T[p];
-        if (HAS_BG) dL_dalpha += __fdiv_rn(-T_final[p], one_m) * bg_dot[p];
+        if (HAS_BG) dL_dalpha += __fdividef(-T_final[p], one_m) * bg_dot[p];
         const float dL_dG = opacity * dL_dalpha;
         const float gdx = G * dx, gdy = G * dy;
         const float dG_ddelx = -gdx * a.z - gdy * a.w;

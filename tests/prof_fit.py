@@ -6,11 +6,11 @@ import torch
 from dge_b200 import fit, scene
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--views", type=int, default=6)
+ap.add_argument("--views", type=int, default=20)
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--P", type=int, default=1_000_000)
 ap.add_argument("--res", type=int, default=512)
-ap.add_argument("--streams", type=int, default=1)
+ap.add_argument("--streams", type=int, default=0)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 g = scene.make_gaussians(args.P, seed=1236)
@@ -20,6 +20,6 @@ targets = [torch.rand(3, args.res, args.res, generator=gen).to(dev) for _ in ran
 model = fit.FitModel(g, dev, fused_adam=True)
 bg = torch.zeros(3, device=dev)
 for _ in range(args.steps):
-    loss = fit.fit_step(model, cams, targets, bg, global_batch=args.views, num_streams=args.streams)
+    loss = fit.fit_step(model, cams, targets, bg, global_batch=args.views, num_streams=max(args.streams, 1), batched=args.streams == 0)
 torch.cuda.synchronize()
 print("ok", float(loss))

@@ -13,8 +13,8 @@ pytestmark = pytest.mark.gpu
 P, W, H, V = 30000, 160, 128, 5
 
 
-def _setup(cuda, fused):
-    g = scene.make_gaussians(P, seed=61, scale_median=0.03)
+def _setup(cuda, fused, P=P, W=W, H=H, V=V, scale_median=0.03):
+    g = scene.make_gaussians(P, seed=61, scale_median=scale_median)
     cams = [scene.camera_to(c, cuda) for c in scene.ring_cameras(V, W, H)]
     gen = torch.Generator().manual_seed(5)
     targets = [torch.rand(3, H, W, generator=gen).to(cuda) for _ in range(V)]
@@ -49,19 +49,23 @@ def test_direct_path_matches_autograd_path(cuda, streams, bgv, batched):
         model.exp_avg_sq.copy_(ref_model.exp_avg_sq)
 
 
-def test_batched_views_bit_identical_to_per_view(cuda):
+@pytest.mark.parametrize("P,W,H,V,sm", [(30000, 160, 128, 5, 0.03),      # 80 tiles: 7 tile-id bits
+                                        (250000, 512, 512, 3, 0.012),    # config-2 shape: 1024 tiles, 10 bits
+                                        (60000, 1264, 832, 2, 0.03)])    # config-4 shape: 4108 tiles (generic sort)
+def test_batched_views_bit_identical_to_per_view(cuda, P, W, H, V, sm):
     """dge_fit_views_forward (all views of the step per launch: batched preprocess, segmented sorts,
-    grid.z = view) must reproduce the per-view API bit for bit: images, depth, and the max of the radii."""
+    single-pass tile partition, grid.z = view) must reproduce the per-view API bit for bit: images,
+    depth, instance lists, tile ranges, and the max of the radii."""
     import ctypes as C
     from dge_b200 import _lib as L
     from dge_b200 import diff_gaussian_rasterization as dgr
     lib = L.load()
-    model, cams, targets, bg = _setup(cuda, True)
+    model, cams, targets, bg = _setup(cuda, True, P, W, H, V, sm)
     bg = bg + 0.25
     fit.fit_step(model, cams, targets, bg, global_batch=V, batched=True, update_stats=False)
     vb = model._batches[0]
     # the step above moved the parameters (Adam): the per-view API renders an untouched twin
-    model2, _, _, _ = _setup(cuda, True)
+    model2, _, _, _ = _setup(cuda, True, P, W, H, V, sm)
     a2 = model2.activations_fused()
     radii_max = torch.zeros(P, dtype=torch.int32, device=cuda)
     total_R = 0
