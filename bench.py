@@ -32,6 +32,12 @@ CONFIGS = {
     # name: P, W, H, views per GPU per step, seed
     "config2": dict(P=1_000_000, W=512, H=512, V=20, seed=1236,
                     desc="DGE global edit fit: 1M Gaussians, 20 views/step/GPU at 512x512, fwd+bwd+Adam"),
+    # BASELINE.json configs[3]: use_original_resolution, 64 views sharded over the GPUs (8 per GPU at 8 GPUs)
+    "config4": dict(P=3_000_000, W=1264, H=832, V=8, seed=1238,
+                    desc="use_original_resolution: 3M Gaussians at 1264x832, 8 views/step/GPU, fwd+bwd+Adam"),
+    # BASELINE.json configs[4] (one point of the sweep): 1080p, sort/duplicate stress
+    "config5": dict(P=2_000_000, W=1920, H=1080, V=8, seed=1239,
+                    desc="densification sweep point: 2M Gaussians at 1920x1080, 8 views/step/GPU, fwd+bwd+Adam"),
     "config1": dict(P=16_384, W=256, H=256, V=1, seed=1235, desc="16k Gaussians, one 256x256 view (parity config)"),
     "tiny": dict(P=50_000, W=256, H=256, V=4, seed=1240, desc="smoke-sized"),
     "hostbound": dict(P=2_000, W=64, H=64, V=20, seed=1241, desc="negligible GPU work: measures host overhead per view"),
@@ -371,7 +377,7 @@ def main():
         out["cpu_baseline"] = {"value": value, "unit": "views/s", "cores": os.cpu_count(), "kind": "reference",
                                "sample": "the reference ships no CPU rasterizer; this arm runs its UNMODIFIED CUDA code rebuilt "
                                          "for sm_100a (oracle/_ref) on one B200 of the same box, same harness, torch.optim.Adam"}
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
     if world > 1 and args.impl == "ours":
         dist.destroy_process_group()
     return 0

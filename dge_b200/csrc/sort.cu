@@ -300,7 +300,9 @@ cudaError_t sort_pairs_segmented(uint32_t* keys[2], uint32_t* vals[2], uint32_t 
   const int passes = sort_num_passes(num_bits);
   if (passes < 1 || passes > MAX_PASSES) return cudaErrorInvalidValue;
   static const int env_ipt = getenv("DGE_SORT_IPT") ? atoi(getenv("DGE_SORT_IPT")) : 0;
-  const int ipt = env_ipt == 8 || env_ipt == 16 ? env_ipt : (n <= (2u << 20) ? 8 : 16);
+  // small single sorts: 2048-item tiles (more CTAs in flight); otherwise 4096-item tiles: the look-back
+  // of a tile walks all its predecessors in the first wave, so fewer, larger tiles cost less
+  const int ipt = env_ipt == 8 || env_ipt == 16 ? env_ipt : ((uint64_t)n * segs <= (2u << 20) ? 8 : 16);
   const uint32_t tiles = sort_num_tiles(n, ipt);
   uint32_t *tickets = ws, *hist, *status;
   size_t pass_stride;  // words between the status tables of consecutive passes
