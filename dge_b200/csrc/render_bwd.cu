@@ -17,13 +17,17 @@
 // kernel in geom_bwd.cu turns them into the reference's output tensors.
 #include "blend.cuh"
 
+#ifndef DGE_BWD_MIN_CTAS
+#define DGE_BWD_MIN_CTAS 12
+#endif
+
 namespace dge {
 
 // HAS_BG: a non-black background adds the -T_final/(1-alpha) * (bg . dL/dpixel) term to dL/dalpha
 // (backward.cu:526-529); for DGE's black background (DGE.py:87) that term, its division and
 // eight registers of per-pixel state disappear at compile time.
 template <bool HAS_BG>
-__global__ void __launch_bounds__(BL_THREADS, 9) render_backward_kernel(
+__global__ void __launch_bounds__(BL_THREADS, DGE_BWD_MIN_CTAS) render_backward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
     const float* __restrict__ background, const float4* __restrict__ means2D,
     const float4* __restrict__ conic_opacity, const float4* __restrict__ rgb_depth,
