@@ -391,10 +391,15 @@ __global__ void __launch_bounds__(256) part_scan_runs_kernel(const uint32_t* __r
   const uint32_t r0 = min(runs, g * per), r1 = min(runs, r0 + per);
   uint32_t* col = table + part_row0(seg_off, v) * (size_t)T + t;
   uint32_t run = partial[((size_t)v * PART_GROUPS + g) * T + t];
-  for (uint32_t r = r0; r < r1; r++) {
-    const uint32_t c = col[(size_t)r * T];
-    col[(size_t)r * T] = run;
-    run += c;
+  for (uint32_t r = r0; r < r1; r += 8) {  // eight independent loads in flight, then the eight stores
+    uint32_t c[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = (r + k < r1) ? col[(size_t)(r + k) * T] : 0u;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (r + k < r1) col[(size_t)(r + k) * T] = run;
+      run += c[k];
+    }
   }
 }
 
@@ -414,7 +419,9 @@ __global__ void __launch_bounds__(PART_THREADS) part_scatter_kernel(
   const uint32_t* keys = tile_ids + o;
   const uint32_t* vals = gids + o;
   uint32_t* out = point_list + o;
-  for (int i = threadIdx.x; i < PART_WARPS * TP; i += PART_THREADS) s_cnt[i] = 0;
+  // (the carve below keeps s_cnt 16-byte aligned and PART_WARPS * TP a multiple of 4 words)
+  for (int i = threadIdx.x; i < PART_WARPS * TP / 4; i += PART_THREADS)
+    reinterpret_cast<uint4*>(s_cnt)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
   // A: per-warp counts of the warp's own PART_WARP_ITEMS consecutive instances. Keys and Gaussian ids
   // are loaded ONCE, all loads in flight together, and stay in registers for the ranking below.
@@ -435,14 +442,20 @@ __global__ void __launch_bounds__(PART_THREADS) part_scatter_kernel(
   for (int k = 0; k < PART_IPL; k++)
     if (key[k] != 0xFFFFFFFFu) atomicAdd(&s_cnt[warp * TP + (key[k] >> 1)], 1u << (16 * (key[k] & 1)));
   __syncthreads();
-  // B: position of each warp's first instance of every tile
+  // B: position of each warp's first instance of every tile, two tiles (one packed counter word) per
+  // step: the table is as large as the run (8 warps x T entries for 4096 instances), so this loop
+  // was 40 % of the kernel's instructions when written tile by tile
   const uint32_t* row = table + (part_row0(seg_off, v) + blockIdx.x) * (size_t)T;
-  for (int t = threadIdx.x; t < T; t += PART_THREADS) {
-    uint32_t run = row[t];
+  for (int t2 = threadIdx.x; t2 < TP; t2 += PART_THREADS) {
+    const int t = 2 * t2;
+    uint32_t run0 = row[t], run1 = (t + 1 < T) ? row[t + 1] : 0u;
 #pragma unroll
     for (int w = 0; w < PART_WARPS; w++) {
-      s_base[w * T + t] = run;
-      run += (s_cnt[w * TP + (t >> 1)] >> (16 * (t & 1))) & 0xFFFFu;
+      const uint32_t c = s_cnt[w * TP + t2];
+      s_base[w * T + t] = run0;
+      if (t + 1 < T) s_base[w * T + t + 1] = run1;
+      run0 += c & 0xFFFFu;
+      run1 += c >> 16;
     }
   }
   __syncthreads();

@@ -207,11 +207,11 @@ def _direct_views(model: FitModel, acts, cameras, targets, bg, scale, host_input
     if getattr(model, "_lane_key", None) != key:
         model._lanes = [ViewLane(model, W, H, torch.cuda.Stream(dev)) for _ in range(S)]
         f32 = dict(dtype=torch.float32, device=dev)
-        model._acc = torch.empty(V, P, 12, **f32)          # blend-stage sums of every view of the step
-        model._cams = torch.empty(V, CAM_FLOATS, **f32)
-        model._cam_cache = {}
+        model._lane_acc = torch.empty(V, P, 12, **f32)          # blend-stage sums of every view of the step
+        model._lane_cams = torch.empty(V, CAM_FLOATS, **f32)
+        model._lane_cam_cache = {}
         model._lane_key = key
-    lanes, acc, cams_dev = model._lanes, model._acc, model._cams
+    lanes, acc, cams_dev = model._lanes, model._lane_acc, model._lane_cams
     a = {k: v.detach() for k, v in acts.items()}
     ptrs = {k: v.data_ptr() for k, v in a.items()}
     M = a["shs"].shape[1]
@@ -227,10 +227,10 @@ def _direct_views(model: FitModel, acts, cameras, targets, bg, scale, host_input
     for i, (cam, target) in enumerate(zip(cameras, targets)):
         ln = lanes[i % S]
         ck = cam.world_view_transform.data_ptr()
-        rec = model._cam_cache.get(ck)
+        rec = model._lane_cam_cache.get(ck)
         if rec is None:
             r = pack_camera(cam)
-            rec = model._cam_cache[ck] = (r, float(r[35]), float(r[36]))
+            rec = model._lane_cam_cache[ck] = (r, float(r[35]), float(r[36]))
         rec, tfx, tfy = rec
         with torch.cuda.stream(ln.stream):
             cams_dev[i].copy_(rec, non_blocking=True)
