@@ -38,6 +38,9 @@ CONFIGS = {
     # BASELINE.json configs[4] (one point of the sweep): 1080p, sort/duplicate stress
     "config5": dict(P=2_000_000, W=1920, H=1080, V=8, seed=1239,
                     desc="densification sweep point: 2M Gaussians at 1920x1080, 8 views/step/GPU, fwd+bwd+Adam"),
+    # BASELINE.json configs[2], first half: DGE.update_mask (DGE.py:101-165) — mask back-projection over 40 views
+    "config3": dict(P=1_000_000, W=512, H=512, V=40, seed=1237,
+                    desc="DGE local edit: mask back-projection (apply_weights) of a disc mask over 40 views of 512x512, 1M Gaussians"),
     "config1": dict(P=16_384, W=256, H=256, V=1, seed=1235, desc="16k Gaussians, one 256x256 view (parity config)"),
     "tiny": dict(P=50_000, W=256, H=256, V=4, seed=1240, desc="smoke-sized"),
     "hostbound": dict(P=2_000, W=64, H=64, V=20, seed=1241, desc="negligible GPU work: measures host overhead per view"),
@@ -160,6 +163,89 @@ KERNEL_OF_STAGE = {"preprocess": "preprocess_kernel", "render_fwd": "render_forw
                    "binning": "onesweep_kernel+expand_kernel", "depth_sort": "onesweep_kernel"}
 
 
+def main_config3(args, cfg):
+    """Mask back-projection (DGE.update_mask, threestudio/systems/DGE.py:101-165): a step = apply_weights of a
+    binary disc mask over all V views into weights/cnt, then the selection weights/(cnt+1e-7) > mask_thres.
+    `value`: masks resident; `e2e`: masks in pinned host memory copied per view, the selection read back."""
+    import numpy as np
+    from dge_b200 import scene
+    from dge_b200 import _lib as L
+    from dge_b200 import diff_gaussian_rasterization as dgr
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    P, W, H, V = cfg["P"], cfg["W"], cfg["H"], cfg["V"]
+    g = scene.make_gaussians(P, seed=cfg["seed"])
+    gd = scene.Gaussians(*[t.to(dev) for t in g])
+    cams = [scene.camera_to(c, dev) for c in scene.ring_cameras(V, W, H)]
+    bg = torch.zeros(3, device=dev)
+    mask_host = scene.disc_mask(W, H, radius=160.0).pin_memory()
+    mask_dev = mask_host.to(dev)
+    weights = torch.zeros(P, 1, device=dev)
+    cnt = torch.zeros(P, 1, dtype=torch.int32, device=dev)
+    lib = L.load()
+    e = torch.empty(0, device=dev)
+    if args.impl == "reference":
+        from oracle import ref
+        tans = [(math.tan(c.FoVx * 0.5), math.tan(c.FoVy * 0.5)) for c in cams]
+
+    def step(host):
+        weights.zero_()
+        cnt.zero_()
+        for i, cam in enumerate(cams):
+            m = mask_host.to(dev, non_blocking=True) if host else mask_dev
+            if args.impl == "ours":
+                rs = scene.raster_settings(cam, bg, 0, module=dgr)
+                dgr.GaussianRasterizer(rs).apply_weights(gd.means3D, None, gd.opacities, None, weights, gd.scales,
+                                                         gd.rotations, None, cnt, m)
+            else:
+                ref.apply_weights(bg, gd.means3D, weights, gd.opacities, gd.scales, gd.rotations, 1.0, e,
+                                  cam.world_view_transform, cam.full_proj_transform, tans[i][0], tans[i][1], H, W, e, 0,
+                                  cam.camera_center, False, m, cnt, False)
+        sel = (weights / (cnt + 1e-7)) > 0.8   # DGE.py:149-152, dge.yaml mask_thres
+        return sel
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    torch.cuda.synchronize()
+    l0 = lib.dge_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        sel = step(False)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = lib.dge_launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        n_sel = int(step(True).sum().item())
+    e3.record()
+    torch.cuda.synchronize()
+    ms_e2e = e2.elapsed_time(e3)
+    sampler = ClockSampler(0, period=0.05)
+    sampler.start()
+    for _ in range(args.steps):
+        step(False)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    views = V * args.steps
+    out = {"metric": "mask back-projection views/s @1M Gaussians 512^2 (DGE.update_mask: apply_weights over 40 views)",
+           "value": views / (ms * 1e-3), "unit": "views/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic",
+           "config": {"workload": f"config3: {cfg['desc']}", "gaussians": P, "resolution": [W, H], "views_per_step": V,
+                      "mask": "binary disc, radius 160 px", "selected": n_sel, "scene": "randgauss-v1"},
+           "clocks": clocks,
+           "e2e": {"value": views / (ms_e2e * 1e-3), "unit": "views/s", "h2d_bytes_per_step": V * W * H * 4,
+                   "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
+           "gpu_launches": int(launches) if args.impl == "ours" else None}
+    if args.impl == "reference":
+        out["impl"] = "reference"
+    print(json.dumps(out), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -175,6 +261,10 @@ def main():
                          "round-robin on N CUDA streams")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
+    if args.config == "config3":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0
+        return main_config3(args, cfg)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
