@@ -48,8 +48,11 @@ class FitModel:
         self.P, self.device, self.sh_degree = P, device, sh_degree
         self.lrs = dict(DEFAULT_LRS if lrs is None else lrs)
         self.fused_adam = fused_adam
-        n = FLOATS_PER_GAUSSIAN * P
-        self.flat = torch.empty(n, dtype=torch.float32, device=device)
+        # every group starts on a 16-byte boundary inside the flat buffers (float4 accesses in the
+        # kernels: rotation rows, vectorised Adam), whatever P is
+        pad4 = lambda x: (x + 3) // 4 * 4
+        n = sum(pad4(k * P) for _, k, _ in GROUPS)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=device)
         # gradient buffer: 59P parameter grads followed by the 3P screen-space gradient sum
         self.flat_grad = torch.zeros(n + 3 * P, dtype=torch.float32, device=device)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=device)
@@ -71,9 +74,10 @@ class FitModel:
             p.requires_grad_(True)  # a leaf: `flat` itself never requires grad
             p.grad = self.flat_grad[sl].view(P, *tail)
             self.params[name] = p
-            off += k * P
+            off += pad4(k * P)
         self.means2D = torch.zeros(P, 3, dtype=torch.float32, device=device, requires_grad=True)
-        self.means2D.grad = self.flat_grad[n:].view(P, 3)
+        self.means2D_slice = slice(n, n + 3 * P)
+        self.means2D.grad = self.flat_grad[self.means2D_slice].view(P, 3)
         # densification statistics (gaussian_model.py:338-339, 811-815; DGE.py:277-284)
         self.xyz_gradient_accum = torch.zeros(P, 1, device=device)
         self.denom = torch.zeros(P, 1, device=device)

@@ -34,8 +34,7 @@ def test_direct_path_matches_autograd_path(cuda, streams, bgv, batched):
                          num_chunks=streams)
         torch.cuda.synchronize()
         assert abs(float(l) - float(l_ref)) <= 1e-5 * abs(float(l_ref))
-        n59 = fit.FLOATS_PER_GAUSSIAN * P
-        for name, sl in list(model.slices.items()) + [("means2D", slice(n59, n59 + 3 * P))]:
+        for name, sl in list(model.slices.items()) + [("means2D", model.means2D_slice)]:
             ok, msg = util.grad_ok(model.flat_grad[sl].cpu().numpy(), g_ref[sl].cpu().numpy())
             assert ok, (step, name, msg)
         assert torch.equal(model.max_radii2D, ref_model.max_radii2D)
@@ -51,7 +50,9 @@ def test_direct_path_matches_autograd_path(cuda, streams, bgv, batched):
 
 @pytest.mark.parametrize("P,W,H,V,sm", [(30000, 160, 128, 5, 0.03),      # 80 tiles: 7 tile-id bits
                                         (250000, 512, 512, 3, 0.012),    # config-2 shape: 1024 tiles, 10 bits
-                                        (60000, 1264, 832, 2, 0.03)])    # config-4 shape: 4108 tiles (generic sort)
+                                        (60000, 1264, 832, 2, 0.03),     # config-4 shape: 4108 tiles (generic sort)
+                                        (30001, 33, 17, 1, 0.1),         # one view, ragged image, odd P
+                                        (3001, 100, 60, 64, 0.05)])      # the largest batch
 def test_batched_views_bit_identical_to_per_view(cuda, P, W, H, V, sm):
     """dge_fit_views_forward (all views of the step per launch: batched preprocess, segmented sorts,
     single-pass tile partition, grid.z = view) must reproduce the per-view API bit for bit: images,
@@ -90,6 +91,37 @@ def test_batched_views_bit_identical_to_per_view(cuda, P, W, H, V, sm):
         radii_max = torch.maximum(radii_max, radii)
         total_R += R
     assert torch.equal(radii_max, vb.radii_max)
+
+
+def test_batched_with_empty_views(cuda):
+    """Views that see nothing (camera looking away: every Gaussian culled, num_rendered == 0) inside a
+    batch, and a batch made only of such views: images are the background, gradients are exact zeros for
+    those views, and the other views are unaffected."""
+    g_model, cams, targets, bg = _setup(cuda, True)
+    away = scene.camera_to(scene.look_at_camera((0.0, 0.0, 6.0), W, H, target=(0.0, 0.0, 12.0)), cuda)
+    bg = bg + 0.5
+    # mixed batch: [cam0, away, cam1]
+    mixed = [cams[0], away, cams[1]]
+    tg = [targets[0], targets[1], targets[2]]
+    a, _, _, _ = _setup(cuda, True)
+    b, _, _, _ = _setup(cuda, True)
+    la = fit.fit_step(a, mixed, tg, bg, global_batch=3, batched=True, update_stats=False)
+    lb = fit.fit_step(b, mixed, tg, bg, global_batch=3, batched=False, num_streams=1, update_stats=False)
+    torch.cuda.synchronize()
+    vb = a._batches[0]
+    assert list(vb.num_rendered)[1] == 0 and list(vb.num_rendered)[0] > 0
+    assert torch.equal(vb.color[1], bg.view(3, 1, 1).expand(3, H, W))
+    assert abs(float(la) - float(lb)) <= 1e-5 * abs(float(lb))
+    for name, sl in a.slices.items():
+        ok, msg = util.grad_ok(a.flat_grad[sl].cpu().numpy(), b.flat_grad[sl].cpu().numpy())
+        assert ok, (name, msg)
+    # a batch in which no view sees anything
+    c, _, _, _ = _setup(cuda, True)
+    lc = fit.fit_step(c, [away, away], [targets[0], targets[1]], bg, global_batch=2, batched=True, update_stats=False)
+    torch.cuda.synchronize()
+    assert sum(c._batches[0].num_rendered) == 0
+    assert not c.flat_grad.any()
+    assert torch.isfinite(lc)
 
 
 def test_host_inputs_equal_resident(cuda):
