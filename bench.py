@@ -254,13 +254,19 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="config2", choices=list(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gaussians", type=int, default=0, help="override the config's number of Gaussians (config 5 sweep)")
+    ap.add_argument("--views", type=int, default=0, help="override the config's views per step per GPU")
     ap.add_argument("--chunks", type=int, default=1, help="batched path: split the step's views into this many "
                     "chunks, each on its own stream")
     ap.add_argument("--streams", type=int, default=0,
                     help="0 (default): all views of a step per launch (batched path); N>0: views one by one, "
                          "round-robin on N CUDA streams")
     args = ap.parse_args()
-    cfg = CONFIGS[args.config]
+    cfg = dict(CONFIGS[args.config])
+    if args.gaussians:
+        cfg["P"] = args.gaussians
+    if args.views:
+        cfg["V"] = args.views
     if args.config == "config3":
         if int(os.environ.get("RANK", "0")) != 0:
             return 0

@@ -327,13 +327,17 @@ cudaError_t launch_preprocess(const ViewParams& vp, const float* means3D, const 
 // writes the per-view records: ~20x less input traffic than V per-view launches. Also produces the
 // running max of the radii over the views (max_radii2D statistics) instead of V radii arrays.
 constexpr int PRE_B_THREADS = 128;
-__global__ void __launch_bounds__(PRE_B_THREADS) preprocess_batched_kernel(
+constexpr int PRE_B_MIN_CTAS = 6;  // 80 registers: the 48 SH floats live in shared memory, not registers
+__global__ void __launch_bounds__(PRE_B_THREADS, PRE_B_MIN_CTAS) preprocess_batched_kernel(
     ViewParams vp, int V, const float* __restrict__ cams, const float* __restrict__ means3D,
     const float* __restrict__ scales, const float* __restrict__ rotations,
     const float* __restrict__ opacities, const float* __restrict__ shs, GeomState g0, size_t geom_stride,
     float4* __restrict__ acc0, size_t acc_stride_floats, int* __restrict__ radii_max) {
-  extern __shared__ float s_cam[];  // V * 40 floats, then V warp-sum rows
+  extern __shared__ float s_cam[];  // V * 40 floats, V per-view instance counts, then the SH block
   uint32_t* s_tiles = reinterpret_cast<uint32_t*>(s_cam + V * 40);  // [V]
+  // this thread's 48 SH floats at s_sh[k * PRE_B_THREADS + tid]: conflict-free, and 48 registers less
+  // than keeping them live across the view loop (4 -> 6 CTAs per SM)
+  float* s_sh = s_cam + V * 41 + threadIdx.x;
   for (int k = threadIdx.x; k < V * 40; k += blockDim.x) s_cam[k] = cams[k];
   for (int k = threadIdx.x; k < V; k += blockDim.x) s_tiles[k] = 0;
   __syncthreads();
@@ -341,7 +345,6 @@ __global__ void __launch_bounds__(PRE_B_THREADS) preprocess_batched_kernel(
   const bool live = idx < vp.P;
   float px = 0.f, py = 0.f, pz = 0.f, opac = 0.f;
   float cov3[6];
-  float4 v[12];
   if (live) {
     px = __ldg(means3D + 3 * idx);
     py = __ldg(means3D + 3 * idx + 1);
@@ -351,10 +354,13 @@ __global__ void __launch_bounds__(PRE_B_THREADS) preprocess_batched_kernel(
                          vp.scale_modifier, q, cov3);
     opac = __ldg(opacities + idx);
     const float* base = shs + 48 * (size_t)idx;
+    float4 v[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) v[i] = ldg4(base + 4 * i);
+    const float* f = reinterpret_cast<const float*>(v);
+#pragma unroll
+    for (int k = 0; k < 48; k++) s_sh[k * PRE_B_THREADS] = f[k];
   }
-  const float* f = reinterpret_cast<const float*>(v);
   int rmax = 0;
   for (int view = 0; view < V; view++) {
     const float* cam = s_cam + view * 40;
@@ -373,7 +379,8 @@ __global__ void __launch_bounds__(PRE_B_THREADS) preprocess_batched_kernel(
             for (int i = 0; i < 6; i++) c[i] = cov3[i];
           },
           [&](float* rgb) -> uint8_t {
-            return sh_color(vp.D, px, py, pz, cam[32], cam[33], cam[34], [&](int k, int c) { return f[3 * k + c]; }, rgb);
+            return sh_color(vp.D, px, py, pz, cam[32], cam[33], cam[34],
+                            [&](int k, int c) { return s_sh[(3 * k + c) * PRE_B_THREADS]; }, rgb);
           },
           [&]() { return opac; });
       const size_t sh_ = (size_t)view * geom_stride;
@@ -409,7 +416,7 @@ cudaError_t launch_preprocess_batched(const ViewParams& vp, const ViewBatch& vb,
   cudaError_t e = cudaMemset2DAsync(g0.counters, vb.geom_stride, 0, 64 * sizeof(uint32_t), (size_t)vb.V, stream);
   if (e != cudaSuccess) return e;
   const int blocks = (vp.P + PRE_B_THREADS - 1) / PRE_B_THREADS;
-  const size_t smem = (size_t)vb.V * (40 * sizeof(float) + sizeof(uint32_t));
+  const size_t smem = (size_t)vb.V * (40 * sizeof(float) + sizeof(uint32_t)) + 48 * PRE_B_THREADS * sizeof(float);
   preprocess_batched_kernel<<<blocks, PRE_B_THREADS, smem, stream>>>(
       vp, vb.V, vb.cams, means3D, scales, rotations, opacities, shs, g0, vb.geom_stride,
       reinterpret_cast<float4*>(acc), acc_stride_floats, radii_max);

@@ -451,8 +451,20 @@ def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence
         if batched is None:
             batched = len(cameras) <= 64
         if batched:
-            loss, radii_max = _batched_views(model, model.activations_fused(), cameras, targets, bg, scale, host_inputs,
-                                             num_chunks)
+            # a chunk's instance lists share one arena addressed with 30-bit positions: when the views of a
+            # chunk hold more than 2^30 instances (6 M Gaussians at 1080p: ~60 M per view), split further
+            chunks = max(num_chunks, getattr(model, "_min_chunks", 1))
+            while True:
+                try:
+                    loss, radii_max = _batched_views(model, model.activations_fused(), cameras, targets, bg, scale,
+                                                     host_inputs, chunks)
+                    break
+                except RuntimeError as ex:
+                    if "2^30" not in str(ex) or chunks >= len(cameras):
+                        raise
+                    torch.cuda.synchronize(dev)
+                    chunks = min(len(cameras), chunks * 2)
+                    model._min_chunks = chunks
         else:
             loss, radii_max = _direct_views(model, model.activations_fused(), cameras, targets, bg, scale, host_inputs,
                                             num_streams)
