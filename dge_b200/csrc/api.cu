@@ -72,9 +72,7 @@ size_t carve_geom(char* base, int P, GeomState* st) {
   GeomState s;
   char* p = base;
   const size_t n = (size_t)P;
-  take(p, s.means2D, n);
-  take(p, s.conic_opacity, n);
-  take(p, s.rgb_depth, n);
+  take(p, s.rec, n * REC_F4);
   take(p, s.rect, n);
   take(p, s.clamped, n);
   take(p, s.sort_key[0], n);
@@ -529,9 +527,9 @@ int dge_mark_visible(int P, const float* means3D, const float* viewmatrix, const
 void dge_geom_pointers(char* chunk, int P, void** out) {
   GeomState g;
   carve_geom(chunk, P, &g);
-  out[0] = g.means2D;
-  out[1] = g.conic_opacity;
-  out[2] = g.rgb_depth;
+  out[0] = g.rec;
+  out[1] = nullptr;
+  out[2] = nullptr;
   out[3] = g.rect;
   out[4] = g.clamped;
   out[5] = g.sort_val[0];

@@ -17,8 +17,7 @@ namespace dge {
 template <int CH>
 __global__ void __launch_bounds__(BL_THREADS) apply_weights_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
-    const float4* __restrict__ means2D, const float4* __restrict__ conic_opacity,
-    const float* __restrict__ image_weights, float* __restrict__ weights, int* __restrict__ cnt) {
+    const float4* __restrict__ rec, const float* __restrict__ image_weights, float* __restrict__ weights, int* __restrict__ cnt) {
   __shared__ BlendSmem s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // pixel p of this thread = (px0 + PX_STEP*(p&1), py0 + PY_STEP*(p>>1)): one pixel in each 8x4
@@ -42,13 +41,14 @@ __global__ void __launch_bounds__(BL_THREADS) apply_weights_kernel(
     for (int c = 0; c < CH; c++) Cw[p][c] = inside ? image_weights[c * HW + (size_t)y * W + x] : 0.0f;
   }
 
+  stage_init(s, tid);
+  uint32_t parity = 0;
   for (uint32_t base = range.x; base < range.y; base += BL_BATCH) {
     const bool all_done = done[0] && done[1] && done[2] && done[3];
     if (__syncthreads_and(all_done)) break;
     const int count = min((uint32_t)BL_BATCH, range.y - base);
-    stage_batch<false>(s, tid, count, [&](int k) { return base + k; }, point_list, means2D,
-                       conic_opacity, (const float4*)nullptr);
-    __syncthreads();
+    stage_batch(s, tid, count, [&](int k) { return base + k; }, point_list, rec, parity);
+    parity ^= 1u;
     if (__all_sync(0xFFFFFFFFu, all_done)) continue;
     uint32_t live = 0;
 #pragma unroll
@@ -57,8 +57,8 @@ __global__ void __launch_bounds__(BL_THREADS) apply_weights_kernel(
     for (int i = 0; i < n; i++) {
       const uint32_t e = s.list[warp][i];  // warp-uniform
       const int j = e & 0xFF;
-      const float4 a = s.a[j];
-      const float4 b = s.b[j];
+      const float4 a = s.rec[j][0];  // x, y, conic.x, conic.y
+      const float4 b = s.rec[j][1];  // conic.z, power threshold, opacity, depth
       float wsum[CH];
 #pragma unroll
       for (int c = 0; c < CH; c++) wsum[c] = 0.0f;
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(BL_THREADS) apply_weights_kernel(
       for (int c = 0; c < CH; c++)
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) wsum[c] += __shfl_xor_sync(0xFFFFFFFFu, wsum[c], o);
-      const uint32_t gid = __float_as_uint(b.w);
+      const uint32_t gid = __float_as_uint(s.rec[j][REC_F4].x);
       if (lane == 0) atomicAdd(cnt + gid, total * CH);
 #pragma unroll
       for (int c = 0; c < CH; c++)
@@ -102,8 +102,7 @@ cudaError_t launch_apply_weights_render(const ViewParams& vp, const GeomState& g
   dim3 grid(vp.grid_x, vp.grid_y);
 #define AW_LAUNCH(CH)                                                                          \
   apply_weights_kernel<CH><<<grid, BL_THREADS, 0, stream>>>(img.ranges, b.point_list, vp.W, vp.H, \
-                                                            g.means2D, g.conic_opacity,        \
-                                                            image_weights, weights, cnt)
+                                                            g.rec, image_weights, weights, cnt)
   if (num_channels == 1) AW_LAUNCH(1);
   else if (num_channels == 2) AW_LAUNCH(2);
   else if (num_channels == 3) AW_LAUNCH(3);

@@ -185,11 +185,11 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(uint32_t R,
 
 __global__ void debug_keys_kernel(uint32_t R, const uint32_t* __restrict__ tile_ids,
                                   const uint32_t* __restrict__ point_list,
-                                  const float4* __restrict__ rgb_depth,
+                                  const float4* __restrict__ rec,
                                   uint64_t* __restrict__ keys_out) {
   const uint32_t i = blockIdx.x * 256u + threadIdx.x;
   if (i >= R) return;
-  keys_out[i] = ((uint64_t)tile_ids[i] << 32) | __float_as_uint(rgb_depth[point_list[i]].w);
+  keys_out[i] = ((uint64_t)tile_ids[i] << 32) | __float_as_uint(rec[(size_t)point_list[i] * REC_F4 + 1].w);
 }
 
 cudaError_t launch_depth_sort(int P, GeomState& g, cudaStream_t stream) {
@@ -563,7 +563,7 @@ cudaError_t launch_debug_keys(const GeomState& g, const BinState& b, int R, uint
                               cudaStream_t stream) {
   if (R == 0) return cudaSuccess;
   debug_keys_kernel<<<(R + 255) / 256, 256, 0, stream>>>((uint32_t)R, b.tile_ids, b.point_list,
-                                                         g.rgb_depth, keys_out);
+                                                         g.rec, keys_out);
   return cudaGetLastError();
 }
 

@@ -38,49 +38,72 @@ struct BlendBatch {
   size_t acc_stride;
 };
 
-struct BlendSmem {
-  float4 a[BL_BATCH];    // x, y, conic.x, conic.y
-  float4 b[BL_BATCH];    // conic.z, power threshold, opacity, gid (bits)
-  float4 c[BL_BATCH];    // r, g, b, depth
-  float4 box[BL_BATCH];  // x - hx, x + hx, y - hy, y + hy
-  float4 d[BL_BATCH];    // -cy/cz, -cy/cx, limit on the quadratic form, 1 if the exact cull applies
+// A staged record occupies 80 bytes of shared memory: the 64-byte record + one float4 holding the
+// Gaussian id. The 80-byte stride (20 words) is what keeps the lane-per-record reads of the compaction
+// conflict-free: with a 64-byte stride the eight lanes of a quarter-warp hit two bank groups (4-way
+// conflicts made both blend kernels 7-11 % slower).
+constexpr int SREC_F4 = REC_F4 + 1;
+struct __align__(128) BlendSmem {
+  float4 rec[BL_BATCH][SREC_F4];      // TMA destination (first 64 bytes of each slot) | id
   uint16_t list[BL_WARPS][BL_BATCH];  // record index | quadrant mask << 8
+  uint64_t bar;                       // mbarrier the bulk copies of a batch complete on
 };
 
-// Lower bound on `power` below which opacity*exp(power) < 1/255 for certain.
-// 0.01 of slack in the exponent is ~1% in alpha; expf and __logf err by < 1e-6.
-__device__ __forceinline__ float power_threshold(float opacity) {
-  return opacity > 0.0f ? -(__logf(255.0f * opacity) + 0.01f) : __int_as_float(0x7f800000);
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Once per CTA, before the first stage_batch: every thread arrives once per batch.
+__device__ __forceinline__ void stage_init(BlendSmem& s, int tid) {
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&s.bar)), "r"(BL_THREADS));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  __syncthreads();
 }
 
-// Cooperative gather of `count` records. src(k) gives the position in point_list of record k.
-template <bool WITH_COLOR, typename SRC>
+// Stages `count` records of the tile's list into shared memory with ONE TMA bulk copy
+// (cp.async.bulk.shared.global, 64 bytes, SASS UBLKCP) per instance: the list is a gather over the
+// per-Gaussian record array, and a bulk copy per record gathers without any register staging or
+// per-instance arithmetic (thresholds, boxes and cull constants are part of the record; the probe
+// profiles/probes/tma_gather_probe.cu stages 21 M records in 0.31 ms this way vs 0.49 ms with LDG.128 +
+// STS). src(k) gives the position in point_list of record k. All threads of the CTA call this (each
+// arrives on the mbarrier once per batch); on return the records and ids of the batch are visible to
+// all of them. `parity` is the mbarrier phase, flipped by the caller after every batch; the caller
+// guarantees that nobody still reads the previous batch. (Double buffering — the next batch in
+// flight during the walk — was measured too: no gain, the other 11 CTAs of the SM already cover it.)
+template <typename SRC>
 __device__ __forceinline__ void stage_batch(BlendSmem& s, int tid, int count, SRC src,
                                             const uint32_t* __restrict__ point_list,
-                                            const float4* __restrict__ means2D,
-                                            const float4* __restrict__ conic_opacity,
-                                            const float4* __restrict__ rgb_depth) {
-  for (int k = tid; k < count; k += BL_THREADS) {
-    const uint32_t gid = point_list[src(k)];
-    const float4 m = means2D[gid];
-    const float4 co = conic_opacity[gid];
-    const float thr = power_threshold(co.w);
-    s.a[k] = make_float4(m.x, m.y, co.x, co.y);
-    s.b[k] = make_float4(co.z, thr, co.w, __uint_as_float(gid));
-    s.box[k] = make_float4(m.x - m.z, m.x + m.z, m.y - m.w, m.y + m.w);
-    // Exact-cull constants (quad_mask): q(u,v) = 0.5 (cx u^2 + cz v^2) + cy u v must stay <= tau =
-    // -thr for a pixel to reach alpha >= 1/255. The limit carries a slack proportional to the
-    // conditioning kappa = cx cz / det of the form: the fp32 `power` of a pixel differs from the
-    // real-number value by < 1e-6 * kappa * q, so a rectangle is only dropped when its minimum of q
-    // exceeds tau by 20x that; ill-conditioned needles (kappa > 1e3) are left to the box test.
-    const float det = co.x * co.z - co.y * co.y;
-    const float ac = co.x * co.z;
-    const bool exact = co.x > 0.0f && co.z > 0.0f && det > 1e-3f * ac && thr < 0.0f;
-    const float kappa = exact ? __fdividef(ac, det) : 1.0f;
-    s.d[k] = make_float4(exact ? __fdividef(-co.y, co.z) : 0.0f, exact ? __fdividef(-co.y, co.x) : 0.0f,
-                         -thr * (1.0f + 2e-5f * kappa) + 1e-4f, exact ? 1.0f : 0.0f);
-    if (WITH_COLOR) s.c[k] = rgb_depth[gid];
+                                            const float4* __restrict__ rec, uint32_t parity) {
+  constexpr int PER = BL_BATCH / BL_THREADS;
+  uint32_t gid[PER];
+  int mine = 0;
+#pragma unroll
+  for (int i = 0; i < PER; i++) {
+    const int k = tid + i * BL_THREADS;
+    if (k < count) {
+      gid[i] = point_list[src(k)];
+      s.rec[k][REC_F4].x = __uint_as_float(gid[i]);
+      mine++;
+    }
   }
+  const uint32_t bar = smem_addr(&s.bar);
+  // arrive (release: the id stores above) + announce this thread's bytes BEFORE issuing its copies
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(mine * 64) : "memory");
+#pragma unroll
+  for (int i = 0; i < PER; i++) {
+    const int k = tid + i * BL_THREADS;
+    if (k < count)
+      asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], 64, [%2];" ::"r"(
+                       smem_addr(&s.rec[k][0])),
+                   "l"(rec + (size_t)gid[i] * REC_F4), "r"(bar)
+                   : "memory");
+  }
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
 }
 
 // Which of the warp's four 8x4 pixel quadrants (origin X0, Y0 of the 16x8 half-tile, pixel-centre
@@ -92,24 +115,25 @@ __device__ __forceinline__ void stage_batch(BlendSmem& s, int tid, int count, SR
 //     minimum lies on an edge facing it: on u = clamp(0) with v = clamp(-cy u / cz), or on
 //     v = clamp(0) with u = clamp(-cy v / cx).
 __device__ __forceinline__ uint32_t quad_mask(const float4 a, const float cz, const float4 bx,
-                                              const float4 d, float X0, float Y0) {
+                                              const float nbc, const float nba, const float lim, float X0,
+                                              float Y0) {
   uint32_t mask = 0;
 #pragma unroll
   for (int p = 0; p < 4; p++) {
     const float xa = X0 + (float)(PX_STEP * (p & 1)), xb = xa + (float)(PX_STEP - 1);
     const float ya = Y0 + (float)(PY_STEP * (p >> 1)), yb = ya + (float)(PY_STEP - 1);
     bool hit = bx.y >= xa && bx.x <= xb && bx.w >= ya && bx.z <= yb;
-    if (hit && d.w != 0.0f) {
+    if (hit && lim >= 0.0f) {
       const float u0 = xa - a.x, u1 = xb - a.x, v0 = ya - a.y, v1 = yb - a.y;
       const float uc = fminf(fmaxf(0.0f, u0), u1), vc = fminf(fmaxf(0.0f, v0), v1);
-      const float vs = fminf(fmaxf(d.x * uc, v0), v1), us = fminf(fmaxf(d.y * vc, u0), u1);
+      const float vs = fminf(fmaxf(nbc * uc, v0), v1), us = fminf(fmaxf(nba * vc, u0), u1);
       const float qu = 0.5f * (a.z * uc * uc + cz * vs * vs) + a.w * uc * vs;  // edge u = uc
       const float qv = 0.5f * (a.z * us * us + cz * vc * vc) + a.w * us * vc;  // edge v = vc
       const float inf = __int_as_float(0x7f800000);
       float m = (uc == 0.0f && vc == 0.0f) ? 0.0f : inf;
       if (uc != 0.0f) m = fminf(m, qu);
       if (vc != 0.0f) m = fminf(m, qv);
-      hit = !(m > d.z);  // NaN keeps the quadrant
+      hit = !(m > lim);  // NaN keeps the quadrant
     }
     mask |= hit ? (1u << p) : 0u;
   }
@@ -130,10 +154,12 @@ __device__ __forceinline__ int compact_batch(BlendSmem& s, int warp, int lane, i
     const int k = c * 32 + lane;
     uint32_t qm = 0;
     if (k < count) {
-      const float4 bx = s.box[k];
+      const float4 a = s.rec[k][0], c = s.rec[k][2], d = s.rec[k][3];
+      // x - hx, x + hx, y - hy, y + hy
+      const float4 bx = make_float4(a.x - c.w, a.x + c.w, a.y - d.x, a.y + d.x);
       if (bx.y >= X0 && bx.x <= X1 && bx.w >= Y0 && bx.z <= Y1) {
         qm = allowed(k);
-        if (qm) qm &= quad_mask(s.a[k], s.b[k].x, bx, s.d[k], X0, Y0);
+        if (qm) qm &= quad_mask(a, s.rec[k][1].x, bx, d.y, d.z, d.w, X0, Y0);
       }
     }
     const uint32_t m = __ballot_sync(0xFFFFFFFFu, qm != 0);

@@ -17,10 +17,8 @@ extern unsigned long long g_kernel_launches;
 // Our own layout of the three opaque blobs (the reference's is
 // DGR/cuda_rasterizer/rasterizer_impl.cu:135-175). All sub-arrays 256-B aligned.
 struct GeomState {
-  float4* means2D;        // [P] pixel-space centre x, y and half-extents hx, hy of the box outside
-                          //     which alpha < 1/255 for certain (conservative; -inf = never visible)
-  float4* conic_opacity;  // [P] conic.x, conic.y, conic.z, opacity
-  float4* rgb_depth;      // [P] r, g, b, view-space depth
+  float4* rec;            // [P][4] one 64-byte blend record per Gaussian (REC_* below): what the blend
+                          //     kernels stage into shared memory with ONE TMA bulk copy per instance
   ushort4* rect;          // [P] tile rect min.x, min.y, max.x, max.y (all 0 <=> culled)
   uint8_t* clamped;       // [P] bit ch set <=> SH colour channel clamped at 0
   uint32_t* sort_key[2];  // [P] depth bits (0xFFFFFFFF for culled), ping-pong
@@ -54,9 +52,7 @@ __host__ __device__ __forceinline__ T* shift_ptr(T* p, size_t bytes) {
   return (T*)((const char*)p + bytes);
 }
 __host__ __device__ __forceinline__ GeomState shift_geom(GeomState g, size_t bytes) {
-  g.means2D = shift_ptr(g.means2D, bytes);
-  g.conic_opacity = shift_ptr(g.conic_opacity, bytes);
-  g.rgb_depth = shift_ptr(g.rgb_depth, bytes);
+  g.rec = shift_ptr(g.rec, bytes);
   g.rect = shift_ptr(g.rect, bytes);
   g.clamped = shift_ptr(g.clamped, bytes);
   g.sort_key[0] = shift_ptr(g.sort_key[0], bytes);
@@ -194,6 +190,40 @@ cudaError_t launch_fused_adam(float* param, const float* grad, float* m, float* 
 // per-Gaussian accumulator slots written by the backward blend
 enum { ACC_MEAN_X = 0, ACC_MEAN_Y, ACC_CONIC_X, ACC_CONIC_Y, ACC_CONIC_W, ACC_OPACITY, ACC_R, ACC_G,
        ACC_B, ACC_FLAGS = 11, ACC_STRIDE = 12 };
+
+// ---- the 64-byte blend record of a Gaussian in a view (written by preprocess) ----
+//  q0: x, y (pixel-space centre), conic.x, conic.y
+//  q1: conic.z, power threshold, opacity, view-space depth
+//  q2: r, g, b, hx
+//  q3: hy, -cy/cz, -cy/cx, limit on the quadratic form (< 0: the exact quadrant cull does not apply)
+// (hx, hy): half-extents of the box outside which alpha < 1/255 for certain (-inf = never visible).
+constexpr int REC_F4 = 4;
+
+// Lower bound on `power` below which opacity*exp(power) < 1/255 for certain.
+// 0.01 of slack in the exponent is ~1% in alpha; expf and __logf err by < 1e-6.
+__device__ __forceinline__ float power_threshold(float opacity) {
+  return opacity > 0.0f ? -(__logf(255.0f * opacity) + 0.01f) : __int_as_float(0x7f800000);
+}
+
+// Packs the record. Exact-cull constants (blend.cuh:quad_mask): q(u,v) = 0.5 (cx u^2 + cz v^2) + cy u v
+// must stay <= tau = -thr for a pixel to reach alpha >= 1/255. The limit carries a slack proportional
+// to the conditioning kappa = cx cz / det of the form: the fp32 `power` of a pixel differs from the
+// real-number value by < 1e-6 * kappa * q, so a rectangle is only dropped when its minimum of q exceeds
+// tau by 20x that; ill-conditioned needles (kappa > 1e3) are left to the box test.
+__device__ __forceinline__ void pack_record(float4* q, float x, float y, float hx, float hy, float cx,
+                                            float cy, float cz, float opacity, float r, float g, float b,
+                                            float depth) {
+  const float thr = power_threshold(opacity);
+  const float det = cx * cz - cy * cy;
+  const float ac = cx * cz;
+  const bool exact = cx > 0.0f && cz > 0.0f && det > 1e-3f * ac && thr < 0.0f;
+  const float kappa = exact ? __fdividef(ac, det) : 1.0f;
+  q[0] = make_float4(x, y, cx, cy);
+  q[1] = make_float4(cz, thr, opacity, depth);
+  q[2] = make_float4(r, g, b, hx);
+  q[3] = make_float4(hy, exact ? __fdividef(-cy, cz) : 0.0f, exact ? __fdividef(-cy, cx) : 0.0f,
+                     exact ? -thr * (1.0f + 2e-5f * kappa) + 1e-4f : -1.0f);
+}
 
 // Tile rect of a Gaussian, bit-exact with getRect (DGR/cuda_rasterizer/auxiliary.h:46-56) as
 // compiled for sm_100a: two separate float adds (+16, -1), *0.0625, truncation, clamp.

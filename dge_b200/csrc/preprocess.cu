@@ -118,7 +118,7 @@ struct PreOut {
   uint32_t tiles, key;
   uint8_t clamp_bits;
   ushort4 rect;
-  float4 m2d, co, rgbd;
+  float4 rec[REC_F4];  // blend record (common.cuh:pack_record), valid when radius > 0
 };
 
 // The per-Gaussian forward of ONE view (forward.cu:186-255), shared by the per-view kernel and the
@@ -182,9 +182,7 @@ __device__ __forceinline__ PreOut preprocess_view(const ViewParams& vp, const fl
             }
           }
         }
-        o.m2d = make_float4(pix_x, pix_y, hx, hy);
-        o.co = make_float4(con_x, con_y, con_z, opac);
-        o.rgbd = make_float4(rgb[0], rgb[1], rgb[2], depth);
+        pack_record(o.rec, pix_x, pix_y, hx, hy, con_x, con_y, con_z, opac, rgb[0], rgb[1], rgb[2], depth);
         o.radius = rad;
         o.rect = make_ushort4(x0, y0, x1, y1);
         o.key = __float_as_uint(depth);
@@ -275,9 +273,8 @@ __global__ void __launch_bounds__(256) preprocess_kernel(
         },
         [&]() { return __ldg(opacities + idx); });
     if (o.radius > 0) {
-      g.means2D[idx] = o.m2d;
-      g.conic_opacity[idx] = o.co;
-      g.rgb_depth[idx] = o.rgbd;
+#pragma unroll
+      for (int k = 0; k < REC_F4; k++) g.rec[(size_t)idx * REC_F4 + k] = o.rec[k];
     }
     tiles = o.tiles;
     radii[idx] = o.radius;
@@ -385,9 +382,9 @@ __global__ void __launch_bounds__(PRE_B_THREADS, PRE_B_MIN_CTAS) preprocess_batc
           [&]() { return opac; });
       const size_t sh_ = (size_t)view * geom_stride;
       if (o.radius > 0) {
-        shift_ptr(g0.means2D, sh_)[idx] = o.m2d;
-        shift_ptr(g0.conic_opacity, sh_)[idx] = o.co;
-        shift_ptr(g0.rgb_depth, sh_)[idx] = o.rgbd;
+        float4* dst = shift_ptr(g0.rec, sh_) + (size_t)idx * REC_F4;
+#pragma unroll
+        for (int k = 0; k < REC_F4; k++) dst[k] = o.rec[k];
       }
       shift_ptr(g0.rect, sh_)[idx] = o.rect;
       shift_ptr(g0.sort_key[0], sh_)[idx] = o.key;

@@ -29,8 +29,7 @@ namespace dge {
 template <bool HAS_BG>
 __global__ void __launch_bounds__(BL_THREADS, DGE_BWD_MIN_CTAS) render_backward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
-    const float* __restrict__ background, const float4* __restrict__ means2D,
-    const float4* __restrict__ conic_opacity, const float4* __restrict__ rgb_depth,
+    const float* __restrict__ background, const float4* __restrict__ rec,
     const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
     const float* __restrict__ dL_dpixels, float* __restrict__ acc, BlendBatch bb) {
   __shared__ BlendSmem s;
@@ -39,9 +38,7 @@ __global__ void __launch_bounds__(BL_THREADS, DGE_BWD_MIN_CTAS) render_backward_
     ranges = shift_ptr(ranges, is);
     final_Ts = shift_ptr(final_Ts, is);
     n_contrib = shift_ptr(n_contrib, is);
-    means2D = shift_ptr(means2D, gs);
-    conic_opacity = shift_ptr(conic_opacity, gs);
-    rgb_depth = shift_ptr(rgb_depth, gs);
+    rec = shift_ptr(rec, gs);
     point_list += bb.seg_off[blockIdx.z];
     dL_dpixels += (size_t)blockIdx.z * 3 * H * W;
     acc += blockIdx.z * bb.acc_stride;
@@ -94,13 +91,14 @@ __global__ void __launch_bounds__(BL_THREADS, DGE_BWD_MIN_CTAS) render_backward_
 
   const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
 
+  stage_init(s, tid);
+  uint32_t parity = 0;
   // positions hi-1 ... 0 of the tile list, back to front, in batches
   for (uint32_t hi = bmax; hi > 0; hi -= min(hi, (uint32_t)BL_BATCH)) {
     const int count = min(hi, (uint32_t)BL_BATCH);
-    __syncthreads();
-    stage_batch<true>(s, tid, count, [&](int k) { return range.x + hi - 1 - k; }, point_list,
-                      means2D, conic_opacity, rgb_depth);
-    __syncthreads();
+    __syncthreads();  // everyone has finished walking the previous batch
+    stage_batch(s, tid, count, [&](int k) { return range.x + hi - 1 - k; }, point_list, rec, parity);
+    parity ^= 1u;
     if (hi - count >= wmax) continue;  // nothing in this batch reaches this warp (warp-uniform)
     const int n = compact_batch(s, warp, lane, count, X0, Y0, [&](int k) {
       const uint32_t pos = hi - 1 - k;
@@ -111,9 +109,9 @@ __global__ void __launch_bounds__(BL_THREADS, DGE_BWD_MIN_CTAS) render_backward_
       const uint32_t e = s.list[warp][i];  // warp-uniform
       const int j = e & 0xFF;
       const uint32_t pos = hi - 1 - j;  // 0-based list position
-      const float4 a = s.a[j];
-      const float4 b = s.b[j];
-      const float4 cd = s.c[j];
+      const float4 a = s.rec[j][0];   // x, y, conic.x, conic.y
+      const float4 b = s.rec[j][1];   // conic.z, power threshold, opacity, depth
+      const float4 cd = s.rec[j][2];  // r, g, b, -
       const float opacity = b.z;
       const float col[3] = {cd.x, cd.y, cd.z};
 
@@ -185,7 +183,7 @@ __global__ void __launch_bounds__(BL_THREADS, DGE_BWD_MIN_CTAS) render_backward_
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) z8 += __shfl_xor_sync(0xFFFFFFFFu, z8, o);
       // lanes 0,4,...,28 own slots 0..7, lane 1 owns slot 8: one red.global for all nine
-      const uint32_t gid = __float_as_uint(b.w);
+      const uint32_t gid = __float_as_uint(s.rec[j][REC_F4].x);
       const bool owner = (lane & 3) == 0 || lane == 1;
       if (owner) {
         const int slot = lane == 1 ? 8 : (lane >> 2);
@@ -200,11 +198,11 @@ static cudaError_t launch_bwd(dim3 grid, const GeomState& g, const BinState& b, 
                               bool black_background, BlendBatch bb, cudaStream_t stream) {
   if (black_background)
     render_backward_kernel<false><<<grid, BL_THREADS, 0, stream>>>(
-        img.ranges, b.point_list, W, H, background, g.means2D, g.conic_opacity, g.rgb_depth, img.final_T,
+        img.ranges, b.point_list, W, H, background, g.rec, img.final_T,
         img.n_contrib, dL_dpix, acc, bb);
   else
     render_backward_kernel<true><<<grid, BL_THREADS, 0, stream>>>(
-        img.ranges, b.point_list, W, H, background, g.means2D, g.conic_opacity, g.rgb_depth, img.final_T,
+        img.ranges, b.point_list, W, H, background, g.rec, img.final_T,
         img.n_contrib, dL_dpix, acc, bb);
   DGE_LAUNCHED(1);
   return cudaGetLastError();

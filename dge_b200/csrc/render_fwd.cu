@@ -18,10 +18,9 @@
 
 namespace dge {
 
-__global__ void __launch_bounds__(BL_THREADS) render_forward_kernel(
+__global__ void __launch_bounds__(BL_THREADS, 14) render_forward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
-    const float4* __restrict__ means2D, const float4* __restrict__ conic_opacity,
-    const float4* __restrict__ rgb_depth, const float* __restrict__ background,
+    const float4* __restrict__ rec, const float* __restrict__ background,
     float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
     float* __restrict__ out_depth, BlendBatch bb) {
   __shared__ BlendSmem s;
@@ -30,9 +29,7 @@ __global__ void __launch_bounds__(BL_THREADS) render_forward_kernel(
     ranges = shift_ptr(ranges, is);
     final_T = shift_ptr(final_T, is);
     n_contrib = shift_ptr(n_contrib, is);
-    means2D = shift_ptr(means2D, gs);
-    conic_opacity = shift_ptr(conic_opacity, gs);
-    rgb_depth = shift_ptr(rgb_depth, gs);
+    rec = shift_ptr(rec, gs);
     point_list += bb.seg_off[blockIdx.z];
     out_color += (size_t)blockIdx.z * 3 * H * W;
     out_depth += (size_t)blockIdx.z * H * W;
@@ -63,13 +60,14 @@ __global__ void __launch_bounds__(BL_THREADS) render_forward_kernel(
     done[p] = !inside[p];
   }
 
+  stage_init(s, tid);
+  uint32_t parity = 0;
   for (uint32_t base = range.x; base < range.y; base += BL_BATCH) {
     const bool all_done = done[0] && done[1] && done[2] && done[3];
-    if (__syncthreads_and(all_done)) break;
+    if (__syncthreads_and(all_done)) break;  // also: everyone has finished walking the previous batch
     const int count = min((uint32_t)BL_BATCH, range.y - base);
-    stage_batch<true>(s, tid, count, [&](int k) { return base + k; }, point_list, means2D,
-                      conic_opacity, rgb_depth);
-    __syncthreads();
+    stage_batch(s, tid, count, [&](int k) { return base + k; }, point_list, rec, parity);
+    parity ^= 1u;
     if (__all_sync(0xFFFFFFFFu, all_done)) continue;  // this half-tile is saturated
     // quadrants in which every pixel has terminated need no further visits
     uint32_t live = 0;
@@ -79,9 +77,9 @@ __global__ void __launch_bounds__(BL_THREADS) render_forward_kernel(
     for (int i = 0; i < n; i++) {
       const uint32_t e = s.list[warp][i];  // warp-uniform
       const int j = e & 0xFF;
-      const float4 a = s.a[j];
-      const float4 b = s.b[j];
-      const float4 cd = s.c[j];
+      const float4 a = s.rec[j][0];   // x, y, conic.x, conic.y
+      const float4 b = s.rec[j][1];   // conic.z, power threshold, opacity, depth
+      const float4 cd = s.rec[j][2];  // r, g, b, -
 #pragma unroll
       for (int p = 0; p < 4; p++) {
         if (!(e & (0x100u << p))) continue;  // warp-uniform branch
@@ -97,7 +95,7 @@ __global__ void __launch_bounds__(BL_THREADS) render_forward_kernel(
         C[p][0] = BFMA(T[p], BMUL(alpha, cd.x), C[p][0]);
         C[p][1] = BFMA(T[p], BMUL(alpha, cd.y), C[p][1]);
         C[p][2] = BFMA(T[p], BMUL(alpha, cd.z), C[p][2]);
-        Dp[p] = BFMA(T[p], BMUL(alpha, cd.w), Dp[p]);
+        Dp[p] = BFMA(T[p], BMUL(alpha, b.w), Dp[p]);
         T[p] = test_T;
         last[p] = base - range.x + j + 1;
       }
@@ -124,7 +122,7 @@ cudaError_t launch_render_forward(const ViewParams& vp, const GeomState& g, cons
                                   float* out_depth, cudaStream_t stream) {
   dim3 grid(vp.grid_x, vp.grid_y);
   render_forward_kernel<<<grid, BL_THREADS, 0, stream>>>(
-      img.ranges, b.point_list, vp.W, vp.H, g.means2D, g.conic_opacity, g.rgb_depth, background,
+      img.ranges, b.point_list, vp.W, vp.H, g.rec, background,
       img.final_T, img.n_contrib, out_color, out_depth, BlendBatch{0, 0, nullptr, 0});
   DGE_LAUNCHED(1);
   return cudaGetLastError();
@@ -135,7 +133,7 @@ cudaError_t launch_render_forward_batched(const ViewParams& vp, const ViewBatch&
                                           float* out_color, float* out_depth, cudaStream_t stream) {
   dim3 grid(vp.grid_x, vp.grid_y, vb.V);
   render_forward_kernel<<<grid, BL_THREADS, 0, stream>>>(
-      img0.ranges, b.point_list, vp.W, vp.H, g0.means2D, g0.conic_opacity, g0.rgb_depth, background,
+      img0.ranges, b.point_list, vp.W, vp.H, g0.rec, background,
       img0.final_T, img0.n_contrib, out_color, out_depth, BlendBatch{vb.geom_stride, vb.img_stride, vb.seg_off, 0});
   DGE_LAUNCHED(1);
   return cudaGetLastError();
