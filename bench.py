@@ -188,9 +188,22 @@ def main_config3(args, cfg):
         from oracle import ref
         tans = [(math.tan(c.FoVx * 0.5), math.tan(c.FoVy * 0.5)) for c in cams]
 
+    from dge_b200 import fit
+    masks_host = [mask_host for _ in cams]
+    masks_dev = torch.stack([mask_dev for _ in cams])
+    masks_stage = torch.empty_like(masks_dev)
+    per_view = args.streams > 0  # --streams N>0: the per-view API loop; default: one batched call
+
     def step(host):
         weights.zero_()
         cnt.zero_()
+        if args.impl == "ours" and not per_view:
+            if host:  # pinned host masks -> one staging block, asynchronously
+                for i, t in enumerate(masks_host):
+                    masks_stage[i].copy_(t, non_blocking=True)
+            m = masks_stage if host else masks_dev
+            fit.backproject_masks(gd.means3D, gd.opacities, gd.scales, gd.rotations, cams, m, weights, cnt)
+            return (weights / (cnt + 1e-7)) > 0.8
         for i, cam in enumerate(cams):
             m = mask_host.to(dev, non_blocking=True) if host else mask_dev
             if args.impl == "ours":
@@ -235,7 +248,8 @@ def main_config3(args, cfg):
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic",
            "config": {"workload": f"config3: {cfg['desc']}", "gaussians": P, "resolution": [W, H], "views_per_step": V,
-                      "mask": "binary disc, radius 160 px", "selected": n_sel, "scene": "randgauss-v1"},
+                      "mask": "binary disc, radius 160 px", "selected": n_sel, "scene": "randgauss-v1",
+                      "views_per_launch": 1 if (args.impl != "ours" or per_view) else V},
            "clocks": clocks,
            "e2e": {"value": views / (ms_e2e * 1e-3), "unit": "views/s", "h2d_bytes_per_step": V * W * H * 4,
                    "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},

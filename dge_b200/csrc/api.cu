@@ -208,7 +208,7 @@ using namespace dge;
 extern "C" {
 
 const char* dge_last_error(void) { return g_err; }
-int dge_abi_version(void) { return 6; }
+int dge_abi_version(void) { return 7; }
 unsigned long long dge_launch_count(void) { return g_kernel_launches; }
 
 void dge_profile_enable(unsigned stage_mask) { g_profile_mask = stage_mask; }
@@ -305,32 +305,24 @@ size_t dge_fit_binning_bytes(int R_total, int V, int width, int height) {
   return carve_binning_batched(nullptr, (uint32_t)(R_total > 0 ? R_total : 0), V, T, nullptr);
 }
 
-int dge_fit_views_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge_alloc_fn imageBuffer,
-                          void* alloc_ctx, int P, int D, int M, int V, const float* background, int width,
-                          int height, const float* means3D, const float* shs, const float* opacities,
-                          const float* scales, float scale_modifier, const float* rotations,
-                          const float* cams, float* out_color, float* out_depth, int* radii_max, float* acc,
-                          size_t acc_stride_floats, int* num_rendered_host, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+// Shared front half of the per-step entry points: batched preprocess .. binning for V views.
+// shs == nullptr: no colour (mask back-projection). Returns R_total (>= 0) or < 0.
+static int bin_views(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge_alloc_fn imageBuffer,
+                     void* alloc_ctx, const ViewParams& vp, int V, const float* means3D, const float* shs,
+                     const float* opacities, const float* scales, const float* rotations, const float* cams,
+                     int* radii_max, float* acc, size_t acc_stride_floats, int* num_rendered_host,
+                     cudaStream_t stream, GeomState& g0, BinState& b, ImgState& img0, ViewBatch& vb) {
   const bool debug = false;
-  if (P == 0 || width <= 0 || height <= 0) return fail_msg("empty problem");
   if (V < 1 || V > DGE_MAX_BATCH_VIEWS) return fail_msg("a batch holds 1..64 views");
-  if (M != 16) return fail_msg("the batched fit path needs SH degree-3 storage (M == 16)");
-  // tan_fov / focal are per view and filled in by the batched preprocess from the camera records
-  const ViewParams vp = make_view(P, D, M, width, height, nullptr, nullptr, nullptr, 1.f, 1.f, scale_modifier);
   if (vp.grid_x > 65535 || vp.grid_y > 65535) return fail_msg("image too large (tile grid > 65535)");
   CK("pinned slot", ensure_slot());
-  const size_t gstride = batch_stride(carve_geom(nullptr, P, nullptr));
-  const size_t istride = batch_stride(carve_image(nullptr, width, height, nullptr));
+  const size_t gstride = batch_stride(carve_geom(nullptr, vp.P, nullptr));
+  const size_t istride = batch_stride(carve_image(nullptr, vp.W, vp.H, nullptr));
   char* gp = geometryBuffer(alloc_ctx, gstride * V);
   char* ip = imageBuffer(alloc_ctx, istride * V);
   if (!gp || !ip) return fail_msg("scratch allocator returned NULL");
-  GeomState g0;
-  ImgState img0;
-  BinState b;
-  carve_geom(gp, P, &g0);
-  carve_image(ip, width, height, &img0);
-  ViewBatch vb;
+  carve_geom(gp, vp.P, &g0);
+  carve_image(ip, vp.W, vp.H, &img0);
   vb.V = V;
   vb.geom_stride = gstride;
   vb.img_stride = istride;
@@ -343,7 +335,7 @@ int dge_fit_views_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffe
   CK("num_rendered copy", cudaMemcpyAsync(g_slot.pinned, batch_seg_off(g0), sizeof(uint32_t) * (V + 1),
                                           cudaMemcpyDeviceToHost, stream));
   CK("event record", cudaEventRecord(g_slot.ev, stream));
-  STAGE(ST_DEPTH_SORT, "depth sort (batched)", launch_depth_sort_batched(P, vb, g0, stream));
+  STAGE(ST_DEPTH_SORT, "depth sort (batched)", launch_depth_sort_batched(vp.P, vb, g0, stream));
   CK("num_rendered wait", cudaEventSynchronize(g_slot.ev));
   const uint32_t R_total = g_slot.pinned[V];
   uint32_t R_max = 0;
@@ -358,9 +350,57 @@ int dge_fit_views_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffe
   if (!bp) return fail_msg("scratch allocator returned NULL");
   carve_binning_batched(bp, R_total, V, T, &b);
   STAGE(ST_BINNING, "binning (batched)", launch_binning_batched(vp, vb, R_total, R_max, g0, b, img0, stream));
+  return (int)R_total;
+}
+
+int dge_fit_views_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge_alloc_fn imageBuffer,
+                          void* alloc_ctx, int P, int D, int M, int V, const float* background, int width,
+                          int height, const float* means3D, const float* shs, const float* opacities,
+                          const float* scales, float scale_modifier, const float* rotations,
+                          const float* cams, float* out_color, float* out_depth, int* radii_max, float* acc,
+                          size_t acc_stride_floats, int* num_rendered_host, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool debug = false;
+  if (P == 0 || width <= 0 || height <= 0) return fail_msg("empty problem");
+  if (M != 16 || shs == nullptr) return fail_msg("the batched fit path needs SH degree-3 storage (M == 16)");
+  // tan_fov / focal are per view and filled in by the batched preprocess from the camera records
+  const ViewParams vp = make_view(P, D, M, width, height, nullptr, nullptr, nullptr, 1.f, 1.f, scale_modifier);
+  GeomState g0;
+  ImgState img0;
+  BinState b;
+  ViewBatch vb;
+  const int R_total = bin_views(geometryBuffer, binningBuffer, imageBuffer, alloc_ctx, vp, V, means3D, shs, opacities,
+                                scales, rotations, cams, radii_max, acc, acc_stride_floats, num_rendered_host, stream,
+                                g0, b, img0, vb);
+  if (R_total < 0) return R_total;
   STAGE(ST_RENDER_FWD, "render forward (batched)",
         launch_render_forward_batched(vp, vb, g0, b, img0, background, out_color, out_depth, stream));
-  return (int)R_total;
+  return R_total;
+}
+
+int dge_fit_views_apply_weights(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge_alloc_fn imageBuffer,
+                                void* alloc_ctx, int P, int V, int width, int height, const float* means3D,
+                                const float* opacities, const float* scales, float scale_modifier,
+                                const float* rotations, const float* cams, const float* image_weights,
+                                int num_channels, float* weights, int* cnt, int* num_rendered_host,
+                                void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool debug = false;
+  if (P == 0) return 0;
+  if (width <= 0 || height <= 0) return fail_msg("empty image");
+  if (num_channels < 1 || num_channels > 3) return fail_msg("Unsupported number of channels");
+  const ViewParams vp = make_view(P, 0, 0, width, height, nullptr, nullptr, nullptr, 1.f, 1.f, scale_modifier);
+  GeomState g0;
+  ImgState img0;
+  BinState b;
+  ViewBatch vb;
+  const int R_total = bin_views(geometryBuffer, binningBuffer, imageBuffer, alloc_ctx, vp, V, means3D, nullptr,
+                                opacities, scales, rotations, cams, nullptr, nullptr, 0, num_rendered_host, stream, g0,
+                                b, img0, vb);
+  if (R_total <= 0) return R_total;
+  STAGE(ST_APPLY_WEIGHTS, "apply_weights blend (batched)",
+        launch_apply_weights_render_batched(vp, &vb, g0, b, img0, weights, cnt, image_weights, num_channels, stream));
+  return R_total;
 }
 
 int dge_fit_views_backward_blend(int P, int V, int R_total, const float* background, int background_is_black,

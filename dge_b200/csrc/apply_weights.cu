@@ -17,8 +17,16 @@ namespace dge {
 template <int CH>
 __global__ void __launch_bounds__(BL_THREADS) apply_weights_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
-    const float4* __restrict__ rec, const float* __restrict__ image_weights, float* __restrict__ weights, int* __restrict__ cnt) {
+    const float4* __restrict__ rec, const float* __restrict__ image_weights, float* __restrict__ weights,
+    int* __restrict__ cnt, BlendBatch bb) {
   __shared__ BlendSmem s;
+  if (bb.seg_off) {  // view blockIdx.z of a batch: its own mask image, the SAME weights / cnt
+    const size_t gs = blockIdx.z * bb.geom_stride, is = blockIdx.z * bb.img_stride;
+    ranges = shift_ptr(ranges, is);
+    rec = shift_ptr(rec, gs);
+    point_list += bb.seg_off[blockIdx.z];
+    image_weights += (size_t)blockIdx.z * CH * H * W;
+  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // pixel p of this thread = (px0 + PX_STEP*(p&1), py0 + PY_STEP*(p>>1)): one pixel in each 8x4
   // quadrant of the warp's 16x8 half-tile (see blend.cuh)
@@ -99,10 +107,19 @@ cudaError_t launch_apply_weights_render(const ViewParams& vp, const GeomState& g
                                         const ImgState& img, float* weights, int* cnt,
                                         const float* image_weights, int num_channels,
                                         cudaStream_t stream) {
-  dim3 grid(vp.grid_x, vp.grid_y);
+  return launch_apply_weights_render_batched(vp, nullptr, g, b, img, weights, cnt, image_weights, num_channels, stream);
+}
+
+// vb == nullptr: one view; otherwise all views of the batch (grid.z), image_weights [V,CH,H,W]
+cudaError_t launch_apply_weights_render_batched(const ViewParams& vp, const ViewBatch* vb, const GeomState& g,
+                                                const BinState& b, const ImgState& img, float* weights, int* cnt,
+                                                const float* image_weights, int num_channels,
+                                                cudaStream_t stream) {
+  dim3 grid(vp.grid_x, vp.grid_y, vb ? vb->V : 1);
+  const BlendBatch bb = vb ? BlendBatch{vb->geom_stride, vb->img_stride, vb->seg_off, 0} : BlendBatch{0, 0, nullptr, 0};
 #define AW_LAUNCH(CH)                                                                          \
   apply_weights_kernel<CH><<<grid, BL_THREADS, 0, stream>>>(img.ranges, b.point_list, vp.W, vp.H, \
-                                                            g.rec, image_weights, weights, cnt)
+                                                            g.rec, image_weights, weights, cnt, bb)
   if (num_channels == 1) AW_LAUNCH(1);
   else if (num_channels == 2) AW_LAUNCH(2);
   else if (num_channels == 3) AW_LAUNCH(3);

@@ -181,6 +181,10 @@ cudaError_t launch_apply_weights_render(const ViewParams& vp, const GeomState& g
                                         const ImgState& img, float* weights, int* cnt,
                                         const float* image_weights, int num_channels,
                                         cudaStream_t stream);
+cudaError_t launch_apply_weights_render_batched(const ViewParams& vp, const ViewBatch* vb, const GeomState& g,
+                                                const BinState& b, const ImgState& img, float* weights, int* cnt,
+                                                const float* image_weights, int num_channels,
+                                                cudaStream_t stream);
 cudaError_t launch_debug_keys(const GeomState& g, const BinState& b, int R, uint64_t* keys_out,
                               cudaStream_t stream);
 cudaError_t launch_fused_adam(float* param, const float* grad, float* m, float* v, size_t n, float lr,

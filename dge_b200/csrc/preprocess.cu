@@ -350,13 +350,15 @@ __global__ void __launch_bounds__(PRE_B_THREADS, PRE_B_MIN_CTAS) preprocess_batc
     cov3d_from_scale_rot(__ldg(scales + 3 * idx), __ldg(scales + 3 * idx + 1), __ldg(scales + 3 * idx + 2),
                          vp.scale_modifier, q, cov3);
     opac = __ldg(opacities + idx);
-    const float* base = shs + 48 * (size_t)idx;
-    float4 v[12];
+    if (shs != nullptr) {  // nullptr: no colour (mask back-projection, K13 of the reference)
+      const float* base = shs + 48 * (size_t)idx;
+      float4 v[12];
 #pragma unroll
-    for (int i = 0; i < 12; i++) v[i] = ldg4(base + 4 * i);
-    const float* f = reinterpret_cast<const float*>(v);
+      for (int i = 0; i < 12; i++) v[i] = ldg4(base + 4 * i);
+      const float* f = reinterpret_cast<const float*>(v);
 #pragma unroll
-    for (int k = 0; k < 48; k++) s_sh[k * PRE_B_THREADS] = f[k];
+      for (int k = 0; k < 48; k++) s_sh[k * PRE_B_THREADS] = f[k];
+    }
   }
   int rmax = 0;
   for (int view = 0; view < V; view++) {
@@ -376,6 +378,10 @@ __global__ void __launch_bounds__(PRE_B_THREADS, PRE_B_MIN_CTAS) preprocess_batc
             for (int i = 0; i < 6; i++) c[i] = cov3[i];
           },
           [&](float* rgb) -> uint8_t {
+            if (shs == nullptr) {
+              rgb[0] = rgb[1] = rgb[2] = 0.0f;
+              return 0;
+            }
             return sh_color(vp.D, px, py, pz, cam[32], cam[33], cam[34],
                             [&](int k, int c) { return s_sh[(3 * k + c) * PRE_B_THREADS]; }, rgb);
           },
@@ -388,18 +394,20 @@ __global__ void __launch_bounds__(PRE_B_THREADS, PRE_B_MIN_CTAS) preprocess_batc
       }
       shift_ptr(g0.rect, sh_)[idx] = o.rect;
       shift_ptr(g0.sort_key[0], sh_)[idx] = o.key;
-      const uint32_t flags = o.radius > 0 ? (1u | ((uint32_t)o.clamp_bits << 1)) : 0u;
-      float4* row = acc0 + (size_t)view * (acc_stride_floats / 4) + 3 * (size_t)idx;
-      row[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-      row[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-      row[2] = make_float4(0.f, 0.f, 0.f, __uint_as_float(flags));
+      if (acc0 != nullptr) {
+        const uint32_t flags = o.radius > 0 ? (1u | ((uint32_t)o.clamp_bits << 1)) : 0u;
+        float4* row = acc0 + (size_t)view * (acc_stride_floats / 4) + 3 * (size_t)idx;
+        row[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        row[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        row[2] = make_float4(0.f, 0.f, 0.f, __uint_as_float(flags));
+      }
       rmax = max(rmax, o.radius);
       tiles = o.tiles;
     }
     const uint32_t s = __reduce_add_sync(0xFFFFFFFFu, tiles);
     if ((threadIdx.x & 31) == 0 && s) atomicAdd(&s_tiles[view], s);
   }
-  if (live) radii_max[idx] = rmax;
+  if (live && radii_max != nullptr) radii_max[idx] = rmax;
   __syncthreads();
   for (int k = threadIdx.x; k < V; k += blockDim.x)
     if (s_tiles[k]) atomicAdd(shift_ptr(g0.counters, (size_t)k * geom_stride), s_tiles[k]);
@@ -409,7 +417,7 @@ cudaError_t launch_preprocess_batched(const ViewParams& vp, const ViewBatch& vb,
                                       const float* scales, const float* rotations, const float* opacities,
                                       const float* shs, GeomState& g0, float* acc, size_t acc_stride_floats,
                                       int* radii_max, cudaStream_t stream) {
-  if (vp.M != 16 || (acc_stride_floats & 3)) return cudaErrorInvalidValue;
+  if ((shs != nullptr && vp.M != 16) || (acc_stride_floats & 3)) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemset2DAsync(g0.counters, vb.geom_stride, 0, 64 * sizeof(uint32_t), (size_t)vb.V, stream);
   if (e != cudaSuccess) return e;
   const int blocks = (vp.P + PRE_B_THREADS - 1) / PRE_B_THREADS;

@@ -143,6 +143,22 @@ class FitModel:
 CAM_FLOATS = 40  # view[16] | proj[16] | campos[3] | tan_fovx | tan_fovy | pad[3]  (include/dge_b200.h "fit step")
 
 
+_CAM_RECORDS = {}
+
+
+def camera_record(cam: scene.Camera) -> torch.Tensor:
+    """pack_camera, memoised on the camera's tensors (cameras are reused from step to step; packing
+    one costs three device-to-host copies when its matrices live on the GPU)."""
+    key = (cam.world_view_transform.data_ptr(), cam.full_proj_transform.data_ptr(), cam.camera_center.data_ptr(),
+           cam.world_view_transform._version, cam.FoVx, cam.FoVy)
+    rec = _CAM_RECORDS.get(key)
+    if rec is None:
+        if len(_CAM_RECORDS) > 4096:
+            _CAM_RECORDS.clear()
+        rec = _CAM_RECORDS[key] = pack_camera(cam)
+    return rec
+
+
 def pack_camera(cam: scene.Camera) -> torch.Tensor:
     """The camera as the pinned 40-float record the fit entry points take."""
     rec = torch.zeros(CAM_FLOATS, dtype=torch.float32)
@@ -410,6 +426,70 @@ def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inpu
         loss += vb.loss
         radii_max = torch.maximum(radii_max, vb.radii_max)
     return loss, radii_max
+
+
+def backproject_masks(means3D, opacities, scales, rotations, cameras, masks, weights, cnt, scale_modifier=1.0):
+    """DGE.update_mask's loop (threestudio/systems/DGE.py:112-147: one GaussianModel.apply_weights per
+    camera, gaussian_model.py:817-832) as ONE call per 64 views: `masks[v]` ([CH,H,W], the 2-D
+    segmentation mask of view v) is back-projected onto the Gaussians it is blended from; `weights`
+    [P,CH] f32 and `cnt` [P(,1)] i32 are accumulated in place, exactly as the per-view calls do (binary
+    masks give identical results bit for bit). Returns the per-view instance counts."""
+    lib = L.load()
+    dev = means3D.device
+    P = means3D.shape[0]
+    H, W = cameras[0].image_height, cameras[0].image_width
+    if not (weights.is_contiguous() and cnt.is_contiguous()) or weights.dtype != torch.float32 or cnt.dtype != torch.int32:
+        raise RuntimeError("backproject_masks: weights must be contiguous float32 and cnt contiguous int32")
+    masks = masks if isinstance(masks, torch.Tensor) else torch.stack(list(masks))
+    masks = masks.to(dev, torch.float32).contiguous()
+    CH = masks.shape[1]
+    means3D, opacities, scales, rotations = (t.detach().to(torch.float32).contiguous() for t in
+                                             (means3D, opacities, scales, rotations))
+    counts = []
+    for lo in range(0, len(cameras), 64):
+        cams = cameras[lo:lo + 64]
+        V = len(cams)
+        recs = torch.stack([camera_record(c) for c in cams]).to(dev, non_blocking=True)
+        arena = _scratch_arena(dev, (P, V, W, H))
+        nr = (L.C.c_int * V)()
+        with torch.cuda.device(dev):
+            L.check(lib.dge_fit_views_apply_weights(
+                arena.cbs[0], arena.cbs[1], arena.cbs[2], None, P, V, W, H, means3D.data_ptr(), opacities.data_ptr(),
+                scales.data_ptr(), float(scale_modifier), rotations.data_ptr(), recs.data_ptr(),
+                masks[lo:lo + V].data_ptr(), CH, weights.data_ptr(), cnt.data_ptr(), nr, L.stream_ptr(dev)),
+                "fit views apply_weights")
+        counts += list(nr)
+    return counts
+
+
+class _GrowingArena:
+    """Three scratch blobs that are kept between calls and only ever grow (update_mask is called with
+    the same sizes every time; 6 GB through the caching allocator per call is not free)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = [torch.empty(0, dtype=torch.uint8, device=device) for _ in range(3)]
+        self.cbs = [L.ALLOC_FN(self._make(i)) for i in range(3)]
+
+    def _make(self, i):
+        def alloc(_ctx, nbytes):
+            if nbytes > self.bufs[i].numel():
+                self.bufs[i] = torch.empty(0, dtype=torch.uint8, device=self.device)  # drop before growing
+                self.bufs[i] = torch.empty(int(nbytes * 1.1) + 256, dtype=torch.uint8, device=self.device)
+            return self.bufs[i].data_ptr()
+        return alloc
+
+
+_ARENAS = {}
+
+
+def _scratch_arena(device, key):
+    k = (str(device),) + tuple(key)
+    if k not in _ARENAS:
+        if len(_ARENAS) >= 2:
+            _ARENAS.clear()
+        _ARENAS[k] = _GrowingArena(device)
+    return _ARENAS[k]
 
 
 def shard_views(num_views: int, rank: int, world: int) -> List[int]:

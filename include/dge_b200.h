@@ -192,6 +192,16 @@ int dge_fit_views_backward_blend(int P, int V, int R_total, const float* backgro
                                  char* image_buffer, const float* dL_dpix, float* acc, size_t acc_stride_floats,
                                  void* stream);
 size_t dge_fit_binning_bytes(int R_total, int V, int width, int height);
+/* DGE.update_mask (threestudio/systems/DGE.py:101-165) in one call: dge_apply_weights for V views at once,
+ * view v with its own mask image image_weights[v] ([V,CH,H,W]) and camera cams[v], all accumulating
+ * into the same weights [P,CH] / cnt [P] (in place, as the reference's per-view calls do). Scratch as
+ * for dge_fit_views_forward. Returns the total number of instances. */
+int dge_fit_views_apply_weights(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge_alloc_fn imageBuffer,
+                                void* alloc_ctx, int P, int V, int width, int height, const float* means3D,
+                                const float* opacities, const float* scales, float scale_modifier,
+                                const float* rotations, const float* cams, const float* image_weights,
+                                int num_channels, float* weights, int* cnt, int* num_rendered_host,
+                                void* stream);
 
 /* GaussianModel's activations (gaussiansplatting/scene/gaussian_model.py:221-258)
  * for the whole model in one pass — shs[P,16,3] = cat(f_dc[P,1,3], f_rest[P,15,3]), opacities =

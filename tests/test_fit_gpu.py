@@ -157,6 +157,32 @@ def test_fused_adam_matches_torch_adam(cuda):
     torch.testing.assert_close(fused.flat, stock.flat, rtol=2e-5, atol=2e-7)
 
 
+@pytest.mark.parametrize("CH", [1, 3])
+def test_batched_mask_backprojection_equals_per_view(cuda, CH):
+    """fit.backproject_masks (dge_fit_views_apply_weights: all views per launch) against the per-view
+    GaussianRasterizer.apply_weights loop of DGE.update_mask: binary masks, so weights and cnt are exact."""
+    from dge_b200 import diff_gaussian_rasterization as dgr
+    model, cams, _, bg = _setup(cuda, True, 40000, 200, 136, 6, 0.03)
+    a = {k: v.detach() for k, v in model.activations().items()}
+    Pn = a["means3D"].shape[0]
+    gen = torch.Generator().manual_seed(9)
+    masks = [(torch.rand(CH, 136, 200, generator=gen) > 0.6).float().to(cuda) for _ in cams]
+    w1 = torch.zeros(Pn, CH, device=cuda)
+    c1 = torch.zeros(Pn, 1, dtype=torch.int32, device=cuda)
+    for cam, m in zip(cams, masks):
+        rs = scene.raster_settings(cam, bg, 0, module=dgr)
+        dgr.GaussianRasterizer(rs).apply_weights(a["means3D"], None, a["opacities"], None, w1, a["scales"], a["rotations"],
+                                                 None, c1, m)
+    w2 = torch.zeros(Pn, CH, device=cuda)
+    c2 = torch.zeros(Pn, 1, dtype=torch.int32, device=cuda)
+    counts = fit.backproject_masks(a["means3D"], a["opacities"], a["scales"], a["rotations"], cams, masks, w2, c2)
+    torch.cuda.synchronize()
+    assert len(counts) == len(cams) and min(counts) > 0
+    assert int(c1.sum()) > 0
+    assert torch.equal(c1, c2)
+    assert torch.equal(w1, w2)
+
+
 def test_local_edit_flow_mask_backprojection_then_masked_fit(cuda):
     """BASELINE.json config 3 at small scale (DGE.update_mask, DGE.py:101-165 + masked fit):
     apply_weights over the views with a binary mask -> weights/cnt -> selection at mask_thres ->
