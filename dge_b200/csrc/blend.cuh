@@ -98,11 +98,14 @@ __device__ __forceinline__ void stage_batch(BlendSmem& s, int tid, int count, SR
                    "l"(rec + (size_t)gid[i] * REC_F4), "r"(bar)
                    : "memory");
   }
+  // try_wait with a suspend-time hint: the hardware parks the thread until the phase completes (or the
+  // hint expires) instead of returning at once — a bare try_wait loop spun through 5-7 % of these
+  // issue-bound kernels' instruction slots (ncu: 1554 M vs 1474 M warp instructions in the forward)
   uint32_t done = 0;
   while (!done)
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
                  : "=r"(done)
-                 : "r"(bar), "r"(parity)
+                 : "r"(bar), "r"(parity), "r"(0x989680)
                  : "memory");
 }
 
