@@ -40,14 +40,51 @@ def inverse_sigmoid(x):
     return torch.log(x / (1 - x))
 
 
+def _build_rotation(r):
+    """gaussiansplatting/utils/general_utils.py:78-100 (rotation matrices of un-normalised quaternions)."""
+    norm = torch.sqrt(r[:, 0] * r[:, 0] + r[:, 1] * r[:, 1] + r[:, 2] * r[:, 2] + r[:, 3] * r[:, 3])
+    q = r / norm[:, None]
+    R = torch.zeros((q.size(0), 3, 3), device=r.device)
+    r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R[:, 0, 0] = 1 - 2 * (y * y + z * z)
+    R[:, 0, 1] = 2 * (x * y - r * z)
+    R[:, 0, 2] = 2 * (x * z + r * y)
+    R[:, 1, 0] = 2 * (x * y + r * z)
+    R[:, 1, 1] = 1 - 2 * (x * x + z * z)
+    R[:, 1, 2] = 2 * (y * z - r * x)
+    R[:, 2, 0] = 2 * (x * z - r * y)
+    R[:, 2, 1] = 2 * (y * z + r * x)
+    R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    return R
+
+
 class FitModel:
     """Flat-buffer replica of GaussianModel's optimisable state."""
 
     def __init__(self, gaussians: scene.Gaussians, device, lrs=None, fused_adam=True, sh_degree=3):
-        P = gaussians.means3D.shape[0]
-        self.P, self.device, self.sh_degree = P, device, sh_degree
+        self.device, self.sh_degree = device, sh_degree
         self.lrs = dict(DEFAULT_LRS if lrs is None else lrs)
         self.fused_adam = fused_adam
+        self.step_count = 0
+        raw = {
+            "xyz": gaussians.means3D, "f_dc": gaussians.shs[:, :1, :], "f_rest": gaussians.shs[:, 1:, :],
+            "opacity": inverse_sigmoid(gaussians.opacities), "scaling": torch.log(gaussians.scales),
+            "rotation": gaussians.rotations,
+        }
+        self._allocate(raw)
+        P = self.P
+        # densification statistics (gaussian_model.py:338-339, 811-815; DGE.py:277-284)
+        self.xyz_gradient_accum = torch.zeros(P, 1, device=device)
+        self.denom = torch.zeros(P, 1, device=device)
+        self.max_radii2D = torch.zeros(P, dtype=torch.int32, device=device)
+        self.grad_mask: Optional[torch.Tensor] = None  # uint8 [P], local editing
+
+    def _allocate(self, raw, exp_avg=None, exp_avg_sq=None):
+        """(Re)builds the flat parameter / gradient / Adam-state buffers for the raw parameter tensors
+        `raw` (name -> [P, ...]); exp_avg / exp_avg_sq: optional per-group Adam state to carry over."""
+        device = self.device
+        P = raw["xyz"].shape[0]
+        self.P = P
         # every group starts on a 16-byte boundary inside the flat buffers (float4 accesses in the
         # kernels: rotation rows, vectorised Adam), whatever P is
         pad4 = lambda x: (x + 3) // 4 * 4
@@ -57,36 +94,138 @@ class FitModel:
         self.flat_grad = torch.zeros(n + 3 * P, dtype=torch.float32, device=device)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=device)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=device)
-        self.step_count = 0
         self.slices = {}
         self.params = {}
         off = 0
-        raw = {
-            "xyz": gaussians.means3D, "f_dc": gaussians.shs[:, :1, :], "f_rest": gaussians.shs[:, 1:, :],
-            "opacity": inverse_sigmoid(gaussians.opacities), "scaling": torch.log(gaussians.scales),
-            "rotation": gaussians.rotations,
-        }
         for name, k, tail in GROUPS:
             sl = slice(off, off + k * P)
             self.slices[name] = sl
             p = self.flat[sl].view(P, *tail)
-            p.copy_(raw[name].to(device).reshape(P, *tail))
+            p.copy_(raw[name].detach().to(device).reshape(P, *tail))
             p.requires_grad_(True)  # a leaf: `flat` itself never requires grad
             p.grad = self.flat_grad[sl].view(P, *tail)
             self.params[name] = p
+            if exp_avg is not None:
+                self.exp_avg[sl].copy_(exp_avg[name].reshape(-1))
+                self.exp_avg_sq[sl].copy_(exp_avg_sq[name].reshape(-1))
             off += pad4(k * P)
         self.means2D = torch.zeros(P, 3, dtype=torch.float32, device=device, requires_grad=True)
         self.means2D_slice = slice(n, n + 3 * P)
         self.means2D.grad = self.flat_grad[self.means2D_slice].view(P, 3)
-        # densification statistics (gaussian_model.py:338-339, 811-815; DGE.py:277-284)
-        self.xyz_gradient_accum = torch.zeros(P, 1, device=device)
-        self.denom = torch.zeros(P, 1, device=device)
-        self.max_radii2D = torch.zeros(P, dtype=torch.int32, device=device)
-        self.grad_mask: Optional[torch.Tensor] = None  # uint8 [P], local editing
-        if not fused_adam:
+        # per-P caches of the fit step (lanes, batches, activations) belong to the old buffers
+        for attr in ("_lane_key", "_batch_key", "_acts", "_lanes", "_batches", "_acc", "_lane_acc", "_min_chunks"):
+            if hasattr(self, attr):
+                delattr(self, attr)
+        if not self.fused_adam:
             # the reference's optimiser, verbatim (gaussian_model.py:374)
             groups = [{"params": [self.params[nm]], "lr": self.lrs[nm], "name": nm} for nm, _, _ in GROUPS]
             self.optimizer = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+            if exp_avg is not None:
+                for nm, _, _ in GROUPS:
+                    sl, pp = self.slices[nm], self.params[nm]
+                    self.optimizer.state[pp] = {"step": torch.tensor(float(self.step_count)),
+                                                "exp_avg": self.exp_avg[sl].view_as(pp),
+                                                "exp_avg_sq": self.exp_avg_sq[sl].view_as(pp)}
+
+    def adam_state(self, name):
+        """(exp_avg, exp_avg_sq) of a parameter group, shaped like the parameter."""
+        if not self.fused_adam and self.params[name] in self.optimizer.state:
+            st = self.optimizer.state[self.params[name]]
+            return st["exp_avg"], st["exp_avg_sq"]
+        sl, pp = self.slices[name], self.params[name]
+        return self.exp_avg[sl].view_as(pp), self.exp_avg_sq[sl].view_as(pp)
+
+    # -- SURVEY.md §8f N4: gaussian_model.py:543-807
+    @torch.no_grad()
+    def densify_and_prune(self, max_grad, max_densify_percent, min_opacity, extent, max_screen_size,
+                          percent_dense=0.01, N=2, generator=None, normal_samples=None):
+        """GaussianModel.densify_and_prune (gaussiansplatting/scene/gaussian_model.py:770-797) on the
+        flat-buffer replica: clone small Gaussians with a large accumulated screen-space gradient
+        (:728-768), split large ones into N samples (:675-726), prune transparent / oversized ones
+        (:786-796), carrying the Adam state the way cat_tensors_to_optimizer / _prune_optimizer do
+        (:543-640: zeros for new rows, rows dropped with their Gaussians) and resetting the statistics as
+        densification_postfix does (:664-666). Only Gaussians inside the edit mask (set_grad_mask)
+        are touched, as in the reference (:774, :795). The flat buffers are rebuilt for the new count.
+        Multi-GPU replicas stay identical when every rank passes a generator seeded alike (the
+        reference draws from the global CUDA generator, :685-687). normal_samples: the N(0,1)-scaled
+        draw to use instead (tests). Returns (P_before, P_after_clone, P_after_split, P_after_prune)."""
+        dev = self.device
+        raw = {k: v.detach() for k, v in self.params.items()}
+        m = {k: self.adam_state(k)[0].detach().clone() for k in raw}
+        v = {k: self.adam_state(k)[1].detach().clone() for k in raw}
+        P0 = self.P
+        mask = torch.ones(P0, dtype=torch.bool, device=dev) if self.grad_mask is None else self.grad_mask.bool()
+        grads = self.xyz_gradient_accum / self.denom
+        grads[grads.isnan()] = 0.0
+        grads[~mask] = 0.0
+        if max_densify_percent < 1:
+            valid_percent = len(grads.nonzero()) * max_densify_percent / grads.shape[0]
+            thresold_value = torch.quantile(grads, 1 - valid_percent)
+            grads[grads < thresold_value] = 0.0
+
+        def extend(new):  # cat_tensors_to_optimizer (:609-640)
+            for k in raw:
+                raw[k] = torch.cat((raw[k], new[k]), dim=0)
+                m[k] = torch.cat((m[k], torch.zeros_like(new[k])), dim=0)
+                v[k] = torch.cat((v[k], torch.zeros_like(new[k])), dim=0)
+
+        def keep(valid):  # _prune_optimizer (:568-587)
+            for k in raw:
+                raw[k], m[k], v[k] = raw[k][valid], m[k][valid], v[k][valid]
+
+        # ---- clone (:728-768)
+        sel = torch.norm(grads, dim=-1) >= max_grad
+        sel = torch.logical_and(sel, torch.max(torch.exp(raw["scaling"]), dim=1).values <= percent_dense * extent)
+        extend({k: raw[k][sel] for k in raw})
+        mask = torch.cat([mask, mask[sel]], dim=0)
+        P1 = raw["xyz"].shape[0]
+        # ---- split (:675-726)
+        padded_grad = torch.zeros(P1, device=dev)
+        padded_grad[:grads.shape[0]] = grads.squeeze()
+        sel = padded_grad >= max_grad
+        scaling = torch.exp(raw["scaling"])
+        sel = torch.logical_and(sel, torch.max(scaling, dim=1).values > percent_dense * extent)
+        stds = scaling[sel].repeat(N, 1)
+        if normal_samples is not None:
+            samples = normal_samples.to(dev)
+        else:
+            samples = torch.normal(mean=torch.zeros((stds.size(0), 3), device=dev), std=stds, generator=generator)
+        rots = _build_rotation(raw["rotation"][sel]).repeat(N, 1, 1)
+        new = {
+            "xyz": torch.bmm(rots, samples.unsqueeze(-1)).squeeze(-1) + raw["xyz"][sel].repeat(N, 1),
+            "scaling": torch.log(scaling[sel].repeat(N, 1) / (0.8 * N)),
+            "rotation": raw["rotation"][sel].repeat(N, 1),
+            "f_dc": raw["f_dc"][sel].repeat(N, 1, 1),
+            "f_rest": raw["f_rest"][sel].repeat(N, 1, 1),
+            "opacity": raw["opacity"][sel].repeat(N, 1),
+        }
+        extend(new)
+        mask = torch.cat([mask] + [mask[sel]] * N, dim=0)
+        P2_all = raw["xyz"].shape[0]
+        prune_filter = torch.cat((sel, torch.zeros(N * int(sel.sum()), device=dev, dtype=torch.bool)))
+        keep(~prune_filter)
+        mask = mask[~prune_filter]
+        P2 = raw["xyz"].shape[0]
+        # densification_postfix (:664-666) reset the statistics for the new count
+        max_radii2D = torch.zeros(P2, dtype=torch.int32, device=dev)
+        # ---- prune (:786-796)
+        prune_mask = (torch.sigmoid(raw["opacity"]) < min_opacity).squeeze()
+        if max_screen_size:
+            big_points_vs = max_radii2D > max_screen_size
+            big_points_ws = torch.exp(raw["scaling"]).max(dim=1).values > 0.1 * extent
+            prune_mask = torch.logical_or(torch.logical_or(prune_mask, big_points_vs), big_points_ws)
+        prune_mask = torch.logical_and(prune_mask, mask)
+        keep(~prune_mask)
+        mask = mask[~prune_mask]
+        P3 = raw["xyz"].shape[0]
+        had_mask = self.grad_mask is not None
+        self._allocate(raw, m, v)
+        self.xyz_gradient_accum = torch.zeros(P3, 1, device=dev)
+        self.denom = torch.zeros(P3, 1, device=dev)
+        self.max_radii2D = torch.zeros(P3, dtype=torch.int32, device=dev)
+        self.grad_mask = mask.to(torch.uint8).contiguous() if had_mask else None
+        del P2_all
+        return P0, P1, P2, P3
 
     # -- gaussian_model.py:221-258
     def activations(self):

@@ -124,6 +124,36 @@ def test_batched_with_empty_views(cuda):
     assert torch.isfinite(lc)
 
 
+def test_densify_then_fit_on_gpu(cuda):
+    """SURVEY.md §8f N4 on the device: fit steps accumulate the statistics, densify_and_prune rebuilds the
+    flat buffers for the new Gaussian count, the next (batched) fit step runs on them; two replicas with
+    generators seeded alike stay bit-identical (no broadcast needed between ranks)."""
+    a, cams, targets, bg = _setup(cuda, True)
+    b, _, _, _ = _setup(cuda, True)
+    for m in (a, b):
+        for _ in range(2):
+            fit.fit_step(m, cams, targets, bg, global_batch=V, batched=True)
+        assert float(m.denom.sum()) > 0
+    # replicas of a multi-GPU fit hold identical state (they apply the same all-reduced gradients); two
+    # independent runs on one GPU differ in the last bits (float atomics), so give b a's state
+    for name in ("flat", "exp_avg", "exp_avg_sq", "xyz_gradient_accum", "denom", "max_radii2D"):
+        getattr(b, name).copy_(getattr(a, name))
+    counts = []
+    for m in (a, b):
+        gen = torch.Generator(device=cuda).manual_seed(3)
+        # thresholds picked so that this small scene clones, splits and prunes something
+        counts.append(m.densify_and_prune(1e-7, 1.0, 0.05, 4.0, 0, generator=gen))
+    assert counts[0] == counts[1]
+    P0, P1, P2, P3 = counts[0]
+    assert P1 > P0 and P2 > P1 and P3 < P2 and a.P == P3
+    assert torch.equal(a.flat, b.flat) and torch.equal(a.exp_avg_sq, b.exp_avg_sq)
+    la = fit.fit_step(a, cams, targets, bg, global_batch=V, batched=True)
+    lb = fit.fit_step(b, cams, targets, bg, global_batch=V, batched=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(la) and abs(float(la) - float(lb)) <= 1e-5 * abs(float(la))
+    assert a._batches[0].radii_max.shape[0] == P3
+
+
 def test_host_inputs_equal_resident(cuda):
     a, cams, targets, bg = _setup(cuda, True)
     b, _, _, _ = _setup(cuda, True)
