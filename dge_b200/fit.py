@@ -127,6 +127,21 @@ class FitModel:
                                                 "exp_avg": self.exp_avg[sl].view_as(pp),
                                                 "exp_avg_sq": self.exp_avg_sq[sl].view_as(pp)}
 
+    @classmethod
+    def from_raw(cls, raw, device, **kw):
+        """A model from the six RAW parameter tensors by group name (e.g. ply.load_ply)."""
+        P = raw["xyz"].shape[0]
+        shs = torch.cat((raw["f_dc"], raw["f_rest"]), dim=1)
+        model = cls(scene.Gaussians(raw["xyz"], torch.exp(raw["scaling"]), raw["rotation"], torch.sigmoid(raw["opacity"]),
+                                    shs), device, **kw)
+        model._allocate({k: v.reshape(P, *[g[2] for g in GROUPS if g[0] == k][0]) for k, v in raw.items()})
+        return model
+
+    def save_ply(self, path):
+        """GaussianModel.save_ply's file (gaussian_model.py:410-445): see dge_b200/ply.py."""
+        from . import ply
+        ply.save_ply(self.params, path)
+
     def adam_state(self, name):
         """(exp_avg, exp_avg_sq) of a parameter group, shaped like the parameter."""
         if not self.fused_adam and self.params[name] in self.optimizer.state:
