@@ -208,7 +208,7 @@ using namespace dge;
 extern "C" {
 
 const char* dge_last_error(void) { return g_err; }
-int dge_abi_version(void) { return 7; }
+int dge_abi_version(void) { return 8; }
 unsigned long long dge_launch_count(void) { return g_kernel_launches; }
 
 void dge_profile_enable(unsigned stage_mask) { g_profile_mask = stage_mask; }
@@ -358,10 +358,12 @@ int dge_fit_views_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffe
                           int height, const float* means3D, const float* shs, const float* opacities,
                           const float* scales, float scale_modifier, const float* rotations,
                           const float* cams, float* out_color, float* out_depth, int* radii_max, float* acc,
-                          size_t acc_stride_floats, int* num_rendered_host, void* stream_) {
+                          size_t acc_stride_floats, int* num_rendered_host, const float* extra, float* out_extra,
+                          void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool debug = false;
   if (P == 0 || width <= 0 || height <= 0) return fail_msg("empty problem");
+  if ((extra == nullptr) != (out_extra == nullptr)) return fail_msg("extra and out_extra go together");
   if (M != 16 || shs == nullptr) return fail_msg("the batched fit path needs SH degree-3 storage (M == 16)");
   // tan_fov / focal are per view and filled in by the batched preprocess from the camera records
   const ViewParams vp = make_view(P, D, M, width, height, nullptr, nullptr, nullptr, 1.f, 1.f, scale_modifier);
@@ -374,7 +376,8 @@ int dge_fit_views_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffe
                                 g0, b, img0, vb);
   if (R_total < 0) return R_total;
   STAGE(ST_RENDER_FWD, "render forward (batched)",
-        launch_render_forward_batched(vp, vb, g0, b, img0, background, out_color, out_depth, stream));
+        launch_render_forward_batched(vp, vb, g0, b, img0, background, out_color, out_depth, stream, extra,
+                                      out_extra));
   return R_total;
 }
 

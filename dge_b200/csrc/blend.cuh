@@ -73,7 +73,8 @@ __device__ __forceinline__ void stage_init(BlendSmem& s, int tid) {
 template <typename SRC>
 __device__ __forceinline__ void stage_batch(BlendSmem& s, int tid, int count, SRC src,
                                             const uint32_t* __restrict__ point_list,
-                                            const float4* __restrict__ rec, uint32_t parity) {
+                                            const float4* __restrict__ rec, uint32_t parity,
+                                            const float* __restrict__ extra = nullptr) {
   constexpr int PER = BL_BATCH / BL_THREADS;
   uint32_t gid[PER];
   int mine = 0;
@@ -83,6 +84,7 @@ __device__ __forceinline__ void stage_batch(BlendSmem& s, int tid, int count, SR
     if (k < count) {
       gid[i] = point_list[src(k)];
       s.rec[k][REC_F4].x = __uint_as_float(gid[i]);
+      if (extra != nullptr) s.rec[k][REC_F4].y = extra[gid[i]];  // a fourth blended channel (forward only)
       mine++;
     }
   }

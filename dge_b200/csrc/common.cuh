@@ -168,7 +168,8 @@ cudaError_t launch_binning_batched(const ViewParams& vp, const ViewBatch& vb, ui
                                    GeomState& g0, BinState& b, ImgState& img0, cudaStream_t stream);
 cudaError_t launch_render_forward_batched(const ViewParams& vp, const ViewBatch& vb, const GeomState& g0,
                                           const BinState& b, ImgState& img0, const float* background,
-                                          float* out_color, float* out_depth, cudaStream_t stream);
+                                          float* out_color, float* out_depth, cudaStream_t stream,
+                                          const float* extra = nullptr, float* out_extra = nullptr);
 cudaError_t launch_render_backward_batched(const ViewParams& vp, const ViewBatch& vb, const GeomState& g0,
                                            const BinState& b, const ImgState& img0, const float* background,
                                            const float* dL_dpix, float* acc, size_t acc_stride_floats,

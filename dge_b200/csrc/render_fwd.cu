@@ -18,11 +18,17 @@
 
 namespace dge {
 
-__global__ void __launch_bounds__(BL_THREADS, 14) render_forward_kernel(
+// EXTRA: additionally blends one per-Gaussian scalar (`extra[P]`) exactly like a colour channel and
+// writes it, background added per channel, as a second image — DGE's "semantic" render of the edit
+// mask (threestudio/systems/DGE.py:198-204: render(..., override_color=mask repeated 3x)) for the price
+// of one FFMA per blended pair instead of a second preprocess + sort + blend of the same view.
+template <bool EXTRA>
+__global__ void __launch_bounds__(BL_THREADS, EXTRA ? 12 : 14) render_forward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
     const float4* __restrict__ rec, const float* __restrict__ background,
     float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
-    float* __restrict__ out_depth, BlendBatch bb) {
+    float* __restrict__ out_depth, BlendBatch bb, const float* __restrict__ extra,
+    float* __restrict__ out_extra) {
   __shared__ BlendSmem s;
   if (bb.seg_off) {  // view blockIdx.z of a fit-step batch (blend.cuh)
     const size_t gs = blockIdx.z * bb.geom_stride, is = blockIdx.z * bb.img_stride;
@@ -33,6 +39,7 @@ __global__ void __launch_bounds__(BL_THREADS, 14) render_forward_kernel(
     point_list += bb.seg_off[blockIdx.z];
     out_color += (size_t)blockIdx.z * 3 * H * W;
     out_depth += (size_t)blockIdx.z * H * W;
+    if (EXTRA) out_extra += (size_t)blockIdx.z * 3 * H * W;
   }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // pixel p of this thread = (px0 + PX_STEP*(p&1), py0 + PY_STEP*(p>>1)): one pixel in each 8x4
@@ -48,7 +55,7 @@ __global__ void __launch_bounds__(BL_THREADS, 14) render_forward_kernel(
   for (int p = 0; p < 4; p++) inside[p] = px0 + PX_STEP * (p & 1) < W && py0 + PY_STEP * (p >> 1) < H;
 
   const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
-  float T[4], C[4][3], Dp[4];
+  float T[4], C[4][3], Dp[4], E[4];
   uint32_t last[4];
   bool done[4];
 #pragma unroll
@@ -56,6 +63,7 @@ __global__ void __launch_bounds__(BL_THREADS, 14) render_forward_kernel(
     T[p] = 1.0f;
     C[p][0] = C[p][1] = C[p][2] = 0.0f;
     Dp[p] = 0.0f;
+    E[p] = 0.0f;
     last[p] = 0;
     done[p] = !inside[p];
   }
@@ -66,7 +74,7 @@ __global__ void __launch_bounds__(BL_THREADS, 14) render_forward_kernel(
     const bool all_done = done[0] && done[1] && done[2] && done[3];
     if (__syncthreads_and(all_done)) break;  // also: everyone has finished walking the previous batch
     const int count = min((uint32_t)BL_BATCH, range.y - base);
-    stage_batch(s, tid, count, [&](int k) { return base + k; }, point_list, rec, parity);
+    stage_batch(s, tid, count, [&](int k) { return base + k; }, point_list, rec, parity, EXTRA ? extra : nullptr);
     parity ^= 1u;
     if (__all_sync(0xFFFFFFFFu, all_done)) continue;  // this half-tile is saturated
     // quadrants in which every pixel has terminated need no further visits
@@ -96,6 +104,7 @@ __global__ void __launch_bounds__(BL_THREADS, 14) render_forward_kernel(
         C[p][1] = BFMA(T[p], BMUL(alpha, cd.y), C[p][1]);
         C[p][2] = BFMA(T[p], BMUL(alpha, cd.z), C[p][2]);
         Dp[p] = BFMA(T[p], BMUL(alpha, b.w), Dp[p]);
+        if (EXTRA) E[p] = BFMA(T[p], BMUL(alpha, s.rec[j][REC_F4].y), E[p]);
         T[p] = test_T;
         last[p] = base - range.x + j + 1;
       }
@@ -114,6 +123,11 @@ __global__ void __launch_bounds__(BL_THREADS, 14) render_forward_kernel(
     out_color[HW + pix] = BFMA(bg1, T[p], C[p][1]);
     out_color[2 * HW + pix] = BFMA(bg2, T[p], C[p][2]);
     out_depth[pix] = Dp[p];
+    if (EXTRA) {
+      out_extra[pix] = BFMA(bg0, T[p], E[p]);
+      out_extra[HW + pix] = BFMA(bg1, T[p], E[p]);
+      out_extra[2 * HW + pix] = BFMA(bg2, T[p], E[p]);
+    }
   }
 }
 
@@ -121,20 +135,27 @@ cudaError_t launch_render_forward(const ViewParams& vp, const GeomState& g, cons
                                   ImgState& img, const float* background, float* out_color,
                                   float* out_depth, cudaStream_t stream) {
   dim3 grid(vp.grid_x, vp.grid_y);
-  render_forward_kernel<<<grid, BL_THREADS, 0, stream>>>(
+  render_forward_kernel<false><<<grid, BL_THREADS, 0, stream>>>(
       img.ranges, b.point_list, vp.W, vp.H, g.rec, background,
-      img.final_T, img.n_contrib, out_color, out_depth, BlendBatch{0, 0, nullptr, 0});
+      img.final_T, img.n_contrib, out_color, out_depth, BlendBatch{0, 0, nullptr, 0}, nullptr, nullptr);
   DGE_LAUNCHED(1);
   return cudaGetLastError();
 }
 
 cudaError_t launch_render_forward_batched(const ViewParams& vp, const ViewBatch& vb, const GeomState& g0,
                                           const BinState& b, ImgState& img0, const float* background,
-                                          float* out_color, float* out_depth, cudaStream_t stream) {
+                                          float* out_color, float* out_depth, cudaStream_t stream,
+                                          const float* extra, float* out_extra) {
   dim3 grid(vp.grid_x, vp.grid_y, vb.V);
-  render_forward_kernel<<<grid, BL_THREADS, 0, stream>>>(
-      img0.ranges, b.point_list, vp.W, vp.H, g0.rec, background,
-      img0.final_T, img0.n_contrib, out_color, out_depth, BlendBatch{vb.geom_stride, vb.img_stride, vb.seg_off, 0});
+  const BlendBatch bb{vb.geom_stride, vb.img_stride, vb.seg_off, 0};
+  if (extra != nullptr && out_extra != nullptr)
+    render_forward_kernel<true><<<grid, BL_THREADS, 0, stream>>>(img0.ranges, b.point_list, vp.W, vp.H, g0.rec,
+                                                                background, img0.final_T, img0.n_contrib, out_color,
+                                                                out_depth, bb, extra, out_extra);
+  else
+    render_forward_kernel<false><<<grid, BL_THREADS, 0, stream>>>(img0.ranges, b.point_list, vp.W, vp.H, g0.rec,
+                                                                 background, img0.final_T, img0.n_contrib, out_color,
+                                                                 out_depth, bb, nullptr, nullptr);
   DGE_LAUNCHED(1);
   return cudaGetLastError();
 }

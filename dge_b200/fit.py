@@ -301,15 +301,21 @@ _CAM_RECORDS = {}
 
 
 def camera_record(cam: scene.Camera) -> torch.Tensor:
-    """pack_camera, memoised on the camera's tensors (cameras are reused from step to step; packing
-    one costs three device-to-host copies when its matrices live on the GPU)."""
-    key = (cam.world_view_transform.data_ptr(), cam.full_proj_transform.data_ptr(), cam.camera_center.data_ptr(),
-           cam.world_view_transform._version, cam.FoVx, cam.FoVy)
-    rec = _CAM_RECORDS.get(key)
-    if rec is None:
-        if len(_CAM_RECORDS) > 4096:
-            _CAM_RECORDS.clear()
-        rec = _CAM_RECORDS[key] = pack_camera(cam)
+    """pack_camera, memoised per camera object (cameras are reused from step to step; packing one costs
+    three device-to-host copies when its matrices live on the GPU). The cache holds a reference to the
+    camera's tensors — so their storage cannot be freed and handed to ANOTHER camera while the entry
+    lives (a key made of data pointers alone went stale exactly that way) — and checks their version
+    counters, so in-place updates are seen."""
+    wv, fp, cc = cam.world_view_transform, cam.full_proj_transform, cam.camera_center
+    key = (id(wv), id(fp), id(cc))
+    ver = (wv._version, fp._version, cc._version, cam.FoVx, cam.FoVy)
+    hit = _CAM_RECORDS.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[2]
+    if len(_CAM_RECORDS) > 4096:
+        _CAM_RECORDS.clear()
+    rec = pack_camera(cam)
+    _CAM_RECORDS[key] = (ver, (wv, fp, cc), rec)
     return rec
 
 
@@ -383,7 +389,6 @@ def _direct_views(model: FitModel, acts, cameras, targets, bg, scale, host_input
         f32 = dict(dtype=torch.float32, device=dev)
         model._lane_acc = torch.empty(V, P, 12, **f32)          # blend-stage sums of every view of the step
         model._lane_cams = torch.empty(V, CAM_FLOATS, **f32)
-        model._lane_cam_cache = {}
         model._lane_key = key
     lanes, acc, cams_dev = model._lanes, model._lane_acc, model._lane_cams
     a = {k: v.detach() for k, v in acts.items()}
@@ -400,12 +405,8 @@ def _direct_views(model: FitModel, acts, cameras, targets, bg, scale, host_input
     n_img = 3 * H * W
     for i, (cam, target) in enumerate(zip(cameras, targets)):
         ln = lanes[i % S]
-        ck = cam.world_view_transform.data_ptr()
-        rec = model._lane_cam_cache.get(ck)
-        if rec is None:
-            r = pack_camera(cam)
-            rec = model._lane_cam_cache[ck] = (r, float(r[35]), float(r[36]))
-        rec, tfx, tfy = rec
+        rec = camera_record(cam)
+        tfx, tfy = float(rec[35]), float(rec[36])
         with torch.cuda.stream(ln.stream):
             cams_dev[i].copy_(rec, non_blocking=True)
             if host_inputs:  # pinned host -> this lane's staging buffer, asynchronously on its stream
@@ -509,7 +510,6 @@ def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inpu
         model._batches = [ViewBatch(model, W, H, bounds[c + 1] - bounds[c], model._acc[bounds[c]:bounds[c + 1]],
                                     model._cams[bounds[c]:bounds[c + 1]], model._cams_host[bounds[c]:bounds[c + 1]])
                           for c in range(C)]
-        model._cam_cache = {}
         model._batch_key = key
     batches, bounds = model._batches, model._chunk_bounds
     main = torch.cuda.current_stream(dev)
@@ -521,11 +521,7 @@ def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inpu
         model._bg_key, model._bg_black = bgp, int(not bool(bg.detach().cpu().any()))
     # cameras: one pinned [V,40] block, one H2D copy
     for i, cam in enumerate(cameras):
-        ck = cam.world_view_transform.data_ptr()
-        rec = model._cam_cache.get(ck)
-        if rec is None:
-            rec = model._cam_cache[ck] = pack_camera(cam)
-        model._cams_host[i].copy_(rec)
+        model._cams_host[i].copy_(camera_record(cam))
     model._cams.copy_(model._cams_host, non_blocking=True)
     resident = isinstance(targets, torch.Tensor) and targets.is_cuda
     acc_stride = P * 12
@@ -556,7 +552,7 @@ def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inpu
                 vb.cb_geom, vb.cb_binning, vb.cb_img, None, P, model.sh_degree, M, vb.V, bgp, W, H, ptrs["means3D"],
                 ptrs["shs"], ptrs["opacities"], ptrs["scales"], 1.0, ptrs["rotations"], vb.cams.data_ptr(),
                 vb.color.data_ptr(), vb.depth.data_ptr(), vb.radii_max.data_ptr(), vb.acc.data_ptr(), acc_stride,
-                vb.num_rendered, vb.stream_ptr), "fit views forward")
+                vb.num_rendered, None, None, vb.stream_ptr), "fit views forward")
     for vb in batches:
         with torch.cuda.stream(vb.stream):
             if host_inputs and not resident:
@@ -580,6 +576,44 @@ def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inpu
         loss += vb.loss
         radii_max = torch.maximum(radii_max, vb.radii_max)
     return loss, radii_max
+
+
+def render_views(means3D, shs, opacities, scales, rotations, cameras, bg, extra=None, sh_degree=3,
+                 scale_modifier=1.0):
+    """Forward-only rendering of many views at once (DGE.render_all_view / the camera loop of DGE.forward
+    without the backward): gaussian_renderer.render() for every camera, ALL views per launch
+    (dge_fit_views_forward). `extra` [P]: a per-Gaussian scalar (DGE: gaussian.mask.float()) blended as an
+    additional channel; the third return value is then the image the reference gets from a SECOND
+    render(..., override_color=extra repeated 3x) of each view (DGE.py:198-204), bit for bit.
+    Returns (color [V,3,H,W], depth [V,1,H,W], extra image [V,3,H,W] or None, max radii [P])."""
+    lib = L.load()
+    dev = means3D.device
+    P = means3D.shape[0]
+    H, W = cameras[0].image_height, cameras[0].image_width
+    means3D, shs, opacities, scales, rotations = (t.detach().to(torch.float32).contiguous() for t in
+                                                  (means3D, shs, opacities, scales, rotations))
+    bg = bg.detach().to(dev, torch.float32).contiguous()
+    f32 = dict(dtype=torch.float32, device=dev)
+    Vt = len(cameras)
+    color, depth = torch.empty(Vt, 3, H, W, **f32), torch.empty(Vt, 1, H, W, **f32)
+    sem = torch.empty(Vt, 3, H, W, **f32) if extra is not None else None
+    ex = None if extra is None else extra.detach().to(dev, torch.float32).reshape(-1).contiguous()
+    radii_max = torch.zeros(P, dtype=torch.int32, device=dev)
+    for lo in range(0, Vt, 64):
+        cams = cameras[lo:lo + 64]
+        V = len(cams)
+        recs = torch.stack([camera_record(c) for c in cams]).to(dev, non_blocking=True)
+        arena = _scratch_arena(dev, ("render", P, V, W, H))
+        rm = torch.empty(P, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            L.check(lib.dge_fit_views_forward(
+                arena.cbs[0], arena.cbs[1], arena.cbs[2], None, P, sh_degree, shs.shape[1], V, bg.data_ptr(), W, H,
+                means3D.data_ptr(), shs.data_ptr(), opacities.data_ptr(), scales.data_ptr(), float(scale_modifier),
+                rotations.data_ptr(), recs.data_ptr(), color[lo:lo + V].data_ptr(), depth[lo:lo + V].data_ptr(),
+                rm.data_ptr(), None, 0, None, None if ex is None else ex.data_ptr(),
+                None if sem is None else sem[lo:lo + V].data_ptr(), L.stream_ptr(dev)), "fit views forward (render)")
+        radii_max = torch.maximum(radii_max, rm)
+    return color, depth, sem, radii_max
 
 
 def backproject_masks(means3D, opacities, scales, rotations, cameras, masks, weights, cnt, scale_modifier=1.0):

@@ -179,13 +179,19 @@ int dge_fit_backward_geom(int P, int D, int M, int V, const float* cams, int wid
  * of 4), radii_max [P] = max over the views of the reference's per-view radii. geometryBuffer is
  * asked for V*dge_geom_bytes(P) bytes, imageBuffer for V*dge_image_bytes(W,H), binningBuffer for
  * dge_fit_binning_bytes(R_total, V, W, H) once the counts are known. num_rendered_host (host, [V], may be
- * NULL) receives the per-view num_rendered. Returns R_total = their sum. */
+ * NULL) receives the per-view num_rendered. Returns R_total = their sum.
+ * acc and radii_max may be NULL (forward-only rendering, e.g. DGE's render_all_view).
+ * extra [P] / out_extra [V,3,H,W] (both or neither): one more per-Gaussian scalar blended like a colour
+ * channel, background added per channel — bit-identical to a second forward of the same view with
+ * colors_precomp = extra repeated three times, which is how DGE.forward renders its "semantic" map of
+ * the edit mask for every view of every step (threestudio/systems/DGE.py:198-204). */
 int dge_fit_views_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge_alloc_fn imageBuffer,
                           void* alloc_ctx, int P, int D, int M, int V, const float* background, int width,
                           int height, const float* means3D, const float* shs, const float* opacities,
                           const float* scales, float scale_modifier, const float* rotations,
                           const float* cams, float* out_color, float* out_depth, int* radii_max, float* acc,
-                          size_t acc_stride_floats, int* num_rendered_host, void* stream);
+                          size_t acc_stride_floats, int* num_rendered_host, const float* extra, float* out_extra,
+                          void* stream);
 /* dL_dpix is [V,3,H,W]; the three blobs are the ones dge_fit_views_forward filled. */
 int dge_fit_views_backward_blend(int P, int V, int R_total, const float* background, int background_is_black,
                                  int width, int height, char* geom_buffer, char* binning_buffer,

@@ -187,6 +187,36 @@ def test_fused_adam_matches_torch_adam(cuda):
     torch.testing.assert_close(fused.flat, stock.flat, rtol=2e-5, atol=2e-7)
 
 
+def test_render_views_with_semantic_channel(cuda):
+    """fit.render_views: all views per launch, and the edit-mask "semantic" image as a fourth blended
+    channel of the SAME launch — bit-identical to the reference's way, a second per-view render with
+    override_color = mask repeated three times (threestudio/systems/DGE.py:198-204)."""
+    from dge_b200 import diff_gaussian_rasterization as dgr
+    model, cams, _, bg = _setup(cuda, True, 40000, 200, 136, 4, 0.03)
+    bg = bg + torch.tensor([0.1, 0.3, 0.2], device=cuda)
+    a = {k: v.detach() for k, v in model.activations().items()}
+    Pn = a["means3D"].shape[0]
+    mask = (torch.rand(Pn, generator=torch.Generator().manual_seed(4)) < 0.4).to(cuda)
+    color, depth, sem, radii_max = fit.render_views(a["means3D"], a["shs"], a["opacities"], a["scales"], a["rotations"],
+                                                    cams, bg, extra=mask.float())
+    rmax = torch.zeros(Pn, dtype=torch.int32, device=cuda)
+    for v, cam in enumerate(cams):
+        rs = scene.raster_settings(cam, bg, 3, module=dgr)
+        zero2d = torch.zeros_like(a["means3D"])
+        c1, r1, d1 = dgr.GaussianRasterizer(rs)(means3D=a["means3D"], means2D=zero2d, shs=a["shs"], colors_precomp=None,
+                                                opacities=a["opacities"], scales=a["scales"], rotations=a["rotations"],
+                                                cov3D_precomp=None)
+        c2, _, _ = dgr.GaussianRasterizer(rs)(means3D=a["means3D"], means2D=zero2d, shs=None,
+                                              colors_precomp=mask[..., None].float().repeat(1, 3),
+                                              opacities=a["opacities"], scales=a["scales"], rotations=a["rotations"],
+                                              cov3D_precomp=None)
+        assert torch.equal(c1, color[v]) and torch.equal(d1, depth[v]), v
+        assert torch.equal(c2, sem[v]), v
+        rmax = torch.maximum(rmax, r1)
+    assert torch.equal(rmax, radii_max)
+    assert 0 < int((torch.norm(sem, dim=1) > 0.8).sum()) < sem[:, 0].numel()
+
+
 @pytest.mark.parametrize("CH", [1, 3])
 def test_batched_mask_backprojection_equals_per_view(cuda, CH):
     """fit.backproject_masks (dge_fit_views_apply_weights: all views per launch) against the per-view

