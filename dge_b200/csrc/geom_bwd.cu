@@ -444,15 +444,37 @@ __global__ void __launch_bounds__(128, 4) geom_backward_batched_kernel(
   // non-empty views, and a warp iterates max-over-lanes(#non-empty) times instead of V times.
   bool any = false;
   unsigned long long todo = 0ull;
-  for (int v = 0; v < V; v++) {
-    const float4* row = reinterpret_cast<const float4*>(acc + (size_t)v * acc_stride) + 3 * i;
-    const float4 a2 = __ldg(row + 2);
-    if (!(__float_as_uint(a2.w) & 1u)) continue;
+  // Four views at a time, all loads of a level issued before any is used: walked one view after the
+  // other, the two dependent loads per view (flags, then the sums) put 2 V memory round trips on
+  // every thread's critical path — that latency, not bandwidth, was the kernel's time (0.58 ms for
+  // 1.4 GB at 16 warps per SM).
+  for (int v0 = 0; v0 < V; v0 += 4) {
+    float4 a2[4];
+    const float4* row[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      row[k] = reinterpret_cast<const float4*>(acc + (size_t)min(v0 + k, V - 1) * acc_stride) + 3 * i;
+      a2[k] = __ldg(row[k] + 2);
+    }
+    unsigned vis = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (v0 + k < V && (__float_as_uint(a2[k].w) & 1u)) vis |= 1u << k;
+    if (!vis) continue;
     any = true;
-    const float4 a0 = __ldg(row), a1 = __ldg(row + 1);
-    if (a0.x != 0.f || a0.y != 0.f || a0.z != 0.f || a0.w != 0.f || a1.x != 0.f || a1.y != 0.f || a1.z != 0.f ||
-        a1.w != 0.f || a2.x != 0.f)
-      todo |= 1ull << v;
+    float4 a0[4], a1[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if ((vis >> k) & 1u) {
+        a0[k] = __ldg(row[k]);
+        a1[k] = __ldg(row[k] + 1);
+      }
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (((vis >> k) & 1u) &&
+          (a0[k].x != 0.f || a0[k].y != 0.f || a0[k].z != 0.f || a0[k].w != 0.f || a1[k].x != 0.f || a1[k].y != 0.f ||
+           a1[k].z != 0.f || a1[k].w != 0.f || a2[k].x != 0.f))
+        todo |= 1ull << (v0 + k);
   }
   while (todo) {
     const int v = __ffsll((long long)todo) - 1;

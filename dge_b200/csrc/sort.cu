@@ -58,6 +58,11 @@ size_t sort_workspace_bytes_segmented(uint32_t n_total, int segs) {
 struct SegArgs {
   size_t stride_bytes;
   const uint32_t* seg_off;
+  // segment = blockIdx.x instead of blockIdx.y (onesweep passes): CTAs are dispatched x-fastest, so
+  // with the segment in x the tiles of ALL segments advance together and a tile's predecessors
+  // (same segment, lower tickets) have mostly finished when it looks back; with the segment in y
+  // one segment's tiles all start at once and each walks back over every predecessor
+  int seg_in_x;
 };
 
 // Digit histograms of every pass in one read of the keys.
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(
     SegArgs sa) {
   constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;
   {
-    const uint32_t seg = blockIdx.y;
+    const uint32_t seg = sa.seg_in_x ? blockIdx.x : blockIdx.y;
     if (sa.seg_off) {
       const uint32_t o = sa.seg_off[seg];
       n = sa.seg_off[seg + 1] - o;
@@ -324,7 +329,9 @@ cudaError_t sort_pairs_segmented(uint32_t* keys[2], uint32_t* vals[2], uint32_t 
     pass_stride = (size_t)seg_total_tiles(n_total, segs) * RADIX;
   }
   if (e != cudaSuccess) return e;
-  const SegArgs sa = {seg_stride_bytes, seg_off};
+  static const bool env_seg_y = getenv("DGE_SORT_SEG_Y") != nullptr;
+  const int seg_in_x = (segs > 1 && tiles <= 65535 && !env_seg_y) ? 1 : 0;
+  const SegArgs sa = {seg_stride_bytes, seg_off, seg_in_x};
   int cur = passes & 1;
   const int hist_blocks = (int)min((uint32_t)(DGE_NUM_SMS * 4), (n + 2047) / 2048);
   sort_histogram_kernel<<<dim3(hist_blocks, segs), 256, 0, stream>>>(keys[cur], n, passes, num_bits, hist, sa);
@@ -335,7 +342,7 @@ cudaError_t sort_pairs_segmented(uint32_t* keys[2], uint32_t* vals[2], uint32_t 
     const int shift = p * per;
     const int bits = (num_bits - shift) < per ? (num_bits - shift) : per;
     const uint32_t* vin = (p == 0 && iota_values) ? nullptr : vals[cur];
-    const dim3 grid(tiles, segs);
+    const dim3 grid = seg_in_x ? dim3(segs, tiles) : dim3(tiles, segs);
     if (ipt == 8)
       onesweep_kernel<8><<<grid, SORT_THREADS, 0, stream>>>(
           keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift, (1u << bits) - 1u,
