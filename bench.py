@@ -367,6 +367,11 @@ def main():
                 Rs.append(R)
                 Pvs.append(int((radii > 0).sum()))
         stats = {"P": P, "P_visible": sum(Pvs) / len(Pvs), "R": sum(Rs) / len(Rs), "views_sampled": len(Rs)}
+        if batched and getattr(model, "_batches", None):
+            # instances actually listed per view by the per-step family (lists pruned to the tiles a
+            # Gaussian can reach with alpha >= 1/255); R above is the reference's count
+            nr = [n for vb_ in model._batches for n in vb_.num_rendered]
+            stats["R_listed"] = sum(nr) / max(len(nr), 1)
         dominant = max((k for k in stage_total if k in ("preprocess", "render_fwd", "render_bwd", "geom_bwd", "binning")),
                        key=lambda k: stage_total[k])  # largest share of the step
         lib.dge_profile_enable(1 << STAGE_NAMES.index(dominant))

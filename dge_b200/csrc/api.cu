@@ -208,7 +208,7 @@ using namespace dge;
 extern "C" {
 
 const char* dge_last_error(void) { return g_err; }
-int dge_abi_version(void) { return 8; }
+int dge_abi_version(void) { return 9; }
 unsigned long long dge_launch_count(void) { return g_kernel_launches; }
 
 void dge_profile_enable(unsigned stage_mask) { g_profile_mask = stage_mask; }
@@ -311,7 +311,8 @@ static int bin_views(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dg
                      void* alloc_ctx, const ViewParams& vp, int V, const float* means3D, const float* shs,
                      const float* opacities, const float* scales, const float* rotations, const float* cams,
                      int* radii_max, float* acc, size_t acc_stride_floats, int* num_rendered_host,
-                     cudaStream_t stream, GeomState& g0, BinState& b, ImgState& img0, ViewBatch& vb) {
+                     bool prune_lists, cudaStream_t stream, GeomState& g0, BinState& b, ImgState& img0,
+                     ViewBatch& vb) {
   const bool debug = false;
   if (V < 1 || V > DGE_MAX_BATCH_VIEWS) return fail_msg("a batch holds 1..64 views");
   if (vp.grid_x > 65535 || vp.grid_y > 65535) return fail_msg("image too large (tile grid > 65535)");
@@ -330,7 +331,7 @@ static int bin_views(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dg
   vb.cams = cams;
   STAGE(ST_PREPROCESS, "preprocess (batched)",
         launch_preprocess_batched(vp, vb, means3D, scales, rotations, opacities, shs, g0, acc, acc_stride_floats,
-                                  radii_max, stream));
+                                  radii_max, prune_lists, stream));
   CK("segment offsets", launch_seg_offsets(vb, g0, batch_seg_off(g0), stream));
   CK("num_rendered copy", cudaMemcpyAsync(g_slot.pinned, batch_seg_off(g0), sizeof(uint32_t) * (V + 1),
                                           cudaMemcpyDeviceToHost, stream));
@@ -359,7 +360,7 @@ int dge_fit_views_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffe
                           const float* scales, float scale_modifier, const float* rotations,
                           const float* cams, float* out_color, float* out_depth, int* radii_max, float* acc,
                           size_t acc_stride_floats, int* num_rendered_host, const float* extra, float* out_extra,
-                          void* stream_) {
+                          int prune_lists, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool debug = false;
   if (P == 0 || width <= 0 || height <= 0) return fail_msg("empty problem");
@@ -372,8 +373,8 @@ int dge_fit_views_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffe
   BinState b;
   ViewBatch vb;
   const int R_total = bin_views(geometryBuffer, binningBuffer, imageBuffer, alloc_ctx, vp, V, means3D, shs, opacities,
-                                scales, rotations, cams, radii_max, acc, acc_stride_floats, num_rendered_host, stream,
-                                g0, b, img0, vb);
+                                scales, rotations, cams, radii_max, acc, acc_stride_floats, num_rendered_host,
+                                prune_lists != 0, stream, g0, b, img0, vb);
   if (R_total < 0) return R_total;
   STAGE(ST_RENDER_FWD, "render forward (batched)",
         launch_render_forward_batched(vp, vb, g0, b, img0, background, out_color, out_depth, stream, extra,
@@ -386,7 +387,7 @@ int dge_fit_views_apply_weights(dge_alloc_fn geometryBuffer, dge_alloc_fn binnin
                                 const float* opacities, const float* scales, float scale_modifier,
                                 const float* rotations, const float* cams, const float* image_weights,
                                 int num_channels, float* weights, int* cnt, int* num_rendered_host,
-                                void* stream_) {
+                                int prune_lists, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool debug = false;
   if (P == 0) return 0;
@@ -398,8 +399,8 @@ int dge_fit_views_apply_weights(dge_alloc_fn geometryBuffer, dge_alloc_fn binnin
   BinState b;
   ViewBatch vb;
   const int R_total = bin_views(geometryBuffer, binningBuffer, imageBuffer, alloc_ctx, vp, V, means3D, nullptr,
-                                opacities, scales, rotations, cams, nullptr, nullptr, 0, num_rendered_host, stream, g0,
-                                b, img0, vb);
+                                opacities, scales, rotations, cams, nullptr, nullptr, 0, num_rendered_host,
+                                prune_lists != 0, stream, g0, b, img0, vb);
   if (R_total <= 0) return R_total;
   STAGE(ST_APPLY_WEIGHTS, "apply_weights blend (batched)",
         launch_apply_weights_render_batched(vp, &vb, g0, b, img0, weights, cnt, image_weights, num_channels, stream));

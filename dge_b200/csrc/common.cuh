@@ -161,7 +161,7 @@ cudaError_t launch_geom_backward(const ViewParams& vp, const float* means3D, con
 cudaError_t launch_preprocess_batched(const ViewParams& vp, const ViewBatch& vb, const float* means3D,
                                       const float* scales, const float* rotations, const float* opacities,
                                       const float* shs, GeomState& g0, float* acc, size_t acc_stride_floats,
-                                      int* radii_max, cudaStream_t stream);
+                                      int* radii_max, bool prune_lists, cudaStream_t stream);
 cudaError_t launch_seg_offsets(const ViewBatch& vb, const GeomState& g0, uint32_t* seg_off, cudaStream_t stream);
 cudaError_t launch_depth_sort_batched(int P, const ViewBatch& vb, GeomState& g0, cudaStream_t stream);
 cudaError_t launch_binning_batched(const ViewParams& vp, const ViewBatch& vb, uint32_t R_total, uint32_t R_max,

@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(PRE_B_THREADS, PRE_B_MIN_CTAS) preprocess_batc
     ViewParams vp, int V, const float* __restrict__ cams, const float* __restrict__ means3D,
     const float* __restrict__ scales, const float* __restrict__ rotations,
     const float* __restrict__ opacities, const float* __restrict__ shs, GeomState g0, size_t geom_stride,
-    float4* __restrict__ acc0, size_t acc_stride_floats, int* __restrict__ radii_max) {
+    float4* __restrict__ acc0, size_t acc_stride_floats, int* __restrict__ radii_max, bool prune_lists) {
   extern __shared__ float s_cam[];  // V * 40 floats, V per-view instance counts, then the SH block
   uint32_t* s_tiles = reinterpret_cast<uint32_t*>(s_cam + V * 40);  // [V]
   // this thread's 48 SH floats at s_sh[k * PRE_B_THREADS + tid]: conflict-free, and 48 registers less
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(PRE_B_THREADS, PRE_B_MIN_CTAS) preprocess_batc
       // rasterizer_impl.cu:190-191 (host float arithmetic in the reference; same operations here)
       w.focal_y = __fdiv_rn((float)vp.H, MUL(2.0f, w.tan_fovy));
       w.focal_x = __fdiv_rn((float)vp.W, MUL(2.0f, w.tan_fovx));
-      const PreOut o = preprocess_view(
+      PreOut o = preprocess_view(
           w, cam, cam + 16, px, py, pz, false,
           [&](float* c) {
 #pragma unroll
@@ -386,6 +386,24 @@ __global__ void __launch_bounds__(PRE_B_THREADS, PRE_B_MIN_CTAS) preprocess_batc
                             [&](int k, int c) { return s_sh[(3 * k + c) * PRE_B_THREADS]; }, rgb);
           },
           [&]() { return opac; });
+      if (prune_lists && o.radius > 0) {
+        // Instance-list pruning (per-step family only): the reference lists a Gaussian in every tile
+        // of the square of its 3-sigma radius; only the tiles that also meet the box outside which alpha
+        // < 1/255 for certain can ever blend it (the same box the blend kernels cull with), so the
+        // others are not emitted — 27 % fewer instances at config 2, identical images and gradients.
+        // The rect only ever SHRINKS (the 3-sigma square still clips, as in the reference); radii,
+        // visibility flags and statistics are untouched.
+        const float x = o.rec[0].x, y = o.rec[0].y, hx = o.rec[2].w, hy = o.rec[3].x;
+        // (float -> int conversions saturate; the min() keeps the + 1 from overflowing for hx = +inf)
+        const int bx0 = max(0, (int)floorf((x - hx) * 0.0625f)), bx1 = min((int)floorf((x + hx) * 0.0625f), 1 << 20) + 1;
+        const int by0 = max(0, (int)floorf((y - hy) * 0.0625f)), by1 = min((int)floorf((y + hy) * 0.0625f), 1 << 20) + 1;
+        const int x0 = max((int)o.rect.x, bx0), y0 = max((int)o.rect.y, by0);
+        const int x1 = max(x0, min((int)o.rect.z, bx1)), y1 = max(y0, min((int)o.rect.w, by1));
+        // (hx, hy = -inf for a Gaussian that can never reach 1/255: floorf(-inf) + 1 clamps to an empty rect)
+        o.rect = make_ushort4(x0, y0, x1, y1);
+        o.tiles = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
+        if (o.tiles == 0) o.rect = make_ushort4(0, 0, 0, 0);
+      }
       const size_t sh_ = (size_t)view * geom_stride;
       if (o.radius > 0) {
         float4* dst = shift_ptr(g0.rec, sh_) + (size_t)idx * REC_F4;
@@ -416,7 +434,7 @@ __global__ void __launch_bounds__(PRE_B_THREADS, PRE_B_MIN_CTAS) preprocess_batc
 cudaError_t launch_preprocess_batched(const ViewParams& vp, const ViewBatch& vb, const float* means3D,
                                       const float* scales, const float* rotations, const float* opacities,
                                       const float* shs, GeomState& g0, float* acc, size_t acc_stride_floats,
-                                      int* radii_max, cudaStream_t stream) {
+                                      int* radii_max, bool prune_lists, cudaStream_t stream) {
   if ((shs != nullptr && vp.M != 16) || (acc_stride_floats & 3)) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemset2DAsync(g0.counters, vb.geom_stride, 0, 64 * sizeof(uint32_t), (size_t)vb.V, stream);
   if (e != cudaSuccess) return e;
@@ -424,7 +442,7 @@ cudaError_t launch_preprocess_batched(const ViewParams& vp, const ViewBatch& vb,
   const size_t smem = (size_t)vb.V * (40 * sizeof(float) + sizeof(uint32_t)) + 48 * PRE_B_THREADS * sizeof(float);
   preprocess_batched_kernel<<<blocks, PRE_B_THREADS, smem, stream>>>(
       vp, vb.V, vb.cams, means3D, scales, rotations, opacities, shs, g0, vb.geom_stride,
-      reinterpret_cast<float4*>(acc), acc_stride_floats, radii_max);
+      reinterpret_cast<float4*>(acc), acc_stride_floats, radii_max, prune_lists);
   DGE_LAUNCHED(1);
   return cudaGetLastError();
 }

@@ -485,7 +485,7 @@ class ViewBatch:
         self.cb_binning = L.ALLOC_FN(growing)
 
 
-def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inputs, num_chunks=1):
+def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inputs, num_chunks=1, prune_lists=True):
     """The step's views through the batched C-ABI: ONE launch per stage for all views of a chunk
     (preprocess that reads the Gaussians once for all its cameras, segmented depth sort / binning, forward
     blend, fused L1 loss+gradient, backward blend), then ONE batched per-Gaussian backward over all
@@ -552,7 +552,7 @@ def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inpu
                 vb.cb_geom, vb.cb_binning, vb.cb_img, None, P, model.sh_degree, M, vb.V, bgp, W, H, ptrs["means3D"],
                 ptrs["shs"], ptrs["opacities"], ptrs["scales"], 1.0, ptrs["rotations"], vb.cams.data_ptr(),
                 vb.color.data_ptr(), vb.depth.data_ptr(), vb.radii_max.data_ptr(), vb.acc.data_ptr(), acc_stride,
-                vb.num_rendered, None, None, vb.stream_ptr), "fit views forward")
+                vb.num_rendered, None, None, int(prune_lists), vb.stream_ptr), "fit views forward")
     for vb in batches:
         with torch.cuda.stream(vb.stream):
             if host_inputs and not resident:
@@ -579,7 +579,7 @@ def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inpu
 
 
 def render_views(means3D, shs, opacities, scales, rotations, cameras, bg, extra=None, sh_degree=3,
-                 scale_modifier=1.0):
+                 scale_modifier=1.0, prune_lists=True):
     """Forward-only rendering of many views at once (DGE.render_all_view / the camera loop of DGE.forward
     without the backward): gaussian_renderer.render() for every camera, ALL views per launch
     (dge_fit_views_forward). `extra` [P]: a per-Gaussian scalar (DGE: gaussian.mask.float()) blended as an
@@ -611,12 +611,14 @@ def render_views(means3D, shs, opacities, scales, rotations, cameras, bg, extra=
                 means3D.data_ptr(), shs.data_ptr(), opacities.data_ptr(), scales.data_ptr(), float(scale_modifier),
                 rotations.data_ptr(), recs.data_ptr(), color[lo:lo + V].data_ptr(), depth[lo:lo + V].data_ptr(),
                 rm.data_ptr(), None, 0, None, None if ex is None else ex.data_ptr(),
-                None if sem is None else sem[lo:lo + V].data_ptr(), L.stream_ptr(dev)), "fit views forward (render)")
+                None if sem is None else sem[lo:lo + V].data_ptr(), int(prune_lists), L.stream_ptr(dev)),
+                "fit views forward (render)")
         radii_max = torch.maximum(radii_max, rm)
     return color, depth, sem, radii_max
 
 
-def backproject_masks(means3D, opacities, scales, rotations, cameras, masks, weights, cnt, scale_modifier=1.0):
+def backproject_masks(means3D, opacities, scales, rotations, cameras, masks, weights, cnt, scale_modifier=1.0,
+                      prune_lists=True):
     """DGE.update_mask's loop (threestudio/systems/DGE.py:112-147: one GaussianModel.apply_weights per
     camera, gaussian_model.py:817-832) as ONE call per 64 views: `masks[v]` ([CH,H,W], the 2-D
     segmentation mask of view v) is back-projected onto the Gaussians it is blended from; `weights`
@@ -644,8 +646,8 @@ def backproject_masks(means3D, opacities, scales, rotations, cameras, masks, wei
             L.check(lib.dge_fit_views_apply_weights(
                 arena.cbs[0], arena.cbs[1], arena.cbs[2], None, P, V, W, H, means3D.data_ptr(), opacities.data_ptr(),
                 scales.data_ptr(), float(scale_modifier), rotations.data_ptr(), recs.data_ptr(),
-                masks[lo:lo + V].data_ptr(), CH, weights.data_ptr(), cnt.data_ptr(), nr, L.stream_ptr(dev)),
-                "fit views apply_weights")
+                masks[lo:lo + V].data_ptr(), CH, weights.data_ptr(), cnt.data_ptr(), nr, int(prune_lists),
+                L.stream_ptr(dev)), "fit views apply_weights")
         counts += list(nr)
     return counts
 
@@ -694,7 +696,7 @@ def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence
              global_batch: int, rasterize: Callable = default_rasterize, settings_module=dgr,
              process_group=None, lambda_l1: float = 10.0, host_inputs: bool = False, update_stats: bool = True,
              num_streams: int = 1, direct: Optional[bool] = None, batched: Optional[bool] = None,
-             num_chunks: int = 1):
+             num_chunks: int = 1, prune_lists: bool = True):
     """One optimisation step over this rank's views. `cameras`/`targets` are this rank's share;
     `global_batch` the number of views in the whole step (L1 is a mean over the global batch,
     DGE.py:672). With host_inputs the cameras/targets live in pinned host memory and are copied
@@ -725,7 +727,7 @@ def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence
             while True:
                 try:
                     loss, radii_max = _batched_views(model, model.activations_fused(), cameras, targets, bg, scale,
-                                                     host_inputs, chunks)
+                                                     host_inputs, chunks, prune_lists)
                     break
                 except RuntimeError as ex:
                     if "2^30" not in str(ex) or chunks >= len(cameras):

@@ -53,7 +53,8 @@ def test_direct_path_matches_autograd_path(cuda, streams, bgv, batched):
                                         (60000, 1264, 832, 2, 0.03),     # config-4 shape: 4108 tiles (generic sort)
                                         (30001, 33, 17, 1, 0.1),         # one view, ragged image, odd P
                                         (3001, 100, 60, 64, 0.05)])      # the largest batch
-def test_batched_views_bit_identical_to_per_view(cuda, P, W, H, V, sm):
+@pytest.mark.parametrize("prune", [False, True])
+def test_batched_views_bit_identical_to_per_view(cuda, P, W, H, V, sm, prune):
     """dge_fit_views_forward (all views of the step per launch: batched preprocess, segmented sorts,
     single-pass tile partition, grid.z = view) must reproduce the per-view API bit for bit: images,
     depth, instance lists, tile ranges, and the max of the radii."""
@@ -63,7 +64,7 @@ def test_batched_views_bit_identical_to_per_view(cuda, P, W, H, V, sm):
     lib = L.load()
     model, cams, targets, bg = _setup(cuda, True, P, W, H, V, sm)
     bg = bg + 0.25
-    fit.fit_step(model, cams, targets, bg, global_batch=V, batched=True, update_stats=False)
+    fit.fit_step(model, cams, targets, bg, global_batch=V, batched=True, update_stats=False, prune_lists=prune)
     vb = model._batches[0]
     # the step above moved the parameters (Adam): the per-view API renders an untouched twin
     model2, _, _, _ = _setup(cuda, True, P, W, H, V, sm)
@@ -77,6 +78,13 @@ def test_batched_views_bit_identical_to_per_view(cuda, P, W, H, V, sm):
                                                                        a2["scales"], a2["rotations"], e, a2["shs"])
         assert torch.equal(color, vb.color[v]), v
         assert torch.equal(depth, vb.depth[v]), v
+        if prune:
+            # pruned lists (prune_lists: tiles outside the alpha >= 1/255 box are not emitted): fewer
+            # instances, identical images; the lists themselves are compared with pruning off
+            assert vb.num_rendered[v] <= R, v
+            radii_max = torch.maximum(radii_max, radii)
+            total_R += vb.num_rendered[v]
+            continue
         assert R == vb.num_rendered[v], v
         # the instance list and the tile ranges of the view inside the batch's arenas
         bp, ip = (C.c_void_p * 2)(), (C.c_void_p * 3)()
