@@ -273,8 +273,11 @@ class FitModel:
     def zero_grad(self):
         self.flat_grad.zero_()
 
-    def adam_step(self):
-        self.step_count += 1
+    def adam_step(self, only=None, skip=(), advance=True):
+        """One Adam step over the parameter groups (`only` / `skip`: a subset of them, so that the
+        groups whose all-reduce has landed can be stepped first; advance=False: same step number)."""
+        if advance:
+            self.step_count += 1
         if not self.fused_adam:
             if self.grad_mask is not None:  # the reference's hooks (gaussian_model.py:837-856)
                 m = self.grad_mask.to(torch.float32)
@@ -286,6 +289,8 @@ class FitModel:
         lib = L.load()
         st = L.stream_ptr(self.device)
         for name, k, _ in GROUPS:
+            if name in skip or (only is not None and name not in only):
+                continue
             sl = self.slices[name]
             mask = self.grad_mask if (self.grad_mask is not None and name in MASKED_GROUPS) else None
             L.check(lib.dge_fused_adam(self.flat[sl].data_ptr(), self.flat_grad[sl].data_ptr(),
@@ -802,11 +807,20 @@ def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence
 
 def _finish_step(model, loss, radii_max, process_group, update_stats):
     world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+    pending = None
     if world > 1:
-        # THE collective: 59P parameter grads + 3P screen-space grads in one SUM
-        dist.all_reduce(model.flat_grad, op=dist.ReduceOp.SUM, group=process_group)
-        dist.all_reduce(radii_max, op=dist.ReduceOp.MAX, group=process_group)
-        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=process_group)
+        # THE collective: 59P parameter grads + 3P screen-space grads, SUM — issued as three
+        # contiguous pieces of the flat buffer so that the optimiser can start on the small parameter
+        # groups (and the statistics on the screen-space gradient) while the 45P floats of f_rest, three
+        # quarters of the bytes, are still on the wire; MAX over the radii, SUM over the loss.
+        a0, a1 = model.slices["f_rest"].start, model.slices["f_rest"].stop
+        pieces = [model.flat_grad[:a0], model.flat_grad[a1:], model.flat_grad[a0:a1]]
+        works = [dist.all_reduce(t, op=dist.ReduceOp.SUM, group=process_group, async_op=True) for t in pieces[:2]]
+        works.append(dist.all_reduce(radii_max, op=dist.ReduceOp.MAX, group=process_group, async_op=True))
+        works.append(dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=process_group, async_op=True))
+        pending = dist.all_reduce(pieces[2], op=dist.ReduceOp.SUM, group=process_group, async_op=True)
+        for w in works:
+            w.wait()
     if update_stats:
         with torch.no_grad():  # DGE.py:266-284, gaussian_model.py:811-815
             vis = radii_max > 0
@@ -814,7 +828,14 @@ def _finish_step(model, loss, radii_max, process_group, update_stats):
             gnorm = model.means2D.grad[:, :2].norm(dim=-1, keepdim=True)
             model.xyz_gradient_accum += torch.where(vis[:, None], gnorm, torch.zeros_like(gnorm))
             model.denom += vis[:, None].to(model.denom.dtype)
-    model.adam_step()
+    if pending is not None and model.fused_adam:
+        model.adam_step(skip=("f_rest",))
+        pending.wait()
+        model.adam_step(only=("f_rest",), advance=False)
+    else:
+        if pending is not None:
+            pending.wait()
+        model.adam_step()
     return loss
 
 
