@@ -516,6 +516,7 @@ def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inpu
                                     model._cams[bounds[c]:bounds[c + 1]], model._cams_host[bounds[c]:bounds[c + 1]])
                           for c in range(C)]
         model._batch_key = key
+        model._cams_key = None
     batches, bounds = model._batches, model._chunk_bounds
     main = torch.cuda.current_stream(dev)
     a = {k: v.detach() for k, v in acts.items()}
@@ -525,9 +526,13 @@ def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inpu
     if getattr(model, "_bg_key", None) != bgp:  # one-time host copy of the (constant) background
         model._bg_key, model._bg_black = bgp, int(not bool(bg.detach().cpu().any()))
     # cameras: one pinned [V,40] block, one H2D copy
-    for i, cam in enumerate(cameras):
-        model._cams_host[i].copy_(camera_record(cam))
-    model._cams.copy_(model._cams_host, non_blocking=True)
+    recs = [camera_record(cam) for cam in cameras]
+    cams_key = tuple(id(r) for r in recs)  # records are memoised per camera: same objects <=> same cameras
+    if getattr(model, "_cams_key", None) != cams_key:
+        for i, rec in enumerate(recs):
+            model._cams_host[i].copy_(rec)
+        model._cams.copy_(model._cams_host, non_blocking=True)
+        model._cams_key = cams_key
     resident = isinstance(targets, torch.Tensor) and targets.is_cuda
     acc_stride = P * 12
     n_img = 3 * H * W
@@ -535,13 +540,23 @@ def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inpu
         vb.stream.wait_stream(main)
     # forward of every chunk first (each call waits once for its instance counts), then loss + backward
     for c, vb in enumerate(batches):
+        with torch.cuda.stream(vb.stream):
+            vb.loss.zero_()
+            vb.R = L.check(lib.dge_fit_views_forward(
+                vb.cb_geom, vb.cb_binning, vb.cb_img, None, P, model.sh_degree, M, vb.V, bgp, W, H, ptrs["means3D"],
+                ptrs["shs"], ptrs["opacities"], ptrs["scales"], 1.0, ptrs["rotations"], vb.cams.data_ptr(),
+                vb.color.data_ptr(), vb.depth.data_ptr(), vb.radii_max.data_ptr(), vb.acc.data_ptr(), acc_stride,
+                vb.num_rendered, None, None, int(prune_lists), vb.stream_ptr), "fit views forward")
+    for c, vb in enumerate(batches):
         lo, hi = bounds[c], bounds[c + 1]
-        # targets: a resident [V,3,H,W] tensor is used as is; host tensors are copied on a side stream
-        # (overlapping preprocess / sorts / the forward blend), device lists are gathered once
+        # targets: a resident [V,3,H,W] tensor is used as is; host tensors are copied on a side stream,
+        # issued AFTER the forward has been queued so that the GPU is already busy while the host
+        # walks through the V copy calls (they then overlap sorts / binning / the forward blend);
+        # device lists are gathered once
         if resident:
             vb.tgt = targets[lo:hi]
         elif host_inputs:
-            vb.copy_stream.wait_stream(main)
+            vb.copy_stream.wait_stream(main)  # the previous step's loss kernel has read vb.targets
             with torch.cuda.stream(vb.copy_stream):
                 for i in range(lo, hi):
                     vb.targets[i - lo].copy_(targets[i], non_blocking=True)
@@ -551,13 +566,6 @@ def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inpu
             with torch.cuda.stream(vb.stream):
                 torch.stack(list(targets[lo:hi]), out=vb.targets)
             vb.tgt = vb.targets
-        with torch.cuda.stream(vb.stream):
-            vb.loss.zero_()
-            vb.R = L.check(lib.dge_fit_views_forward(
-                vb.cb_geom, vb.cb_binning, vb.cb_img, None, P, model.sh_degree, M, vb.V, bgp, W, H, ptrs["means3D"],
-                ptrs["shs"], ptrs["opacities"], ptrs["scales"], 1.0, ptrs["rotations"], vb.cams.data_ptr(),
-                vb.color.data_ptr(), vb.depth.data_ptr(), vb.radii_max.data_ptr(), vb.acc.data_ptr(), acc_stride,
-                vb.num_rendered, None, None, int(prune_lists), vb.stream_ptr), "fit views forward")
     for vb in batches:
         with torch.cuda.stream(vb.stream):
             if host_inputs and not resident:
