@@ -52,7 +52,10 @@ def test_direct_path_matches_autograd_path(cuda, streams, bgv, batched):
                                         (250000, 512, 512, 3, 0.012),    # config-2 shape: 1024 tiles, 10 bits
                                         (60000, 1264, 832, 2, 0.03),     # config-4 shape: 4108 tiles (generic sort)
                                         (30001, 33, 17, 1, 0.1),         # one view, ragged image, odd P
-                                        (3001, 100, 60, 64, 0.05)])      # the largest batch
+                                        (3001, 100, 60, 64, 0.05),       # the largest batch
+                                        (1, 64, 64, 2, 0.1),             # a single Gaussian
+                                        (500, 17, 150, 3, 0.05),         # tall, narrow, ragged
+                                        (2000, 129, 65, 5, 0.5)])        # Gaussians larger than the image
 @pytest.mark.parametrize("prune", [False, True])
 def test_batched_views_bit_identical_to_per_view(cuda, P, W, H, V, sm, prune):
     """dge_fit_views_forward (all views of the step per launch: batched preprocess, segmented sorts,

@@ -224,6 +224,40 @@ def test_mark_visible_and_edge_cases(cuda):
     assert not radii.any() and not color.any() and not depth.any()
 
 
+def test_randomised_small_scenes_vs_reference(cuda):
+    """Twenty seeded random scenes at the awkward end of the parameter space — 1 to a few thousand
+    Gaussians, images from 1x1 up to a few tiles with ragged edges, every active SH degree, random
+    backgrounds, scales from sub-pixel to larger than the image — through the per-view API against the
+    live reference: lists, ranges, images bit-exact; gradients within the tolerance."""
+    if not _ref_available():
+        pytest.skip("oracle/_ref/libref_rast.so not built")
+    rng = np.random.RandomState(2024)
+    for case in range(20):
+        P = int(rng.choice([1, 2, 7, 33, 257, 1000, 4000]))
+        W, H = int(rng.randint(1, 150)), int(rng.randint(1, 150))
+        deg = int(rng.randint(0, 4))
+        sm = float(rng.choice([0.002, 0.02, 0.2, 1.0]))
+        g = scene.make_gaussians(P, seed=1000 + case, scale_median=sm, scale_sigma=float(rng.choice([0.3, 1.0])))
+        bg = torch.tensor(rng.rand(3).astype(np.float32))
+        cam = scene.ring_cameras(7, W, H)[case % 7]
+        (color, radii, depth), leaves, rs = util.ours_forward(g, cam, bg, cuda, sh_degree=deg, requires_grad=True)
+        mine = util.ours_intermediates(rs, g, cuda)
+        refi, state = util.ref_forward(g, cam, bg, cuda, sh_degree=deg)
+        tag = (case, P, W, H, deg, sm)
+        assert mine["num_rendered"] == refi["num_rendered"], tag
+        assert util.compare_exact(mine, refi) == {}, tag
+        assert np.array_equal(color.detach().cpu().numpy(), refi["out_color"]), tag
+        assert np.array_equal(depth.detach().cpu().numpy(), refi["out_depth"]), tag
+        dL = scene.upstream_grad(W, H, case) * 50
+        (color * dL.to(cuda)).sum().backward()
+        rb = util.ref_backward(state, dL.to(cuda))
+        for leaf, name in GRAD_PAIRS:
+            if sm >= 0.2 and name in ("dL_dmeans3D", "dL_dscales", "dL_drotations"):
+                continue  # huge, mostly clipped Gaussians: ill-conditioned like the needle scenes above
+            ok, msg = util.grad_ok(leaves[leaf].grad.cpu().numpy(), rb[name], None, GRAD_TOL)
+            assert ok, (tag, name, msg)
+
+
 def test_golden_fixtures(cuda):
     """The CUDA path against the committed outputs of the reference (no oracle/_ref needed)."""
     files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "c[0-9]*.npz")))
