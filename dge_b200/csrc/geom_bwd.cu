@@ -423,8 +423,11 @@ __global__ void __launch_bounds__(128, 4) geom_backward_batched_kernel(
   for (int k = threadIdx.x; k < V * CAM_FLOATS; k += blockDim.x) s_cam[k] = cams[k];
   __syncthreads();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= P) return;
-  const size_t i = (size_t)idx;
+  if (!RAW && idx >= P) return;
+  // RAW: every thread reaches the barrier of the staged f_rest store; threads past the end work on the
+  // last Gaussian and write nothing
+  const bool live = idx < P;
+  const size_t i = (size_t)min(idx, P - 1);
   const float mx = __ldg(means3D + 3 * i), my = __ldg(means3D + 3 * i + 1), mz = __ldg(means3D + 3 * i + 2);
   const float4 q = __ldg(reinterpret_cast<const float4*>(rotations) + i);
   const float sc[3] = {__ldg(scales + 3 * i), __ldg(scales + 3 * i + 1), __ldg(scales + 3 * i + 2)};
@@ -541,21 +544,59 @@ __global__ void __launch_bounds__(128, 4) geom_backward_batched_kernel(
   float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
   if (any) cov3d_backward(q, sc, scale_modifier, dcov, dscale, dq);
   if (RAW) {
-    out3<false>(dL_dmean3D, i, dmean[0], dmean[1], dmean[2]);
-    out3<false>(dL_dmean2D, i, dm2x, dm2y, 0.f);
     const float o = __ldg(opacities + i);
-    dL_dopacity[i] = dop * o * (1.0f - o);                                   // sigmoid
-    out3<false>(dL_dscale, i, dscale[0] * sc[0], dscale[1] * sc[1], dscale[2] * sc[2]);  // exp
     const float4 qr = __ldg(reinterpret_cast<const float4*>(rotation_raw) + i);  // normalize
     const float nrm = fmaxf(sqrtf(qr.x * qr.x + qr.y * qr.y + qr.z * qr.z + qr.w * qr.w), 1e-12f);
     const float qd = q.x * dq.x + q.y * dq.y + q.z * dq.z + q.w * dq.w;
     const float inv = 1.0f / nrm;
-    out4<false>(dL_drot, i, make_float4((dq.x - q.x * qd) * inv, (dq.y - q.y * qd) * inv,
-                                        (dq.z - q.z * qd) * inv, (dq.w - q.w * qd) * inv));
-    out3<false>(dL_dsh, i, dsh[0], dsh[1], dsh[2]);                          // f_dc
-    float* r = dL_drest + 45 * i;                                            // f_rest
+    if (live) {
+      dL_dopacity[i] = dop * o * (1.0f - o);                                 // sigmoid
+      out4<false>(dL_drot, i, make_float4((dq.x - q.x * qd) * inv, (dq.y - q.y * qd) * inv,
+                                          (dq.z - q.z * qd) * inv, (dq.w - q.w * qd) * inv));
+    }
+    const int first = blockIdx.x * blockDim.x;
+    const int rows = min((int)blockDim.x, P - first);
+    __syncthreads();  // s_cam is dead: reuse the dynamic shared memory as the staging area
+    // The four [P,3] outputs: three scalar stores each with a 12-byte stride touch every sector three
+    // times; staged (stride 3 words: conflict-free), each leaves as one contiguous block of the CTA.
+    {
+      float* s3 = s_cam;
+      const float vals[4][3] = {{dmean[0], dmean[1], dmean[2]},
+                                {dm2x, dm2y, 0.f},
+                                {dscale[0] * sc[0], dscale[1] * sc[1], dscale[2] * sc[2]},  // exp
+                                {dsh[0], dsh[1], dsh[2]}};                                 // f_dc
 #pragma unroll
-    for (int k = 0; k < 45; k++) r[k] = dsh[3 + k];
+      for (int b = 0; b < 4; b++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) s3[b * 3 * 128 + threadIdx.x * 3 + k] = vals[b][k];
+      __syncthreads();
+      float* const outs[4] = {dL_dmean3D, dL_dmean2D, dL_dscale, dL_dsh};
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        float* dst = outs[b] + 3 * (size_t)first;  // 128 rows x 12 B: 16-byte aligned when the tensor is
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+          const int n4 = rows * 3 / 4;
+          for (int j = threadIdx.x; j < n4; j += blockDim.x)
+            reinterpret_cast<float4*>(dst)[j] = reinterpret_cast<const float4*>(s3 + b * 3 * 128)[j];
+          for (int j = n4 * 4 + threadIdx.x; j < rows * 3; j += blockDim.x) dst[j] = s3[b * 3 * 128 + j];
+        } else {
+          for (int j = threadIdx.x; j < rows * 3; j += blockDim.x) dst[j] = s3[b * 3 * 128 + j];
+        }
+      }
+    }
+    // f_rest: 45 floats per Gaussian. Written straight from the registers, each of the 45 store
+    // instructions of a warp touches 32 different sectors (stride 180 B); staged through shared memory
+    // (stride 45 words: conflict-free) the CTA's 128 rows leave as one contiguous, 16-byte-aligned block.
+    __syncthreads();  // the [P,3] blocks have left the staging area
+    float* s_rest = s_cam;
+#pragma unroll
+    for (int k = 0; k < 45; k++) s_rest[threadIdx.x * 45 + k] = dsh[3 + k];
+    __syncthreads();
+    float4* dst = reinterpret_cast<float4*>(dL_drest + 45 * (size_t)first);
+    const float4* src = reinterpret_cast<const float4*>(s_rest);
+    const int n4 = rows * 45 / 4;
+    for (int j = threadIdx.x; j < n4; j += blockDim.x) dst[j] = src[j];
+    for (int j = n4 * 4 + threadIdx.x; j < rows * 45; j += blockDim.x) dL_drest[45 * (size_t)first + j] = s_rest[j];
     return;
   }
   if (accumulate) {
@@ -635,9 +676,10 @@ cudaError_t launch_geom_backward_batched(int P, int D, int M, int V, const float
                                          const float* opacities, const float* rotation_raw,
                                          float* dL_drest) {
   if (V < 1 || V > MAX_BATCH_VIEWS) return cudaErrorInvalidValue;
-  const size_t smem = V * CAM_FLOATS * sizeof(float);
+  size_t smem = V * CAM_FLOATS * sizeof(float);
   if (rotation_raw != nullptr) {
-    if (M != 16) return cudaErrorInvalidValue;
+    smem = smem > 128 * 45 * sizeof(float) ? smem : 128 * 45 * sizeof(float);  // the staged f_rest block
+    if (M != 16 || (reinterpret_cast<uintptr_t>(dL_drest) & 15)) return cudaErrorInvalidValue;  // 16-byte aligned f_rest rows
     geom_backward_batched_kernel<true><<<(P + 127) / 128, 128, smem, stream>>>(
         P, D, M, V, cams, W, H, scale_modifier, acc, acc_stride, means3D, shs, scales, rotations, opacities,
         rotation_raw, dL_dmean3D, dL_dmean2D, dL_dsh, dL_drest, dL_dopacity, dL_dscale, dL_drot, false);
