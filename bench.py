@@ -229,6 +229,9 @@ def main_config3(args, cfg):
     torch.cuda.synchronize()
     launches = lib.dge_launch_count() - l0
     ms = e0.elapsed_time(e1)
+    for _ in range(max(args.warmup, 3)):
+        step(True)
+    torch.cuda.synchronize()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for _ in range(args.steps):
@@ -424,7 +427,11 @@ def main():
                 "views_per_launch": units,
                 "note": "blend kernels are issue/atomic bound, not HBM bound (SURVEY.md §8d); see DESIGN.md"}
 
-    # ---- timed region 2: K steps end to end (pinned host inputs copied inside, loss read back)
+    # ---- timed region 2: K steps end to end (pinned host inputs copied inside, loss read back),
+    # after its own W warm-up steps (the first host-input step allocates the staging buffers, the copy
+    # stream and the camera records of the host cameras)
+    for _ in range(max(args.warmup, 3)):
+        step(True).item()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()

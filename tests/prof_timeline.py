@@ -14,21 +14,29 @@ ap.add_argument("--P", type=int, default=1_000_000)
 ap.add_argument("--res", type=int, default=512)
 ap.add_argument("--streams", type=int, default=0, help="0 = batched path")
 ap.add_argument("--out", default="")
+ap.add_argument("--e2e", action="store_true", help="pinned host inputs + loss read back each step; prints the idle gaps")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 g = scene.make_gaussians(args.P, seed=1236)
 cams = [scene.camera_to(c, dev) for c in scene.ring_cameras(20, args.res, args.res)[:args.views]]
 gen = torch.Generator().manual_seed(3)
 targets = [torch.rand(3, args.res, args.res, generator=gen).to(dev) for _ in range(args.views)]
-if args.streams == 0:
+if args.e2e:
+    cams = [scene.Camera(*[t.pin_memory() if isinstance(t, torch.Tensor) else t for t in c]) for c in scene.ring_cameras(20, args.res, args.res)[:args.views]]
+    targets = [t.cpu().pin_memory() for t in targets]
+elif args.streams == 0:
     targets = torch.stack(targets)
 model = fit.FitModel(g, dev, fused_adam=True)
 bg = torch.zeros(3, device=dev)
+kw = dict(global_batch=args.views, num_streams=max(args.streams, 1), batched=args.streams == 0, host_inputs=args.e2e)
 for _ in range(3):
-    fit.fit_step(model, cams, targets, bg, global_batch=args.views, num_streams=max(args.streams, 1), batched=args.streams == 0)
+    fit.fit_step(model, cams, targets, bg, **kw).item()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    fit.fit_step(model, cams, targets, bg, global_batch=args.views, num_streams=max(args.streams, 1), batched=args.streams == 0)
+    for _ in range(3 if args.e2e else 1):
+        l = fit.fit_step(model, cams, targets, bg, **kw)
+        if args.e2e:
+            l.item()
     torch.cuda.synchronize()
 ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 iv = sorted((e.time_range.start, e.time_range.end, e.name) for e in ev)
@@ -52,5 +60,12 @@ print(f"span {span / 1e3:.3f} ms, busy(union) {busy / 1e3:.3f} ms, sum of kernel
       f"{len(iv)} device activities, streams={args.streams}")
 for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{n:60s} {c:5d} {t / 1e3:9.3f} ms {t / c:9.1f} us")
+if args.e2e:
+    kern = [x for x in iv if not x[2].startswith("Memcpy HtoD")]
+    end = kern[0][1]
+    for s_, e_, n_ in kern[1:]:
+        if s_ - end > 15:
+            print(f"gap {s_ - end:8.1f} us before {n_[:50]} at {(s_ - iv[0][0]) / 1e3:.3f} ms")
+        end = max(end, e_)
 if args.out:
     json.dump([(s - iv[0][0], e - iv[0][0], n.split("(")[0][:40]) for s, e, n in iv], open(args.out, "w"))
