@@ -273,6 +273,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gaussians", type=int, default=0, help="override the config's number of Gaussians (config 5 sweep)")
     ap.add_argument("--views", type=int, default=0, help="override the config's views per step per GPU")
+    ap.add_argument("--geom-splits", type=int, default=0, help="per-Gaussian backward launches per step (0: "
+                    "fit.py's default; > 1 on several GPUs sends finished ranges' f_rest rows early)")
     ap.add_argument("--chunks", type=int, default=1, help="batched path: split the step's views into this many "
                     "chunks, each on its own stream")
     ap.add_argument("--streams", type=int, default=0,
@@ -336,7 +338,7 @@ def main():
         return fit.fit_step(model, cams_host if host else cams_dev, tg, bg,
                             global_batch=V * n_gpus, rasterize=rasterize, settings_module=module, host_inputs=host,
                             num_streams=max(args.streams, 1) if args.impl == "ours" else 1, batched=batched,
-                            num_chunks=args.chunks)
+                            num_chunks=args.chunks, geom_splits=args.geom_splits or None)
 
     def barrier():
         if world > 1 and args.impl == "ours":

@@ -490,12 +490,16 @@ class ViewBatch:
         self.cb_binning = L.ALLOC_FN(growing)
 
 
-def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inputs, num_chunks=1, prune_lists=True):
+def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inputs, num_chunks=1, prune_lists=True,
+                   geom_splits=1, on_range_done=None):
     """The step's views through the batched C-ABI: ONE launch per stage for all views of a chunk
     (preprocess that reads the Gaussians once for all its cameras, segmented depth sort / binning, forward
     blend, fused L1 loss+gradient, backward blend), then ONE batched per-Gaussian backward over all
     views. With num_chunks > 1 the views are split into that many chunks, each on its own stream, so
     one chunk's bandwidth-bound stages (preprocess, sorts) overlap another's issue-bound blends.
+    The per-Gaussian backward may be issued as geom_splits launches over consecutive Gaussian ranges;
+    on_range_done(first, count) is called after each (multi-GPU: the all-reduce of a finished range's
+    gradients then overlaps the next range's kernel).
     Returns (loss, max radii); leaves the step's raw-parameter gradients in model.flat_grad."""
     lib = L.load()
     dev = model.device
@@ -579,11 +583,20 @@ def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inpu
     for vb in batches:
         main.wait_stream(vb.stream)
     gp = {k: v.grad.data_ptr() for k, v in model.params.items()}
-    L.check(lib.dge_fit_backward_geom_raw(
-        P, model.sh_degree, V, model._cams.data_ptr(), W, H, 1.0, model._acc.data_ptr(), acc_stride, ptrs["means3D"],
-        ptrs["shs"], ptrs["opacities"], ptrs["scales"], ptrs["rotations"], model.params["rotation"].data_ptr(),
-        gp["xyz"], model.means2D.grad.data_ptr(), gp["f_dc"], gp["f_rest"], gp["opacity"], gp["scaling"],
-        gp["rotation"], L.stream_ptr(dev)), "fit backward geom")
+    # ranges start at multiples of 128 Gaussians: every per-Gaussian array stays 16-byte aligned
+    splits = max(1, min(geom_splits, P // 128))
+    cuts = [(P * k // splits) // 128 * 128 for k in range(splits)] + [P]
+    rot_raw, m2d = model.params["rotation"].data_ptr(), model.means2D.grad.data_ptr()
+    for first, stop in zip(cuts[:-1], cuts[1:]):
+        f = 4 * first  # bytes per float column
+        L.check(lib.dge_fit_backward_geom_raw(
+            stop - first, model.sh_degree, V, model._cams.data_ptr(), W, H, 1.0, model._acc.data_ptr() + 12 * f,
+            acc_stride, ptrs["means3D"] + 3 * f, ptrs["shs"] + 48 * f, ptrs["opacities"] + f, ptrs["scales"] + 3 * f,
+            ptrs["rotations"] + 4 * f, rot_raw + 4 * f, gp["xyz"] + 3 * f, m2d + 3 * f, gp["f_dc"] + 3 * f,
+            gp["f_rest"] + 45 * f, gp["opacity"] + f, gp["scaling"] + 3 * f, gp["rotation"] + 4 * f,
+            L.stream_ptr(dev)), "fit backward geom")
+        if on_range_done is not None:
+            on_range_done(first, stop - first)
     loss, radii_max = batches[0].loss.clone(), batches[0].radii_max
     for vb in batches[1:]:
         loss += vb.loss
@@ -709,7 +722,7 @@ def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence
              global_batch: int, rasterize: Callable = default_rasterize, settings_module=dgr,
              process_group=None, lambda_l1: float = 10.0, host_inputs: bool = False, update_stats: bool = True,
              num_streams: int = 1, direct: Optional[bool] = None, batched: Optional[bool] = None,
-             num_chunks: int = 1, prune_lists: bool = True):
+             num_chunks: int = 1, prune_lists: bool = True, geom_splits: Optional[int] = None):
     """One optimisation step over this rank's views. `cameras`/`targets` are this rank's share;
     `global_batch` the number of views in the whole step (L1 is a mean over the global batch,
     DGE.py:672). With host_inputs the cameras/targets live in pinned host memory and are copied
@@ -737,10 +750,13 @@ def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence
             # a chunk's instance lists share one arena addressed with 30-bit positions: when the views of a
             # chunk hold more than 2^30 instances (6 M Gaussians at 1080p: ~60 M per view), split further
             chunks = max(num_chunks, getattr(model, "_min_chunks", 1))
+            world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+            splits = geom_splits if geom_splits is not None else (GEOM_SPLITS_MULTI_GPU if world > 1 else 1)
+            early = _EarlyRestReduce(model, process_group) if (world > 1 and splits > 1) else None
             while True:
                 try:
                     loss, radii_max = _batched_views(model, model.activations_fused(), cameras, targets, bg, scale,
-                                                     host_inputs, chunks, prune_lists)
+                                                     host_inputs, chunks, prune_lists, splits, early)
                     break
                 except RuntimeError as ex:
                     if "2^30" not in str(ex) or chunks >= len(cameras):
@@ -749,9 +765,10 @@ def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence
                     chunks = min(len(cameras), chunks * 2)
                     model._min_chunks = chunks
         else:
+            early = None
             loss, radii_max = _direct_views(model, model.activations_fused(), cameras, targets, bg, scale, host_inputs,
                                             num_streams)
-        return _finish_step(model, loss, radii_max, process_group, update_stats)
+        return _finish_step(model, loss, radii_max, process_group, update_stats, early)
     model.zero_grad()
     acts_graph = model.activations()
     S = max(1, min(num_streams, len(cameras)))
@@ -813,7 +830,32 @@ def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence
     return _finish_step(model, loss, radii_max, process_group, update_stats)
 
 
-def _finish_step(model, loss, radii_max, process_group, update_stats):
+# Measured on 2 B200s (bench.py --gpus 2 --geom-splits 1/2/4/8: 8.36 / 8.43 / 8.37 / 8.43 ms per step): sending
+# three quarters of f_rest under the per-Gaussian backward buys nothing — that kernel is bandwidth-bound and
+# short (0.46 ms), NCCL's copy kernels take their share of it back — so one launch stays the default.
+GEOM_SPLITS_MULTI_GPU = 1
+
+
+class _EarlyRestReduce:
+    """Multi-GPU: the per-Gaussian backward runs as a few launches over consecutive Gaussian ranges; as
+    soon as a range is queued, the all-reduce of its f_rest gradient rows (45 of the 62 floats per
+    Gaussian, contiguous in the group-major flat buffer) is issued on NCCL's stream and runs under the
+    next range's kernel. The LAST range is left to _finish_step, which sends the small groups first."""
+
+    def __init__(self, model, process_group):
+        self.model, self.group, self.works, self.done_rows = model, process_group, [], 0
+
+    def __call__(self, first, count):
+        if first == 0:
+            self.works, self.done_rows = [], 0
+        if first + count >= self.model.P:  # last range: reduced after the small groups
+            return
+        g = self.model.params["f_rest"].grad.view(self.model.P, -1)
+        self.works.append(dist.all_reduce(g[first:first + count], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self.done_rows = first + count
+
+
+def _finish_step(model, loss, radii_max, process_group, update_stats, early=None):
     world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
     pending = None
     if world > 1:
@@ -822,7 +864,8 @@ def _finish_step(model, loss, radii_max, process_group, update_stats):
         # groups (and the statistics on the screen-space gradient) while the 45P floats of f_rest, three
         # quarters of the bytes, are still on the wire; MAX over the radii, SUM over the loss.
         a0, a1 = model.slices["f_rest"].start, model.slices["f_rest"].stop
-        pieces = [model.flat_grad[:a0], model.flat_grad[a1:], model.flat_grad[a0:a1]]
+        sent = 45 * early.done_rows if early is not None else 0  # f_rest rows already on the wire
+        pieces = [model.flat_grad[:a0], model.flat_grad[a1:], model.flat_grad[a0 + sent:a1]]
         works = [dist.all_reduce(t, op=dist.ReduceOp.SUM, group=process_group, async_op=True) for t in pieces[:2]]
         works.append(dist.all_reduce(radii_max, op=dist.ReduceOp.MAX, group=process_group, async_op=True))
         works.append(dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=process_group, async_op=True))
@@ -838,9 +881,13 @@ def _finish_step(model, loss, radii_max, process_group, update_stats):
             model.denom += vis[:, None].to(model.denom.dtype)
     if pending is not None and model.fused_adam:
         model.adam_step(skip=("f_rest",))
+        for w in (early.works if early is not None else []):
+            w.wait()
         pending.wait()
         model.adam_step(only=("f_rest",), advance=False)
     else:
+        for w in (early.works if early is not None else []):
+            w.wait()
         if pending is not None:
             pending.wait()
         model.adam_step()

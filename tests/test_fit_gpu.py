@@ -284,3 +284,41 @@ def test_local_edit_flow_mask_backprojection_then_masked_fit(cuda):
         assert m[sel].any(), name
     sl = model.slices["rotation"]
     assert moved[sl].view(P, 4).any(1)[~sel].any()              # rotation is not masked in the reference
+
+
+def test_per_gaussian_backward_over_ranges_is_bit_identical(cuda):
+    """dge_fit_backward_geom_raw over consecutive Gaussian ranges (offset pointers; what fit_step does on
+    several GPUs so that a finished range's all-reduce overlaps the next range's kernel) writes exactly the
+    rows one launch over all Gaussians writes."""
+    from dge_b200 import _lib as L
+    lib = L.load()
+    Pn, Vn, Wn, Hn = 5000, 6, 128, 96
+    model = fit.FitModel(scene.make_gaussians(Pn, seed=9), cuda)
+    a = model.activations_fused()
+    cams = torch.stack([fit.camera_record(scene.camera_to(c, cuda)) for c in scene.ring_cameras(Vn, Wn, Hn)]).to(cuda)
+    gen = torch.Generator().manual_seed(4)
+    acc = (torch.randn(Vn, Pn, 12, generator=gen) * 1e-3).to(cuda)
+    flags = torch.randint(0, 16, (Vn, Pn), generator=gen, dtype=torch.int32).to(cuda)
+    flags = torch.where(torch.rand(Vn, Pn, generator=gen).to(cuda) < 0.5, flags | 1, torch.zeros_like(flags))
+    acc.view(torch.int32)[:, :, 11] = flags
+    st = L.stream_ptr(cuda)
+
+    def run(cuts, fill):
+        out = {k: torch.full_like(v.grad, fill) for k, v in model.params.items()}
+        m2d = torch.full((Pn, 3), fill, device=cuda)
+        for first, stop in zip(cuts[:-1], cuts[1:]):
+            f = 4 * first
+            L.check(lib.dge_fit_backward_geom_raw(
+                stop - first, 3, Vn, cams.data_ptr(), Wn, Hn, 1.0, acc.data_ptr() + 12 * f, Pn * 12,
+                a["means3D"].data_ptr() + 3 * f, a["shs"].data_ptr() + 48 * f, a["opacities"].data_ptr() + f,
+                a["scales"].data_ptr() + 3 * f, a["rotations"].data_ptr() + 4 * f,
+                model.params["rotation"].data_ptr() + 4 * f, out["xyz"].data_ptr() + 3 * f, m2d.data_ptr() + 3 * f,
+                out["f_dc"].data_ptr() + 3 * f, out["f_rest"].data_ptr() + 45 * f, out["opacity"].data_ptr() + f,
+                out["scaling"].data_ptr() + 3 * f, out["rotation"].data_ptr() + 4 * f, st), "geom raw")
+        torch.cuda.synchronize()
+        return {**out, "m2d": m2d}
+
+    whole = run([0, Pn], 0.0)
+    parts = run([0, 1280, 1408, 3840, Pn], 7.0)   # every row is written: the fill value never survives
+    for k in whole:
+        assert torch.equal(whole[k].view(torch.int32), parts[k].view(torch.int32)), k
