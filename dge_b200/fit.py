@@ -273,9 +273,10 @@ class FitModel:
     def zero_grad(self):
         self.flat_grad.zero_()
 
-    def adam_step(self, only=None, skip=(), advance=True):
+    def adam_step(self, only=None, skip=(), advance=True, rows=None):
         """One Adam step over the parameter groups (`only` / `skip`: a subset of them, so that the
-        groups whose all-reduce has landed can be stepped first; advance=False: same step number)."""
+        groups whose all-reduce has landed can be stepped first; advance=False: same step number;
+        rows=(r0, r1): only these Gaussians of the selected groups, r0 a multiple of 4; fused path only)."""
         if advance:
             self.step_count += 1
         if not self.fused_adam:
@@ -293,9 +294,14 @@ class FitModel:
                 continue
             sl = self.slices[name]
             mask = self.grad_mask if (self.grad_mask is not None and name in MASKED_GROUPS) else None
-            L.check(lib.dge_fused_adam(self.flat[sl].data_ptr(), self.flat_grad[sl].data_ptr(),
-                                       self.exp_avg[sl].data_ptr(), self.exp_avg_sq[sl].data_ptr(), k * self.P,
-                                       self.lrs[name], 0.9, 0.999, 1e-15, self.step_count, L.ptr(mask), k, st),
+            r0, r1 = rows if rows is not None else (0, self.P)
+            if r1 <= r0:
+                continue
+            off = 4 * k * r0  # bytes; r0 % 4 == 0 keeps the float4 path aligned
+            L.check(lib.dge_fused_adam(self.flat[sl].data_ptr() + off, self.flat_grad[sl].data_ptr() + off,
+                                       self.exp_avg[sl].data_ptr() + off, self.exp_avg_sq[sl].data_ptr() + off,
+                                       k * (r1 - r0), self.lrs[name], 0.9, 0.999, 1e-15, self.step_count,
+                                       None if mask is None else mask.data_ptr() + r0, k, st),
                     "fused adam")
 
 
@@ -834,6 +840,10 @@ def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence
 # three quarters of f_rest under the per-Gaussian backward buys nothing — that kernel is bandwidth-bound and
 # short (0.46 ms), NCCL's copy kernels take their share of it back — so one launch stays the default.
 GEOM_SPLITS_MULTI_GPU = 1
+# all-reduce pieces of the f_rest gradient, each followed by its own Adam launch. Measured on 2 B200s: four pieces
+# take 0.55 ms on the wire against 0.38 ms for one (smaller messages, and Adam competing for HBM), which eats the
+# 0.14 ms of Adam they hide: 8.38 vs 8.36 ms per step. One piece.
+REST_PIECES = 1
 
 
 class _EarlyRestReduce:
@@ -859,17 +869,24 @@ def _finish_step(model, loss, radii_max, process_group, update_stats, early=None
     world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
     pending = None
     if world > 1:
-        # THE collective: 59P parameter grads + 3P screen-space grads, SUM — issued as three
+        # THE collective: 59P parameter grads + 3P screen-space grads, SUM — issued as
         # contiguous pieces of the flat buffer so that the optimiser can start on the small parameter
         # groups (and the statistics on the screen-space gradient) while the 45P floats of f_rest, three
         # quarters of the bytes, are still on the wire; MAX over the radii, SUM over the loss.
         a0, a1 = model.slices["f_rest"].start, model.slices["f_rest"].stop
-        sent = 45 * early.done_rows if early is not None else 0  # f_rest rows already on the wire
-        pieces = [model.flat_grad[:a0], model.flat_grad[a1:], model.flat_grad[a0 + sent:a1]]
-        works = [dist.all_reduce(t, op=dist.ReduceOp.SUM, group=process_group, async_op=True) for t in pieces[:2]]
-        works.append(dist.all_reduce(radii_max, op=dist.ReduceOp.MAX, group=process_group, async_op=True))
-        works.append(dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=process_group, async_op=True))
-        pending = dist.all_reduce(pieces[2], op=dist.ReduceOp.SUM, group=process_group, async_op=True)
+        sent = early.done_rows if early is not None else 0  # f_rest rows already on the wire
+        ar = lambda t, op=dist.ReduceOp.SUM: dist.all_reduce(t, op=op, group=process_group, async_op=True)
+        # what the statistics and the small groups need goes first
+        works = [ar(model.flat_grad[a1:]), ar(radii_max, dist.ReduceOp.MAX), ar(loss), ar(model.flat_grad[:a0])]
+        # f_rest in REST_PIECES row ranges: Adam on a piece runs under the next piece's transfer, so only
+        # the last piece's Adam is left exposed after the wire goes quiet
+        P = model.P
+        cuts = [sent] + [max(sent, (P * k // REST_PIECES) // 4 * 4) for k in range(1, REST_PIECES)] + [P]
+        rest = [(r0, r1, ar(model.flat_grad[a0 + 45 * r0:a0 + 45 * r1])) for r0, r1 in zip(cuts[:-1], cuts[1:]) if r1 > r0]
+        if not model.fused_adam:
+            works += [w for _, _, w in rest]
+            rest = []
+        pending = rest
         for w in works:
             w.wait()
     if update_stats:
@@ -881,15 +898,16 @@ def _finish_step(model, loss, radii_max, process_group, update_stats, early=None
             model.denom += vis[:, None].to(model.denom.dtype)
     if pending is not None and model.fused_adam:
         model.adam_step(skip=("f_rest",))
-        for w in (early.works if early is not None else []):
+        if early is not None and early.done_rows:
+            for w in early.works:
+                w.wait()
+            model.adam_step(only=("f_rest",), advance=False, rows=(0, early.done_rows))
+        for r0, r1, w in pending:
             w.wait()
-        pending.wait()
-        model.adam_step(only=("f_rest",), advance=False)
+            model.adam_step(only=("f_rest",), advance=False, rows=(r0, r1))
     else:
         for w in (early.works if early is not None else []):
             w.wait()
-        if pending is not None:
-            pending.wait()
         model.adam_step()
     return loss
 

@@ -16,7 +16,12 @@ ap.add_argument("--streams", type=int, default=0, help="0 = batched path")
 ap.add_argument("--out", default="")
 ap.add_argument("--e2e", action="store_true", help="pinned host inputs + loss read back each step; prints the idle gaps")
 args = ap.parse_args()
-dev = torch.device("cuda:0")
+rank = int(os.environ.get("RANK", "0"))
+dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+torch.cuda.set_device(dev)
+if "RANK" in os.environ:  # under torchrun: every rank runs the same 20 views, gradients all-reduced
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
 g = scene.make_gaussians(args.P, seed=1236)
 cams = [scene.camera_to(c, dev) for c in scene.ring_cameras(20, args.res, args.res)[:args.views]]
 gen = torch.Generator().manual_seed(3)
@@ -38,6 +43,8 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         if args.e2e:
             l.item()
     torch.cuda.synchronize()
+if rank != 0:
+    dist.barrier(); dist.destroy_process_group(); sys.exit(0)
 ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 iv = sorted((e.time_range.start, e.time_range.end, e.name) for e in ev)
 agg = collections.OrderedDict()
@@ -60,7 +67,7 @@ print(f"span {span / 1e3:.3f} ms, busy(union) {busy / 1e3:.3f} ms, sum of kernel
       f"{len(iv)} device activities, streams={args.streams}")
 for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{n:60s} {c:5d} {t / 1e3:9.3f} ms {t / c:9.1f} us")
-if args.e2e:
+if args.e2e or "RANK" in os.environ:
     kern = [x for x in iv if not x[2].startswith("Memcpy HtoD")]
     end = kern[0][1]
     for s_, e_, n_ in kern[1:]:
@@ -69,3 +76,9 @@ if args.e2e:
         end = max(end, e_)
 if args.out:
     json.dump([(s - iv[0][0], e - iv[0][0], n.split("(")[0][:40]) for s, e, n in iv], open(args.out, "w"))
+if "RANK" in os.environ:
+    t0 = iv[0][0]
+    for s_, e_, n_ in iv:
+        if "nccl" in n_.lower() or "adam" in n_ or "geom_backward" in n_:
+            print(f"{(s_ - t0) / 1e3:8.3f} .. {(e_ - t0) / 1e3:8.3f} ms  {n_[:70]}")
+    dist.barrier(); dist.destroy_process_group()
