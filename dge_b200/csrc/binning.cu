@@ -403,9 +403,10 @@ __global__ void __launch_bounds__(256) part_scan_runs_kernel(const uint32_t* __r
   }
 }
 
+template <int BITS>  // bits of a tile id (T <= 1 << BITS), compile-time so that the ranking unrolls
 __global__ void __launch_bounds__(PART_THREADS) part_scatter_kernel(
     const uint32_t* __restrict__ tile_ids, const uint32_t* __restrict__ gids,
-    const uint32_t* __restrict__ seg_off, int T, int tile_bits, const uint32_t* __restrict__ table,
+    const uint32_t* __restrict__ seg_off, int T, const uint32_t* __restrict__ table,
     uint32_t* __restrict__ point_list) {
   extern __shared__ uint32_t s_part[];
   const int TP = (T + 1) >> 1;                      // packed u16 pairs per warp row
@@ -467,15 +468,11 @@ __global__ void __launch_bounds__(PART_THREADS) part_scatter_kernel(
     if (wlo + k * 32 >= whi) break;  // warp-uniform
     const uint32_t t = key[k];
     const bool valid = t != 0xFFFFFFFFu;
-    // lanes holding the same tile id, from one ballot per tile-id bit (a single match.any is one
-    // instruction but takes 0.78 ms instead of 0.51 ms for this kernel: it iterates over the distinct values)
+    // lanes holding the same tile id (common.cuh:same_value_lanes; with match.any this kernel took
+    // 0.78 ms instead of 0.51 ms)
     uint32_t peers = __ballot_sync(0xFFFFFFFFu, valid);
     if (!valid) peers = ~peers;
-    for (int bit = 0; bit < tile_bits; bit++) {
-      const uint32_t m = 0u - ((t >> bit) & 1u);
-      const uint32_t vote = __ballot_sync(0xFFFFFFFFu, m != 0u);
-      peers &= ~(vote ^ m);
-    }
+    peers = same_value_lanes<BITS>(t, peers);
     const int leader = __ffs(peers) - 1;
     uint32_t prev = 0;
     if (valid && lane == leader) {
@@ -496,20 +493,28 @@ static cudaError_t partition_by_tile(const ViewBatch& vb, int T, int bits, uint3
   uint32_t* partial = ws + part_table_rows(R_total, vb.V) * (size_t)T;
   const int runs = (int)((R_max + PART_RUN - 1) / PART_RUN);
   const int tb = (T + 255) / 256;
-  static bool attr_set = false;
   const size_t scatter_smem = sizeof(uint32_t) * PART_WARPS * (size_t)(((T + 1) >> 1) + T);
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(part_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  int id_bits = 1;  // bits that tell tile ids 0 .. T-1 apart
+  while ((1 << id_bits) < T) id_bits++;
+  using scatter_fn = void (*)(const uint32_t*, const uint32_t*, const uint32_t*, int, const uint32_t*, uint32_t*);
+  static const scatter_fn scatter[12] = {nullptr, part_scatter_kernel<1>, part_scatter_kernel<2>, part_scatter_kernel<3>,
+                                         part_scatter_kernel<4>, part_scatter_kernel<5>, part_scatter_kernel<6>,
+                                         part_scatter_kernel<7>, part_scatter_kernel<8>, part_scatter_kernel<9>,
+                                         part_scatter_kernel<10>, part_scatter_kernel<11>};
+  static bool attr_set[12] = {};
+  if (id_bits > 11) return cudaErrorInvalidValue;  // T <= PART_MAX_TILES = 2048
+  if (!attr_set[id_bits]) {
+    cudaError_t e = cudaFuncSetAttribute(scatter[id_bits], cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(sizeof(uint32_t) * PART_WARPS * (size_t)(PART_MAX_TILES / 2 + PART_MAX_TILES)));
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[id_bits] = true;
   }
   part_count_kernel<<<dim3(runs, vb.V), PART_THREADS, sizeof(uint32_t) * T, stream>>>(keys, vb.seg_off, T, table);
   part_scan_partial_kernel<<<dim3(tb, PART_GROUPS, vb.V), 256, 0, stream>>>(vb.seg_off, T, table, partial);
   part_scan_tiles_kernel<<<vb.V, 1024, 0, stream>>>(T, partial, img0.ranges, vb.img_stride);
   part_scan_runs_kernel<<<dim3(tb, PART_GROUPS, vb.V), 256, 0, stream>>>(vb.seg_off, T, table, partial);
-  part_scatter_kernel<<<dim3(runs, vb.V), PART_THREADS, scatter_smem, stream>>>(keys, vals, vb.seg_off, T, bits,
-                                                                              table, point_list);
+  scatter[id_bits]<<<dim3(runs, vb.V), PART_THREADS, scatter_smem, stream>>>(keys, vals, vb.seg_off, T, table,
+                                                                            point_list);
   DGE_LAUNCHED(5);
   return cudaGetLastError();
 }

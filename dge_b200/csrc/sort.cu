@@ -101,8 +101,9 @@ __global__ void __launch_bounds__(256) sort_histogram_kernel(const uint32_t* __r
     if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 
-template <int SORT_IPT>
-__global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(
+// DIGIT_BITS: width of this pass's digit, compile-time so that the ranking unrolls
+template <int SORT_IPT, int DIGIT_BITS>
+__global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_kernel(
     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
     uint32_t digit_mask, const uint32_t* __restrict__ hist, uint32_t* status, uint32_t* ticket,
@@ -140,7 +141,6 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(
   __shared__ uint32_t s_tile;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int digit_bits = __popc(digit_mask);
   if (tid == 0) s_tile = atomicAdd(ticket, 1u);
   for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&s_cnt[0][0])[i] = 0;
   __syncthreads();
@@ -177,13 +177,7 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(
     // instead: constant cost whatever the digit distribution.
     uint32_t peers = __ballot_sync(0xFFFFFFFFu, valid);
     if (!valid) peers = ~peers;
-#pragma unroll
-    for (int b = 0; b < RADIX_BITS; b++) {
-      if (b >= digit_bits) break;  // warp-uniform: 5-bit tile digits need 5 ballots, not 8
-      const uint32_t m = 0u - ((d >> b) & 1u);  // all ones if this lane's bit is set
-      const uint32_t vote = __ballot_sync(0xFFFFFFFFu, m != 0u);
-      peers &= ~(vote ^ m);
-    }
+    peers = same_value_lanes<DIGIT_BITS>(d, peers);
     const int leader = __ffs(peers) - 1;
     uint32_t prev = 0;
     if (valid && lane == leader) {
@@ -343,14 +337,28 @@ cudaError_t sort_pairs_segmented(uint32_t* keys[2], uint32_t* vals[2], uint32_t 
     const int bits = (num_bits - shift) < per ? (num_bits - shift) : per;
     const uint32_t* vin = (p == 0 && iota_values) ? nullptr : vals[cur];
     const dim3 grid = seg_in_x ? dim3(segs, tiles) : dim3(tiles, segs);
-    if (ipt == 8)
-      onesweep_kernel<8><<<grid, SORT_THREADS, 0, stream>>>(
-          keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift, (1u << bits) - 1u,
-          hist + p * RADIX, status + (size_t)p * pass_stride, tickets + p, sa);
-    else
-      onesweep_kernel<16><<<grid, SORT_THREADS, 0, stream>>>(
-          keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift, (1u << bits) - 1u,
-          hist + p * RADIX, status + (size_t)p * pass_stride, tickets + p, sa);
+#define DGE_ONESWEEP(IPT, BITS)                                                                 \
+  onesweep_kernel<IPT, BITS><<<grid, SORT_THREADS, 0, stream>>>(                                \
+      keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift, (1u << bits) - 1u, hist + p * RADIX, \
+      status + (size_t)p * pass_stride, tickets + p, sa)
+#define DGE_ONESWEEP_BITS(IPT)                                                                  \
+  switch (bits) {                                                                               \
+    case 1: DGE_ONESWEEP(IPT, 1); break;                                                        \
+    case 2: DGE_ONESWEEP(IPT, 2); break;                                                        \
+    case 3: DGE_ONESWEEP(IPT, 3); break;                                                        \
+    case 4: DGE_ONESWEEP(IPT, 4); break;                                                        \
+    case 5: DGE_ONESWEEP(IPT, 5); break;                                                        \
+    case 6: DGE_ONESWEEP(IPT, 6); break;                                                        \
+    case 7: DGE_ONESWEEP(IPT, 7); break;                                                        \
+    default: DGE_ONESWEEP(IPT, 8); break;                                                       \
+  }
+    if (ipt == 8) {
+      DGE_ONESWEEP_BITS(8)
+    } else {
+      DGE_ONESWEEP_BITS(16)
+    }
+#undef DGE_ONESWEEP_BITS
+#undef DGE_ONESWEEP
     cur ^= 1;
   }
   DGE_LAUNCHED(1 + passes);
