@@ -290,21 +290,69 @@ size_t part_workspace_bytes(uint32_t R_total, int V, int T) {
   return sizeof(uint32_t) * (part_table_rows(R_total, V) * (size_t)T + (size_t)V * PART_GROUPS * T) + 256;
 }
 
+// Which run of PART_RUN instances a CTA of part_count / part_scatter owns. S_flat == 0: grid (run, segment).
+// S_flat > 0 (second level of the two-level partition, many short segments of unknown length): a flat grid
+// over the rows of the count table; the segment q owning row r is the last one with part_row0(q) <= r
+// (part_row0 is strictly increasing), rows past the segment's last run do nothing.
+struct PartRunRef {
+  uint32_t o, n, lo;  // segment start in the arena, segment length, first instance of the run in the segment
+  size_t row;         // row of the count table
+  int seg;
+};
+__device__ __forceinline__ bool part_locate(const uint32_t* __restrict__ seg_off, int S_flat, PartRunRef& pr) {
+  if (S_flat == 0) {
+    pr.seg = blockIdx.y;
+    pr.row = part_row0(seg_off, pr.seg) + blockIdx.x;
+    pr.lo = blockIdx.x * (uint32_t)PART_RUN;
+  } else {
+    const size_t row = blockIdx.x;
+    int a = 0, b = S_flat - 1;
+    while (a < b) {
+      const int m = (a + b + 1) >> 1;
+      if (part_row0(seg_off, m) <= row) a = m; else b = m - 1;
+    }
+    pr.seg = a;
+    pr.row = row;
+    const size_t r = row - part_row0(seg_off, a);
+    if (r >= (size_t)(0xFFFFFFFFu / PART_RUN)) return false;
+    pr.lo = (uint32_t)r * (uint32_t)PART_RUN;
+  }
+  pr.o = seg_off[pr.seg];
+  pr.n = seg_off[pr.seg + 1] - pr.o;
+  return pr.lo < pr.n;
+}
+
+// bucket of an instance = (tile id >> shift) & mask: the tile id itself (single level), the tile group
+// (first level of the two-level partition) or the tile inside its group (second level)
 __global__ void __launch_bounds__(PART_THREADS) part_count_kernel(const uint32_t* __restrict__ tile_ids,
                                                                   const uint32_t* __restrict__ seg_off,
-                                                                  int T, uint32_t* __restrict__ table) {
+                                                                  int T, uint32_t* __restrict__ table, int S_flat,
+                                                                  int shift, uint32_t mask) {
   extern __shared__ uint32_t s_cnt[];  // [T]
-  const int v = blockIdx.y;
-  const uint32_t o = seg_off[v], n = seg_off[v + 1] - o;
-  const uint32_t lo = blockIdx.x * (uint32_t)PART_RUN;
-  if (lo >= n) return;
+  PartRunRef pr;
+  if (!part_locate(seg_off, S_flat, pr)) return;
+  const uint32_t lo = pr.lo, n = pr.n;
   const uint32_t hi = min(n, lo + (uint32_t)PART_RUN);
   for (int t = threadIdx.x; t < T; t += PART_THREADS) s_cnt[t] = 0;
   __syncthreads();
-  const uint32_t* keys = tile_ids + o;
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += PART_THREADS) atomicAdd(&s_cnt[keys[i]], 1u);
+  const uint32_t* keys = tile_ids + pr.o;
+  if (shift == 0 || T > 64) {
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += PART_THREADS) atomicAdd(&s_cnt[(keys[i] >> shift) & mask], 1u);
+  } else {
+    // first level with few buckets (tile groups): neighbouring instances mostly share one, so a warp adds once per
+    // distinct bucket instead of serialising 32 same-address atomics
+    for (uint32_t i0 = lo + (threadIdx.x & ~31u); i0 < hi; i0 += PART_THREADS) {
+      const uint32_t i = i0 + (threadIdx.x & 31u);
+      const bool valid = i < hi;
+      const uint32_t bk = valid ? (keys[i] >> shift) & mask : 0u;
+      uint32_t peers = __ballot_sync(0xFFFFFFFFu, valid);
+      if (!valid) peers = ~peers;
+      peers = same_value_lanes<6>(bk, peers);
+      if (valid && (int)(threadIdx.x & 31u) == __ffs(peers) - 1) atomicAdd(&s_cnt[bk], (uint32_t)__popc(peers));
+    }
+  }
   __syncthreads();
-  uint32_t* row = table + (part_row0(seg_off, v) + blockIdx.x) * (size_t)T;
+  uint32_t* row = table + pr.row * (size_t)T;
   for (int t = threadIdx.x; t < T; t += PART_THREADS) row[t] = s_cnt[t];
 }
 
@@ -325,16 +373,43 @@ __global__ void __launch_bounds__(256) part_scan_partial_kernel(const uint32_t* 
   partial[((size_t)v * PART_GROUPS + g) * T + t] = sum;
 }
 
-// per view: totals per tile -> exclusive scan over tiles = ranges; partial[v][g][t] becomes the position
-// of group g's first instance of tile t
+// Where the per-segment exclusive scan over the buckets goes (CTA = segment):
+//  single level   segment = view, bucket = tile: the scan IS the view's `ranges` array
+//  first level    segment = view, bucket = tile group c: start of segment q = view * G + c of the second
+//                 level, seg2[q] = view_off[view] + scan (absolute arena offsets; seg2[V * G] = end)
+//  second level   segment = q, bucket = tile c * 2^ts_shift + t of view q / G: `ranges` again, relative to
+//                 the VIEW's list (the blend kernels add view_off[view] themselves)
+struct PartScanOut {
+  uint2* ranges;
+  size_t img_stride;
+  uint32_t* seg2;             // first level only
+  const uint32_t* view_off;   // first and second level
+  const uint32_t* seg_abs;    // second level: seg2
+  int G, ts_shift, T_total;
+};
+
+// per segment: totals per bucket -> exclusive scan over buckets (PartScanOut); partial[v][g][t] becomes the
+// position of group g's first instance of bucket t
 __global__ void __launch_bounds__(1024) part_scan_tiles_kernel(int T, uint32_t* __restrict__ partial,
-                                                               uint2* __restrict__ ranges, size_t img_stride) {
+                                                               PartScanOut po) {
   __shared__ uint32_t ws[32];
   __shared__ uint32_t carry_s;
   const int v = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t* part = partial + (size_t)v * PART_GROUPS * T;
-  uint2* rg = shift_ptr(ranges, v * img_stride);
+  uint2* rg = nullptr;
+  uint32_t shift_by = 0;  // second level: the segment's start inside its view's list
+  int tile0 = 0;
+  if (po.seg_abs) {
+    const int view = v / po.G;
+    rg = shift_ptr(po.ranges, view * po.img_stride);
+    shift_by = po.seg_abs[v] - po.view_off[view];
+    tile0 = (v - view * po.G) << po.ts_shift;
+  } else if (!po.seg2) {
+    rg = shift_ptr(po.ranges, v * po.img_stride);
+  } else if (v == 0 && threadIdx.x == 0) {
+    po.seg2[(size_t)gridDim.x * po.G] = po.view_off[gridDim.x];
+  }
   if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
   for (int base = 0; base < T; base += 1024) {
@@ -364,7 +439,10 @@ __global__ void __launch_bounds__(1024) part_scan_tiles_kernel(int T, uint32_t* 
     const uint32_t excl = carry_s + (warp ? ws[warp - 1] : 0) + x - total;
     if (t < T) {
       // identifyTileRanges leaves (0, 0) for tiles without instances (rasterizer_impl.cu:263-271)
-      rg[t] = total ? make_uint2(excl, excl + total) : make_uint2(0u, 0u);
+      if (po.seg2)
+        po.seg2[(size_t)v * po.G + t] = po.view_off[v] + excl;
+      else if (tile0 + t < po.T_total)
+        rg[tile0 + t] = total ? make_uint2(shift_by + excl, shift_by + excl + total) : make_uint2(0u, 0u);
       uint32_t run = excl;
 #pragma unroll
       for (int g = 0; g < PART_GROUPS; g++) {
@@ -403,24 +481,24 @@ __global__ void __launch_bounds__(256) part_scan_runs_kernel(const uint32_t* __r
   }
 }
 
-template <int BITS>  // bits of a tile id (T <= 1 << BITS), compile-time so that the ranking unrolls
+template <int BITS>  // bits of a bucket index (T <= 1 << BITS), compile-time so that the ranking unrolls
 __global__ void __launch_bounds__(PART_THREADS) part_scatter_kernel(
     const uint32_t* __restrict__ tile_ids, const uint32_t* __restrict__ gids,
     const uint32_t* __restrict__ seg_off, int T, const uint32_t* __restrict__ table,
-    uint32_t* __restrict__ point_list) {
+    uint32_t* __restrict__ point_list, uint32_t* __restrict__ keys_out, int S_flat, int shift, uint32_t mask) {
   extern __shared__ uint32_t s_part[];
   const int TP = (T + 1) >> 1;                      // packed u16 pairs per warp row
   uint32_t* s_cnt = s_part;                         // [PART_WARPS][TP]  two 16-bit counters per word
   uint32_t* s_base = s_part + PART_WARPS * TP;      // [PART_WARPS][T]
-  const int v = blockIdx.y;
-  const uint32_t o = seg_off[v], n = seg_off[v + 1] - o;
-  const uint32_t lo = blockIdx.x * (uint32_t)PART_RUN;
-  if (lo >= n) return;
+  PartRunRef pr;
+  if (!part_locate(seg_off, S_flat, pr)) return;
+  const uint32_t lo = pr.lo, n = pr.n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t* keys = tile_ids + o;
-  const uint32_t* vals = gids + o;
-  uint32_t* out = point_list + o;
-  // (the carve below keeps s_cnt 16-byte aligned and PART_WARPS * TP a multiple of 4 words)
+  const uint32_t* keys = tile_ids + pr.o;
+  const uint32_t* vals = gids + pr.o;
+  uint32_t* out = point_list + pr.o;
+  uint32_t* kout = keys_out ? keys_out + pr.o : nullptr;  // first level: the tile ids travel along
+  // (PART_WARPS * TP is a multiple of 4 words and s_cnt is 16-byte aligned)
   for (int i = threadIdx.x; i < PART_WARPS * TP / 4; i += PART_THREADS)
     reinterpret_cast<uint4*>(s_cnt)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
@@ -441,12 +519,15 @@ __global__ void __launch_bounds__(PART_THREADS) part_scatter_kernel(
   }
 #pragma unroll
   for (int k = 0; k < PART_IPL; k++)
-    if (key[k] != 0xFFFFFFFFu) atomicAdd(&s_cnt[warp * TP + (key[k] >> 1)], 1u << (16 * (key[k] & 1)));
+    if (key[k] != 0xFFFFFFFFu) {
+      const uint32_t bk = (key[k] >> shift) & mask;
+      atomicAdd(&s_cnt[warp * TP + (bk >> 1)], 1u << (16 * (bk & 1)));
+    }
   __syncthreads();
-  // B: position of each warp's first instance of every tile, two tiles (one packed counter word) per
+  // B: position of each warp's first instance of every bucket, two buckets (one packed counter word) per
   // step: the table is as large as the run (8 warps x T entries for 4096 instances), so this loop
   // was 40 % of the kernel's instructions when written tile by tile
-  const uint32_t* row = table + (part_row0(seg_off, v) + blockIdx.x) * (size_t)T;
+  const uint32_t* row = table + pr.row * (size_t)T;
   for (int t2 = threadIdx.x; t2 < TP; t2 += PART_THREADS) {
     const int t = 2 * t2;
     uint32_t run0 = row[t], run1 = (t + 1 < T) ? row[t + 1] : 0u;
@@ -466,9 +547,9 @@ __global__ void __launch_bounds__(PART_THREADS) part_scatter_kernel(
 #pragma unroll
   for (int k = 0; k < PART_IPL; k++) {
     if (wlo + k * 32 >= whi) break;  // warp-uniform
-    const uint32_t t = key[k];
-    const bool valid = t != 0xFFFFFFFFu;
-    // lanes holding the same tile id (common.cuh:same_value_lanes; with match.any this kernel took
+    const bool valid = key[k] != 0xFFFFFFFFu;
+    const uint32_t t = (key[k] >> shift) & mask;
+    // lanes holding the same bucket (common.cuh:same_value_lanes; with match.any this kernel took
     // 0.78 ms instead of 0.51 ms)
     uint32_t peers = __ballot_sync(0xFFFFFFFFu, valid);
     if (!valid) peers = ~peers;
@@ -480,23 +561,29 @@ __global__ void __launch_bounds__(PART_THREADS) part_scatter_kernel(
       my_base[t] = prev + __popc(peers);
     }
     prev = __shfl_sync(0xFFFFFFFFu, prev, leader);
-    if (valid) out[prev + __popc(peers & lt_mask)] = val[k];
+    if (valid) {
+      const uint32_t pos = prev + __popc(peers & lt_mask);
+      out[pos] = val[k];
+      if (kout) kout[pos] = key[k];
+    }
     __syncwarp();
   }
 }
 
-static cudaError_t partition_by_tile(const ViewBatch& vb, int T, int bits, uint32_t R_total, uint32_t R_max,
-                                     const uint32_t* keys, const uint32_t* vals, uint32_t* point_list,
-                                     uint32_t* ws, size_t ws_bytes, ImgState& img0, cudaStream_t stream) {
-  if (part_workspace_bytes(R_total, vb.V, T) > ws_bytes) return cudaErrorInvalidValue;
-  uint32_t* table = ws;
-  uint32_t* partial = ws + part_table_rows(R_total, vb.V) * (size_t)T;
-  const int runs = (int)((R_max + PART_RUN - 1) / PART_RUN);
+// One level of the partition: the instances of every segment (seg[s] .. seg[s + 1] of the arena, S
+// segments) are stably partitioned by bucket = (tile id >> shift) & mask, T buckets per segment.
+// flat_rows == 0: grid (runs_max, S), the caller knows an upper bound on a segment's runs; otherwise a
+// flat grid of flat_rows count-table rows (part_locate).
+static cudaError_t part_level(const uint32_t* seg, int S, int runs_max, size_t flat_rows, int T, int shift,
+                              uint32_t mask, const uint32_t* keys, const uint32_t* vals, uint32_t* vals_out,
+                              uint32_t* keys_out, uint32_t* table, uint32_t* partial, const PartScanOut& po,
+                              cudaStream_t stream) {
   const int tb = (T + 255) / 256;
   const size_t scatter_smem = sizeof(uint32_t) * PART_WARPS * (size_t)(((T + 1) >> 1) + T);
-  int id_bits = 1;  // bits that tell tile ids 0 .. T-1 apart
+  int id_bits = 1;  // bits that tell buckets 0 .. T-1 apart
   while ((1 << id_bits) < T) id_bits++;
-  using scatter_fn = void (*)(const uint32_t*, const uint32_t*, const uint32_t*, int, const uint32_t*, uint32_t*);
+  using scatter_fn = void (*)(const uint32_t*, const uint32_t*, const uint32_t*, int, const uint32_t*, uint32_t*,
+                              uint32_t*, int, int, uint32_t);
   static const scatter_fn scatter[12] = {nullptr, part_scatter_kernel<1>, part_scatter_kernel<2>, part_scatter_kernel<3>,
                                          part_scatter_kernel<4>, part_scatter_kernel<5>, part_scatter_kernel<6>,
                                          part_scatter_kernel<7>, part_scatter_kernel<8>, part_scatter_kernel<9>,
@@ -509,20 +596,102 @@ static cudaError_t partition_by_tile(const ViewBatch& vb, int T, int bits, uint3
     if (e != cudaSuccess) return e;
     attr_set[id_bits] = true;
   }
-  part_count_kernel<<<dim3(runs, vb.V), PART_THREADS, sizeof(uint32_t) * T, stream>>>(keys, vb.seg_off, T, table);
-  part_scan_partial_kernel<<<dim3(tb, PART_GROUPS, vb.V), 256, 0, stream>>>(vb.seg_off, T, table, partial);
-  part_scan_tiles_kernel<<<vb.V, 1024, 0, stream>>>(T, partial, img0.ranges, vb.img_stride);
-  part_scan_runs_kernel<<<dim3(tb, PART_GROUPS, vb.V), 256, 0, stream>>>(vb.seg_off, T, table, partial);
-  scatter[id_bits]<<<dim3(runs, vb.V), PART_THREADS, scatter_smem, stream>>>(keys, vals, vb.seg_off, T, table,
-                                                                            point_list);
+  const dim3 run_grid = flat_rows ? dim3((unsigned)flat_rows) : dim3(runs_max, S);
+  const int S_flat = flat_rows ? S : 0;
+  part_count_kernel<<<run_grid, PART_THREADS, sizeof(uint32_t) * T, stream>>>(keys, seg, T, table, S_flat, shift, mask);
+  part_scan_partial_kernel<<<dim3(tb, PART_GROUPS, S), 256, 0, stream>>>(seg, T, table, partial);
+  part_scan_tiles_kernel<<<S, 1024, 0, stream>>>(T, partial, po);
+  part_scan_runs_kernel<<<dim3(tb, PART_GROUPS, S), 256, 0, stream>>>(seg, T, table, partial);
+  scatter[id_bits]<<<run_grid, PART_THREADS, scatter_smem, stream>>>(keys, vals, seg, T, table, vals_out, keys_out,
+                                                                     S_flat, shift, mask);
   DGE_LAUNCHED(5);
   return cudaGetLastError();
+}
+
+static cudaError_t partition_by_tile(const ViewBatch& vb, int T, int bits, uint32_t R_total, uint32_t R_max,
+                                     const uint32_t* keys, const uint32_t* vals, uint32_t* point_list,
+                                     uint32_t* ws, size_t ws_bytes, ImgState& img0, cudaStream_t stream) {
+  (void)bits;
+  if (part_workspace_bytes(R_total, vb.V, T) > ws_bytes) return cudaErrorInvalidValue;
+  uint32_t* table = ws;
+  uint32_t* partial = ws + part_table_rows(R_total, vb.V) * (size_t)T;
+  const int runs = (int)((R_max + PART_RUN - 1) / PART_RUN);
+  const PartScanOut po{img0.ranges, vb.img_stride, nullptr, nullptr, nullptr, 1, 0, T};
+  return part_level(vb.seg_off, vb.V, runs, 0, T, 0, 0xFFFFFFFFu, keys, vals, point_list, nullptr, table, partial,
+                    po, stream);
+}
+
+// ---- two-level partition (fit step, T > PART_MAX_TILES) --------------------------------------------
+// 1264x832 has 4108 tiles and 1080p 8160: too many for the per-warp tables of part_scatter, and a view's
+// list (270 MB at 6 M Gaussians / 1080p) is far larger than the L2 in which the scattered 4-byte stores of a
+// single pass have to meet. Two passes of the SAME kernels keep both bounded:
+//   level 1  by tile group (tile id >> PART2 shift; G = ceil(T / TS) groups of TS = 256 tiles): few
+//            output streams per view, every warp writes long pieces; the tile ids travel with the
+//            Gaussian ids. Its scan over the groups is the segment table of level 2.
+//   level 2  inside every (view, group) segment by the low bits of the tile id: TS buckets, the
+//            scattered stores stay inside the group's piece of the list (a few MB); its scan is `ranges`.
+// Both levels are stable, so the result equals the stable sort by tile id (and the reference's list).
+// Traffic per instance: 8 B written by expand, 8 + 8 read and 8 written (level 1), 4 + 8 read and 4
+// written (level 2) = 48 B against 8 + 2 x (4 + 16 + 16) + 4 = 84 B of the generic two-pass onesweep,
+// with no look-back and no spinning.
+static int part2_shift() {
+  static const int s = [] {
+    const char* e = getenv("DGE_PART2_SHIFT");
+    const int v = e ? atoi(e) : 8;
+    return v < 1 ? 1 : (v > 11 ? 11 : v);
+  }();
+  return s;
+}
+static int part2_groups(int T) { return (T + (1 << part2_shift()) - 1) >> part2_shift(); }
+static size_t align64w(size_t words) { return (words + 63) & ~(size_t)63; }
+size_t part2_workspace_bytes(uint32_t R_total, int V, int T) {
+  const int G = part2_groups(T), TS = 1 << part2_shift();
+  const size_t S = (size_t)V * G;
+  const size_t words = align64w(part_table_rows(R_total, V) * (size_t)G) + align64w((size_t)V * PART_GROUPS * G) +
+                       align64w(S + 1) + align64w(part_table_rows(R_total, (int)S) * (size_t)TS) +
+                       align64w(S * PART_GROUPS * TS);
+  return sizeof(uint32_t) * words + 256;
+}
+
+static cudaError_t partition_two_level(const ViewBatch& vb, int T, uint32_t R_total, uint32_t R_max,
+                                       const uint32_t* keys, const uint32_t* vals, uint32_t* keys_tmp,
+                                       uint32_t* vals_tmp, uint32_t* point_list, uint32_t* ws, size_t ws_bytes,
+                                       ImgState& img0, cudaStream_t stream) {
+  if (part2_workspace_bytes(R_total, vb.V, T) > ws_bytes) return cudaErrorInvalidValue;
+  const int shift = part2_shift(), TS = 1 << shift, G = part2_groups(T);
+  const int S = vb.V * G;
+  if (G > PART_MAX_TILES || S > 65535) return cudaErrorInvalidValue;
+  uint32_t* table1 = ws;
+  uint32_t* partial1 = table1 + align64w(part_table_rows(R_total, vb.V) * (size_t)G);
+  uint32_t* seg2 = partial1 + align64w((size_t)vb.V * PART_GROUPS * G);
+  uint32_t* table2 = seg2 + align64w((size_t)S + 1);
+  uint32_t* partial2 = table2 + align64w(part_table_rows(R_total, S) * (size_t)TS);
+  const int runs = (int)((R_max + PART_RUN - 1) / PART_RUN);
+  const PartScanOut po1{nullptr, 0, seg2, vb.seg_off, nullptr, G, shift, T};
+  cudaError_t e = part_level(vb.seg_off, vb.V, runs, 0, G, shift, 0xFFFFFFFFu, keys, vals, vals_tmp, keys_tmp,
+                             table1, partial1, po1, stream);
+  if (e != cudaSuccess) return e;
+  const PartScanOut po2{img0.ranges, vb.img_stride, nullptr, vb.seg_off, seg2, G, shift, T};
+  return part_level(seg2, S, 0, part_table_rows(R_total, S), TS, 0, (uint32_t)TS - 1u, keys_tmp, vals_tmp,
+                    point_list, nullptr, table2, partial2, po2, stream);
+}
+
+// T > PART_MAX_TILES goes through the two-level partition. DGE_PART2=0 puts the generic onesweep passes
+// back (A/B), DGE_PART2=2 forces the two-level partition for EVERY tile count (tests; with DGE_PART2_SHIFT=4
+// even small images have several tile groups).
+static int part2_mode() {
+  static const int m = [] {
+    const char* e = getenv("DGE_PART2");
+    return e ? atoi(e) : 1;
+  }();
+  return m;
 }
 
 size_t binning_batched_workspace_bytes(uint32_t R_total, int V, int T) {
   const size_t a = sort_workspace_bytes_segmented(R_total, V);
   const size_t b = T <= PART_MAX_TILES ? part_workspace_bytes(R_total, V, T) : 0;
-  return a > b ? a : b;
+  const size_t c = part2_mode() ? part2_workspace_bytes(R_total, V, T) : 0;
+  return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
 cudaError_t launch_binning_batched(const ViewParams& vp, const ViewBatch& vb, uint32_t R_total, uint32_t R_max,
@@ -539,17 +708,24 @@ cudaError_t launch_binning_batched(const ViewParams& vp, const ViewBatch& vb, ui
   const int bits = tile_bits(T);
   const int passes = sort_num_passes(bits);
   static const bool no_part = getenv("DGE_NO_PARTITION") != nullptr;
-  const bool one_pass = passes > 0 && T <= PART_MAX_TILES && !no_part;
+  const bool two_level = passes > 0 && !no_part && part2_groups(T) <= PART_MAX_TILES &&
+                         (size_t)vb.V * part2_groups(T) <= 65535 &&
+                         (part2_mode() == 2 || (part2_mode() == 1 && T > PART_MAX_TILES));
+  const bool one_pass = passes > 0 && T <= PART_MAX_TILES && !no_part && !two_level;
   uint32_t* keys[2] = {b.tile_ids, b.key_alt};
   uint32_t* vals[2] = {b.point_list, b.val_alt};
-  // the single-pass partition reads (key_alt, val_alt) and writes point_list; the generic sort
-  // ping-pongs and must END in (tile_ids, point_list)
-  const int src = one_pass ? 1 : (passes & 1);
+  // the single-pass partition reads (key_alt, val_alt) and writes point_list; the two-level one goes
+  // (tile_ids, point_list) -> (key_alt, val_alt) -> point_list; the generic sort ping-pongs and must
+  // END in (tile_ids, point_list)
+  const int src = two_level ? 0 : one_pass ? 1 : (passes & 1);
   expand_kernel<<<dim3(blocks, vb.V), SCAN_THREADS, 0, stream>>>(P, vp.grid_x, order, g0.rect, g0.block_sums,
                                                                  g0.offsets, keys[src], vals[src],
                                                                  vb.geom_stride, vb.seg_off);
   DGE_LAUNCHED(3);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (two_level)
+    return partition_two_level(vb, T, R_total, R_max, keys[0], vals[0], keys[1], vals[1], b.point_list, b.sort_ws,
+                               b.sort_ws_bytes, img0, stream);
   if (one_pass)  // one deterministic pass; writes point_list and ranges
     return partition_by_tile(vb, T, bits, R_total, R_max, keys[1], vals[1], b.point_list, b.sort_ws,
                              b.sort_ws_bytes, img0, stream);
