@@ -29,7 +29,22 @@ def _newer(src, dst, extra=()):
     return any(os.path.getmtime(p) > t for p in (src, *extra))
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant/defines: an A/B build of the same library with extra -D flags, written to
+    _build/var_<variant>/libdge_b200.so and selected at run time with DGE_B200_LIB=<that path>."""
+    global OUT, LIB
+    if variant:
+        saved = OUT, LIB
+        OUT = os.path.join(saved[0], "var_" + variant)
+        LIB = os.path.join(OUT, "libdge_b200.so")
+        try:
+            return _build(True, verbose, tuple(defines))
+        finally:
+            OUT, LIB = saved
+    return _build(force, verbose, ())
+
+
+def _build(force, verbose, defines):
     os.makedirs(OUT, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "dge_b200.h"))
@@ -43,7 +58,7 @@ def build(force=False, verbose=False):
 
     def cc(job):
         src, obj = job
-        r = subprocess.run([NVCC, *FLAGS, "-c", src, "-o", obj], capture_output=True, text=True)
+        r = subprocess.run([NVCC, *FLAGS, *defines, "-c", src, "-o", obj], capture_output=True, text=True)
         with open(obj[:-2] + ".ptxas.log", "w") as fh:
             fh.write(r.stderr)
         if r.returncode != 0:
@@ -63,4 +78,7 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # python -m dge_b200.build [--force] [-v] [--variant NAME -DX=1 -DY=2 ...]
+    name = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=name,
+                defines=[a for a in sys.argv if a.startswith("-D")]))
