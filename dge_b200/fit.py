@@ -267,6 +267,39 @@ class FitModel:
                                           a["rotations"].data_ptr(), L.stream_ptr(self.device)), "activate")
         return {"means3D": p["xyz"].detach(), **a}
 
+    def training_setup(self, position_lr_max_steps, position_lr_init=0.00016, position_lr_final=0.000016,
+                       position_lr_delay_mult=0.01, spatial_lr_scale=1.0, feature_lr=0.0125, opacity_lr=0.05,
+                       scaling_lr=0.005, rotation_lr=0.001):
+        """The learning rates of GaussianModel.training_setup (gaussian_model.py:341-380) with the defaults of
+        OptimizationParams (gaussiansplatting/arguments/__init__.py:72-81; DGE passes trainer.max_steps and the
+        camera extent as spatial_lr_scale, DGE.py:503-515): xyz scaled by the scene extent and scheduled by
+        update_learning_rate, f_rest at feature_lr / 20. Adam state is kept."""
+        self.lrs = {"xyz": position_lr_init * spatial_lr_scale, "f_dc": feature_lr, "f_rest": feature_lr / 20.0,
+                    "opacity": opacity_lr, "scaling": scaling_lr, "rotation": rotation_lr}
+        self._xyz_schedule = (position_lr_init * spatial_lr_scale, position_lr_final * spatial_lr_scale,
+                              position_lr_delay_mult, position_lr_max_steps)
+        self._sync_optimizer_lrs()
+
+    def update_learning_rate(self, iteration: int) -> float:
+        """GaussianModel.update_learning_rate (gaussian_model.py:382-388, called every step from
+        DGE.training_step, DGE.py:621): log-linear interpolation of the xyz rate from lr_init at step 0 to
+        lr_final at max_steps (utils/general_utils.py:29-62 with lr_delay_steps = 0, as training_setup
+        calls it); the other groups keep their rates. Returns the new xyz rate."""
+        lr_init, lr_final, _delay_mult, max_steps = getattr(self, "_xyz_schedule", (self.lrs["xyz"],) * 2 + (1.0, 1))
+        if iteration < 0 or (lr_init == 0.0 and lr_final == 0.0):
+            lr = 0.0
+        else:
+            t = min(max(iteration / max_steps, 0.0), 1.0)
+            lr = math.exp(math.log(lr_init) * (1.0 - t) + math.log(lr_final) * t)
+        self.lrs["xyz"] = lr
+        self._sync_optimizer_lrs()
+        return lr
+
+    def _sync_optimizer_lrs(self):
+        if not self.fused_adam:  # the fused path reads self.lrs at every step
+            for group in self.optimizer.param_groups:
+                group["lr"] = self.lrs[group["name"]]
+
     def set_grad_mask(self, mask: Optional[torch.Tensor]):
         self.grad_mask = None if mask is None else mask.to(self.device).to(torch.uint8).contiguous()
 
