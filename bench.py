@@ -501,7 +501,7 @@ def main():
         out["roofline"] = roof
         out["stages_ms_per_launch"] = stage_ms
         out["stages_launches_per_step"] = stage_launches
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and n_gpus == 1:  # rank 0 at N=1 only (torchrun pins OMP_NUM_THREADS=1)
             try:
                 out["cpu_baseline"] = cpu_baseline(cfg, g, ring, targets_all)
             except Exception as ex:  # the checker is optional for the number, never for the tests

@@ -39,6 +39,30 @@ def test_scratch_sizes_scale():
     assert lib.dge_image_bytes(512, 512) >= 8 * 512 * 512 + 8 * 1024
 
 
+def test_batched_binning_arena_holds_the_partition_tables():
+    """dge_fit_binning_bytes: four u32 arrays of R_total instances + the workspace of whichever tile
+    partition the tile count selects (binning.cu): one count-table row of T words per run of 4096
+    instances up to 2048 tiles, the two levels' tables (tile groups of 256 tiles) above."""
+    from dge_b200 import _lib
+    lib = _lib.load()
+    run = 4096
+    for (W, H, V, R) in [(512, 512, 20, 56_000_000), (1264, 832, 8, 130_000_000), (1920, 1080, 8, 367_000_000),
+                         (33, 17, 1, 10), (1920, 1080, 64, 1)]:
+        T = ((W + 15) // 16) * ((H + 15) // 16)
+        got = lib.dge_fit_binning_bytes(R, V, W, H)
+        lists = 16 * R
+        if T <= 2048:
+            need = 4 * ((R // run + V + 1) * T + V * 16 * T)
+        else:
+            G, S = (T + 255) // 256, V * ((T + 255) // 256)
+            need = 4 * ((R // run + V + 1) * G + V * 16 * G + S + 1 + (R // run + S + 1) * 256 + S * 16 * 256)
+        assert got >= lists + need, (W, H, V, R, got, lists + need)
+        # ... and not wildly more: the arena also has to hold the generic onesweep passes' look-back status
+        # (DGE_PART2=0 / DGE_NO_PARTITION A/B runs), ~2 B per instance
+        assert got <= lists + max(2 * need, 3 * R) + (64 << 20), (W, H, V, R, got)
+        assert lib.dge_fit_binning_bytes(2 * R + 4096, V, W, H) > got  # (arrays are padded to 256 bytes)
+
+
 def test_python_surface_matches_reference():
     import dge_b200
     mod = dge_b200.install()
