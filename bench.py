@@ -432,10 +432,27 @@ def main():
             traffic = traffic * units if traffic is not None else None  # the capture is of ONE view
         except Exception:
             pass
+        # the ALU floor next to the byte roofline: warp instructions of the launch (ncu,
+        # smsp__inst_executed.sum of the same kernel on this workload) over its live duration, against the
+        # issue rate of the part: SMs x 4 schedulers x SM clock
+        issue = None
+        try:
+            nvtx = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["warp_instructions"]
+            wi = nvtx.get(KERNEL_OF_STAGE[dominant])
+            if wi is not None and args.config == "config2":
+                sms = torch.cuda.get_device_properties(dev).multi_processor_count
+                peak_issue = sms * 4 * 1.965e9
+                issue = {"warp_instructions_per_launch": wi * units, "achieved": wi * units / (avg_ms * 1e-3),
+                         "peak": peak_issue, "unit": "warp-instr/s", "frac": wi * units / (avg_ms * 1e-3) / peak_issue,
+                         "source": "instruction count from profiles/ncu_full_r1g.md (same kernel, same workload), "
+                                   "duration live; peak = SMs x 4 schedulers x 1.965 GHz"}
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": KERNEL_OF_STAGE[dominant], "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": which,
                 "avg_launch_ms": avg_ms, "launches_timed": int(cnt[i]), "algorithmic_bytes_per_launch": abytes,
                 "views_per_launch": units,
+                "issue": issue,
                 "note": "blend kernels are issue/atomic bound, not HBM bound (SURVEY.md §8d); see DESIGN.md"}
 
     # ---- timed region 2: K steps end to end (pinned host inputs copied inside, loss read back),
@@ -501,6 +518,20 @@ def main():
         out["roofline"] = roof
         out["stages_ms_per_launch"] = stage_ms
         out["stages_launches_per_step"] = stage_launches
+        # sort keys/s. One launch of a stage covers `vpl` views: the depth sort orders P
+        # (depth bits, id) pairs per view, binning turns them into R_listed (tile, id) instances per view
+        # in (tile, depth, id) order — the work the reference does as ONE sort of R 64-bit keys.
+        vpl = (-(-V // args.chunks)) if batched else 1
+        listed = stats.get("R_listed", stats.get("R", 0.0))
+        rates = {}
+        if stage_ms.get("depth_sort"):
+            rates["depth_sort_pairs_per_s"] = vpl * P / (stage_ms["depth_sort"] * 1e-3)
+        if stage_ms.get("binning"):
+            rates["binning_instances_per_s"] = vpl * listed / (stage_ms["binning"] * 1e-3)
+            if stage_ms.get("depth_sort"):
+                rates["reference_equivalent_sort_keys_per_s"] = vpl * stats.get("R", 0.0) / (
+                    (stage_ms["binning"] + stage_ms["depth_sort"]) * 1e-3)
+        out["rates"] = rates
         if not args.no_cpu_baseline and n_gpus == 1:  # rank 0 at N=1 only (torchrun pins OMP_NUM_THREADS=1)
             try:
                 out["cpu_baseline"] = cpu_baseline(cfg, g, ring, targets_all)
