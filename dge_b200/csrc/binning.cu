@@ -336,21 +336,9 @@ __global__ void __launch_bounds__(PART_THREADS) part_count_kernel(const uint32_t
   for (int t = threadIdx.x; t < T; t += PART_THREADS) s_cnt[t] = 0;
   __syncthreads();
   const uint32_t* keys = tile_ids + pr.o;
-  if (shift == 0 || T > 64) {
-    for (uint32_t i = lo + threadIdx.x; i < hi; i += PART_THREADS) atomicAdd(&s_cnt[(keys[i] >> shift) & mask], 1u);
-  } else {
-    // first level with few buckets (tile groups): neighbouring instances mostly share one, so a warp adds once per
-    // distinct bucket instead of serialising 32 same-address atomics
-    for (uint32_t i0 = lo + (threadIdx.x & ~31u); i0 < hi; i0 += PART_THREADS) {
-      const uint32_t i = i0 + (threadIdx.x & 31u);
-      const bool valid = i < hi;
-      const uint32_t bk = valid ? (keys[i] >> shift) & mask : 0u;
-      uint32_t peers = __ballot_sync(0xFFFFFFFFu, valid);
-      if (!valid) peers = ~peers;
-      peers = same_value_lanes<6>(bk, peers);
-      if (valid && (int)(threadIdx.x & 31u) == __ffs(peers) - 1) atomicAdd(&s_cnt[bk], (uint32_t)__popc(peers));
-    }
-  }
+  // plain shared-memory atomics also for the few buckets of the first level: a warp-aggregated variant
+  // (ballots per bucket bit, one add per distinct bucket) took 0.29 ms where this takes 0.08 ms (1080p / 2 M)
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += PART_THREADS) atomicAdd(&s_cnt[(keys[i] >> shift) & mask], 1u);
   __syncthreads();
   uint32_t* row = table + pr.row * (size_t)T;
   for (int t = threadIdx.x; t < T; t += PART_THREADS) row[t] = s_cnt[t];
