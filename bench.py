@@ -148,7 +148,7 @@ def cpu_baseline(cfg, g, cams, targets, budget_s=12.0):
     return {"value": n / dt, "unit": "views/s", "cores": int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1)),
             "kind": "port",
             "sample": f"{n} views fwd+bwd of the same workload ({cfg['P']} Gaussians, {cfg['W']}x{cfg['H']}) with oracle/splat_oracle.c "
-                      f"(per-Gaussian and forward stages OpenMP, backward blend single-threaded); {dt:.1f} s"}
+                      f"(OpenMP over Gaussians and pixels); {dt:.1f} s"}
 
 
 def algorithmic_bytes(stage, P, Pv, R, Npix, T, n_pass=6):

@@ -365,8 +365,10 @@ void oracle_render_forward(int W, int H, const uint32_t* ranges, const uint32_t*
 }
 
 /* K7 renderCUDA backward (DGR/cuda_rasterizer/backward.cu:399-557). Sums over pixels are taken
- * in double, in pixel order, so they are the order-independent value the reference's float
- * atomics approximate. Outputs must be zeroed by the caller (they are accumulated). */
+ * in double, so they are the order-independent value the reference's float atomics approximate
+ * (pixels run on all host threads; the order of the double additions then varies at the 1e-16
+ * level, twelve orders of magnitude below the 1e-4 the gradients are compared with). Outputs
+ * must be zeroed by the caller (they are accumulated). */
 void oracle_render_backward(int W, int H, const uint32_t* ranges, const uint32_t* point_list,
                             const float* bg, const float* means2D, const float* conic_opacity,
                             const float* colors, const float* final_T, const uint32_t* n_contrib,
@@ -375,6 +377,7 @@ void oracle_render_backward(int W, int H, const uint32_t* ranges, const uint32_t
   const int gx = (W + TILE - 1) / TILE;
   const size_t HW = (size_t)H * W;
   const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+#pragma omp parallel for schedule(dynamic, 256)
   for (int pix = 0; pix < H * W; pix++) {
     const int px = pix % W, py = pix / W;
     const int tile = (py / TILE) * gx + px / TILE;
@@ -400,6 +403,7 @@ void oracle_render_backward(int W, int H, const uint32_t* ranges, const uint32_t
         accum[c] = last_alpha * last_color[c] + (1.0f - last_alpha) * accum[c];
         last_color[c] = col;
         dL_dalpha += (col - accum[c]) * g3[c];
+#pragma omp atomic
         dL_dcolor[3 * (size_t)g + c] += dchannel_dcolor * g3[c];
       }
       dL_dalpha *= T;
@@ -411,11 +415,17 @@ void oracle_render_backward(int W, int H, const uint32_t* ranges, const uint32_t
       const float gdx = G * dx, gdy = G * dy;
       const float dG_ddelx = -gdx * co[0] - gdy * co[1];
       const float dG_ddely = -gdy * co[2] - gdx * co[1];
+#pragma omp atomic
       dL_dmean2D[2 * (size_t)g] += dL_dG * dG_ddelx * ddelx_dx;
+#pragma omp atomic
       dL_dmean2D[2 * (size_t)g + 1] += dL_dG * dG_ddely * ddely_dy;
+#pragma omp atomic
       dL_dconic[3 * (size_t)g] += -0.5f * gdx * dx * dL_dG;
+#pragma omp atomic
       dL_dconic[3 * (size_t)g + 1] += -0.5f * gdx * dy * dL_dG;
+#pragma omp atomic
       dL_dconic[3 * (size_t)g + 2] += -0.5f * gdy * dy * dL_dG;
+#pragma omp atomic
       dL_dopacity[g] += G * dL_dalpha;
     }
   }
