@@ -477,7 +477,14 @@ def main():
     sampler = ClockSampler(local_rank, period=0.05)
     if rank == 0:
         sampler.start()
-    for _ in range(args.steps):
+    # at least ~0.6 s of load so that the median rests on a dozen samples (same count on every rank:
+    # the steps hold a collective)
+    n_clock_steps = max(args.steps, min(200, int(math.ceil(600.0 / max(ms_resident / args.steps, 0.05)))))
+    if world > 1 and args.impl == "ours":
+        tn = torch.tensor([n_clock_steps], device=dev, dtype=torch.int64)
+        dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+        n_clock_steps = int(tn[0])
+    for _ in range(n_clock_steps):
         step(False)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
