@@ -752,6 +752,43 @@ def shard_views(num_views: int, rank: int, world: int) -> List[int]:
     return list(range(rank, num_views, world))
 
 
+class ViewSampler:
+    """The batch of edited views of a step, drawn as GSLoadIterableDataset does (threestudio/data/gs_load.py:
+    213-222 constructor, 256-272 collate, 286-292 update_cameras): `max_view_num` of the scene's cameras are
+    sampled once with seed 0, a step takes `batch_size` of them at random WITHOUT replacement from a stack
+    that is refilled when it runs empty. The reference seeds Python's global `random`; here the same
+    generator is private to the sampler, so every rank that builds it with the same arguments draws the same
+    batches whatever else uses `random` — the precondition of sharding a step's views."""
+
+    def __init__(self, total_view_num: int, max_view_num: int, batch_size: int, seed: int = 0):
+        import random
+        self._random = random
+        self.total_view_num, self.max_view_num, self.batch_size = total_view_num, max_view_num, batch_size
+        self.update_cameras(seed)
+
+    def update_cameras(self, random_seed: int = 0):
+        self._rng = self._random.Random(random_seed)
+        self.n2n_view_index = self._rng.sample(range(0, self.total_view_num),
+                                               min(self.total_view_num, self.max_view_num))
+        self.view_index_stack = self.n2n_view_index.copy()
+
+    def next_batch(self) -> List[int]:
+        """View indices of the next step (`batch["index"]` of the reference's collate)."""
+        out = []
+        for _ in range(self.batch_size):
+            if not self.view_index_stack:
+                self.view_index_stack = self.n2n_view_index.copy()
+            view_index = self._rng.choice(self.view_index_stack)
+            self.view_index_stack.remove(view_index)
+            out.append(view_index)
+        return out
+
+    def next_shard(self, rank: int, world: int):
+        """(whole batch, this rank's share of it): view i of the batch goes to rank i mod world."""
+        batch = self.next_batch()
+        return batch, [batch[i] for i in shard_views(len(batch), rank, world)]
+
+
 def default_rasterize(rs, means3D, means2D, shs, opacities, scales, rotations):
     return dgr.GaussianRasterizer(rs)(means3D=means3D, means2D=means2D, shs=shs, colors_precomp=None,
                                       opacities=opacities, scales=scales, rotations=rotations, cov3D_precomp=None)

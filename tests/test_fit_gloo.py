@@ -75,6 +75,45 @@ def test_shard_views():
     assert sorted(sum((fit.shard_views(20, r, 8) for r in range(8)), [])) == list(range(20))
 
 
+def test_view_sampler_draws_the_reference_batches():
+    """fit.ViewSampler against the reference's own statements (threestudio/data/gs_load.py:218-222, 256-272,
+    286-292) executed on Python's global generator, over several refills of the stack and a re-seed."""
+    import random
+
+    def reference_batches(total, max_view, batch, steps, seed=None):
+        if seed is None:
+            random.seed(0)  # gs_load.py:218
+        else:
+            random.seed(seed)  # gs_load.py:287
+        n2n = random.sample(range(0, total), min(total, max_view))
+        stack = n2n.copy()
+        out = []
+        for _ in range(steps):
+            idx = []
+            for _ in range(batch):
+                if not stack:
+                    stack = n2n.copy()
+                v = random.choice(stack)
+                stack.remove(v)
+                idx.append(v)
+            out.append(idx)
+        return n2n, out
+
+    for total, max_view, batch in [(37, 20, 5), (12, 48, 5), (100, 30, 7)]:
+        n2n, want = reference_batches(total, max_view, batch, 11)
+        s = fit.ViewSampler(total, max_view, batch)
+        random.seed(12345)  # whatever else touches the global generator must not matter
+        assert s.n2n_view_index == n2n
+        assert [s.next_batch() for _ in range(11)] == want
+        n2n, want = reference_batches(total, max_view, batch, 4, seed=3)
+        s.update_cameras(3)
+        assert s.n2n_view_index == n2n and [s.next_batch() for _ in range(4)] == want
+    # two ranks: same batch, disjoint shares that cover it
+    a, b = fit.ViewSampler(37, 20, 5), fit.ViewSampler(37, 20, 5)
+    (ba, sa), (bb, sb) = a.next_shard(0, 2), b.next_shard(1, 2)
+    assert ba == bb and sorted(sa + sb) == sorted(ba) and not set(sa) & set(sb)
+
+
 def test_flat_views_are_leaves():
     g, _, _ = _data()
     m = fit.FitModel(g, torch.device("cpu"), fused_adam=False)
