@@ -710,9 +710,10 @@ static cudaError_t partition_by_tile(const ViewBatch& vb, int T, int bits, uint3
 //   level 2  inside every (view, group) segment by the low bits of the tile id: TS buckets, the
 //            scattered stores stay inside the group's piece of the list (a few MB); its scan is `ranges`.
 // Both levels are stable, so the result equals the stable sort by tile id (and the reference's list).
-// Traffic per instance: 8 B written by expand, 8 + 8 read and 8 written (level 1), 4 + 8 read and 4
-// written (level 2) = 48 B against 8 + 2 x (4 + 16 + 16) + 4 = 84 B of the generic two-pass onesweep,
-// with no look-back and no spinning.
+// Traffic per instance: 8 B written by expand, 4 + 8 read and 8 written (level 1), 4 + 8 read and 4
+// written (level 2) = 44 B — about what the generic path moves (8 + 4 for the histogram + 2 x 16 for the two
+// onesweep passes + 4 for identifyTileRanges = 48 B); what it saves is the decoupled look-back (status traffic,
+// spinning, 5 warp-instructions per instance): 2.62 -> 1.96 ms per 8 views at 1080p / 2 M Gaussians.
 static int part2_shift() {
   static const int s = [] {
     const char* e = getenv("DGE_PART2_SHIFT");
