@@ -142,6 +142,32 @@ class FitModel:
         from . import ply
         ply.save_ply(self.params, path)
 
+    def state_dict(self):
+        """Everything a resumed fit needs (the reference checkpoints through Lightning + save_ply,
+        threestudio/systems/DGE.py:497; a PLY alone loses the optimiser): raw parameters, Adam moments and
+        step, learning rates and the xyz schedule, densification statistics, edit mask. CPU tensors."""
+        cpu = lambda t: t.detach().to("cpu").clone()
+        moments = {nm: tuple(cpu(m) for m in self.adam_state(nm)) for nm, _, _ in GROUPS}
+        return {
+            "params": {nm: cpu(p) for nm, p in self.params.items()},
+            "exp_avg": {nm: m[0] for nm, m in moments.items()}, "exp_avg_sq": {nm: m[1] for nm, m in moments.items()},
+            "step_count": self.step_count, "lrs": dict(self.lrs), "xyz_schedule": getattr(self, "_xyz_schedule", None),
+            "sh_degree": self.sh_degree, "xyz_gradient_accum": cpu(self.xyz_gradient_accum), "denom": cpu(self.denom),
+            "max_radii2D": cpu(self.max_radii2D), "grad_mask": None if self.grad_mask is None else cpu(self.grad_mask),
+        }
+
+    def load_state_dict(self, sd):
+        """Inverse of state_dict(); the number of Gaussians may differ from the current one (densification)."""
+        self.step_count, self.lrs, self.sh_degree = int(sd["step_count"]), dict(sd["lrs"]), int(sd["sh_degree"])
+        if sd.get("xyz_schedule") is not None:
+            self._xyz_schedule = tuple(sd["xyz_schedule"])
+        self._allocate(sd["params"], sd["exp_avg"], sd["exp_avg_sq"])
+        dev = self.device
+        self.xyz_gradient_accum = sd["xyz_gradient_accum"].to(dev).clone()
+        self.denom = sd["denom"].to(dev).clone()
+        self.max_radii2D = sd["max_radii2D"].to(dev).clone()
+        self.set_grad_mask(sd.get("grad_mask"))
+
     def adam_state(self, name):
         """(exp_avg, exp_avg_sq) of a parameter group, shaped like the parameter."""
         if not self.fused_adam and self.params[name] in self.optimizer.state:

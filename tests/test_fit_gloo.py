@@ -114,6 +114,38 @@ def test_view_sampler_draws_the_reference_batches():
     assert ba == bb and sorted(sa + sb) == sorted(ba) and not set(sa) & set(sb)
 
 
+@pytest.mark.parametrize("fused", [False])
+def test_checkpoint_resume_continues_identically(fused, tmp_path):
+    """state_dict / load_state_dict: a fit resumed from a checkpoint (through torch.save) takes exactly the
+    steps the uninterrupted one takes — parameters, Adam moments and step, xyz rate, statistics, mask."""
+    g, cams, targets = _data()
+    bg = torch.zeros(3)
+    mask = (torch.arange(P) % 3 != 0)
+
+    def steps(model, n, first):
+        for it in range(first, first + n):
+            model.update_learning_rate(it)
+            fit.fit_step(model, cams, targets, bg, global_batch=V, rasterize=fake_rasterize)
+
+    a = fit.FitModel(g, torch.device("cpu"), fused_adam=fused)
+    a.training_setup(40, spatial_lr_scale=2.0)
+    a.set_grad_mask(mask)
+    steps(a, 3, 0)
+    torch.save(a.state_dict(), tmp_path / "fit.pt")
+    steps(a, 3, 3)
+    b = fit.FitModel(scene.make_gaussians(7, seed=1), torch.device("cpu"), fused_adam=fused)  # another size
+    b.load_state_dict(torch.load(tmp_path / "fit.pt", weights_only=False))
+    assert b.P == P and b.step_count == 3
+    steps(b, 3, 3)
+    assert torch.equal(a.flat, b.flat)
+    for nm, _, _ in fit.GROUPS:
+        for x, y in zip(a.adam_state(nm), b.adam_state(nm)):
+            assert torch.equal(x, y), nm
+    assert torch.equal(a.xyz_gradient_accum, b.xyz_gradient_accum) and torch.equal(a.denom, b.denom)
+    assert torch.equal(a.max_radii2D, b.max_radii2D) and torch.equal(a.grad_mask, b.grad_mask)
+    assert a.lrs == b.lrs and a.step_count == b.step_count == 6
+
+
 def test_flat_views_are_leaves():
     g, _, _ = _data()
     m = fit.FitModel(g, torch.device("cpu"), fused_adam=False)
