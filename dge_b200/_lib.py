@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # DGE_B200_LIB: an alternative build of the SAME library (A/B measurements of kernel variants)
 LIB_PATH = os.environ.get("DGE_B200_LIB") or os.path.join(_HERE, "_build", "libdge_b200.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
@@ -39,6 +39,7 @@ _SIGNATURES = {
     "dge_image_pointers": (None, [_p, _i, _i, C.POINTER(_p)]),
     "dge_debug_sorted_keys": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
     "dge_launch_count": (C.c_ulonglong, []),
+    "dge_clock_probe": (_i, [_p, _p]),
     "dge_profile_enable": (None, [C.c_uint]),
     "dge_profile_read": (_i, [C.POINTER(C.c_float), C.POINTER(_i)]),
     "dge_fit_forward": (_i, [ALLOC_FN, ALLOC_FN, ALLOC_FN, _p, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _f, _p, _p,

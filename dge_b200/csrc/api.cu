@@ -201,6 +201,21 @@ static int bin_view(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge
   return (int)R;
 }
 
+// Measurement hook: every SM that gets a block stores its cycle counter and the global nanosecond timer.
+// Two probes on the same stream, one before and one after a timed region, give the AVERAGE SM clock the
+// region ran at (cycles / ns per SM) without a single driver query in between (an NVML / nvidia-smi
+// poll stalls the launching thread for ~25 ms on this driver).
+__global__ void clock_probe_kernel(unsigned long long* out) {
+  if (threadIdx.x == 0) {
+    unsigned smid;
+    unsigned long long t;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    out[2 * smid] = (unsigned long long)clock64();
+    out[2 * smid + 1] = t;
+  }
+}
+
 }  // namespace dge
 
 using namespace dge;
@@ -208,8 +223,14 @@ using namespace dge;
 extern "C" {
 
 const char* dge_last_error(void) { return g_err; }
-int dge_abi_version(void) { return 9; }
+int dge_abi_version(void) { return 10; }
 unsigned long long dge_launch_count(void) { return g_kernel_launches; }
+
+int dge_clock_probe(unsigned long long* out, void* stream_) {
+  clock_probe_kernel<<<DGE_NUM_SMS * 8, 32, 0, (cudaStream_t)stream_>>>(out);
+  CK("clock probe", cudaGetLastError());
+  return 0;
+}
 
 void dge_profile_enable(unsigned stage_mask) { g_profile_mask = stage_mask; }
 // Sums (and clears) the event-timed durations recorded since the last call.

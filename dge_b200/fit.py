@@ -30,8 +30,9 @@ from . import scene
 GROUPS = [("xyz", 3, (3,)), ("f_dc", 3, (1, 3)), ("f_rest", 45, (15, 3)), ("opacity", 1, (1,)),
           ("scaling", 3, (3,)), ("rotation", 4, (4,))]
 FLOATS_PER_GAUSSIAN = sum(g[1] for g in GROUPS)  # 59
-# configs/dge.yaml + gaussiansplatting/arguments/__init__.py defaults
-DEFAULT_LRS = {"xyz": 0.00016, "f_dc": 0.0025, "f_rest": 0.0025 / 20.0, "opacity": 0.05, "scaling": 0.005,
+# gaussiansplatting/arguments/__init__.py:72-81 (OptimizationParams: position_lr_init, feature_lr, opacity_lr,
+# scaling_lr, rotation_lr; f_rest at feature_lr / 20, gaussian_model.py:344); configs/dge.yaml scales them by 1
+DEFAULT_LRS = {"xyz": 0.00016, "f_dc": 0.0125, "f_rest": 0.0125 / 20.0, "opacity": 0.05, "scaling": 0.005,
                "rotation": 0.001}
 MASKED_GROUPS = ("xyz", "f_dc", "f_rest", "opacity", "scaling")  # gaussian_model.py:848 (no rotation)
 
@@ -441,6 +442,17 @@ class ViewLane:
         self.radii_max.zero_()
 
 
+def _background_is_black(model, bg) -> int:
+    """1 when the background is (0,0,0): the blend backward then runs without the background term of
+    dL/dalpha (dge_fit_*_backward_blend's promise). The answer is cached per background TENSOR OBJECT and
+    version counter — never per data pointer: the caching allocator hands a freed tensor's address to the
+    next one, and an in-place update keeps it."""
+    hit = getattr(model, "_bg_seen", None)
+    if hit is None or hit[0] is not bg or hit[1] != bg._version:
+        model._bg_seen = (bg, bg._version, int(not bool(bg.detach().cpu().any())))
+    return model._bg_seen[2]
+
+
 def _direct_views(model: FitModel, acts, cameras, targets, bg, scale, host_inputs, num_streams):
     """The step's views through the C-ABI, round-robin over `num_streams` lanes (no autograd):
     per view forward -> fused L1 loss+gradient -> blend backward into that view's acc rows; then ONE
@@ -450,6 +462,9 @@ def _direct_views(model: FitModel, acts, cameras, targets, bg, scale, host_input
     dev = model.device
     H, W = cameras[0].image_height, cameras[0].image_width
     V = len(cameras)
+    if V > 64:
+        raise ValueError("a step holds at most 64 views per rank (dge_fit_backward_geom_raw): shard the batch "
+                         "over more ranks or take two steps")
     S = max(1, min(num_streams, V))
     P = model.P
     main = torch.cuda.current_stream(dev)
@@ -469,9 +484,7 @@ def _direct_views(model: FitModel, acts, cameras, targets, bg, scale, host_input
         with torch.cuda.stream(ln.stream):
             ln.reset()
     bgp = bg.data_ptr()
-    if getattr(model, "_bg_key", None) != bgp:  # one-time host copy of the (constant) background
-        model._bg_key, model._bg_black = bgp, int(not bool(bg.detach().cpu().any()))
-    bg_black = model._bg_black
+    bg_black = _background_is_black(model, bg)
     n_img = 3 * H * W
     for i, (cam, target) in enumerate(zip(cameras, targets)):
         ln = lanes[i % S]
@@ -592,12 +605,14 @@ def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inpu
     ptrs = {k: v.data_ptr() for k, v in a.items()}
     M = a["shs"].shape[1]
     bgp = bg.data_ptr()
-    if getattr(model, "_bg_key", None) != bgp:  # one-time host copy of the (constant) background
-        model._bg_key, model._bg_black = bgp, int(not bool(bg.detach().cpu().any()))
+    bg_black = _background_is_black(model, bg)
     # cameras: one pinned [V,40] block, one H2D copy
     recs = [camera_record(cam) for cam in cameras]
-    cams_key = tuple(id(r) for r in recs)  # records are memoised per camera: same objects <=> same cameras
-    if getattr(model, "_cams_key", None) != cams_key:
+    # records are memoised per camera: same objects <=> same cameras. The key HOLDS the records (an id()
+    # of a freed record can be reused by another camera's)
+    cams_key = getattr(model, "_cams_key", None)
+    if cams_key is None or len(cams_key) != len(recs) or any(a is not b for a, b in zip(cams_key, recs)):
+        cams_key = tuple(recs)
         for i, rec in enumerate(recs):
             model._cams_host[i].copy_(rec)
         model._cams.copy_(model._cams_host, non_blocking=True)
@@ -641,7 +656,7 @@ def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inpu
                 vb.stream.wait_event(vb.copied)
             L.check(lib.dge_l1_loss_grad(vb.color.data_ptr(), vb.tgt.data_ptr(), vb.V * n_img, scale, vb.dL.data_ptr(),
                                          vb.loss.data_ptr(), vb.stream_ptr), "l1 loss")
-            L.check(lib.dge_fit_views_backward_blend(P, vb.V, vb.R, bgp, model._bg_black, W, H, vb.geom.data_ptr(),
+            L.check(lib.dge_fit_views_backward_blend(P, vb.V, vb.R, bgp, bg_black, W, H, vb.geom.data_ptr(),
                                                      vb.binning.data_ptr(), vb.img.data_ptr(), vb.dL.data_ptr(),
                                                      vb.acc.data_ptr(), acc_stride, vb.stream_ptr),
                     "fit views backward blend")
@@ -824,7 +839,8 @@ def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence
              global_batch: int, rasterize: Callable = default_rasterize, settings_module=dgr,
              process_group=None, lambda_l1: float = 10.0, host_inputs: bool = False, update_stats: bool = True,
              num_streams: int = 1, direct: Optional[bool] = None, batched: Optional[bool] = None,
-             num_chunks: int = 1, prune_lists: bool = True, geom_splits: Optional[int] = None):
+             num_chunks: int = 1, prune_lists: bool = True, geom_splits: Optional[int] = None,
+             image_size: Optional[Sequence[int]] = None):
     """One optimisation step over this rank's views. `cameras`/`targets` are this rank's share;
     `global_batch` the number of views in the whole step (L1 is a mean over the global batch,
     DGE.py:672). With host_inputs the cameras/targets live in pinned host memory and are copied
@@ -841,7 +857,15 @@ def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence
     issues the views one by one round-robin on num_streams CUDA streams (_direct_views). The autograd path below is the reference-shaped one (per-view tensors,
     torch ops for the loss, AccumulateGrad) and is what `rasterize` overrides go through."""
     dev = model.device
+    if len(cameras) == 0:
+        # this rank's share of the batch is empty (fewer views than ranks): it contributes zero gradients,
+        # zero loss and zero radii, and still joins every collective of the step
+        model.flat_grad.zero_()
+        return _finish_step(model, torch.zeros((), device=dev), torch.zeros(model.P, dtype=torch.int32, device=dev),
+                            process_group, update_stats)
     H, W = cameras[0].image_height, cameras[0].image_width
+    if image_size is not None and (int(image_size[0]), int(image_size[1])) != (W, H):
+        raise ValueError(f"image_size {tuple(image_size)} does not match the cameras' {W}x{H}")
     scale = lambda_l1 / float(global_batch * 3 * H * W)
     if direct is None:
         direct = dev.type == "cuda" and rasterize is default_rasterize and model.sh_degree == 3

@@ -140,6 +140,10 @@ unsigned long long dge_launch_count(void);
  * 0 preprocess, 1 depth sort, 2 binning (scan+expand+tile sort+ranges), 3 blend forward,
  * 4 blend backward, 5 per-Gaussian backward, 6 apply_weights blend. */
 #define DGE_NUM_STAGES 7
+/* out: device, 2*256 uint64, zero-filled by the caller. Every SM that runs a block of the probe stores
+ * (clock64, globaltimer ns) at out[2*smid]. Two probes on one stream, before and after a timed region,
+ * give the average SM clock of that region (delta cycles / delta ns) with no driver query in between. */
+int dge_clock_probe(unsigned long long* out, void* stream);
 void dge_profile_enable(unsigned stage_mask);
 int dge_profile_read(float* ms_out, int* count_out);
 

@@ -39,6 +39,8 @@ def load():
         lib.ref_apply_weights.restype = _i
         lib.ref_apply_weights.argtypes = [ALLOC_FN, ALLOC_FN, ALLOC_FN, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p,
                                           _f, _p, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p, _i, _i]
+        lib.ref_clock_probe.restype = None
+        lib.ref_clock_probe.argtypes = [_p]
         lib.ref_mark_visible.restype = None
         lib.ref_mark_visible.argtypes = [_i, _p, _p, _p, _p]
         for n in ("ref_geom_pointers", "ref_binning_pointers", "ref_img_pointers"):

@@ -19,11 +19,27 @@
 
 typedef char* (*ref_alloc_fn)(size_t);
 
+// Measurement hook of bench.py's reference arm (my code, not the reference's): every SM that gets a
+// block stores (clock64, globaltimer ns); two probes around a timed region give its average SM clock.
+__global__ void ref_clock_probe_kernel(unsigned long long* out) {
+  if (threadIdx.x == 0) {
+    unsigned smid;
+    unsigned long long t;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    out[2 * smid] = (unsigned long long)clock64();
+    out[2 * smid + 1] = t;
+  }
+}
+
 static thread_local char g_err[512];
 
 extern "C" {
 
 const char* ref_last_error() { return g_err; }
+
+// legacy default stream, like every launch of the reference
+void ref_clock_probe(unsigned long long* out) { ref_clock_probe_kernel<<<148 * 8, 32>>>(out); }
 
 // DGR/cuda_rasterizer/rasterizer.h:31-56 (Rasterizer::forward)
 int ref_forward(ref_alloc_fn geom, ref_alloc_fn binning, ref_alloc_fn img,

@@ -37,15 +37,15 @@ def _data():
     return g, cams, targets
 
 
-def _run_steps(rank, world, steps=3):
+def _run_steps(rank, world, steps=3, batch=V):
     g, cams, targets = _data()
     model = fit.FitModel(g, torch.device("cpu"), fused_adam=False)
-    mine = fit.shard_views(V, rank, world)
+    mine = fit.shard_views(batch, rank, world)
     grad_ptr = model.flat_grad.data_ptr()
     losses = []
     for _ in range(steps):
-        loss = fit.fit_step(model, [cams[i] for i in mine], [targets[i] for i in mine], torch.zeros(3), global_batch=V,
-                            rasterize=fake_rasterize)
+        loss = fit.fit_step(model, [cams[i] for i in mine], [targets[i] for i in mine], torch.zeros(3), global_batch=batch,
+                            rasterize=fake_rasterize, image_size=(W, H))
         losses.append(float(loss))
     assert model.flat_grad.data_ptr() == grad_ptr
     for name, p in model.params.items():  # .grad still aliases the flat buffer
@@ -53,11 +53,11 @@ def _run_steps(rank, world, steps=3):
     return model, losses
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, batch=V):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        model, losses = _run_steps(rank, world)
+        model, losses = _run_steps(rank, world, batch=batch)
         q.put((rank, model.flat.numpy().copy(), model.xyz_gradient_accum.numpy().copy(), model.denom.numpy().copy(),
                model.max_radii2D.numpy().copy(), losses))  # numpy: pickled by value, no shared-memory handles
     finally:
@@ -146,6 +146,21 @@ def test_checkpoint_resume_continues_identically(fused, tmp_path):
     assert a.lrs == b.lrs and a.step_count == b.step_count == 6
 
 
+def test_black_background_flag_follows_the_tensor_not_its_address():
+    """fit._background_is_black: cached per tensor object AND version counter (the flag compiles the background
+    term out of the blend backward; a stale 'black' would silently drop it)."""
+    class M:
+        pass
+    m = M()
+    bg = torch.zeros(3)
+    assert fit._background_is_black(m, bg) == 1
+    bg[1] = 0.5  # in place: same object, same address
+    assert fit._background_is_black(m, bg) == 0
+    other = torch.zeros(3)
+    assert fit._background_is_black(m, other) == 1
+    assert fit._background_is_black(m, torch.ones(3)) == 0
+
+
 def test_flat_views_are_leaves():
     g, _, _ = _data()
     m = fit.FitModel(g, torch.device("cpu"), fused_adam=False)
@@ -157,12 +172,13 @@ def test_flat_views_are_leaves():
     torch.testing.assert_close(a["shs"], g.shs)
 
 
-def test_two_ranks_match_single_process():
-    single, losses1 = _run_steps(0, 1)
+@pytest.mark.parametrize("batch", [V, 1])  # batch 1 on 2 ranks: rank 1's share is EMPTY and it still joins the collectives
+def test_two_ranks_match_single_process(batch):
+    single, losses1 = _run_steps(0, 1, batch=batch)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, batch)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
