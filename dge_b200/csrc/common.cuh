@@ -146,7 +146,7 @@ cudaError_t launch_binning(const ViewParams& vp, int R, GeomState& g, BinState& 
 cudaError_t launch_render_forward(const ViewParams& vp, const GeomState& g, const BinState& b,
                                   ImgState& img, const float* background, float* out_color,
                                   float* out_depth, cudaStream_t stream);
-// acc: [P][12] floats, zeroed by the caller: dmean2D.xy, dconic.xyz(w), dopacity, dcolor.rgb
+// acc: [P][12] floats, zeroed by the caller: the ACC_* slots below
 cudaError_t launch_render_backward(const ViewParams& vp, const GeomState& g, const BinState& b,
                                    const ImgState& img, const float* background,
                                    const float* dL_dpix, float* acc, bool black_background,
@@ -192,8 +192,11 @@ cudaError_t launch_fused_adam(float* param, const float* grad, float* m, float* 
                               float beta1, float beta2, float eps, int step, const uint8_t* mask,
                               int stride, cudaStream_t stream);
 
-// per-Gaussian accumulator slots written by the backward blend
-enum { ACC_MEAN_X = 0, ACC_MEAN_Y, ACC_CONIC_X, ACC_CONIC_Y, ACC_CONIC_W, ACC_OPACITY, ACC_R, ACC_G,
+// per-Gaussian accumulator slots written by the backward blend: moments of q = dL/dG * G over the
+// Gaussian's pixels with d = centre - pixel (sum q dx, q dy, q dx^2, q dx dy, q dy^2), dL/dopacity and
+// dL/dcolour; slot 11 carries the view's visibility / clamp flags (preprocess). geom_bwd.cu turns the
+// moments into dL/dmean2D and dL/dconic.
+enum { ACC_SX = 0, ACC_SY, ACC_SXX, ACC_SXY, ACC_SYY, ACC_OPACITY, ACC_R, ACC_G,
        ACC_B, ACC_FLAGS = 11, ACC_STRIDE = 12 };
 
 // ---- the 64-byte blend record of a Gaussian in a view (written by preprocess) ----

@@ -56,12 +56,24 @@ __device__ __forceinline__ void out4(float* p, size_t idx, float4 v) {
 // ---- K8 + projection part of K9 for ONE view (backward.cu:144-274, :366-387): given the
 // blend-stage sums of this Gaussian, the view's camera and the Gaussian's cov3D, returns the
 // view's contribution to dL/dmean3D (without the SH term) and dL/dcov3D.
+// The blend backward (render_bwd.cu) leaves MOMENT sums over the Gaussian's pixels, with q = dL/dG * G and
+// d = centre - pixel: S = (sum q dx, sum q dy, sum q dx^2, sum q dx dy, sum q dy^2). The reference's
+// per-pair expressions (backward.cu:537-551) are linear in them:
+//   dL/dmean2D.x = -W/2 (cx Sx + cy Sy),  dL/dmean2D.y = -H/2 (cz Sy + cy Sx),
+//   dL/dconic    = -1/2 (Sxx, Sxy, Syy)
+// with the conic (cx, cy, cz) recomputed here bit-identically to the forward's (math_ref.cuh:conic_ref).
+// dblend returns (dL/dmean2D.x, .y, dL/dconic.x, .y, .w).
 __device__ __forceinline__ void view_geom_backward(float mx, float my, float mz, const float* c3,
                                                    const float* V, const float* Pm, float tan_fovx,
-                                                   float tan_fovy, float focal_x, float focal_y,
-                                                   float dm2x, float dm2y, float dcon_x, float dcon_y,
-                                                   float dcon_w, float dmean[3], float dcov[6]) {
+                                                   float tan_fovy, float focal_x, float focal_y, int W, int H,
+                                                   float Sx, float Sy, float Sxx, float Sxy, float Syy,
+                                                   float dblend[5], float dmean[3], float dcov[6]) {
   struct { float tan_fovx, tan_fovy, focal_x, focal_y; } vp = {tan_fovx, tan_fovy, focal_x, focal_y};
+  const float3 con = conic_ref(mx, my, mz, tan_fovx, tan_fovy, focal_x, focal_y, V, c3);
+  const float dm2x = (-0.5f * (float)W) * (con.x * Sx + con.y * Sy);
+  const float dm2y = (-0.5f * (float)H) * (con.z * Sy + con.y * Sx);
+  const float dcon_x = -0.5f * Sxx, dcon_y = -0.5f * Sxy, dcon_w = -0.5f * Syy;
+  dblend[0] = dm2x; dblend[1] = dm2y; dblend[2] = dcon_x; dblend[3] = dcon_y; dblend[4] = dcon_w;
   // ---------------- K8: conic -> cov2D -> cov3D, mean (backward.cu:144-274) ----------------
   float tx = V[0] * mx + V[4] * my + V[8] * mz + V[12];
   float ty = V[1] * mx + V[5] * my + V[9] * mz + V[13];
@@ -267,17 +279,8 @@ __global__ void __launch_bounds__(256) geom_backward_kernel(
   const float4 a0 = __ldg(reinterpret_cast<const float4*>(acc) + 3 * i);
   const float4 a1 = __ldg(reinterpret_cast<const float4*>(acc) + 3 * i + 1);
   const float4 a2 = __ldg(reinterpret_cast<const float4*>(acc) + 3 * i + 2);
-  const float dm2x = a0.x, dm2y = a0.y;
-  const float dcon_x = a0.z, dcon_y = a0.w, dcon_w = a1.x;
   const float dop = a1.y;
   float dcol[3] = {a1.z, a1.w, a2.x};
-
-  out3<ACC>(dL_dmean2D, i, dm2x, dm2y, 0.f);
-  if (dL_dopacity) {
-    if (ACC) dL_dopacity[i] += dop; else dL_dopacity[i] = dop;
-  }
-  if (dL_dconic) out4<ACC>(dL_dconic, i, make_float4(dcon_x, dcon_y, 0.f, dcon_w));
-  if (dL_dcolor) out3<ACC>(dL_dcolor, i, dcol[0], dcol[1], dcol[2]);
 
   float V[16], Pm[16];
 #pragma unroll
@@ -304,9 +307,15 @@ __global__ void __launch_bounds__(256) geom_backward_kernel(
   }
 
   // ---------------- K8 + projection (backward.cu:144-274, :366-387) ----------------
-  float dmean[3], dcov[6];
-  view_geom_backward(mx, my, mz, c3, V, Pm, vp.tan_fovx, vp.tan_fovy, vp.focal_x, vp.focal_y, dm2x, dm2y,
-                     dcon_x, dcon_y, dcon_w, dmean, dcov);
+  float dmean[3], dcov[6], db[5];
+  view_geom_backward(mx, my, mz, c3, V, Pm, vp.tan_fovx, vp.tan_fovy, vp.focal_x, vp.focal_y, vp.W, vp.H, a0.x, a0.y,
+                     a0.z, a0.w, a1.x, db, dmean, dcov);
+  out3<ACC>(dL_dmean2D, i, db[0], db[1], 0.f);
+  if (dL_dopacity) {
+    if (ACC) dL_dopacity[i] += dop; else dL_dopacity[i] = dop;
+  }
+  if (dL_dconic) out4<ACC>(dL_dconic, i, make_float4(db[2], db[3], 0.f, db[4]));
+  if (dL_dcolor) out3<ACC>(dL_dcolor, i, dcol[0], dcol[1], dcol[2]);
   if (dL_dcov3D)
 #pragma unroll
     for (int k = 0; k < 6; k++) {
@@ -488,13 +497,13 @@ __global__ void __launch_bounds__(128, 4) geom_backward_batched_kernel(
     const float* cam = s_cam + v * CAM_FLOATS;
     const float tan_fovx = cam[35], tan_fovy = cam[36];
     const float focal_y = H / (2.0f * tan_fovy), focal_x = W / (2.0f * tan_fovx);
-    float vm[3], vc[6];
-    view_geom_backward(mx, my, mz, c3, cam, cam + 16, tan_fovx, tan_fovy, focal_x, focal_y, a0.x, a0.y, a0.z,
-                       a0.w, a1.x, vm, vc);
+    float vm[3], vc[6], db[5];
+    view_geom_backward(mx, my, mz, c3, cam, cam + 16, tan_fovx, tan_fovy, focal_x, focal_y, W, H, a0.x, a0.y, a0.z,
+                       a0.w, a1.x, db, vm, vc);
 #pragma unroll
     for (int k = 0; k < 6; k++) dcov[k] += vc[k];
-    dm2x += a0.x;
-    dm2y += a0.y;
+    dm2x += db[0];
+    dm2y += db[1];
     dop += a1.y;
     // SH part (backward.cu:20-139)
     const float ox = mx - cam[32], oy = my - cam[33], oz = mz - cam[34];

@@ -63,6 +63,55 @@ __device__ __forceinline__ void cov3d_from_scale_rot(float sx, float sy, float s
   cov[5] = dot3_ref(M20, M20, M21, M21, M22, M22);
 }
 
+// DGR/cuda_rasterizer/forward.cu:74-113 computeCov2D. t = view-space mean.
+__device__ __forceinline__ float3 cov2d_ref(float tx, float ty, float tz, float tan_fovx, float tan_fovy,
+                                            float focal_x, float focal_y, const float* V, const float* c) {
+  const float limx = MUL(tan_fovx, 1.3f), limy = MUL(tan_fovy, 1.3f);
+  const float txtz = __fdiv_rn(tx, tz), tytz = __fdiv_rn(ty, tz);
+  const float cx = fminf(fmaxf(txtz, -limx), limx);
+  const float cy = fminf(fmaxf(tytz, -limy), limy);
+  const float tz2 = MUL(tz, tz);
+  const float J00 = __fdiv_rn(focal_x, tz);
+  const float J02 = __fdiv_rn(MUL(MUL(tz, -cx), focal_x), tz2);
+  const float J11 = __fdiv_rn(focal_y, tz);
+  const float J12 = __fdiv_rn(MUL(MUL(tz, -cy), focal_y), tz2);
+  // T = W * J (GLM): T[i][j] = W[0][j]*J[i][0] + W[1][j]*J[i][1] + W[2][j]*J[i][2], J's literal zeros kept
+  // (they only decide the sign of zero results, as in the reference's SASS)
+  const float Z = 0.0f;
+  const float T00 = dot3_ref(V[0], J00, V[1], Z, V[2], J02);
+  const float T01 = dot3_ref(V[4], J00, V[5], Z, V[6], J02);
+  const float T02 = dot3_ref(V[8], J00, V[9], Z, V[10], J02);
+  const float T10 = dot3_ref(V[0], Z, V[1], J11, V[2], J12);
+  const float T11 = dot3_ref(V[4], Z, V[5], J11, V[6], J12);
+  const float T12 = dot3_ref(V[8], Z, V[9], J11, V[10], J12);
+  // A = T^T * Vrk^T ; A[k][j] = fma(Tj2, Vrk[2][k], fma(Tj0, Vrk[0][k], Tj1*Vrk[1][k]))
+  const float A00 = dot3_ref(T00, c[0], T01, c[1], T02, c[2]);
+  const float A10 = dot3_ref(T00, c[1], T01, c[3], T02, c[4]);
+  const float A20 = dot3_ref(T00, c[2], T01, c[4], T02, c[5]);
+  const float A01 = dot3_ref(T10, c[0], T11, c[1], T12, c[2]);
+  const float A11 = dot3_ref(T10, c[1], T11, c[3], T12, c[4]);
+  const float A21 = dot3_ref(T10, c[2], T11, c[4], T12, c[5]);
+  // cov[i][j] = fma(A[2][j], T[i][2], fma(A[0][j], T[i][0], A[1][j]*T[i][1]))
+  float3 cov;
+  cov.x = ADD(dot3_ref(T00, A00, T01, A10, T02, A20), 0.3f);
+  cov.y = dot3_ref(T00, A01, T01, A11, T02, A21);
+  cov.z = ADD(dot3_ref(T10, A01, T11, A11, T12, A21), 0.3f);
+  return cov;
+}
+
+// The conic (inverse 2-D covariance) of a Gaussian in a view exactly as the forward computes and stores it
+// (preprocess.cu:preprocess_view; forward.cu:218-226): the per-Gaussian backward turns the blend stage's
+// moment sums into dL/dmean2D with it instead of reading the 64-byte record back.
+__device__ __forceinline__ float3 conic_ref(float px, float py, float pz, float tan_fovx, float tan_fovy,
+                                            float focal_x, float focal_y, const float* V, const float* cov3) {
+  const float depth = xform_row(V, 2, px, py, pz);
+  const float tx = xform_row(V, 0, px, py, pz), ty = xform_row(V, 1, px, py, pz);
+  const float3 cov = cov2d_ref(tx, ty, depth, tan_fovx, tan_fovy, focal_x, focal_y, V, cov3);
+  const float det = FMA(cov.x, cov.z, -MUL(cov.y, cov.y));
+  const float inv = __frcp_rn(det);
+  return make_float3(MUL(cov.z, inv), MUL(cov.y, -inv), MUL(cov.x, inv));
+}
+
 // SH constants, DGR/cuda_rasterizer/auxiliary.h:22-39
 #define SH_C0 0.28209479177387814f
 #define SH_C1 0.4886025119029199f

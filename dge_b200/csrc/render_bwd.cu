@@ -6,8 +6,15 @@
 // and alpha arithmetic), but:
 //  * the traversal starts at the tile's largest n_contrib instead of the end of the
 //    tile list, so occluded instances are never touched;
-//  * each thread owns a 2x2 quad and sums its pixels' contributions in registers;
-//  * the nine per-Gaussian partial gradients are reduced across the warp with a
+//  * each thread owns four pixels (one per 8x4 quadrant, blend.cuh) and sums their contributions in registers;
+//  * what a pair contributes is reduced to the MOMENTS of q = dL/dG * G over the Gaussian's pixels
+//    (sum q d, sum q d d^T with d = centre - pixel): the reference's per-pair products with the conic and
+//    with W/2, H/2 (backward.cu:537-551) are linear in them and are applied once per (Gaussian, view) by the
+//    per-Gaussian backward (geom_bwd.cu:view_geom_backward) — 9 instead of 18 instructions per pair;
+//  * the colour behind a pixel (accum_rec) only ever enters dL/dalpha through its dot product with the
+//    pixel's dL/dpixel, so ONE scalar per pixel carries that recurrence instead of three (6 instead of 12
+//    instructions per pair, 8 registers less);
+//  * the nine per-Gaussian partial sums are reduced across the warp with a
 //    transposing butterfly (14 shuffles instead of 45) and leave the SM as ONE
 //    red.global instruction per warp and Gaussian (9 active lanes) instead of the
 //    reference's 9 atomics per contributing (pixel, Gaussian) pair;
@@ -17,8 +24,12 @@
 // kernel in geom_bwd.cu turns them into the reference's output tensors.
 #include "blend.cuh"
 
+// 16 CTAs (32 warps) per SM at 64 registers: measured 2.39 / 2.32 / 2.25 ms per 20-view launch at 12 / 14 / 16
+// (config 2) — once the pair body shrank, hiding the staging and shared-memory latencies mattered more
+// than the 12 bytes of spills the tighter budget costs. (The HAS_BG variant — per-view API, whose launches
+// of ~1000 CTAs cannot fill the SMs anyway — keeps 80 registers.)
 #ifndef DGE_BWD_MIN_CTAS
-#define DGE_BWD_MIN_CTAS 12
+#define DGE_BWD_MIN_CTAS 16
 #endif
 
 namespace dge {
@@ -27,7 +38,7 @@ namespace dge {
 // (backward.cu:526-529); for DGE's black background (DGE.py:87) that term, its division and
 // eight registers of per-pixel state disappear at compile time.
 template <bool HAS_BG>
-__global__ void __launch_bounds__(BL_THREADS, DGE_BWD_MIN_CTAS) render_backward_kernel(
+__global__ void __launch_bounds__(BL_THREADS, HAS_BG ? 12 : DGE_BWD_MIN_CTAS) render_backward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
     const float* __restrict__ background, const float4* __restrict__ rec,
     const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
@@ -55,11 +66,12 @@ __global__ void __launch_bounds__(BL_THREADS, DGE_BWD_MIN_CTAS) render_backward_
   const size_t HW = (size_t)H * W;
   const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
 
-  // behind[p] = colour accumulated behind the current list position, i.e. the reference's
-  // accum_rec AFTER its next update: alpha*c + (1-alpha)*accum is folded in right after a
-  // Gaussian is used instead of right before the next one (same operations, same values, no
-  // last_alpha / last_color registers).
-  float T[4], T_final[4], behind[4][3], dpix[4][3], bg_dot[4];
+  // behind[p] = (colour accumulated behind the current list position) . dL/dpixel, i.e. the reference's
+  // accum_rec AFTER its next update, dotted with this pixel's upstream gradient: alpha*c + (1-alpha)*accum
+  // is folded in right after a Gaussian is used instead of right before the next one, and since
+  // dL/dalpha only needs sum_ch (c_ch - accum_ch) * dL/dpixel_ch, the dot product is carried instead of
+  // the three channels.
+  float T[4], T_final[4], behind[4], dpix[4][3], bg_dot[4];
   uint32_t last[4];
   const float bg0 = __ldg(background), bg1 = __ldg(background + 1), bg2 = __ldg(background + 2);
   uint32_t tmax = 0;
@@ -73,10 +85,8 @@ __global__ void __launch_bounds__(BL_THREADS, DGE_BWD_MIN_CTAS) render_backward_
     last[p] = inside ? n_contrib[pix] : 0;
     tmax = max(tmax, last[p]);
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-      dpix[p][c] = inside ? dL_dpixels[c * HW + pix] : 0.0f;
-      behind[p][c] = 0.0f;
-    }
+    for (int c = 0; c < 3; c++) dpix[p][c] = inside ? dL_dpixels[c * HW + pix] : 0.0f;
+    behind[p] = 0.0f;
     bg_dot[p] = HAS_BG ? bg0 * dpix[p][0] + bg1 * dpix[p][1] + bg2 * dpix[p][2] : 0.0f;
   }
   const uint32_t wmax = __reduce_max_sync(0xFFFFFFFFu, tmax);
@@ -89,7 +99,6 @@ __global__ void __launch_bounds__(BL_THREADS, DGE_BWD_MIN_CTAS) render_backward_
 #pragma unroll
   for (int w = 0; w < BL_WARPS; w++) bmax = max(bmax, s_max[w]);
 
-  const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
 
   stage_init(s, tid);
   uint32_t parity = 0;
@@ -111,9 +120,8 @@ __global__ void __launch_bounds__(BL_THREADS, DGE_BWD_MIN_CTAS) render_backward_
       const uint32_t pos = hi - 1 - j;  // 0-based list position
       const float4 a = s.rec[j][0];   // x, y, conic.x, conic.y
       const float4 b = s.rec[j][1];   // conic.z, power threshold, opacity, depth
-      const float4 cd = s.rec[j][2];  // r, g, b, -
+      const float cd0 = s.rec[j][2].x, cd1 = s.rec[j][2].y, cd2 = s.rec[j][2].z;  // r, g, b
       const float opacity = b.z;
-      const float col[3] = {cd.x, cd.y, cd.z};
 
       float g[9];
 #pragma unroll
@@ -126,34 +134,35 @@ __global__ void __launch_bounds__(BL_THREADS, DGE_BWD_MIN_CTAS) render_backward_
         const float power = pixel_power(a, b.x, dx, dy);
         if (pos >= last[p] || power > 0.0f || power < b.y) continue;
         const float G = expf(power);
-        const float alpha = fminf(0.99f, BMUL(opacity, G));
+        const float oG = BMUL(opacity, G);  // the forward's alpha before the 0.99 clamp, bit for bit
+        const float alpha = fminf(0.99f, oG);
         if (alpha < 1.0f / 255.0f) continue;
         touched = true;
         const float one_m = 1.0f - alpha;
         // the reference's recurrence T /= (1 - alpha) (backward.cu:505); the quotient only feeds
-        // gradients (tolerance 1e-4), so the 2-instruction reciprocal-multiply replaces the IEEE
-        // division sequence (its error, ~1 ulp per step, stays below 1e-5 over a whole list)
-        T[p] = __fdividef(T[p], one_m);
+        // gradients (tolerance 1e-4), so MUFU.RCP + FMUL replace the IEEE division sequence (1 - alpha is in
+        // [0.01, 1]: no range handling needed; ~1 ulp per step stays below 1e-5 over a whole list)
+        float rcp;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(one_m));
+        T[p] *= rcp;
+        const float cd = cd0 * dpix[p][0] + cd1 * dpix[p][1] + cd2 * dpix[p][2];  // colour . dL/dpixel
+        float dL_dalpha = (cd - behind[p]) * T[p];
+        behind[p] = alpha * cd + one_m * behind[p];
+        if (HAS_BG) dL_dalpha -= (T_final[p] * rcp) * bg_dot[p];
         const float w = alpha * T[p];
-        float dL_dalpha = 0.0f;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-          dL_dalpha += (col[c] - behind[p][c]) * dpix[p][c];
-          g[ACC_R + c] += w * dpix[p][c];
-          behind[p][c] = alpha * col[c] + one_m * behind[p][c];
-        }
-        dL_dalpha *= T[p];
-        if (HAS_BG) dL_dalpha += __fdividef(-T_final[p], one_m) * bg_dot[p];
-        const float dL_dG = opacity * dL_dalpha;
-        const float gdx = G * dx, gdy = G * dy;
-        const float dG_ddelx = -gdx * a.z - gdy * a.w;
-        const float dG_ddely = -gdy * b.x - gdx * a.w;
-        g[ACC_MEAN_X] += dL_dG * dG_ddelx * ddelx_dx;
-        g[ACC_MEAN_Y] += dL_dG * dG_ddely * ddely_dy;
-        g[ACC_CONIC_X] += -0.5f * gdx * dx * dL_dG;
-        g[ACC_CONIC_Y] += -0.5f * gdx * dy * dL_dG;
-        g[ACC_CONIC_W] += -0.5f * gdy * dy * dL_dG;
+        g[ACC_R] += w * dpix[p][0];
+        g[ACC_G] += w * dpix[p][1];
+        g[ACC_B] += w * dpix[p][2];
         g[ACC_OPACITY] += G * dL_dalpha;
+        // q = dL/dG * G with dL/dG = opacity * dL/dalpha (the reference back-propagates a clamped alpha as if
+        // it were not, backward.cu:531); moments of q over the pixels
+        const float q = oG * dL_dalpha;
+        const float qx = q * dx, qy = q * dy;
+        g[ACC_SX] += qx;
+        g[ACC_SY] += qy;
+        g[ACC_SXX] += qx * dx;
+        g[ACC_SXY] += qx * dy;
+        g[ACC_SYY] += qy * dy;
       }
       if (!__any_sync(0xFFFFFFFFu, touched)) continue;
 

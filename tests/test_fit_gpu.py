@@ -21,11 +21,56 @@ def _setup(cuda, fused, P=P, W=W, H=H, V=V, scale_median=0.03):
     return fit.FitModel(g, cuda, fused_adam=fused), cams, targets, torch.zeros(3, device=cuda)
 
 
+def _share_fused_activations(model):
+    """model.activations() -> the values of the fused activation kernel (dge_fit_activate) with torch's backward
+    formulas. The autograd path then sees bit-identical activated tensors to the direct path's: torch's own
+    exp / sigmoid / normalize differ from the kernel's by an ulp, which the L1 loss' sign() and the blend's
+    alpha >= 1/255 decisions turn into 1e-5 ... 1e-3 gradient differences that have nothing to do with the
+    rasterizer (measured with tests/gpu_bg_diag.py; the activations themselves are compared in
+    test_fused_activations_match_torch)."""
+    class Acts(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, f_dc, f_rest, op, sc, rot):
+            a = model.activations_fused()
+            out = [a[k].clone() for k in ("shs", "opacities", "scales", "rotations")]
+            ctx.save_for_backward(out[1], out[2], out[3], rot)
+            return tuple(out)
+
+        @staticmethod
+        def backward(ctx, g_sh, g_op, g_sc, g_rot):
+            o, s, q, raw = ctx.saved_tensors
+            nrm = raw.norm(dim=1, keepdim=True).clamp_min(1e-12)
+            return (g_sh[:, :1].contiguous(), g_sh[:, 1:].contiguous(), g_op * o * (1 - o), g_sc * s,
+                    (g_rot - q * (q * g_rot).sum(1, keepdim=True)) / nrm)
+
+    def acts():
+        p = model.params
+        shs, op, sc, rot = Acts.apply(p["f_dc"], p["f_rest"], p["opacity"], p["scaling"], p["rotation"])
+        return {"means3D": p["xyz"], "shs": shs, "opacities": op, "scales": sc, "rotations": rot}
+    model.activations = acts
+
+
+def test_fused_activations_match_torch(cuda):
+    """dge_fit_activate against GaussianModel's activations (gaussian_model.py:221-258) as torch evaluates them,
+    after an optimiser step has made the raw quaternions non-unit: equal to a few ulp."""
+    model, cams, targets, bg = _setup(cuda, True)
+    fit.fit_step(model, cams, targets, bg, global_batch=V)
+    want, got = model.activations(), model.activations_fused()
+    torch.cuda.synchronize()
+    for k in ("shs", "opacities", "scales", "rotations"):
+        w, g = want[k].detach(), got[k]
+        err = float(((g - w).abs() / w.abs().clamp_min(1e-30)).max())
+        print(f"activations {k}: max relative difference {err:.2e}")
+        assert err <= 5e-7, (k, err)
+    assert torch.equal(got["shs"], want["shs"].detach())  # a concatenation: exact
+
+
 @pytest.mark.parametrize("streams,bgv,batched", [(1, 0.0, False), (3, 0.0, False), (2, 0.4, False), (1, 0.0, True),
                                                  (1, 0.4, True), (2, 0.0, True)])
 def test_direct_path_matches_autograd_path(cuda, streams, bgv, batched):
     ref_model, cams, targets, bg = _setup(cuda, True)
     model, _, _, _ = _setup(cuda, True)
+    _share_fused_activations(ref_model)
     bg = bg + bgv
     for step in range(2):
         l_ref = fit.fit_step(ref_model, cams, targets, bg, global_batch=V, direct=False, num_streams=1)
@@ -36,6 +81,7 @@ def test_direct_path_matches_autograd_path(cuda, streams, bgv, batched):
         assert abs(float(l) - float(l_ref)) <= 1e-5 * abs(float(l_ref))
         for name, sl in list(model.slices.items()) + [("means2D", model.means2D_slice)]:
             ok, msg = util.grad_ok(model.flat_grad[sl].cpu().numpy(), g_ref[sl].cpu().numpy())
+            print(f"step {step} {name}: {msg}")
             assert ok, (step, name, msg)
         assert torch.equal(model.max_radii2D, ref_model.max_radii2D)
         assert torch.equal(model.denom, ref_model.denom)
