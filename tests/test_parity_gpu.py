@@ -152,10 +152,12 @@ def _all_cov3d(g):
     return torch.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], 1).contiguous()
 
 
-@pytest.mark.parametrize("CH", [1, 3])
-def test_apply_weights_vs_reference(cuda, CH):
+@pytest.mark.parametrize("CH,soft", [(1, False), (2, False), (3, False), (1, True), (2, True)])
+def test_apply_weights_vs_reference(cuda, CH, soft):
     """DGE mask back-projection over several views, accumulated in place (DGE.py:112-147). Binary masks:
-    float sums are exact integers, so weights and cnt must be IDENTICAL to the reference's."""
+    float sums are exact integers, so weights and cnt must be IDENTICAL to the reference's. Soft masks
+    (fractional values, one different image per channel): cnt identical, weights equal up to the order of the
+    float atomics (1e-5 relative)."""
     if not _ref_available():
         pytest.skip("oracle/_ref/libref_rast.so not built")
     from dge_b200 import diff_gaussian_rasterization as dgr
@@ -163,7 +165,10 @@ def test_apply_weights_vs_reference(cuda, CH):
     P, W, H, V = 30000, 200, 136, 3
     g = scene.make_gaussians(P, seed=31, scale_median=0.03)
     gd = util.to_dev(g, cuda)
-    mask = scene.disc_mask(W, H, radius=50).repeat(CH, 1, 1).contiguous().to(cuda)
+    if soft:
+        mask = torch.rand(CH, H, W, generator=torch.Generator().manual_seed(12)).contiguous().to(cuda)
+    else:
+        mask = scene.disc_mask(W, H, radius=50).repeat(CH, 1, 1).contiguous().to(cuda)
     w_ours = torch.zeros(P, CH, device=cuda)
     c_ours = torch.zeros(P, 1, dtype=torch.int32, device=cuda)
     w_ref, c_ref = torch.zeros_like(w_ours), torch.zeros_like(c_ours)
@@ -186,12 +191,19 @@ def test_apply_weights_vs_reference(cuda, CH):
     torch.cuda.synchronize()
     assert c_ours.sum().item() > 0
     assert torch.equal(c_ours, c_ref)
-    assert torch.equal(w_ours, w_ref)
     assert np.array_equal(c_ours.cpu().numpy().reshape(-1), c_or)
-    assert np.array_equal(w_ours.cpu().numpy().astype(np.float64), w_or)
-    # DGE's selection (DGE.py:149-152) is therefore identical too
-    sel = (w_ours / (c_ours + 1e-7)) > 0.8
-    assert torch.equal(sel, (w_ref / (c_ref + 1e-7)) > 0.8)
+    if soft:
+        err = util.rel_err(w_ours.cpu().numpy(), w_ref.cpu().numpy())
+        err_o = util.rel_err(w_ours.cpu().numpy().astype(np.float64), w_or)
+        print(f"apply_weights CH={CH} soft mask: max|ours-ref|/max|ref| = {err:.2e}, vs oracle {err_o:.2e}")
+        assert err <= 1e-5 and err_o <= 1e-5
+    else:
+        assert torch.equal(w_ours, w_ref)
+        assert np.array_equal(w_ours.cpu().numpy().astype(np.float64), w_or)
+    # DGE's selection (DGE.py:149-152) is therefore identical too (binary masks)
+    if not soft:
+        sel = (w_ours / (c_ours + 1e-7)) > 0.8
+        assert torch.equal(sel, (w_ref / (c_ref + 1e-7)) > 0.8)
 
 
 def test_mark_visible_and_edge_cases(cuda):
@@ -203,8 +215,13 @@ def test_mark_visible_and_edge_cases(cuda):
     rast = dgr.GaussianRasterizer(rs)
     gd = util.to_dev(g, cuda)
     vis = rast.markVisible(gd.means3D)
-    pv = torch.cat([gd.means3D, torch.ones(5000, 1, device=cuda)], 1) @ cam.world_view_transform
-    assert vis.dtype == torch.bool and (vis != (pv[:, 2] > 0.2)).sum().item() <= 2  # fp contraction at the threshold
+    assert vis.dtype == torch.bool and 0 < int(vis.sum()) <= 5000
+    if _ref_available():  # K12 checkFrustum of the reference (rasterizer_impl.cu:53-63, :128-133): identical
+        from oracle import ref
+        for c in [cam] + [scene.camera_to(c, cuda) for c in scene.ring_cameras(5, 64, 64)[1:]]:
+            r = dgr.GaussianRasterizer(scene.raster_settings(c, bg, 3, module=dgr))
+            pts = torch.cat([gd.means3D, c.camera_center[None] + 0.2 * torch.randn(500, 3, device=cuda)])  # some near the plane
+            assert torch.equal(r.markVisible(pts), ref.mark_visible(pts, c.world_view_transform, c.full_proj_transform))
     # exactly-one-of checks (DGR/diff_gaussian_rasterization/__init__.py:271-283)
     with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
         rast(gd.means3D, torch.zeros_like(gd.means3D), gd.opacities, scales=gd.scales, rotations=gd.rotations)
