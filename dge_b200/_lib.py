@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # DGE_B200_LIB: an alternative build of the SAME library (A/B measurements of kernel variants)
 LIB_PATH = os.environ.get("DGE_B200_LIB") or os.path.join(_HERE, "_build", "libdge_b200.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
@@ -43,19 +43,19 @@ _SIGNATURES = {
     "dge_profile_enable": (None, [C.c_uint]),
     "dge_profile_read": (_i, [C.POINTER(C.c_float), C.POINTER(_i)]),
     "dge_fit_forward": (_i, [ALLOC_FN, ALLOC_FN, ALLOC_FN, _p, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _f, _p, _p,
-                             _f, _f, _p, _p, _p, _p, _p]),
+                             _f, _f, _p, _p, _p, _p, _p, _p]),
     "dge_fit_backward_blend": (_i, [_i, _i, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "dge_fit_views_forward": (_i, [ALLOC_FN, ALLOC_FN, ALLOC_FN, _p, _i, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _f, _p,
-                                   _p, _p, _p, _p, _p, C.c_size_t, _p, _p, _p, _i, _p]),
+                                   _p, _p, _p, _p, _p, C.c_size_t, _p, C.c_size_t, _p, _p, _p, _i, _p]),
     "dge_fit_views_backward_blend": (_i, [_i, _i, _i, _p, _i, _i, _i, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "dge_fit_binning_bytes": (C.c_size_t, [_i, _i, _i, _i]),
     "dge_fit_views_apply_weights": (_i, [ALLOC_FN, ALLOC_FN, ALLOC_FN, _p, _i, _i, _i, _i, _p, _p, _p, _f, _p, _p, _p, _i,
                                          _p, _p, _p, _i, _p]),
-    "dge_fit_backward_geom": (_i, [_i, _i, _i, _i, _p, _i, _i, _f, _p, C.c_size_t, _p, _p, _p, _p, _p, _p, _p, _p,
-                                   _p, _p, _i, _p]),
+    "dge_fit_backward_geom": (_i, [_i, _i, _i, _i, _p, _i, _i, _f, _p, C.c_size_t, _p, C.c_size_t, _p, _p, _p, _p, _p, _p,
+                                   _p, _p, _p, _p, _i, _p]),
     "dge_fit_activate": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
-    "dge_fit_backward_geom_raw": (_i, [_i, _i, _i, _p, _i, _i, _f, _p, C.c_size_t, _p, _p, _p, _p, _p, _p, _p, _p, _p,
-                                       _p, _p, _p, _p, _p]),
+    "dge_fit_backward_geom_raw": (_i, [_i, _i, _i, _p, _i, _i, _f, _p, C.c_size_t, _p, C.c_size_t, _p, _p, _p, _p, _p,
+                                       _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "dge_l1_loss_grad": (_i, [_p, _p, C.c_size_t, _f, _p, _p, _p]),
     "dge_fused_adam": (_i, [_p, _p, _p, _p, C.c_size_t, _f, _f, _f, _f, _i, _p, _i, _p]),
 }

@@ -175,7 +175,7 @@ static int bin_view(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge
                     const float* colors_precomp, int colors_mode, const float* opacities,
                     const float* scales, const float* rotations, const float* cov3D_precomp,
                     bool prefiltered, int* radii, bool debug, cudaStream_t stream, GeomState& g,
-                    BinState& b, ImgState& img, float* acc_init = nullptr) {
+                    BinState& b, ImgState& img, uint8_t* flags_out = nullptr) {
   if (vp.grid_x > 65535 || vp.grid_y > 65535) return fail_msg("image too large (tile grid > 65535)");
   if (cov3D_precomp == nullptr && (scales == nullptr || rotations == nullptr))
     return fail_msg("need scales+rotations or cov3D_precomp");
@@ -186,7 +186,7 @@ static int bin_view(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge
   carve_geom(gp, vp.P, &g);
   carve_image(ip, vp.W, vp.H, &img);
   STAGE(ST_PREPROCESS, "preprocess", launch_preprocess(vp, means3D, scales, rotations, opacities, shs, cov3D_precomp,
-                                        colors_precomp, colors_mode, prefiltered, radii, g, acc_init, stream));
+                                        colors_precomp, colors_mode, prefiltered, radii, g, flags_out, stream));
   CK("num_rendered copy", cudaMemcpyAsync(g_slot.pinned, g.counters, sizeof(uint32_t),
                                           cudaMemcpyDeviceToHost, stream));
   CK("event record", cudaEventRecord(g_slot.ev, stream));
@@ -199,6 +199,50 @@ static int bin_view(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge
   carve_binning(bp, (int)R, vp.W, vp.H, &b);
   STAGE(ST_BINNING, "binning", launch_binning(vp, (int)R, g, b, img, stream));
   return (int)R;
+}
+
+// Zeroing of a step's blend-stage sums beside the forward blend: forked from `stream` onto a side stream;
+// the backward blend of the same `acc` joins it (wait_acc_zero). One slot per in-flight batch (the chunks of
+// a step each have their own rows).
+struct AccZero { const void* acc; cudaEvent_t done; };
+static thread_local cudaStream_t g_zero_stream = nullptr;
+static thread_local cudaEvent_t g_zero_fork = nullptr;
+static thread_local AccZero g_zero[16];
+
+static cudaError_t zero_acc_async(float* acc, size_t acc_stride_floats, int P, int V, cudaStream_t stream) {
+  cudaError_t e;
+  if (g_zero_stream == nullptr) {
+    if ((e = cudaStreamCreateWithFlags(&g_zero_stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&g_zero_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+    for (AccZero& z : g_zero) {
+      z.acc = nullptr;
+      if ((e = cudaEventCreateWithFlags(&z.done, cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+  }
+  AccZero* slot = nullptr;
+  for (AccZero& z : g_zero)
+    if (z.acc == acc || (slot == nullptr && z.acc == nullptr)) { slot = &z; if (z.acc == acc) break; }
+  if (slot == nullptr) {  // more batches in flight than slots: zero in line
+    return cudaMemset2DAsync(acc, acc_stride_floats * sizeof(float), 0, sizeof(float) * ACC_STRIDE * (size_t)P, V, stream);
+  }
+  if ((e = cudaEventRecord(g_zero_fork, stream)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(g_zero_stream, g_zero_fork, 0)) != cudaSuccess) return e;
+  if (acc_stride_floats == (size_t)ACC_STRIDE * P)
+    e = cudaMemsetAsync(acc, 0, sizeof(float) * acc_stride_floats * (size_t)V, g_zero_stream);
+  else
+    e = cudaMemset2DAsync(acc, acc_stride_floats * sizeof(float), 0, sizeof(float) * ACC_STRIDE * (size_t)P, V, g_zero_stream);
+  if (e != cudaSuccess) return e;
+  slot->acc = acc;
+  return cudaEventRecord(slot->done, g_zero_stream);
+}
+
+static cudaError_t wait_acc_zero(const float* acc, cudaStream_t stream) {
+  for (AccZero& z : g_zero)
+    if (z.acc == acc && acc != nullptr) {
+      z.acc = nullptr;
+      return cudaStreamWaitEvent(stream, z.done, 0);
+    }
+  return cudaSuccess;  // the caller zeroed the rows itself
 }
 
 // Measurement hook: every SM that gets a block stores its cycle counter and the global nanosecond timer.
@@ -223,7 +267,7 @@ using namespace dge;
 extern "C" {
 
 const char* dge_last_error(void) { return g_err; }
-int dge_abi_version(void) { return 10; }
+int dge_abi_version(void) { return 11; }
 unsigned long long dge_launch_count(void) { return g_kernel_launches; }
 
 int dge_clock_probe(unsigned long long* out, void* stream_) {
@@ -298,17 +342,18 @@ int dge_fit_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge
                         int height, const float* means3D, const float* shs, const float* opacities,
                         const float* scales, float scale_modifier, const float* rotations,
                         const float* cam, float tan_fovx, float tan_fovy, float* out_color,
-                        float* out_depth, int* radii, float* acc, void* stream_) {
+                        float* out_depth, int* radii, float* acc, uint8_t* flags, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool debug = false;
   if (P == 0 || width <= 0 || height <= 0) return fail_msg("empty problem");
+  if (acc != nullptr) CK("acc memset", cudaMemsetAsync(acc, 0, sizeof(float) * ACC_STRIDE * (size_t)P, stream));
   const ViewParams vp = make_view(P, D, M, width, height, cam, cam + 16, cam + 32, tan_fovx, tan_fovy,
                                   scale_modifier);
   GeomState g;
   BinState b;
   ImgState img;
   const int R = bin_view(geometryBuffer, binningBuffer, imageBuffer, alloc_ctx, vp, means3D, shs, nullptr, 0,
-                         opacities, scales, rotations, nullptr, false, radii, debug, stream, g, b, img, acc);
+                         opacities, scales, rotations, nullptr, false, radii, debug, stream, g, b, img, flags);
   if (R < 0) return R;
   STAGE(ST_RENDER_FWD, "render forward",
         launch_render_forward(vp, g, b, img, background, out_color, out_depth, stream));
@@ -331,7 +376,7 @@ size_t dge_fit_binning_bytes(int R_total, int V, int width, int height) {
 static int bin_views(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge_alloc_fn imageBuffer,
                      void* alloc_ctx, const ViewParams& vp, int V, const float* means3D, const float* shs,
                      const float* opacities, const float* scales, const float* rotations, const float* cams,
-                     int* radii_max, float* acc, size_t acc_stride_floats, int* num_rendered_host,
+                     int* radii_max, uint8_t* flags, size_t flags_stride, int* num_rendered_host,
                      bool prune_lists, cudaStream_t stream, GeomState& g0, BinState& b, ImgState& img0,
                      ViewBatch& vb) {
   const bool debug = false;
@@ -351,7 +396,7 @@ static int bin_views(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dg
   vb.seg_off = batch_seg_off(g0);
   vb.cams = cams;
   STAGE(ST_PREPROCESS, "preprocess (batched)",
-        launch_preprocess_batched(vp, vb, means3D, scales, rotations, opacities, shs, g0, acc, acc_stride_floats,
+        launch_preprocess_batched(vp, vb, means3D, scales, rotations, opacities, shs, g0, flags, flags_stride,
                                   radii_max, prune_lists, stream));
   CK("segment offsets", launch_seg_offsets(vb, g0, batch_seg_off(g0), stream));
   CK("num_rendered copy", cudaMemcpyAsync(g_slot.pinned, batch_seg_off(g0), sizeof(uint32_t) * (V + 1),
@@ -380,11 +425,14 @@ int dge_fit_views_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffe
                           int height, const float* means3D, const float* shs, const float* opacities,
                           const float* scales, float scale_modifier, const float* rotations,
                           const float* cams, float* out_color, float* out_depth, int* radii_max, float* acc,
-                          size_t acc_stride_floats, int* num_rendered_host, const float* extra, float* out_extra,
-                          int prune_lists, void* stream_) {
+                          size_t acc_stride_floats, uint8_t* flags, size_t flags_stride, int* num_rendered_host,
+                          const float* extra, float* out_extra, int prune_lists, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool debug = false;
   if (P == 0 || width <= 0 || height <= 0) return fail_msg("empty problem");
+  if ((acc == nullptr) != (flags == nullptr)) return fail_msg("acc and flags go together");
+  if (acc != nullptr && (acc_stride_floats < (size_t)ACC_STRIDE * P || (acc_stride_floats & 3) || flags_stride < (size_t)P))
+    return fail_msg("acc_stride_floats >= 12 P (a multiple of 4) and flags_stride >= P are required");
   if ((extra == nullptr) != (out_extra == nullptr)) return fail_msg("extra and out_extra go together");
   if (M != 16 || shs == nullptr) return fail_msg("the batched fit path needs SH degree-3 storage (M == 16)");
   // tan_fov / focal are per view and filled in by the batched preprocess from the camera records
@@ -394,9 +442,12 @@ int dge_fit_views_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffe
   BinState b;
   ViewBatch vb;
   const int R_total = bin_views(geometryBuffer, binningBuffer, imageBuffer, alloc_ctx, vp, V, means3D, shs, opacities,
-                                scales, rotations, cams, radii_max, acc, acc_stride_floats, num_rendered_host,
+                                scales, rotations, cams, radii_max, flags, flags_stride, num_rendered_host,
                                 prune_lists != 0, stream, g0, b, img0, vb);
   if (R_total < 0) return R_total;
+  // the views' rows of blend-stage sums start at zero: a memset on a side stream, forked here so that it runs
+  // beside the forward blend (issue-bound, 3 % of the DRAM bandwidth) instead of inside preprocess
+  if (acc != nullptr) CK("acc zero", zero_acc_async(acc, acc_stride_floats, P, V, stream));
   STAGE(ST_RENDER_FWD, "render forward (batched)",
         launch_render_forward_batched(vp, vb, g0, b, img0, background, out_color, out_depth, stream, extra,
                                       out_extra));
@@ -447,6 +498,7 @@ int dge_fit_views_backward_blend(int P, int V, int R_total, const float* backgro
   carve_binning_batched(binning_buffer, (uint32_t)R_total, V, vp.grid_x * vp.grid_y, &b);
   vb.seg_off = batch_seg_off(g0);
   vb.cams = nullptr;
+  CK("acc zero wait", wait_acc_zero(acc, stream));
   STAGE(ST_RENDER_BWD, "render backward (batched)",
         launch_render_backward_batched(vp, vb, g0, b, img0, background, dL_dpix, acc, acc_stride_floats,
                                        background_is_black != 0, stream));
@@ -473,7 +525,7 @@ int dge_fit_backward_blend(int P, int R, const float* background, int background
 
 int dge_fit_backward_geom(int P, int D, int M, int V, const float* cams, int width, int height,
                           float scale_modifier, const float* acc, size_t acc_stride_floats,
-                          const float* means3D, const float* shs, const float* scales, const float* rotations,
+                          const uint8_t* flags, size_t flags_stride, const float* means3D, const float* shs, const float* scales, const float* rotations,
                           float* dL_dmean3D, float* dL_dmean2D, float* dL_dsh, float* dL_dopacity,
                           float* dL_dscale, float* dL_drot, int accumulate, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -481,7 +533,7 @@ int dge_fit_backward_geom(int P, int D, int M, int V, const float* cams, int wid
   if (P == 0) return 0;
   STAGE(ST_GEOM_BWD, "batched geometry backward",
         launch_geom_backward_batched(P, D, M, V, cams, width, height, scale_modifier, acc, acc_stride_floats,
-                                     means3D, shs, scales, rotations, dL_dmean3D, dL_dmean2D, dL_dsh,
+                                     flags, flags_stride, means3D, shs, scales, rotations, dL_dmean3D, dL_dmean2D, dL_dsh,
                                      dL_dopacity, dL_dscale, dL_drot, accumulate != 0, stream));
   return 0;
 }
@@ -497,7 +549,7 @@ int dge_fit_activate(int P, const float* f_dc, const float* f_rest, const float*
 
 int dge_fit_backward_geom_raw(int P, int D, int V, const float* cams, int width, int height,
                               float scale_modifier, const float* acc, size_t acc_stride_floats,
-                              const float* means3D, const float* shs, const float* opacities,
+                              const uint8_t* flags, size_t flags_stride, const float* means3D, const float* shs, const float* opacities,
                               const float* scales, const float* rotations, const float* rotation_raw,
                               float* d_xyz, float* d_means2D, float* d_f_dc, float* d_f_rest,
                               float* d_opacity_raw, float* d_scaling_raw, float* d_rotation_raw,
@@ -508,7 +560,7 @@ int dge_fit_backward_geom_raw(int P, int D, int V, const float* cams, int width,
   if (rotation_raw == nullptr) return fail_msg("rotation_raw is required");
   STAGE(ST_GEOM_BWD, "batched geometry backward (raw)",
         launch_geom_backward_batched(P, D, 16, V, cams, width, height, scale_modifier, acc, acc_stride_floats,
-                                     means3D, shs, scales, rotations, d_xyz, d_means2D, d_f_dc, d_opacity_raw,
+                                     flags, flags_stride, means3D, shs, scales, rotations, d_xyz, d_means2D, d_f_dc, d_opacity_raw,
                                      d_scaling_raw, d_rotation_raw, false, stream, opacities, rotation_raw,
                                      d_f_rest));
   return 0;

@@ -124,10 +124,11 @@ cudaError_t launch_preprocess(const ViewParams& vp, const float* means3D, const 
                               const float* rotations, const float* opacities, const float* shs,
                               const float* cov3D_precomp, const float* colors_precomp,
                               int colors_mode, bool prefiltered, int* radii, GeomState& g,
-                              float* acc_init, cudaStream_t stream);
+                              uint8_t* flags_out, cudaStream_t stream);
 // fit step: per-Gaussian backward of V views in one pass (cams: V records of 40 floats)
 cudaError_t launch_geom_backward_batched(int P, int D, int M, int V, const float* cams, int W, int H,
                                          float scale_modifier, const float* acc, size_t acc_stride,
+                                         const uint8_t* flags, size_t flags_stride,
                                          const float* means3D, const float* shs, const float* scales,
                                          const float* rotations, float* dL_dmean3D, float* dL_dmean2D,
                                          float* dL_dsh, float* dL_dopacity, float* dL_dscale,
@@ -160,7 +161,7 @@ cudaError_t launch_geom_backward(const ViewParams& vp, const float* means3D, con
 // fit step: all V views of a step per launch (preprocess.cu, binning.cu, render_fwd.cu, render_bwd.cu)
 cudaError_t launch_preprocess_batched(const ViewParams& vp, const ViewBatch& vb, const float* means3D,
                                       const float* scales, const float* rotations, const float* opacities,
-                                      const float* shs, GeomState& g0, float* acc, size_t acc_stride_floats,
+                                      const float* shs, GeomState& g0, uint8_t* flags, size_t flags_stride,
                                       int* radii_max, bool prune_lists, cudaStream_t stream);
 cudaError_t launch_seg_offsets(const ViewBatch& vb, const GeomState& g0, uint32_t* seg_off, cudaStream_t stream);
 cudaError_t launch_depth_sort_batched(int P, const ViewBatch& vb, GeomState& g0, cudaStream_t stream);
@@ -194,10 +195,10 @@ cudaError_t launch_fused_adam(float* param, const float* grad, float* m, float* 
 
 // per-Gaussian accumulator slots written by the backward blend: moments of q = dL/dG * G over the
 // Gaussian's pixels with d = centre - pixel (sum q dx, q dy, q dx^2, q dx dy, q dy^2), dL/dopacity and
-// dL/dcolour; slot 11 carries the view's visibility / clamp flags (preprocess). geom_bwd.cu turns the
-// moments into dL/dmean2D and dL/dconic.
+// dL/dcolour. geom_bwd.cu turns the
+// moments into dL/dmean2D and dL/dconic. Rows are 12 floats (three 16-byte loads), slots 9-11 unused.
 enum { ACC_SX = 0, ACC_SY, ACC_SXX, ACC_SXY, ACC_SYY, ACC_OPACITY, ACC_R, ACC_G,
-       ACC_B, ACC_FLAGS = 11, ACC_STRIDE = 12 };
+       ACC_B, ACC_STRIDE = 12 };
 
 // ---- the 64-byte blend record of a Gaussian in a view (written by preprocess) ----
 //  q0: x, y (pixel-space centre), conic.x, conic.y

@@ -422,7 +422,8 @@ constexpr int MAX_BATCH_VIEWS = 64;
 template <bool RAW>
 __global__ void __launch_bounds__(128, 4) geom_backward_batched_kernel(
     int P, int D, int M, int V, const float* __restrict__ cams, int W, int H, float scale_modifier,
-    const float* __restrict__ acc, size_t acc_stride, const float* __restrict__ means3D,
+    const float* __restrict__ acc, size_t acc_stride, const uint8_t* __restrict__ flags, size_t flags_stride,
+    const float* __restrict__ means3D,
     const float* __restrict__ shs, const float* __restrict__ scales, const float* __restrict__ rotations,
     const float* __restrict__ opacities, const float* __restrict__ rotation_raw,
     float* __restrict__ dL_dmean3D, float* __restrict__ dL_dmean2D, float* __restrict__ dL_dsh,
@@ -454,46 +455,48 @@ __global__ void __launch_bounds__(128, 4) geom_backward_batched_kernel(
   // lanes had work per view when the views were walked in lock-step). Every term below is
   // linear in the nine sums, so such views are skipped; each lane then walks ITS OWN list of
   // non-empty views, and a warp iterates max-over-lanes(#non-empty) times instead of V times.
+  // Visibility and the SH clamp mask come from the view's flag bytes (one coalesced byte load per view),
+  // the sums of the visible views from their 48-byte rows.
   bool any = false;
   unsigned long long todo = 0ull;
+  unsigned long long clampbits[3] = {0ull, 0ull, 0ull};  // bit v: channel clamped in view v
   // Four views at a time, all loads of a level issued before any is used: walked one view after the
-  // other, the two dependent loads per view (flags, then the sums) put 2 V memory round trips on
-  // every thread's critical path — that latency, not bandwidth, was the kernel's time (0.58 ms for
-  // 1.4 GB at 16 warps per SM).
+  // other, the dependent loads per view put 2 V memory round trips on every thread's critical path —
+  // that latency, not bandwidth, was the kernel's time.
   for (int v0 = 0; v0 < V; v0 += 4) {
-    float4 a2[4];
-    const float4* row[4];
+    uint32_t fl[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      row[k] = reinterpret_cast<const float4*>(acc + (size_t)min(v0 + k, V - 1) * acc_stride) + 3 * i;
-      a2[k] = __ldg(row[k] + 2);
-    }
+    for (int k = 0; k < 4; k++) fl[k] = v0 + k < V ? (uint32_t)__ldg(flags + (size_t)(v0 + k) * flags_stride + i) : 0u;
     unsigned vis = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++)
-      if (v0 + k < V && (__float_as_uint(a2[k].w) & 1u)) vis |= 1u << k;
+      if (fl[k] & 1u) vis |= 1u << k;
     if (!vis) continue;
     any = true;
-    float4 a0[4], a1[4];
+    float4 a0[4], a1[4], a2[4];
 #pragma unroll
     for (int k = 0; k < 4; k++)
       if ((vis >> k) & 1u) {
-        a0[k] = __ldg(row[k]);
-        a1[k] = __ldg(row[k] + 1);
+        const float4* row = reinterpret_cast<const float4*>(acc + (size_t)(v0 + k) * acc_stride) + 3 * i;
+        a0[k] = __ldg(row);
+        a1[k] = __ldg(row + 1);
+        a2[k] = __ldg(row + 2);
       }
 #pragma unroll
     for (int k = 0; k < 4; k++)
       if (((vis >> k) & 1u) &&
           (a0[k].x != 0.f || a0[k].y != 0.f || a0[k].z != 0.f || a0[k].w != 0.f || a1[k].x != 0.f || a1[k].y != 0.f ||
-           a1[k].z != 0.f || a1[k].w != 0.f || a2[k].x != 0.f))
+           a1[k].z != 0.f || a1[k].w != 0.f || a2[k].x != 0.f)) {
         todo |= 1ull << (v0 + k);
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) clampbits[ch] |= (unsigned long long)((fl[k] >> (1 + ch)) & 1u) << (v0 + k);
+      }
   }
   while (todo) {
     const int v = __ffsll((long long)todo) - 1;
     todo &= todo - 1ull;
     const float4* row = reinterpret_cast<const float4*>(acc + (size_t)v * acc_stride) + 3 * i;
     const float4 a0 = __ldg(row), a1 = __ldg(row + 1), a2 = __ldg(row + 2);
-    const uint32_t flags = __float_as_uint(a2.w);
     const float* cam = s_cam + v * CAM_FLOATS;
     const float tan_fovx = cam[35], tan_fovy = cam[36];
     const float focal_y = H / (2.0f * tan_fovy), focal_x = W / (2.0f * tan_fovx);
@@ -512,7 +515,7 @@ __global__ void __launch_bounds__(128, 4) geom_backward_batched_kernel(
     float dRGB[3] = {a1.z, a1.w, a2.x};
 #pragma unroll
     for (int ch = 0; ch < 3; ch++)
-      if ((flags >> (1 + ch)) & 1u) dRGB[ch] = 0.f;
+      if ((clampbits[ch] >> v) & 1ull) dRGB[ch] = 0.f;
     float b[16], gx[16], gy[16], gz[16];
     sh_basis_grad(D, x, y, z, b, gx, gy, gz);
     float ddx = 0.f, ddy = 0.f, ddz = 0.f;
@@ -678,24 +681,25 @@ cudaError_t launch_activate(int P, const float* f_dc, const float* f_rest, const
 
 cudaError_t launch_geom_backward_batched(int P, int D, int M, int V, const float* cams, int W, int H,
                                          float scale_modifier, const float* acc, size_t acc_stride,
+                                         const uint8_t* flags, size_t flags_stride,
                                          const float* means3D, const float* shs, const float* scales,
                                          const float* rotations, float* dL_dmean3D, float* dL_dmean2D,
                                          float* dL_dsh, float* dL_dopacity, float* dL_dscale,
                                          float* dL_drot, bool accumulate, cudaStream_t stream,
                                          const float* opacities, const float* rotation_raw,
                                          float* dL_drest) {
-  if (V < 1 || V > MAX_BATCH_VIEWS) return cudaErrorInvalidValue;
+  if (V < 1 || V > MAX_BATCH_VIEWS || flags == nullptr) return cudaErrorInvalidValue;
   size_t smem = V * CAM_FLOATS * sizeof(float);
   if (rotation_raw != nullptr) {
     smem = smem > 128 * 45 * sizeof(float) ? smem : 128 * 45 * sizeof(float);  // the staged f_rest block
     if (M != 16 || (reinterpret_cast<uintptr_t>(dL_drest) & 15)) return cudaErrorInvalidValue;  // 16-byte aligned f_rest rows
     geom_backward_batched_kernel<true><<<(P + 127) / 128, 128, smem, stream>>>(
-        P, D, M, V, cams, W, H, scale_modifier, acc, acc_stride, means3D, shs, scales, rotations, opacities,
-        rotation_raw, dL_dmean3D, dL_dmean2D, dL_dsh, dL_drest, dL_dopacity, dL_dscale, dL_drot, false);
+        P, D, M, V, cams, W, H, scale_modifier, acc, acc_stride, flags, flags_stride, means3D, shs, scales, rotations,
+        opacities, rotation_raw, dL_dmean3D, dL_dmean2D, dL_dsh, dL_drest, dL_dopacity, dL_dscale, dL_drot, false);
   } else {
     geom_backward_batched_kernel<false><<<(P + 127) / 128, 128, smem, stream>>>(
-        P, D, M, V, cams, W, H, scale_modifier, acc, acc_stride, means3D, shs, scales, rotations, nullptr,
-        nullptr, dL_dmean3D, dL_dmean2D, dL_dsh, nullptr, dL_dopacity, dL_dscale, dL_drot, accumulate);
+        P, D, M, V, cams, W, H, scale_modifier, acc, acc_stride, flags, flags_stride, means3D, shs, scales, rotations,
+        nullptr, nullptr, dL_dmean3D, dL_dmean2D, dL_dsh, nullptr, dL_dopacity, dL_dscale, dL_drot, accumulate);
   }
   DGE_LAUNCHED(1);
   return cudaGetLastError();

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(
     const float* __restrict__ rotations, const float* __restrict__ opacities,
     const float* __restrict__ shs, const float* __restrict__ cov3D_precomp,
     const float* __restrict__ colors_precomp, int colors_mode, bool prefiltered,
-    int* __restrict__ radii, GeomState g, float4* __restrict__ acc_init) {
+    int* __restrict__ radii, GeomState g, uint8_t* __restrict__ flags_out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t tiles = 0;
   if (idx < vp.P) {
@@ -244,15 +244,9 @@ __global__ void __launch_bounds__(256) preprocess_kernel(
     radii[idx] = o.radius;
     g.rect[idx] = o.rect;
     g.sort_key[0][idx] = o.key;
-    if (acc_init != nullptr) {
-      // fit step: this view's row of blend-stage sums starts at zero and carries, in slot 11, what
-      // the batched per-Gaussian backward needs to know about this view: bit 0 visible, bits 1-3
-      // the SH clamp mask (instead of a separate memset and per-view radii / clamped arrays).
-      const uint32_t flags = o.radius > 0 ? (1u | ((uint32_t)o.clamp_bits << 1)) : 0u;
-      acc_init[3 * (size_t)idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-      acc_init[3 * (size_t)idx + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-      acc_init[3 * (size_t)idx + 2] = make_float4(0.f, 0.f, 0.f, __uint_as_float(flags));
-    }
+    // fit step: what the batched per-Gaussian backward needs to know about this view, one byte per Gaussian:
+    // bit 0 visible, bits 1-3 the SH clamp mask (instead of per-view radii / clamped arrays)
+    if (flags_out != nullptr) flags_out[idx] = o.radius > 0 ? (uint8_t)(1u | ((uint32_t)o.clamp_bits << 1)) : (uint8_t)0;
   }
   // num_rendered = sum of tiles_touched (integer, order-independent)
   uint32_t s = __reduce_add_sync(0xFFFFFFFFu, tiles);
@@ -271,13 +265,13 @@ cudaError_t launch_preprocess(const ViewParams& vp, const float* means3D, const 
                               const float* rotations, const float* opacities, const float* shs,
                               const float* cov3D_precomp, const float* colors_precomp,
                               int colors_mode, bool prefiltered, int* radii, GeomState& g,
-                              float* acc_init, cudaStream_t stream) {
+                              uint8_t* flags_out, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(g.counters, 0, 64 * sizeof(uint32_t), stream);
   if (e != cudaSuccess) return e;
   const int blocks = (vp.P + 255) / 256;
   preprocess_kernel<<<blocks, 256, 0, stream>>>(vp, means3D, scales, rotations, opacities, shs,
                                                 cov3D_precomp, colors_precomp, colors_mode, prefiltered,
-                                                radii, g, reinterpret_cast<float4*>(acc_init));
+                                                radii, g, flags_out);
   DGE_LAUNCHED(1);
   return cudaGetLastError();
 }
@@ -293,7 +287,7 @@ __global__ void __launch_bounds__(PRE_B_THREADS, PRE_B_MIN_CTAS) preprocess_batc
     ViewParams vp, int V, const float* __restrict__ cams, const float* __restrict__ means3D,
     const float* __restrict__ scales, const float* __restrict__ rotations,
     const float* __restrict__ opacities, const float* __restrict__ shs, GeomState g0, size_t geom_stride,
-    float4* __restrict__ acc0, size_t acc_stride_floats, int* __restrict__ radii_max, bool prune_lists) {
+    uint8_t* __restrict__ flags0, size_t flags_stride, int* __restrict__ radii_max, bool prune_lists) {
   extern __shared__ float s_cam[];  // V * 40 floats, V per-view instance counts, then the SH block
   uint32_t* s_tiles = reinterpret_cast<uint32_t*>(s_cam + V * 40);  // [V]
   // this thread's 48 SH floats at s_sh[k * PRE_B_THREADS + tid]: conflict-free, and 48 registers less
@@ -376,13 +370,11 @@ __global__ void __launch_bounds__(PRE_B_THREADS, PRE_B_MIN_CTAS) preprocess_batc
       }
       shift_ptr(g0.rect, sh_)[idx] = o.rect;
       shift_ptr(g0.sort_key[0], sh_)[idx] = o.key;
-      if (acc0 != nullptr) {
-        const uint32_t flags = o.radius > 0 ? (1u | ((uint32_t)o.clamp_bits << 1)) : 0u;
-        float4* row = acc0 + (size_t)view * (acc_stride_floats / 4) + 3 * (size_t)idx;
-        row[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-        row[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        row[2] = make_float4(0.f, 0.f, 0.f, __uint_as_float(flags));
-      }
+      // one flag byte per (view, Gaussian) for the per-Gaussian backward: bit 0 visible, bits 1-3 SH clamp mask.
+      // (The view's rows of blend-stage sums are zeroed by a memset that runs beside the forward blend,
+      // api.cu: written from here they were 0.96 of this kernel's 2.24 GB of stores at config 2.)
+      if (flags0 != nullptr)
+        flags0[(size_t)view * flags_stride + idx] = o.radius > 0 ? (uint8_t)(1u | ((uint32_t)o.clamp_bits << 1)) : (uint8_t)0;
       rmax = max(rmax, o.radius);
       tiles = o.tiles;
     }
@@ -397,16 +389,16 @@ __global__ void __launch_bounds__(PRE_B_THREADS, PRE_B_MIN_CTAS) preprocess_batc
 
 cudaError_t launch_preprocess_batched(const ViewParams& vp, const ViewBatch& vb, const float* means3D,
                                       const float* scales, const float* rotations, const float* opacities,
-                                      const float* shs, GeomState& g0, float* acc, size_t acc_stride_floats,
+                                      const float* shs, GeomState& g0, uint8_t* flags, size_t flags_stride,
                                       int* radii_max, bool prune_lists, cudaStream_t stream) {
-  if ((shs != nullptr && vp.M != 16) || (acc_stride_floats & 3)) return cudaErrorInvalidValue;
+  if (shs != nullptr && vp.M != 16) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemset2DAsync(g0.counters, vb.geom_stride, 0, 64 * sizeof(uint32_t), (size_t)vb.V, stream);
   if (e != cudaSuccess) return e;
   const int blocks = (vp.P + PRE_B_THREADS - 1) / PRE_B_THREADS;
   const size_t smem = (size_t)vb.V * (40 * sizeof(float) + sizeof(uint32_t)) + 48 * PRE_B_THREADS * sizeof(float);
   preprocess_batched_kernel<<<blocks, PRE_B_THREADS, smem, stream>>>(
       vp, vb.V, vb.cams, means3D, scales, rotations, opacities, shs, g0, vb.geom_stride,
-      reinterpret_cast<float4*>(acc), acc_stride_floats, radii_max, prune_lists);
+      flags, flags_stride, radii_max, prune_lists);
   DGE_LAUNCHED(1);
   return cudaGetLastError();
 }

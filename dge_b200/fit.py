@@ -114,7 +114,8 @@ class FitModel:
         self.means2D_slice = slice(n, n + 3 * P)
         self.means2D.grad = self.flat_grad[self.means2D_slice].view(P, 3)
         # per-P caches of the fit step (lanes, batches, activations) belong to the old buffers
-        for attr in ("_lane_key", "_batch_key", "_acts", "_lanes", "_batches", "_acc", "_lane_acc", "_min_chunks"):
+        for attr in ("_lane_key", "_batch_key", "_acts", "_lanes", "_batches", "_acc", "_flags", "_lane_acc",
+                     "_lane_flags", "_min_chunks"):
             if hasattr(self, attr):
                 delattr(self, attr)
         if not self.fused_adam:
@@ -473,9 +474,10 @@ def _direct_views(model: FitModel, acts, cameras, targets, bg, scale, host_input
         model._lanes = [ViewLane(model, W, H, torch.cuda.Stream(dev)) for _ in range(S)]
         f32 = dict(dtype=torch.float32, device=dev)
         model._lane_acc = torch.empty(V, P, 12, **f32)          # blend-stage sums of every view of the step
+        model._lane_flags = torch.empty(V, P, dtype=torch.uint8, device=dev)  # visible / SH-clamp bits
         model._lane_cams = torch.empty(V, CAM_FLOATS, **f32)
         model._lane_key = key
-    lanes, acc, cams_dev = model._lanes, model._lane_acc, model._lane_cams
+    lanes, acc, flags, cams_dev = model._lanes, model._lane_acc, model._lane_flags, model._lane_cams
     a = {k: v.detach() for k, v in acts.items()}
     ptrs = {k: v.data_ptr() for k, v in a.items()}
     M = a["shs"].shape[1]
@@ -499,7 +501,8 @@ def _direct_views(model: FitModel, acts, cameras, targets, bg, scale, host_input
             R = lib.dge_fit_forward(
                 ln.cb_geom, ln.cb_binning, ln.cb_img, None, P, model.sh_degree, M, bgp, W, H, ptrs["means3D"],
                 ptrs["shs"], ptrs["opacities"], ptrs["scales"], 1.0, ptrs["rotations"], cam_ptr, tfx,
-                tfy, ln.color.data_ptr(), ln.depth.data_ptr(), ln.radii.data_ptr(), acc_ptr, ln.stream_ptr)
+                tfy, ln.color.data_ptr(), ln.depth.data_ptr(), ln.radii.data_ptr(), acc_ptr, flags[i].data_ptr(),
+                ln.stream_ptr)
             L.check(R, "fit forward")
             L.check(lib.dge_l1_loss_grad(ln.color.data_ptr(), target.data_ptr(), n_img, scale, ln.dL.data_ptr(),
                                          ln.loss.data_ptr(), ln.stream_ptr), "l1 loss")
@@ -514,7 +517,8 @@ def _direct_views(model: FitModel, acts, cameras, targets, bg, scale, host_input
     # row is written, so the buffer needs no zero fill either)
     gp = {k: v.grad.data_ptr() for k, v in model.params.items()}
     L.check(lib.dge_fit_backward_geom_raw(
-        P, model.sh_degree, V, cams_dev.data_ptr(), W, H, 1.0, acc.data_ptr(), P * 12, ptrs["means3D"], ptrs["shs"],
+        P, model.sh_degree, V, cams_dev.data_ptr(), W, H, 1.0, acc.data_ptr(), P * 12, flags.data_ptr(), P,
+        ptrs["means3D"], ptrs["shs"],
         ptrs["opacities"], ptrs["scales"], ptrs["rotations"], model.params["rotation"].data_ptr(), gp["xyz"],
         model.means2D.grad.data_ptr(), gp["f_dc"], gp["f_rest"], gp["opacity"], gp["scaling"], gp["rotation"],
         L.stream_ptr(dev)), "fit backward geom")
@@ -531,7 +535,7 @@ class ViewBatch:
     Geometry / image blobs hold V views at a uniform stride, the binning arena only grows. Each chunk
     has its own stream; `acc` and `cams` are this chunk's rows of the step-wide buffers."""
 
-    def __init__(self, model: "FitModel", W: int, H: int, V: int, acc, cams, cams_host):
+    def __init__(self, model: "FitModel", W: int, H: int, V: int, acc, flags, cams, cams_host):
         lib = L.load()
         dev, P = model.device, model.P
         self.W, self.H, self.V, self.P = W, H, V, P
@@ -544,7 +548,7 @@ class ViewBatch:
         self.targets = torch.empty(V, 3, H, W, **f32)       # staging for host / listed targets
         self.radii_max = torch.zeros(P, dtype=torch.int32, device=dev)
         self.loss = torch.zeros((), **f32)
-        self.acc, self.cams, self.cams_host = acc, cams, cams_host
+        self.acc, self.flags, self.cams, self.cams_host = acc, flags, cams, cams_host
         self.geom = torch.empty((lib.dge_geom_bytes(P) + 255) // 256 * 256 * V, **u8)
         self.img = torch.empty((lib.dge_image_bytes(W, H) + 255) // 256 * 256 * V, **u8)
         self.binning = torch.empty(0, **u8)
@@ -590,12 +594,14 @@ def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inpu
     if getattr(model, "_batch_key", None) != key:
         f32 = dict(dtype=torch.float32, device=dev)
         model._acc = torch.empty(V, P, 12, **f32)          # blend-stage sums of every view of the step
+        model._flags = torch.empty(V, P, dtype=torch.uint8, device=dev)  # visible / SH-clamp bits per (view, Gaussian)
         model._cams = torch.empty(V, CAM_FLOATS, **f32)
         model._cams_host = torch.empty(V, CAM_FLOATS, dtype=torch.float32).pin_memory()
         bounds = [V * c // C for c in range(C + 1)]
         model._chunk_bounds = bounds
         model._batches = [ViewBatch(model, W, H, bounds[c + 1] - bounds[c], model._acc[bounds[c]:bounds[c + 1]],
-                                    model._cams[bounds[c]:bounds[c + 1]], model._cams_host[bounds[c]:bounds[c + 1]])
+                                    model._flags[bounds[c]:bounds[c + 1]], model._cams[bounds[c]:bounds[c + 1]],
+                                    model._cams_host[bounds[c]:bounds[c + 1]])
                           for c in range(C)]
         model._batch_key = key
         model._cams_key = None
@@ -630,7 +636,7 @@ def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inpu
                 vb.cb_geom, vb.cb_binning, vb.cb_img, None, P, model.sh_degree, M, vb.V, bgp, W, H, ptrs["means3D"],
                 ptrs["shs"], ptrs["opacities"], ptrs["scales"], 1.0, ptrs["rotations"], vb.cams.data_ptr(),
                 vb.color.data_ptr(), vb.depth.data_ptr(), vb.radii_max.data_ptr(), vb.acc.data_ptr(), acc_stride,
-                vb.num_rendered, None, None, int(prune_lists), vb.stream_ptr), "fit views forward")
+                vb.flags.data_ptr(), P, vb.num_rendered, None, None, int(prune_lists), vb.stream_ptr), "fit views forward")
     for c, vb in enumerate(batches):
         lo, hi = bounds[c], bounds[c + 1]
         # targets: a resident [V,3,H,W] tensor is used as is; host tensors are copied on a side stream,
@@ -671,7 +677,7 @@ def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inpu
         f = 4 * first  # bytes per float column
         L.check(lib.dge_fit_backward_geom_raw(
             stop - first, model.sh_degree, V, model._cams.data_ptr(), W, H, 1.0, model._acc.data_ptr() + 12 * f,
-            acc_stride, ptrs["means3D"] + 3 * f, ptrs["shs"] + 48 * f, ptrs["opacities"] + f, ptrs["scales"] + 3 * f,
+            acc_stride, model._flags.data_ptr() + first, P, ptrs["means3D"] + 3 * f, ptrs["shs"] + 48 * f, ptrs["opacities"] + f, ptrs["scales"] + 3 * f,
             ptrs["rotations"] + 4 * f, rot_raw + 4 * f, gp["xyz"] + 3 * f, m2d + 3 * f, gp["f_dc"] + 3 * f,
             gp["f_rest"] + 45 * f, gp["opacity"] + f, gp["scaling"] + 3 * f, gp["rotation"] + 4 * f,
             L.stream_ptr(dev)), "fit backward geom")
@@ -716,7 +722,7 @@ def render_views(means3D, shs, opacities, scales, rotations, cameras, bg, extra=
                 arena.cbs[0], arena.cbs[1], arena.cbs[2], None, P, sh_degree, shs.shape[1], V, bg.data_ptr(), W, H,
                 means3D.data_ptr(), shs.data_ptr(), opacities.data_ptr(), scales.data_ptr(), float(scale_modifier),
                 rotations.data_ptr(), recs.data_ptr(), color[lo:lo + V].data_ptr(), depth[lo:lo + V].data_ptr(),
-                rm.data_ptr(), None, 0, None, None if ex is None else ex.data_ptr(),
+                rm.data_ptr(), None, 0, None, 0, None, None if ex is None else ex.data_ptr(),
                 None if sem is None else sem[lo:lo + V].data_ptr(), int(prune_lists), L.stream_ptr(dev)),
                 "fit views forward (render)")
         radii_max = torch.maximum(radii_max, rm)

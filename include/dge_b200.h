@@ -149,28 +149,31 @@ int dge_profile_read(float* ms_out, int* count_out);
 
 /* ---- fit step: the views of one optimisation step --------------------
  * `cam` is a device record of 40 floats: viewmatrix[16] | projmatrix[16] | campos[3] | tan_fovx |
- * tan_fovy | pad[3]. `acc` is this view's [P][12] row block of blend-stage sums.
+ * tan_fovy | pad[3]. `acc` is this view's [P][12] row block of blend-stage sums (moments of dL/dG * G over the
+ * Gaussian's pixels, dL/dopacity, dL/dcolour: ACC_* in csrc/common.cuh), `flags` its [P] bytes (bit 0: the
+ * Gaussian is visible in the view, bits 1-3: SH colour channel clamped at 0).
  *
  * dge_fit_forward = dge_rasterize_forward (SH colours, scale/rotation covariances) that also
- * initialises `acc` (zeros + per-view visibility / clamp flags) from inside preprocess.
+ * zeroes `acc` and writes `flags`.
  * dge_fit_backward_blend = the blend backward of the view into `acc` (K7 only);
  * background_is_black != 0 is the caller's promise that background == (0,0,0) (DGE.py:87), which
  * removes the background term of dL/dalpha at compile time.
  * dge_fit_backward_geom = K8 + K9 of rasterizer_impl.cu:324-340 for ALL V views of the step in one
- * pass over the Gaussians (acc of view v at acc + v*acc_stride_floats); with accumulate != 0 the six
+ * pass over the Gaussians (acc of view v at acc + v*acc_stride_floats, its flags at flags + v*flags_stride);
+ * with accumulate != 0 the six
  * outputs are added to, otherwise every row is written. */
 int dge_fit_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge_alloc_fn imageBuffer,
                     void* alloc_ctx, int P, int D, int M, const float* background, int width,
                     int height, const float* means3D, const float* shs, const float* opacities,
                     const float* scales, float scale_modifier, const float* rotations,
                     const float* cam, float tan_fovx, float tan_fovy, float* out_color,
-                    float* out_depth, int* radii, float* acc, void* stream);
+                    float* out_depth, int* radii, float* acc, uint8_t* flags, void* stream);
 int dge_fit_backward_blend(int P, int R, const float* background, int background_is_black,
                            int width, int height, char* geom_buffer, char* binning_buffer,
                            char* image_buffer, const float* dL_dpix, float* acc, void* stream);
 int dge_fit_backward_geom(int P, int D, int M, int V, const float* cams, int width, int height,
                           float scale_modifier, const float* acc, size_t acc_stride_floats,
-                          const float* means3D, const float* shs, const float* scales,
+                          const uint8_t* flags, size_t flags_stride, const float* means3D, const float* shs, const float* scales,
                           const float* rotations, float* dL_dmean3D, float* dL_dmean2D,
                           float* dL_dsh, float* dL_dopacity, float* dL_dscale, float* dL_drot,
                           int accumulate, void* stream);
@@ -180,11 +183,13 @@ int dge_fit_backward_geom(int P, int D, int M, int V, const float* cams, int wid
  * the 148 SMs idle, the 236 B of per-Gaussian inputs are read once per step instead of once per
  * view, and the host waits for the instance counts once per step. `cams` is [V][40], out_color
  * [V,3,H,W], out_depth [V,1,H,W], acc [V][acc_stride_floats] (acc_stride_floats >= 12*P, multiple
- * of 4), radii_max [P] = max over the views of the reference's per-view radii. geometryBuffer is
+ * of 4; zeroed by a memset that the library runs beside the forward blend and that
+ * dge_fit_views_backward_blend of the same acc waits for), flags [V][flags_stride] (flags_stride >= P),
+ * radii_max [P] = max over the views of the reference's per-view radii. geometryBuffer is
  * asked for V*dge_geom_bytes(P) bytes, imageBuffer for V*dge_image_bytes(W,H), binningBuffer for
  * dge_fit_binning_bytes(R_total, V, W, H) once the counts are known. num_rendered_host (host, [V], may be
  * NULL) receives the per-view num_rendered. Returns R_total = their sum.
- * acc and radii_max may be NULL (forward-only rendering, e.g. DGE's render_all_view).
+ * acc + flags (both or neither) and radii_max may be NULL (forward-only rendering, e.g. DGE's render_all_view).
  * extra [P] / out_extra [V,3,H,W] (both or neither): one more per-Gaussian scalar blended like a colour
  * channel, background added per channel — bit-identical to a second forward of the same view with
  * colors_precomp = extra repeated three times, which is how DGE.forward renders its "semantic" map of
@@ -199,8 +204,8 @@ int dge_fit_views_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffe
                           int height, const float* means3D, const float* shs, const float* opacities,
                           const float* scales, float scale_modifier, const float* rotations,
                           const float* cams, float* out_color, float* out_depth, int* radii_max, float* acc,
-                          size_t acc_stride_floats, int* num_rendered_host, const float* extra, float* out_extra,
-                          int prune_lists, void* stream);
+                          size_t acc_stride_floats, uint8_t* flags, size_t flags_stride, int* num_rendered_host,
+                          const float* extra, float* out_extra, int prune_lists, void* stream);
 /* dL_dpix is [V,3,H,W]; the three blobs are the ones dge_fit_views_forward filled. */
 int dge_fit_views_backward_blend(int P, int V, int R_total, const float* background, int background_is_black,
                                  int width, int height, char* geom_buffer, char* binning_buffer,
@@ -227,7 +232,7 @@ int dge_fit_activate(int P, const float* f_dc, const float* f_rest, const float*
                      float* opacities, float* scales, float* rotations, void* stream);
 int dge_fit_backward_geom_raw(int P, int D, int V, const float* cams, int width, int height,
                               float scale_modifier, const float* acc, size_t acc_stride_floats,
-                              const float* means3D, const float* shs, const float* opacities,
+                              const uint8_t* flags, size_t flags_stride, const float* means3D, const float* shs, const float* opacities,
                               const float* scales, const float* rotations,
                               const float* rotation_raw, float* d_xyz, float* d_means2D,
                               float* d_f_dc, float* d_f_rest, float* d_opacity_raw,

@@ -346,7 +346,7 @@ def test_per_gaussian_backward_over_ranges_is_bit_identical(cuda):
     acc = (torch.randn(Vn, Pn, 12, generator=gen) * 1e-3).to(cuda)
     flags = torch.randint(0, 16, (Vn, Pn), generator=gen, dtype=torch.int32).to(cuda)
     flags = torch.where(torch.rand(Vn, Pn, generator=gen).to(cuda) < 0.5, flags | 1, torch.zeros_like(flags))
-    acc.view(torch.int32)[:, :, 11] = flags
+    flags = flags.to(torch.uint8).contiguous()  # bit 0 visible, bits 1-3 SH clamp mask (include/dge_b200.h)
     st = L.stream_ptr(cuda)
 
     def run(cuts, fill):
@@ -356,7 +356,7 @@ def test_per_gaussian_backward_over_ranges_is_bit_identical(cuda):
             f = 4 * first
             L.check(lib.dge_fit_backward_geom_raw(
                 stop - first, 3, Vn, cams.data_ptr(), Wn, Hn, 1.0, acc.data_ptr() + 12 * f, Pn * 12,
-                a["means3D"].data_ptr() + 3 * f, a["shs"].data_ptr() + 48 * f, a["opacities"].data_ptr() + f,
+                flags.data_ptr() + first, Pn, a["means3D"].data_ptr() + 3 * f, a["shs"].data_ptr() + 48 * f, a["opacities"].data_ptr() + f,
                 a["scales"].data_ptr() + 3 * f, a["rotations"].data_ptr() + 4 * f,
                 model.params["rotation"].data_ptr() + 4 * f, out["xyz"].data_ptr() + 3 * f, m2d.data_ptr() + 3 * f,
                 out["f_dc"].data_ptr() + 3 * f, out["f_rest"].data_ptr() + 45 * f, out["opacity"].data_ptr() + f,
