@@ -6,6 +6,7 @@
 #include "../../include/dge_b200.h"
 #include "common.cuh"
 
+#include <mutex>
 #include <vector>
 
 namespace dge {
@@ -204,12 +205,15 @@ static int bin_view(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge
 // Zeroing of a step's blend-stage sums beside the forward blend: forked from `stream` onto a side stream;
 // the backward blend of the same `acc` joins it (wait_acc_zero). One slot per in-flight batch (the chunks of
 // a step each have their own rows).
+// (Process-wide, not per thread: the backward half of a step may run on autograd's worker thread.)
 struct AccZero { const void* acc; cudaEvent_t done; };
-static thread_local cudaStream_t g_zero_stream = nullptr;
-static thread_local cudaEvent_t g_zero_fork = nullptr;
-static thread_local AccZero g_zero[16];
+static std::mutex g_zero_mutex;
+static cudaStream_t g_zero_stream = nullptr;
+static cudaEvent_t g_zero_fork = nullptr;
+static AccZero g_zero[16];
 
 static cudaError_t zero_acc_async(float* acc, size_t acc_stride_floats, int P, int V, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(g_zero_mutex);
   cudaError_t e;
   if (g_zero_stream == nullptr) {
     if ((e = cudaStreamCreateWithFlags(&g_zero_stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
@@ -237,6 +241,7 @@ static cudaError_t zero_acc_async(float* acc, size_t acc_stride_floats, int P, i
 }
 
 static cudaError_t wait_acc_zero(const float* acc, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(g_zero_mutex);
   for (AccZero& z : g_zero)
     if (z.acc == acc && acc != nullptr) {
       z.acc = nullptr;

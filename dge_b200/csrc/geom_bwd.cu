@@ -69,52 +69,42 @@ __device__ __forceinline__ void view_geom_backward(float mx, float my, float mz,
                                                    float Sx, float Sy, float Sxx, float Sxy, float Syy,
                                                    float dblend[5], float dmean[3], float dcov[6]) {
   struct { float tan_fovx, tan_fovy, focal_x, focal_y; } vp = {tan_fovx, tan_fovy, focal_x, focal_y};
-  const float3 con = conic_ref(mx, my, mz, tan_fovx, tan_fovy, focal_x, focal_y, V, c3);
+  // ---------------- K8: conic -> cov2D -> cov3D, mean (backward.cu:144-274) ----------------
+  // The forward's own T = W J, T Sigma and cov2D (math_ref.cuh, bit-identical to preprocess) serve both the
+  // conic that turns the moment sums into dL/dmean2D and the backward, which the reference recomputes them for.
+  const float txe = xform_row(V, 0, mx, my, mz), tye = xform_row(V, 1, mx, my, mz);
+  const float tz = xform_row(V, 2, mx, my, mz);
+  float Tf[6], Af[6];
+  const float3 cov = cov2d_parts(txe, tye, tz, tan_fovx, tan_fovy, focal_x, focal_y, V, c3, Tf, Af);
+  const float a = cov.x, b = cov.y, c = cov.z;
+  const float det = FMA(a, c, -MUL(b, b));
+  const float inv = __frcp_rn(det);
+  const float3 con = make_float3(MUL(c, inv), MUL(b, -inv), MUL(a, inv));  // preprocess_view
   const float dm2x = (-0.5f * (float)W) * (con.x * Sx + con.y * Sy);
   const float dm2y = (-0.5f * (float)H) * (con.z * Sy + con.y * Sx);
   const float dcon_x = -0.5f * Sxx, dcon_y = -0.5f * Sxy, dcon_w = -0.5f * Syy;
   dblend[0] = dm2x; dblend[1] = dm2y; dblend[2] = dcon_x; dblend[3] = dcon_y; dblend[4] = dcon_w;
-  // ---------------- K8: conic -> cov2D -> cov3D, mean (backward.cu:144-274) ----------------
-  float tx = V[0] * mx + V[4] * my + V[8] * mz + V[12];
-  float ty = V[1] * mx + V[5] * my + V[9] * mz + V[13];
-  const float tz = V[2] * mx + V[6] * my + V[10] * mz + V[14];
   const float limx = 1.3f * vp.tan_fovx, limy = 1.3f * vp.tan_fovy;
-  const float txtz = tx / tz, tytz = ty / tz;
-  tx = fminf(limx, fmaxf(-limx, txtz)) * tz;
-  ty = fminf(limy, fmaxf(-limy, tytz)) * tz;
+  const float txtz = txe / tz, tytz = tye / tz;
+  const float tx = fminf(limx, fmaxf(-limx, txtz)) * tz;
+  const float ty = fminf(limy, fmaxf(-limy, tytz)) * tz;
   const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
   const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
   const float hx = vp.focal_x, hy = vp.focal_y;
-
-  M3 J, Wm, Vrk;
-  J.m[0][0] = hx / tz; J.m[0][1] = 0.f; J.m[0][2] = -(hx * tx) / (tz * tz);
-  J.m[1][0] = 0.f; J.m[1][1] = hy / tz; J.m[1][2] = -(hy * ty) / (tz * tz);
-  J.m[2][0] = 0.f; J.m[2][1] = 0.f; J.m[2][2] = 0.f;
+  M3 Wm;
   Wm.m[0][0] = V[0]; Wm.m[0][1] = V[4]; Wm.m[0][2] = V[8];
   Wm.m[1][0] = V[1]; Wm.m[1][1] = V[5]; Wm.m[1][2] = V[9];
   Wm.m[2][0] = V[2]; Wm.m[2][1] = V[6]; Wm.m[2][2] = V[10];
-  Vrk.m[0][0] = c3[0]; Vrk.m[0][1] = c3[1]; Vrk.m[0][2] = c3[2];
-  Vrk.m[1][0] = c3[1]; Vrk.m[1][1] = c3[3]; Vrk.m[1][2] = c3[4];
-  Vrk.m[2][0] = c3[2]; Vrk.m[2][1] = c3[4]; Vrk.m[2][2] = c3[5];
-  const M3 Tm = mul(Wm, J);
-  // cov2D = T^T * Vrk^T * T ; only [0][0], [0][1], [1][1] needed. Vrk symmetric.
-  float TV[2][3];  // (T^T Vrk)[row j of T^T = col j of T][k]
-#pragma unroll
-  for (int j = 0; j < 2; j++)
-#pragma unroll
-    for (int k = 0; k < 3; k++)
-      TV[j][k] = Tm.m[j][0] * Vrk.m[0][k] + Tm.m[j][1] * Vrk.m[1][k] + Tm.m[j][2] * Vrk.m[2][k];
-  const float a = TV[0][0] * Tm.m[0][0] + TV[0][1] * Tm.m[0][1] + TV[0][2] * Tm.m[0][2] + 0.3f;
-  const float b = TV[1][0] * Tm.m[0][0] + TV[1][1] * Tm.m[0][1] + TV[1][2] * Tm.m[0][2];
-  const float c = TV[1][0] * Tm.m[1][0] + TV[1][1] * Tm.m[1][1] + TV[1][2] * Tm.m[1][2] + 0.3f;
+  // TV[j][k] = sum_l T[j][l] Sigma[l][k]
+  const float TV[2][3] = {{Af[0], Af[1], Af[2]}, {Af[3], Af[4], Af[5]}};
 
   const float denom = a * c - b * b;
   float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
   const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
 #pragma unroll
   for (int k = 0; k < 6; k++) dcov[k] = 0.f;
-  const float T00 = Tm.m[0][0], T01 = Tm.m[0][1], T02 = Tm.m[0][2];
-  const float T10 = Tm.m[1][0], T11 = Tm.m[1][1], T12 = Tm.m[1][2];
+  const float T00 = Tf[0], T01 = Tf[1], T02 = Tf[2];
+  const float T10 = Tf[3], T11 = Tf[4], T12 = Tf[5];
   if (denom2inv != 0.f) {
     dL_da = denom2inv * (-c * c * dcon_x + 2 * b * c * dcon_y + (denom - a * c) * dcon_w);
     dL_dc = denom2inv * (-a * a * dcon_w + 2 * a * b * dcon_y + (denom - a * c) * dcon_x);
@@ -459,7 +449,6 @@ __global__ void __launch_bounds__(128, 4) geom_backward_batched_kernel(
   // the sums of the visible views from their 48-byte rows.
   bool any = false;
   unsigned long long todo = 0ull;
-  unsigned long long clampbits[3] = {0ull, 0ull, 0ull};  // bit v: channel clamped in view v
   // Four views at a time, all loads of a level issued before any is used: walked one view after the
   // other, the dependent loads per view put 2 V memory round trips on every thread's critical path —
   // that latency, not bandwidth, was the kernel's time.
@@ -486,17 +475,15 @@ __global__ void __launch_bounds__(128, 4) geom_backward_batched_kernel(
     for (int k = 0; k < 4; k++)
       if (((vis >> k) & 1u) &&
           (a0[k].x != 0.f || a0[k].y != 0.f || a0[k].z != 0.f || a0[k].w != 0.f || a1[k].x != 0.f || a1[k].y != 0.f ||
-           a1[k].z != 0.f || a1[k].w != 0.f || a2[k].x != 0.f)) {
+           a1[k].z != 0.f || a1[k].w != 0.f || a2[k].x != 0.f))
         todo |= 1ull << (v0 + k);
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++) clampbits[ch] |= (unsigned long long)((fl[k] >> (1 + ch)) & 1u) << (v0 + k);
-      }
   }
   while (todo) {
     const int v = __ffsll((long long)todo) - 1;
     todo &= todo - 1ull;
     const float4* row = reinterpret_cast<const float4*>(acc + (size_t)v * acc_stride) + 3 * i;
     const float4 a0 = __ldg(row), a1 = __ldg(row + 1), a2 = __ldg(row + 2);
+    const uint32_t fl = __ldg(flags + (size_t)v * flags_stride + i);  // (L1-resident from pass 1)
     const float* cam = s_cam + v * CAM_FLOATS;
     const float tan_fovx = cam[35], tan_fovy = cam[36];
     const float focal_y = H / (2.0f * tan_fovy), focal_x = W / (2.0f * tan_fovx);
@@ -515,7 +502,7 @@ __global__ void __launch_bounds__(128, 4) geom_backward_batched_kernel(
     float dRGB[3] = {a1.z, a1.w, a2.x};
 #pragma unroll
     for (int ch = 0; ch < 3; ch++)
-      if ((clampbits[ch] >> v) & 1ull) dRGB[ch] = 0.f;
+      if ((fl >> (1 + ch)) & 1u) dRGB[ch] = 0.f;
     float b[16], gx[16], gy[16], gz[16];
     sh_basis_grad(D, x, y, z, b, gx, gy, gz);
     float ddx = 0.f, ddy = 0.f, ddz = 0.f;

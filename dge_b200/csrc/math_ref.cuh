@@ -63,9 +63,12 @@ __device__ __forceinline__ void cov3d_from_scale_rot(float sx, float sy, float s
   cov[5] = dot3_ref(M20, M20, M21, M21, M22, M22);
 }
 
-// DGR/cuda_rasterizer/forward.cu:74-113 computeCov2D. t = view-space mean.
-__device__ __forceinline__ float3 cov2d_ref(float tx, float ty, float tz, float tan_fovx, float tan_fovy,
-                                            float focal_x, float focal_y, const float* V, const float* c) {
+// DGR/cuda_rasterizer/forward.cu:74-113 computeCov2D. t = view-space mean. Also hands out the intermediate
+// T = W * J (upper 2x3: T[0..2] = row 0, T[3..5] = row 1) and A = T * Sigma (same layout), which the
+// per-Gaussian backward needs again (backward.cu:160-273 recomputes them).
+__device__ __forceinline__ float3 cov2d_parts(float tx, float ty, float tz, float tan_fovx, float tan_fovy,
+                                              float focal_x, float focal_y, const float* V, const float* c,
+                                              float* T, float* A) {
   const float limx = MUL(tan_fovx, 1.3f), limy = MUL(tan_fovy, 1.3f);
   const float txtz = __fdiv_rn(tx, tz), tytz = __fdiv_rn(ty, tz);
   const float cx = fminf(fmaxf(txtz, -limx), limx);
@@ -96,20 +99,15 @@ __device__ __forceinline__ float3 cov2d_ref(float tx, float ty, float tz, float 
   cov.x = ADD(dot3_ref(T00, A00, T01, A10, T02, A20), 0.3f);
   cov.y = dot3_ref(T00, A01, T01, A11, T02, A21);
   cov.z = ADD(dot3_ref(T10, A01, T11, A11, T12, A21), 0.3f);
+  if (T != nullptr) {
+    T[0] = T00; T[1] = T01; T[2] = T02; T[3] = T10; T[4] = T11; T[5] = T12;
+    A[0] = A00; A[1] = A10; A[2] = A20; A[3] = A01; A[4] = A11; A[5] = A21;
+  }
   return cov;
 }
-
-// The conic (inverse 2-D covariance) of a Gaussian in a view exactly as the forward computes and stores it
-// (preprocess.cu:preprocess_view; forward.cu:218-226): the per-Gaussian backward turns the blend stage's
-// moment sums into dL/dmean2D with it instead of reading the 64-byte record back.
-__device__ __forceinline__ float3 conic_ref(float px, float py, float pz, float tan_fovx, float tan_fovy,
-                                            float focal_x, float focal_y, const float* V, const float* cov3) {
-  const float depth = xform_row(V, 2, px, py, pz);
-  const float tx = xform_row(V, 0, px, py, pz), ty = xform_row(V, 1, px, py, pz);
-  const float3 cov = cov2d_ref(tx, ty, depth, tan_fovx, tan_fovy, focal_x, focal_y, V, cov3);
-  const float det = FMA(cov.x, cov.z, -MUL(cov.y, cov.y));
-  const float inv = __frcp_rn(det);
-  return make_float3(MUL(cov.z, inv), MUL(cov.y, -inv), MUL(cov.x, inv));
+__device__ __forceinline__ float3 cov2d_ref(float tx, float ty, float tz, float tan_fovx, float tan_fovy,
+                                            float focal_x, float focal_y, const float* V, const float* c) {
+  return cov2d_parts(tx, ty, tz, tan_fovx, tan_fovy, focal_x, focal_y, V, c, nullptr, nullptr);
 }
 
 // SH constants, DGR/cuda_rasterizer/auxiliary.h:22-39

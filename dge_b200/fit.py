@@ -572,17 +572,14 @@ class ViewBatch:
         self.cb_binning = L.ALLOC_FN(growing)
 
 
-def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inputs, num_chunks=1, prune_lists=True,
-                   geom_splits=1, on_range_done=None):
-    """The step's views through the batched C-ABI: ONE launch per stage for all views of a chunk
+def _batched_forward(model: FitModel, acts, cameras, bg, num_chunks=1, prune_lists=True, extra=None):
+    """Forward half of a step through the batched C-ABI: ONE launch per stage for all views of a chunk
     (preprocess that reads the Gaussians once for all its cameras, segmented depth sort / binning, forward
-    blend, fused L1 loss+gradient, backward blend), then ONE batched per-Gaussian backward over all
-    views. With num_chunks > 1 the views are split into that many chunks, each on its own stream, so
+    blend). With num_chunks > 1 the views are split into that many chunks, each on its own stream, so
     one chunk's bandwidth-bound stages (preprocess, sorts) overlap another's issue-bound blends.
-    The per-Gaussian backward may be issued as geom_splits launches over consecutive Gaussian ranges;
-    on_range_done(first, count) is called after each (multi-GPU: the all-reduce of a finished range's
-    gradients then overlaps the next range's kernel).
-    Returns (loss, max radii); leaves the step's raw-parameter gradients in model.flat_grad."""
+    `extra` [P] (DGE: gaussian.mask.float()): blended as a fourth channel into vb.sem, the image of DGE.forward's
+    second, mask-colour render of every view (DGE.py:198-204). Leaves images / depth / scratch in
+    model._batches and what the backward half needs in model._fw; the chunk streams are left running."""
     lib = L.load()
     dev = model.device
     H, W = cameras[0].image_height, cameras[0].image_width
@@ -605,38 +602,101 @@ def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inpu
                           for c in range(C)]
         model._batch_key = key
         model._cams_key = None
-    batches, bounds = model._batches, model._chunk_bounds
+    batches = model._batches
     main = torch.cuda.current_stream(dev)
     a = {k: v.detach() for k, v in acts.items()}
     ptrs = {k: v.data_ptr() for k, v in a.items()}
     M = a["shs"].shape[1]
     bgp = bg.data_ptr()
-    bg_black = _background_is_black(model, bg)
     # cameras: one pinned [V,40] block, one H2D copy
     recs = [camera_record(cam) for cam in cameras]
     # records are memoised per camera: same objects <=> same cameras. The key HOLDS the records (an id()
     # of a freed record can be reused by another camera's)
     cams_key = getattr(model, "_cams_key", None)
-    if cams_key is None or len(cams_key) != len(recs) or any(a is not b for a, b in zip(cams_key, recs)):
+    if cams_key is None or len(cams_key) != len(recs) or any(x is not y for x, y in zip(cams_key, recs)):
         cams_key = tuple(recs)
         for i, rec in enumerate(recs):
             model._cams_host[i].copy_(rec)
         model._cams.copy_(model._cams_host, non_blocking=True)
         model._cams_key = cams_key
-    resident = isinstance(targets, torch.Tensor) and targets.is_cuda
+    ex = None if extra is None else extra.detach().to(dev, torch.float32).reshape(-1).contiguous()
     acc_stride = P * 12
-    n_img = 3 * H * W
     for vb in batches:
         vb.stream.wait_stream(main)
-    # forward of every chunk first (each call waits once for its instance counts), then loss + backward
-    for c, vb in enumerate(batches):
+    # forward of every chunk (each call waits once for its instance counts)
+    for vb in batches:
         with torch.cuda.stream(vb.stream):
-            vb.loss.zero_()
+            if ex is not None and getattr(vb, "sem", None) is None:
+                vb.sem = torch.empty(vb.V, 3, H, W, dtype=torch.float32, device=dev)
             vb.R = L.check(lib.dge_fit_views_forward(
                 vb.cb_geom, vb.cb_binning, vb.cb_img, None, P, model.sh_degree, M, vb.V, bgp, W, H, ptrs["means3D"],
                 ptrs["shs"], ptrs["opacities"], ptrs["scales"], 1.0, ptrs["rotations"], vb.cams.data_ptr(),
                 vb.color.data_ptr(), vb.depth.data_ptr(), vb.radii_max.data_ptr(), vb.acc.data_ptr(), acc_stride,
-                vb.flags.data_ptr(), P, vb.num_rendered, None, None, int(prune_lists), vb.stream_ptr), "fit views forward")
+                vb.flags.data_ptr(), P, vb.num_rendered, None if ex is None else ex.data_ptr(),
+                None if ex is None else vb.sem.data_ptr(), int(prune_lists), vb.stream_ptr), "fit views forward")
+    model._fw = dict(acts=a, ptrs=ptrs, bg=bg, bg_black=_background_is_black(model, bg), W=W, H=H, V=V, main=main)
+
+
+def _batched_backward(model: FitModel, dL=None, geom_splits=1, on_range_done=None):
+    """Backward half: the blend backward of every chunk (dL: [V,3,H,W] upstream gradient of the images, or None
+    when the chunks' vb.dL already hold it, e.g. from the fused L1), then ONE batched per-Gaussian backward over
+    all views with the activations' backward in its epilogue. The per-Gaussian backward may be issued as
+    geom_splits launches over consecutive Gaussian ranges; on_range_done(first, count) is called after each
+    (multi-GPU: the all-reduce of a finished range's gradients then overlaps the next range's kernel).
+    Leaves the step's raw-parameter gradients in model.flat_grad; returns the max of the radii."""
+    lib = L.load()
+    fw, dev, P = model._fw, model.device, model.P
+    W, H, V, main, ptrs = fw["W"], fw["H"], fw["V"], fw["main"], fw["ptrs"]
+    batches, bounds = model._batches, model._chunk_bounds
+    acc_stride = P * 12
+    bgp = fw["bg"].data_ptr()
+    for c, vb in enumerate(batches):
+        with torch.cuda.stream(vb.stream):
+            if dL is not None:
+                vb.stream.wait_stream(main)  # dL was produced on the caller's stream
+                g = dL[bounds[c]:bounds[c + 1]]
+            else:
+                g = vb.dL
+            L.check(lib.dge_fit_views_backward_blend(P, vb.V, vb.R, bgp, fw["bg_black"], W, H, vb.geom.data_ptr(),
+                                                     vb.binning.data_ptr(), vb.img.data_ptr(), g.data_ptr(),
+                                                     vb.acc.data_ptr(), acc_stride, vb.stream_ptr),
+                    "fit views backward blend")
+    for vb in batches:
+        main.wait_stream(vb.stream)
+    gp = {k: v.grad.data_ptr() for k, v in model.params.items()}
+    # ranges start at multiples of 128 Gaussians: every per-Gaussian array stays 16-byte aligned
+    splits = max(1, min(geom_splits, P // 128))
+    cuts = [(P * k // splits) // 128 * 128 for k in range(splits)] + [P]
+    rot_raw, m2d = model.params["rotation"].data_ptr(), model.means2D.grad.data_ptr()
+    with torch.cuda.stream(main):
+        for first, stop in zip(cuts[:-1], cuts[1:]):
+            f = 4 * first  # bytes per float column
+            L.check(lib.dge_fit_backward_geom_raw(
+                stop - first, model.sh_degree, V, model._cams.data_ptr(), W, H, 1.0, model._acc.data_ptr() + 12 * f,
+                acc_stride, model._flags.data_ptr() + first, P, ptrs["means3D"] + 3 * f, ptrs["shs"] + 48 * f,
+                ptrs["opacities"] + f, ptrs["scales"] + 3 * f, ptrs["rotations"] + 4 * f, rot_raw + 4 * f,
+                gp["xyz"] + 3 * f, m2d + 3 * f, gp["f_dc"] + 3 * f, gp["f_rest"] + 45 * f, gp["opacity"] + f,
+                gp["scaling"] + 3 * f, gp["rotation"] + 4 * f, L.C.c_void_p(main.cuda_stream)), "fit backward geom")
+            if on_range_done is not None:
+                on_range_done(first, stop - first)
+    radii_max = batches[0].radii_max
+    for vb in batches[1:]:
+        radii_max = torch.maximum(radii_max, vb.radii_max)
+    return radii_max
+
+
+def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inputs, num_chunks=1, prune_lists=True,
+                   geom_splits=1, on_range_done=None):
+    """The step's views through the batched C-ABI (_batched_forward, the fused L1 loss + gradient against
+    `targets`, _batched_backward). Returns (loss, max radii); leaves the step's raw-parameter gradients in
+    model.flat_grad."""
+    lib = L.load()
+    _batched_forward(model, acts, cameras, bg, num_chunks, prune_lists)
+    fw = model._fw
+    W, H, main = fw["W"], fw["H"], fw["main"]
+    batches, bounds = model._batches, model._chunk_bounds
+    resident = isinstance(targets, torch.Tensor) and targets.is_cuda
+    n_img = 3 * H * W
     for c, vb in enumerate(batches):
         lo, hi = bounds[c], bounds[c + 1]
         # targets: a resident [V,3,H,W] tensor is used as is; host tensors are copied on a side stream,
@@ -660,33 +720,13 @@ def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inpu
         with torch.cuda.stream(vb.stream):
             if host_inputs and not resident:
                 vb.stream.wait_event(vb.copied)
+            vb.loss.zero_()
             L.check(lib.dge_l1_loss_grad(vb.color.data_ptr(), vb.tgt.data_ptr(), vb.V * n_img, scale, vb.dL.data_ptr(),
                                          vb.loss.data_ptr(), vb.stream_ptr), "l1 loss")
-            L.check(lib.dge_fit_views_backward_blend(P, vb.V, vb.R, bgp, bg_black, W, H, vb.geom.data_ptr(),
-                                                     vb.binning.data_ptr(), vb.img.data_ptr(), vb.dL.data_ptr(),
-                                                     vb.acc.data_ptr(), acc_stride, vb.stream_ptr),
-                    "fit views backward blend")
-    for vb in batches:
-        main.wait_stream(vb.stream)
-    gp = {k: v.grad.data_ptr() for k, v in model.params.items()}
-    # ranges start at multiples of 128 Gaussians: every per-Gaussian array stays 16-byte aligned
-    splits = max(1, min(geom_splits, P // 128))
-    cuts = [(P * k // splits) // 128 * 128 for k in range(splits)] + [P]
-    rot_raw, m2d = model.params["rotation"].data_ptr(), model.means2D.grad.data_ptr()
-    for first, stop in zip(cuts[:-1], cuts[1:]):
-        f = 4 * first  # bytes per float column
-        L.check(lib.dge_fit_backward_geom_raw(
-            stop - first, model.sh_degree, V, model._cams.data_ptr(), W, H, 1.0, model._acc.data_ptr() + 12 * f,
-            acc_stride, model._flags.data_ptr() + first, P, ptrs["means3D"] + 3 * f, ptrs["shs"] + 48 * f, ptrs["opacities"] + f, ptrs["scales"] + 3 * f,
-            ptrs["rotations"] + 4 * f, rot_raw + 4 * f, gp["xyz"] + 3 * f, m2d + 3 * f, gp["f_dc"] + 3 * f,
-            gp["f_rest"] + 45 * f, gp["opacity"] + f, gp["scaling"] + 3 * f, gp["rotation"] + 4 * f,
-            L.stream_ptr(dev)), "fit backward geom")
-        if on_range_done is not None:
-            on_range_done(first, stop - first)
-    loss, radii_max = batches[0].loss.clone(), batches[0].radii_max
+    radii_max = _batched_backward(model, None, geom_splits, on_range_done)
+    loss = batches[0].loss.clone()
     for vb in batches[1:]:
         loss += vb.loss
-        radii_max = torch.maximum(radii_max, vb.radii_max)
     return loss, radii_max
 
 
@@ -834,6 +874,86 @@ class ViewSampler:
         """(whole batch, this rank's share of it): view i of the batch goes to rank i mod world."""
         batch = self.next_batch()
         return batch, [batch[i] for i in shard_views(len(batch), rank, world)]
+
+
+class _ImagesWithBackward(torch.autograd.Function):
+    """The step's rendered images as a differentiable tensor: whatever torch loss sits on top (L1, LPIPS, ...),
+    its dL/dimages arrives here and goes through the batched backward into model.flat_grad."""
+
+    @staticmethod
+    def forward(ctx, hook, images, adapter):
+        ctx.adapter = adapter
+        return images.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        ctx.adapter._backward(g.contiguous())
+        return torch.zeros_like(ctx.adapter._hook), None, None
+
+
+class DGEFitAdapter:
+    """DGE's training step mapped onto the per-step family: what
+    DGE.forward (threestudio/systems/DGE.py:170-239), loss.backward() and DGE.on_before_optimizer_step (:266-296)
+    do around gaussian_renderer.render(), for this rank's share of the step's cameras, with ALL views per launch.
+
+        out = adapter.forward(cameras, bg, mask=gaussian_mask)   # images, depth, semantic masks, radii
+        loss = any_torch_loss(out["comp_rgb"], ...)               # e.g. DGE.py:637-683: 10 L1 + 10 LPIPS
+        loss.backward()                                           # -> batched backward, raw-parameter gradients
+        adapter.on_before_optimizer_step()                        # all-reduce over the ranks + densification stats
+        adapter.optimizer_step()                                  # fused Adam (FitModel.adam_step)
+
+    The loss must be the GLOBAL batch's loss restricted to this rank's views (e.g. an L1 mean over the global
+    batch: sum over this rank's pixels / global pixel count), so that the all-reduced gradient is the step's.
+    The second, mask-colour render DGE makes of every view (DGE.py:198-204) rides as a fourth blended channel of
+    the same launches; `semantic` / `masks` are what DGE.forward derives from it."""
+
+    def __init__(self, model: FitModel, process_group=None, prune_lists: bool = True, num_chunks: int = 1):
+        self.model, self.group, self.prune_lists, self.num_chunks = model, process_group, prune_lists, num_chunks
+        self._hook = torch.zeros((), device=model.device, requires_grad=True)
+        self._radii = None
+
+    def forward(self, cameras, bg, mask: Optional[torch.Tensor] = None):
+        model = self.model
+        if len(cameras) == 0:
+            raise ValueError("DGEFitAdapter.forward needs at least one camera on every rank")
+        _batched_forward(model, model.activations_fused(), cameras, bg, self.num_chunks, self.prune_lists,
+                         extra=None if mask is None else mask.reshape(-1).float())
+        batches, main = model._batches, model._fw["main"]
+        for vb in batches:
+            main.wait_stream(vb.stream)
+        cat = lambda ts: ts[0] if len(ts) == 1 else torch.cat(ts)
+        images, depth = cat([vb.color for vb in batches]), cat([vb.depth for vb in batches])
+        radii = batches[0].radii_max
+        for vb in batches[1:]:
+            radii = torch.maximum(radii, vb.radii_max)
+        self._radii = radii
+        comp = _ImagesWithBackward.apply(self._hook, images, self)
+        depths = depth.permute(0, 2, 3, 1)
+        out = {"comp_rgb": comp.permute(0, 2, 3, 1), "depth": depths, "opacity": depths / (depths.max() + 1e-5),
+               "radii": radii, "visibility_filter": radii > 0}
+        if mask is not None:
+            sem = cat([vb.sem for vb in batches])               # [V,3,H,W]: render(..., override_color=mask x3)
+            semantic_map = torch.norm(sem, dim=1) > 0.8          # DGE.py:205-206
+            viz = images.detach().clone().permute(0, 2, 3, 1)    # DGE.py:207-216
+            viz[semantic_map] = 0.40 * viz[semantic_map] + 0.60 * torch.tensor([1.0, 0.0, 0.0], device=viz.device)
+            out["semantic"], out["masks"], out["semantic_render"] = viz.permute(0, 3, 1, 2), semantic_map, sem
+        return out
+
+    __call__ = forward
+
+    def _backward(self, dL_dimages):
+        early = None
+        self._radii = _batched_backward(self.model, dL_dimages, 1, early)
+
+    def on_before_optimizer_step(self, update_stats: bool = True):
+        """DGE.py:266-284 (+ the collective of SURVEY.md §8e): the gradients of all ranks' views summed, the
+        radii maxed, xyz_gradient_accum / denom / max_radii2D updated. Densification itself
+        (FitModel.densify_and_prune, DGE.py:286-296) stays with the caller's schedule."""
+        zero = torch.zeros((), device=self.model.device)
+        _finish_step(self.model, zero, self._radii, self.group, update_stats, None, adam=False)
+
+    def optimizer_step(self):
+        self.model.adam_step()
 
 
 def default_rasterize(rs, means3D, means2D, shs, opacities, scales, rotations):
@@ -991,7 +1111,9 @@ class _EarlyRestReduce:
         self.done_rows = first + count
 
 
-def _finish_step(model, loss, radii_max, process_group, update_stats, early=None):
+def _finish_step(model, loss, radii_max, process_group, update_stats, early=None, adam=True):
+    """The collective, the densification statistics and (adam=True) the optimiser step. With adam=False the
+    gradients are left reduced in model.flat_grad for a separate FitModel.adam_step() (DGEFitAdapter)."""
     world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
     pending = None
     if world > 1:
@@ -1022,6 +1144,10 @@ def _finish_step(model, loss, radii_max, process_group, update_stats, early=None
             gnorm = model.means2D.grad[:, :2].norm(dim=-1, keepdim=True)
             model.xyz_gradient_accum += torch.where(vis[:, None], gnorm, torch.zeros_like(gnorm))
             model.denom += vis[:, None].to(model.denom.dtype)
+    if not adam:
+        for w in ([w for _, _, w in pending] if pending else []) + (early.works if early is not None else []):
+            w.wait()
+        return loss
     if pending is not None and model.fused_adam:
         model.adam_step(skip=("f_rest",))
         if early is not None and early.done_rows:

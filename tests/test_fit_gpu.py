@@ -368,3 +368,78 @@ def test_per_gaussian_backward_over_ranges_is_bit_identical(cuda):
     parts = run([0, 1280, 1408, 3840, Pn], 7.0)   # every row is written: the fill value never survives
     for k in whole:
         assert torch.equal(whole[k].view(torch.int32), parts[k].view(torch.int32)), k
+
+
+def test_dge_fit_adapter_training_step(cuda):
+    """fit.DGEFitAdapter: one DGE.training_step-shaped iteration (threestudio/systems/DGE.py:170-296, 617-699) —
+    a batch of views with a local edit mask, a TORCH loss on top of the returned images (L1 plus a smooth
+    term standing in for LPIPS), loss.backward(), on_before_optimizer_step — through the per-step family, against
+    the same iteration through the per-view API the way DGE.forward drives it (render() twice per view: SH colours,
+    then override_color = mask repeated three times)."""
+    from dge_b200 import diff_gaussian_rasterization as dgr
+    Pn, Wn, Hn, Vn = 40000, 200, 136, 20
+    g = scene.make_gaussians(Pn, seed=17, scale_median=0.03)
+    cams = [scene.camera_to(c, cuda) for c in scene.ring_cameras(Vn, Wn, Hn)]
+    gen = torch.Generator().manual_seed(5)
+    targets = torch.rand(Vn, Hn, Wn, 3, generator=gen).to(cuda)
+    bg = torch.zeros(3, device=cuda)
+    mask = (torch.rand(Pn, generator=gen) < 0.4).to(cuda)           # gaussian.mask of a local edit
+
+    def loss_fn(images):  # [V,H,W,3]; any torch loss: L1 + a smooth second term
+        return 10.0 * (images - targets).abs().mean() + 3.0 * ((images - targets) ** 2).mean()
+
+    # --- the per-step family behind the adapter
+    model = fit.FitModel(g, cuda)
+    ad = fit.DGEFitAdapter(model)
+    out = ad.forward(cams, bg, mask=mask)
+    loss = loss_fn(out["comp_rgb"])
+    loss.backward()
+    ad.on_before_optimizer_step()
+    torch.cuda.synchronize()
+
+    # --- DGE.forward's loop over render() on the per-view API (twin model, same fused activations)
+    twin = fit.FitModel(g, cuda)
+    _share_fused_activations(twin)
+    a = twin.activations()
+    images, depths, sems, vsp, radii = [], [], [], [], None
+    for cam in cams:
+        rs = scene.raster_settings(cam, bg, 3, module=dgr)
+        pts = torch.zeros_like(a["means3D"], requires_grad=True)
+        img, r, d = dgr.GaussianRasterizer(rs)(means3D=a["means3D"], means2D=pts, shs=a["shs"], colors_precomp=None,
+                                               opacities=a["opacities"], scales=a["scales"], rotations=a["rotations"],
+                                               cov3D_precomp=None)
+        sem, _, _ = dgr.GaussianRasterizer(rs)(means3D=a["means3D"], means2D=torch.zeros_like(pts), shs=None,
+                                               colors_precomp=mask[..., None].float().repeat(1, 3),
+                                               opacities=a["opacities"], scales=a["scales"], rotations=a["rotations"],
+                                               cov3D_precomp=None)
+        images.append(img.permute(1, 2, 0)); depths.append(d.permute(1, 2, 0)); sems.append(sem.detach()); vsp.append(pts)
+        radii = r if radii is None else torch.max(r, radii)
+    ref_images = torch.stack(images, 0)
+    twin.zero_grad()
+    loss_ref = loss_fn(ref_images)
+    loss_ref.backward()
+    torch.cuda.synchronize()
+    # forward products: bit-identical
+    assert torch.equal(out["comp_rgb"].detach(), ref_images.detach())
+    assert torch.equal(out["depth"], torch.stack(depths, 0))
+    assert torch.equal(out["semantic_render"], torch.stack(sems, 0))
+    assert torch.equal(out["masks"], torch.norm(torch.stack(sems, 0), dim=1) > 0.8)
+    assert torch.equal(out["radii"], radii) and torch.equal(out["visibility_filter"], radii > 0)
+    assert abs(float(loss) - float(loss_ref)) <= 1e-6 * abs(float(loss_ref))
+    # gradients: raw parameters + the summed screen-space gradient (DGE.py:269-276)
+    vs_grad = sum(v.grad for v in vsp)
+    for name, sl in model.slices.items():
+        ok, msg = util.grad_ok(model.flat_grad[sl].cpu().numpy(), twin.flat_grad[sl].cpu().numpy())
+        print(f"adapter d/d{name}: {msg}")
+        assert ok, (name, msg)
+    ok, msg = util.grad_ok(model.means2D.grad.cpu().numpy(), vs_grad.cpu().numpy())
+    assert ok, ("viewspace", msg)
+    # statistics of on_before_optimizer_step (gaussian_model.py:811-815)
+    vis = radii > 0
+    assert torch.equal(model.denom.view(-1) > 0, vis)
+    want = torch.where(vis, vs_grad[:, :2].norm(dim=-1), torch.zeros(Pn, device=cuda))
+    torch.testing.assert_close(model.xyz_gradient_accum.view(-1), want, rtol=1e-3, atol=1e-4 * float(want.max()))
+    assert torch.equal(model.max_radii2D, torch.where(vis, radii, torch.zeros_like(radii)))
+    before = model.flat.clone()
+    ad.optimizer_step()
+    assert not torch.equal(before, model.flat) and model.step_count == 1
