@@ -370,6 +370,11 @@ def run_reference(args, cfg):
                   sampled="sm_mhz / sm_mhz_e2e: measured on the device over the timed regions (per-SM clock64 / "
                           "globaltimer probes at both ends); reasons and sm_mhz_nvml: NVML over identical steps run "
                           "right after them")
+    extras = {}
+    if args.extras:
+        del model
+        torch.cuda.empty_cache()
+        extras["boundary"] = measure_boundary(rasterize, Settings, wl, dev, max(3, min(args.steps, 6)), 3)
     assert "dge_b200._lib" not in sys.modules and "dge_b200.fit" not in sys.modules
     out = {
         "metric": METRIC, "value": res["value"], "unit": "views/s", "n_gpus": 1, "steps": args.steps, "warmup": W_,
@@ -378,7 +383,7 @@ def run_reference(args, cfg):
         "workload_stats": stats, "timing": {"resident": res, "e2e": e2e}, "clocks": clocks,
         "e2e": {"value": e2e["value"], "unit": "views/s", "h2d_bytes_per_step": V * (3 * H * W * 4 + (16 + 16 + 3) * 4),
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e["ms_per_step"], "loss": last[0]},
-        "gpu_launches": None, "impl": "reference",
+        "gpu_launches": None, "impl": "reference", "extras": extras,
         "path": "DGE training step (render() per view with per-view activations, stacked L1, one backward, "
                 "on_before_optimizer_step statistics, torch.optim.Adam) around the unmodified reference rasterizer",
         "cpu_baseline": {"value": res["value"], "unit": "views/s", "cores": os.cpu_count(), "kind": "reference",
@@ -555,12 +560,45 @@ def measure_dropin(args, cfg, dev, K, W_):
         step(True).item()
     total2, per2 = timed_steps(lambda: step(True).item(), K, barrier)
     res, e2e = summarize(total, per, V), summarize(total2, per2, V)
-    del model, wl
+    del model
+    torch.cuda.empty_cache()
+    boundary = measure_boundary(rasterize, make_settings, wl, dev, K, W_)
+    del wl
     torch.cuda.empty_cache()
     return {"workload": "config2 through the drop-in boundary: the reference arm's loop, import swapped",
+            "boundary": boundary,
             "value": res["value"], "unit": "views/s", "ms_per_step": res["ms_per_step"],
             "ms_per_step_median": res["ms_per_step_median"], "steps": K,
             "e2e": {"value": e2e["value"], "ms_per_step": e2e["ms_per_step"], "ms_per_step_median": e2e["ms_per_step_median"]}}
+
+
+def measure_boundary(rasterize, make_settings, wl, dev, K, W_):
+    """SURVEY.md §8d's metric at its own boundary: GaussianRasterizer.forward + the autograd backward per view,
+    nothing else — activated tensors given as leaves, a fixed random dL/dcolor as the upstream gradient, no
+    activations, loss or optimiser. views/s over the workload's views, K passes."""
+    g = wl.g
+    leaves = [t.to(dev).contiguous().requires_grad_(True) for t in (g.means3D, g.shs, g.opacities, g.scales, g.rotations)]
+    m2d = torch.zeros(g.means3D.shape[0], 3, device=dev, requires_grad=True)
+    gen = torch.Generator().manual_seed(99)
+    H, W = wl.cfg["H"], wl.cfg["W"]
+    dL = (torch.randn(3, H, W, generator=gen) / (3.0 * H * W)).to(dev)
+
+    def one_pass():
+        for cam in wl.cams_dev:
+            for t in leaves + [m2d]:
+                t.grad = None  # AccumulateGrad then keeps the returned tensor: no add kernels in the loop
+            color, _radii, _depth = rasterize(make_settings(cam, wl.bg, 3), leaves[0], m2d, leaves[1], leaves[2], leaves[3],
+                                              leaves[4])
+            color.backward(dL)
+
+    for _ in range(W_):
+        one_pass()
+    total, per = timed_steps(one_pass, K, torch.cuda.synchronize)
+    r = summarize(total, per, len(wl.cams_dev))
+    return {"workload": "config2 scene, per view: GaussianRasterizer.forward + autograd backward with a fixed dL/dcolor "
+                        "(SURVEY.md 8d boundary; no activations, loss or optimiser)",
+            "value": r["value"], "unit": "views/s", "value_median": r["value_median"],
+            "ms_per_view": r["ms_per_step"] / len(wl.cams_dev), "passes": K, "views_per_pass": len(wl.cams_dev)}
 
 
 def measure_config3(args, cfg, dev, K, W_, per_view=False, impl="ours"):
@@ -780,6 +818,7 @@ def run_ours(args, cfg):
                                                    "split over the ranks)", "strong")
             if world == 1:
                 extras["dropin"] = measure_dropin(args, cfg, dev, Kx, Wx)
+                extras["boundary"] = extras["dropin"].pop("boundary")
                 extras["config3"] = measure_config3(args, CONFIGS["config3"], dev, Kx, Wx)
                 extras["config5"] = measure_fit(args, CONFIGS["config5"], d, CONFIGS["config5"]["V"], Kx, Wx,
                                                 "config5 (2M point)", "weak")
