@@ -504,8 +504,10 @@ def measure_fit(args, cfg, d, views_global, K, W_, name, scaling, device_targets
     W, H = cfg["W"], cfg["H"]
 
     def step(host):
-        return fit.fit_step(model, wl.cams_host if host else wl.cams_dev, wl.targets_host if host else wl.targets_stacked,
-                            wl.bg, global_batch=views_global, host_inputs=host, image_size=(W, H))
+        cams = wl.cams_host if host else wl.cams_dev
+        return fit.fit_step(model, cams, wl.targets_host if host else wl.targets_stacked,
+                            wl.bg, global_batch=views_global, host_inputs=host, image_size=(W, H),
+                            next_cameras=cams if d.world > 1 else None)
 
     for _ in range(W_):
         step(False)
@@ -711,12 +713,17 @@ def run_ours(args, cfg):
     wl = Workload(cfg, dev, V * world, fit.shard_views(V * world, rank, world), device_targets=cfg["P"] > 1_500_000)
     model = fit.FitModel(wl.g, dev, lrs=LRS, fused_adam=True)
     batched = args.streams == 0
+    pipeline = (world > 1 and args.pipeline != 0) or args.pipeline == 1
 
     def step(host):
         tg = wl.targets_host if host else (wl.targets_stacked if batched else wl.targets_dev)
-        return fit.fit_step(model, wl.cams_host if host else wl.cams_dev, tg, wl.bg, global_batch=V * world,
+        cams = wl.cams_host if host else wl.cams_dev
+        # several GPUs: the next step's cameras are known (here: the same ones), so its projection / depth sort /
+        # binning run under this step's f_rest all-reduce (fit.fit_step: next_cameras)
+        return fit.fit_step(model, cams, tg, wl.bg, global_batch=V * world,
                             host_inputs=host, num_streams=max(args.streams, 1), batched=batched, num_chunks=args.chunks,
-                            geom_splits=args.geom_splits or None, image_size=(W, H))
+                            geom_splits=args.geom_splits or None, image_size=(W, H),
+                            next_cameras=cams if (pipeline and batched) else None)
 
     W_ = max(args.warmup, 3)
     for _ in range(W_):
@@ -836,7 +843,7 @@ def run_ours(args, cfg):
         "workload_stats": stats, "timing": {"resident": res, "e2e": e2e},
         "path": {"impl": "per-step C-ABI family (fit.fit_step)", "parallelism": f"dp{world} (views)",
                  "views_per_launch": -(-V // args.chunks) if batched else 1, "chunks": args.chunks if batched else None,
-                 "streams_per_gpu": max(args.streams, 1)},
+                 "streams_per_gpu": max(args.streams, 1), "next_step_front_prefetched": bool(pipeline and batched)},
         "clocks": clocks,
         "e2e": {"value": e2e["value"], "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * world,
                 "ms_per_step": e2e["ms_per_step"], "loss": last[0]},
@@ -883,6 +890,8 @@ def main():
     ap.add_argument("--views", type=int, default=0, help="override the config's views per step per GPU")
     ap.add_argument("--geom-splits", type=int, default=0, help="per-Gaussian backward launches per step (0: "
                     "fit.py's default; > 1 on several GPUs sends finished ranges' f_rest rows early)")
+    ap.add_argument("--pipeline", type=int, default=-1, help="-1 (default): prefetch the next step's front half under the "
+                    "f_rest all-reduce when there are several GPUs; 0: never; 1: always (also on one GPU)")
     ap.add_argument("--chunks", type=int, default=1, help="batched path: split the step's views into this many "
                     "chunks, each on its own stream")
     ap.add_argument("--streams", type=int, default=0,

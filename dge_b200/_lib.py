@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # DGE_B200_LIB: an alternative build of the SAME library (A/B measurements of kernel variants)
 LIB_PATH = os.environ.get("DGE_B200_LIB") or os.path.join(_HERE, "_build", "libdge_b200.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
@@ -47,6 +47,10 @@ _SIGNATURES = {
     "dge_fit_backward_blend": (_i, [_i, _i, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "dge_fit_views_forward": (_i, [ALLOC_FN, ALLOC_FN, ALLOC_FN, _p, _i, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _f, _p,
                                    _p, _p, _p, _p, _p, C.c_size_t, _p, C.c_size_t, _p, _p, _p, _i, _p]),
+    "dge_fit_views_front": (_i, [ALLOC_FN, ALLOC_FN, ALLOC_FN, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p,
+                                 _p, C.c_size_t, _p, _i, _p]),
+    "dge_fit_views_colour": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, C.c_size_t, _p]),
+    "dge_fit_views_blend": (_i, [_i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, C.c_size_t, _p, _p, _p]),
     "dge_fit_views_backward_blend": (_i, [_i, _i, _i, _p, _i, _i, _i, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "dge_fit_binning_bytes": (C.c_size_t, [_i, _i, _i, _i]),
     "dge_fit_views_apply_weights": (_i, [ALLOC_FN, ALLOC_FN, ALLOC_FN, _p, _i, _i, _i, _i, _p, _p, _p, _f, _p, _p, _p, _i,

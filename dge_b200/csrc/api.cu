@@ -272,7 +272,7 @@ using namespace dge;
 extern "C" {
 
 const char* dge_last_error(void) { return g_err; }
-int dge_abi_version(void) { return 11; }
+int dge_abi_version(void) { return 12; }
 unsigned long long dge_launch_count(void) { return g_kernel_launches; }
 
 int dge_clock_probe(unsigned long long* out, void* stream_) {
@@ -425,6 +425,68 @@ static int bin_views(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dg
   return (int)R_total;
 }
 
+int dge_fit_views_front(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge_alloc_fn imageBuffer,
+                        void* alloc_ctx, int P, int D, int M, int V, int width, int height, const float* means3D,
+                        const float* shs, const float* opacities, const float* scales, float scale_modifier,
+                        const float* rotations, const float* cams, int* radii_max, uint8_t* flags,
+                        size_t flags_stride, int* num_rendered_host, int prune_lists, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (P == 0 || width <= 0 || height <= 0) return fail_msg("empty problem");
+  if (flags != nullptr && flags_stride < (size_t)P) return fail_msg("flags_stride >= P is required");
+  if (shs != nullptr && M != 16) return fail_msg("the batched fit path needs SH degree-3 storage (M == 16)");
+  // tan_fov / focal are per view and filled in by the batched preprocess from the camera records
+  const ViewParams vp = make_view(P, D, M, width, height, nullptr, nullptr, nullptr, 1.f, 1.f, scale_modifier);
+  GeomState g0;
+  ImgState img0;
+  BinState b;
+  ViewBatch vb;
+  return bin_views(geometryBuffer, binningBuffer, imageBuffer, alloc_ctx, vp, V, means3D, shs, opacities, scales,
+                   rotations, cams, radii_max, flags, flags_stride, num_rendered_host, prune_lists != 0, stream, g0,
+                   b, img0, vb);
+}
+
+int dge_fit_views_colour(int P, int D, int M, int V, const float* means3D, const float* shs, const float* cams,
+                         char* geom_buffer, uint8_t* flags, size_t flags_stride, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (P == 0) return 0;
+  if (M != 16 || shs == nullptr || flags == nullptr) return fail_msg("dge_fit_views_colour needs SH degree-3 storage and the flags of the front half");
+  if (V < 1 || V > DGE_MAX_BATCH_VIEWS) return fail_msg("a batch holds 1..64 views");
+  GeomState g0;
+  const size_t gstride = batch_stride(carve_geom(geom_buffer, P, &g0));
+  CK("colour (batched)", launch_colour_batched(P, D, V, cams, means3D, shs, g0, gstride, flags, flags_stride, stream));
+  return 0;
+}
+
+int dge_fit_views_blend(int P, int V, int R_total, const float* background, int width, int height, char* geom_buffer,
+                        char* binning_buffer, char* image_buffer, float* out_color, float* out_depth, float* acc,
+                        size_t acc_stride_floats, const float* extra, float* out_extra, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool debug = false;
+  if (P == 0 || width <= 0 || height <= 0) return fail_msg("empty problem");
+  if (V < 1 || V > DGE_MAX_BATCH_VIEWS) return fail_msg("a batch holds 1..64 views");
+  if (acc != nullptr && (acc_stride_floats < (size_t)ACC_STRIDE * P || (acc_stride_floats & 3)))
+    return fail_msg("acc_stride_floats >= 12 P (a multiple of 4) is required");
+  if ((extra == nullptr) != (out_extra == nullptr)) return fail_msg("extra and out_extra go together");
+  const ViewParams vp = make_view(P, 0, 0, width, height, nullptr, nullptr, nullptr, 1.f, 1.f, 1.f);
+  GeomState g0;
+  BinState b;
+  ImgState img0;
+  ViewBatch vb;
+  vb.V = V;
+  vb.geom_stride = batch_stride(carve_geom(geom_buffer, P, &g0));
+  vb.img_stride = batch_stride(carve_image(image_buffer, width, height, &img0));
+  carve_binning_batched(binning_buffer, (uint32_t)R_total, V, vp.grid_x * vp.grid_y, &b);
+  vb.seg_off = batch_seg_off(g0);
+  vb.cams = nullptr;
+  // the views' rows of blend-stage sums start at zero: a memset on a side stream, forked here so that it runs
+  // beside the forward blend (issue-bound, 3 % of the DRAM bandwidth) instead of inside preprocess
+  if (acc != nullptr) CK("acc zero", zero_acc_async(acc, acc_stride_floats, P, V, stream));
+  STAGE(ST_RENDER_FWD, "render forward (batched)",
+        launch_render_forward_batched(vp, vb, g0, b, img0, background, out_color, out_depth, stream, extra,
+                                      out_extra));
+  return 0;
+}
+
 int dge_fit_views_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge_alloc_fn imageBuffer,
                           void* alloc_ctx, int P, int D, int M, int V, const float* background, int width,
                           int height, const float* means3D, const float* shs, const float* opacities,
@@ -450,8 +512,6 @@ int dge_fit_views_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffe
                                 scales, rotations, cams, radii_max, flags, flags_stride, num_rendered_host,
                                 prune_lists != 0, stream, g0, b, img0, vb);
   if (R_total < 0) return R_total;
-  // the views' rows of blend-stage sums start at zero: a memset on a side stream, forked here so that it runs
-  // beside the forward blend (issue-bound, 3 % of the DRAM bandwidth) instead of inside preprocess
   if (acc != nullptr) CK("acc zero", zero_acc_async(acc, acc_stride_floats, P, V, stream));
   STAGE(ST_RENDER_FWD, "render forward (batched)",
         launch_render_forward_batched(vp, vb, g0, b, img0, background, out_color, out_depth, stream, extra,

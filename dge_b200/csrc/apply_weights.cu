@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(BL_THREADS) apply_weights_kernel(
     const bool all_done = done[0] && done[1] && done[2] && done[3];
     if (__syncthreads_and(all_done)) break;
     const int count = min((uint32_t)BL_BATCH, range.y - base);
-    stage_batch(s, tid, count, [&](int k) { return base + k; }, point_list, rec, parity);
+    stage_batch(s, tid, count, [&](int k) { return base + k; }, point_list, rec, parity, nullptr, bb.P);
     parity ^= 1u;
     if (__all_sync(0xFFFFFFFFu, all_done)) continue;
     uint32_t live = 0;
@@ -116,7 +116,7 @@ cudaError_t launch_apply_weights_render_batched(const ViewParams& vp, const View
                                                 const float* image_weights, int num_channels,
                                                 cudaStream_t stream) {
   dim3 grid(vp.grid_x, vp.grid_y, vb ? vb->V : 1);
-  const BlendBatch bb = vb ? BlendBatch{vb->geom_stride, vb->img_stride, vb->seg_off, 0} : BlendBatch{0, 0, nullptr, 0};
+  const BlendBatch bb = vb ? BlendBatch{vb->geom_stride, vb->img_stride, vb->seg_off, 0, (uint32_t)vp.P} : BlendBatch{0, 0, nullptr, 0, (uint32_t)vp.P};
 #define AW_LAUNCH(CH)                                                                          \
   apply_weights_kernel<CH><<<grid, BL_THREADS, 0, stream>>>(img.ranges, b.point_list, vp.W, vp.H, \
                                                             g.rec, image_weights, weights, cnt, bb)

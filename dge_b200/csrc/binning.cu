@@ -152,6 +152,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) expand_kernel(
     const uint32_t w = q.z - q.x;
     const uint32_t row = __float2uint_rz(((float)j + 0.5f) * s_invw[warp][l]);
     const uint32_t ty = q.y + row, tx = q.x + (j - row * w);
+    DGE_CHECK(seg_off == nullptr || target < seg_off[blockIdx.y + 1] - seg_off[blockIdx.y]);
+    DGE_CHECK(j < (uint32_t)(q.z - q.x) * (uint32_t)(q.w - q.y) && tx < (uint32_t)grid_x);
     keys_out[target] = ty * (uint32_t)grid_x + tx;
     vals_out[target] = s_gid[warp][l];
   }
@@ -551,6 +553,7 @@ __global__ void __launch_bounds__(PART_THREADS) part_scatter_kernel(
     prev = __shfl_sync(0xFFFFFFFFu, prev, leader);
     if (valid) {
       const uint32_t pos = prev + __popc(peers & lt_mask);
+      DGE_CHECK(pos < n);
       out[pos] = val[k];
       if (kout) kout[pos] = key[k];
     }
@@ -634,6 +637,7 @@ __global__ void __launch_bounds__(PART_THREADS, DGE_PART_SMALL_MIN_CTAS) part_sc
     base += __popc(mine);
     if (valid) {
       const uint32_t pos = prev + __popc(peers & lt_mask);
+      DGE_CHECK(pos < n);
       out[pos] = val[k];
       if (kout) kout[pos] = key[k];
     }

@@ -36,6 +36,7 @@ struct BlendBatch {
   size_t geom_stride, img_stride;
   const uint32_t* seg_off;
   size_t acc_stride;
+  uint32_t P;  // number of Gaussians (checked builds: bound of the staged ids)
 };
 
 // A staged record occupies 80 bytes of shared memory: the 64-byte record + one float4 holding the
@@ -74,7 +75,8 @@ template <typename SRC>
 __device__ __forceinline__ void stage_batch(BlendSmem& s, int tid, int count, SRC src,
                                             const uint32_t* __restrict__ point_list,
                                             const float4* __restrict__ rec, uint32_t parity,
-                                            const float* __restrict__ extra = nullptr) {
+                                            const float* __restrict__ extra = nullptr, uint32_t num_gaussians = 0) {
+  (void)num_gaussians;
   constexpr int PER = BL_BATCH / BL_THREADS;
   uint32_t gid[PER];
   int mine = 0;
@@ -83,6 +85,7 @@ __device__ __forceinline__ void stage_batch(BlendSmem& s, int tid, int count, SR
     const int k = tid + i * BL_THREADS;
     if (k < count) {
       gid[i] = point_list[src(k)];
+      DGE_CHECK(num_gaussians == 0 || gid[i] < num_gaussians);
       s.rec[k][REC_F4].x = __uint_as_float(gid[i]);
       if (extra != nullptr) s.rec[k][REC_F4].y = extra[gid[i]];  // a fourth blended channel (forward only)
       mine++;

@@ -7,6 +7,27 @@
 #define DGE_TILE 16            // DGR/cuda_rasterizer/config.h:16-17 (BLOCK_X/BLOCK_Y)
 #define DGE_NUM_SMS 148
 
+// Checked build (python -m dge_b200.build --variant checks -DDGE_CHECKS=1; tests/gpu_checked_build.sh): bounds
+// assertions on every scattered global store of the sort / partition / expand kernels and on every gathered
+// index of the blend staging. compute-sanitizer is closed on the GPU pool this was developed on, so the GPU
+// suite is run once against this build instead; a failure prints its site and traps.
+#ifndef DGE_CHECKS
+#define DGE_CHECKS 0
+#endif
+#if DGE_CHECKS
+#include <cstdio>
+#define DGE_CHECK(cond)                                                                          \
+  do {                                                                                           \
+    if (!(cond)) {                                                                               \
+      printf("DGE_CHECK failed: %s at %s:%d (block %d,%d,%d thread %d)\n", #cond, __FILE__, __LINE__, \
+             blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);                                   \
+      __trap();                                                                                  \
+    }                                                                                            \
+  } while (0)
+#else
+#define DGE_CHECK(cond) ((void)0)
+#endif
+
 namespace dge {
 
 // Number of kernels this library has launched (read by bench.py through dge_launch_count()).
@@ -163,6 +184,11 @@ cudaError_t launch_preprocess_batched(const ViewParams& vp, const ViewBatch& vb,
                                       const float* scales, const float* rotations, const float* opacities,
                                       const float* shs, GeomState& g0, uint8_t* flags, size_t flags_stride,
                                       int* radii_max, bool prune_lists, cudaStream_t stream);
+// colours (SH -> rgb + clamp bits) of the visible (view, Gaussian) pairs into the records of a batched preprocess
+// that ran without SH (geometry only)
+cudaError_t launch_colour_batched(int P, int D, int V, const float* cams, const float* means3D, const float* shs,
+                                  GeomState& g0, size_t geom_stride, uint8_t* flags, size_t flags_stride,
+                                  cudaStream_t stream);
 cudaError_t launch_seg_offsets(const ViewBatch& vb, const GeomState& g0, uint32_t* seg_off, cudaStream_t stream);
 cudaError_t launch_depth_sort_batched(int P, const ViewBatch& vb, GeomState& g0, cudaStream_t stream);
 cudaError_t launch_binning_batched(const ViewParams& vp, const ViewBatch& vb, uint32_t R_total, uint32_t R_max,

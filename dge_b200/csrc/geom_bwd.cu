@@ -637,18 +637,22 @@ __global__ void __launch_bounds__(256) activate_kernel(int P, const float* __res
                                                        const float* __restrict__ scaling_raw,
                                                        const float* __restrict__ rotation_raw,
                                                        float* __restrict__ shs, float* __restrict__ opacities,
-                                                       float* __restrict__ scales, float* __restrict__ rotations) {
+                                                       float* __restrict__ scales, float* __restrict__ rotations,
+                                                       int which) {  // bit 0: opacity / scaling / rotation, bit 1: features
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= P) return;
   const size_t i = (size_t)idx;
-  float v[48];
+  if (which & 2) {  // features: shs = cat(f_dc, f_rest)
+    float v[48];
 #pragma unroll
-  for (int k = 0; k < 3; k++) v[k] = __ldg(f_dc + 3 * i + k);
+    for (int k = 0; k < 3; k++) v[k] = __ldg(f_dc + 3 * i + k);
 #pragma unroll
-  for (int k = 0; k < 45; k++) v[3 + k] = __ldg(f_rest + 45 * i + k);
+    for (int k = 0; k < 45; k++) v[3 + k] = __ldg(f_rest + 45 * i + k);
 #pragma unroll
-  for (int j = 0; j < 12; j++)
-    reinterpret_cast<float4*>(shs + 48 * i)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    for (int j = 0; j < 12; j++)
+      reinterpret_cast<float4*>(shs + 48 * i)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+  if (!(which & 1)) return;
   opacities[i] = 1.0f / (1.0f + expf(-__ldg(opacity_raw + i)));
 #pragma unroll
   for (int k = 0; k < 3; k++) scales[3 * i + k] = expf(__ldg(scaling_raw + 3 * i + k));
@@ -660,8 +664,12 @@ __global__ void __launch_bounds__(256) activate_kernel(int P, const float* __res
 cudaError_t launch_activate(int P, const float* f_dc, const float* f_rest, const float* opacity_raw,
                             const float* scaling_raw, const float* rotation_raw, float* shs,
                             float* opacities, float* scales, float* rotations, cudaStream_t stream) {
+  // either half may be left out (NULL inputs): the geometry activations of the next step run before its
+  // features have been stepped (multi-GPU pipelining, fit.py)
+  const int which = (opacity_raw != nullptr ? 1 : 0) | (f_dc != nullptr ? 2 : 0);
+  if (which == 0) return cudaSuccess;
   activate_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw,
-                                                       shs, opacities, scales, rotations);
+                                                       shs, opacities, scales, rotations, which);
   DGE_LAUNCHED(1);
   return cudaGetLastError();
 }

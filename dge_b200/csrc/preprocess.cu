@@ -403,6 +403,59 @@ cudaError_t launch_preprocess_batched(const ViewParams& vp, const ViewBatch& vb,
   return cudaGetLastError();
 }
 
+// ---- colours of a geometry-only batched preprocess -------------------------------------------------
+// Multi-GPU fit: the next step's projection, depth sort and binning do not depend on the SH coefficients, so
+// they run (preprocess_batched_kernel with shs == nullptr) while the all-reduce of the f_rest gradient — three
+// quarters of the step's bytes — is still on the wire; once f_rest has been stepped, this kernel fills in
+// what was left out: rgb of every visible (view, Gaussian) pair into its blend record and the SH clamp bits
+// into its flag byte. Same sh_color as the fused path: records and flags end up bit-identical.
+__global__ void __launch_bounds__(PRE_B_THREADS, PRE_B_MIN_CTAS) colour_batched_kernel(
+    int P, int D, int V, const float* __restrict__ cams, const float* __restrict__ means3D,
+    const float* __restrict__ shs, float4* __restrict__ rec0, size_t geom_stride, uint8_t* __restrict__ flags,
+    size_t flags_stride) {
+  extern __shared__ float s_cam[];  // V * 40 floats, then the SH block
+  float* s_sh = s_cam + V * 40 + threadIdx.x;
+  for (int k = threadIdx.x; k < V * 40; k += blockDim.x) s_cam[k] = cams[k];
+  __syncthreads();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  const float px = __ldg(means3D + 3 * idx), py = __ldg(means3D + 3 * idx + 1), pz = __ldg(means3D + 3 * idx + 2);
+  bool loaded = false;
+  for (int view = 0; view < V; view++) {
+    uint8_t* fp = flags + (size_t)view * flags_stride + idx;
+    if (!(*fp & 1u)) continue;
+    if (!loaded) {  // Gaussians no view sees never touch their 192 bytes of SH
+      const float* base = shs + 48 * (size_t)idx;
+      float4 v[12];
+#pragma unroll
+      for (int i = 0; i < 12; i++) v[i] = ldg4(base + 4 * i);
+      const float* f = reinterpret_cast<const float*>(v);
+#pragma unroll
+      for (int k = 0; k < 48; k++) s_sh[k * PRE_B_THREADS] = f[k];
+      loaded = true;
+    }
+    const float* cam = s_cam + view * 40;
+    float rgb[3];
+    const uint8_t cl = sh_color(D, px, py, pz, cam[32], cam[33], cam[34],
+                                [&](int k, int c) { return s_sh[(3 * k + c) * PRE_B_THREADS]; }, rgb);
+    float4* q2 = shift_ptr(rec0, (size_t)view * geom_stride) + (size_t)idx * REC_F4 + 2;
+    const float hx = q2->w;
+    *q2 = make_float4(rgb[0], rgb[1], rgb[2], hx);
+    *fp = (uint8_t)(1u | ((uint32_t)cl << 1));
+  }
+}
+
+cudaError_t launch_colour_batched(int P, int D, int V, const float* cams, const float* means3D, const float* shs,
+                                  GeomState& g0, size_t geom_stride, uint8_t* flags, size_t flags_stride,
+                                  cudaStream_t stream) {
+  const int blocks = (P + PRE_B_THREADS - 1) / PRE_B_THREADS;
+  const size_t smem = (size_t)V * 40 * sizeof(float) + 48 * PRE_B_THREADS * sizeof(float);
+  colour_batched_kernel<<<blocks, PRE_B_THREADS, smem, stream>>>(P, D, V, cams, means3D, shs, g0.rec, geom_stride, flags,
+                                                                  flags_stride);
+  DGE_LAUNCHED(1);
+  return cudaGetLastError();
+}
+
 // K12 checkFrustum (DGR/cuda_rasterizer/rasterizer_impl.cu:53-63)
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
                                     const float* __restrict__ view,

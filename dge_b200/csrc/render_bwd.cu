@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(BL_THREADS, HAS_BG ? 12 : DGE_BWD_MIN_CTAS) re
   for (uint32_t hi = bmax; hi > 0; hi -= min(hi, (uint32_t)BL_BATCH)) {
     const int count = min(hi, (uint32_t)BL_BATCH);
     __syncthreads();  // everyone has finished walking the previous batch
-    stage_batch(s, tid, count, [&](int k) { return range.x + hi - 1 - k; }, point_list, rec, parity);
+    stage_batch(s, tid, count, [&](int k) { return range.x + hi - 1 - k; }, point_list, rec, parity, nullptr, bb.P);
     parity ^= 1u;
     if (hi - count >= wmax) continue;  // nothing in this batch reaches this warp (warp-uniform)
     const int n = compact_batch(s, warp, lane, count, X0, Y0, [&](int k) {
@@ -222,7 +222,7 @@ cudaError_t launch_render_backward(const ViewParams& vp, const GeomState& g, con
                                    const float* dL_dpix, float* acc, bool black_background,
                                    cudaStream_t stream) {
   return launch_bwd(dim3(vp.grid_x, vp.grid_y), g, b, img, vp.W, vp.H, background, dL_dpix, acc, black_background,
-                    BlendBatch{0, 0, nullptr, 0}, stream);
+                    BlendBatch{0, 0, nullptr, 0, (uint32_t)vp.P}, stream);
 }
 
 cudaError_t launch_render_backward_batched(const ViewParams& vp, const ViewBatch& vb, const GeomState& g0,
@@ -230,7 +230,7 @@ cudaError_t launch_render_backward_batched(const ViewParams& vp, const ViewBatch
                                            const float* dL_dpix, float* acc, size_t acc_stride_floats,
                                            bool black_background, cudaStream_t stream) {
   return launch_bwd(dim3(vp.grid_x, vp.grid_y, vb.V), g0, b, img0, vp.W, vp.H, background, dL_dpix, acc,
-                    black_background, BlendBatch{vb.geom_stride, vb.img_stride, vb.seg_off, acc_stride_floats},
+                    black_background, BlendBatch{vb.geom_stride, vb.img_stride, vb.seg_off, acc_stride_floats, (uint32_t)vp.P},
                     stream);
 }
 

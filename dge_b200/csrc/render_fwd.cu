@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(BL_THREADS, EXTRA ? 12 : DGE_FWD_MIN_CTAS) ren
     const bool all_done = pmax[0] < 0.0f && pmax[1] < 0.0f && pmax[2] < 0.0f && pmax[3] < 0.0f;
     if (__syncthreads_and(all_done)) break;  // also: everyone has finished walking the previous batch
     const int count = min((uint32_t)BL_BATCH, range.y - base);
-    stage_batch(s, tid, count, [&](int k) { return base + k; }, point_list, rec, parity, EXTRA ? extra : nullptr);
+    stage_batch(s, tid, count, [&](int k) { return base + k; }, point_list, rec, parity, EXTRA ? extra : nullptr, bb.P);
     parity ^= 1u;
     if (__all_sync(0xFFFFFFFFu, all_done)) continue;  // this half-tile is saturated
     // quadrants in which every pixel has terminated need no further visits
@@ -146,7 +146,7 @@ cudaError_t launch_render_forward(const ViewParams& vp, const GeomState& g, cons
   dim3 grid(vp.grid_x, vp.grid_y);
   render_forward_kernel<false><<<grid, BL_THREADS, 0, stream>>>(
       img.ranges, b.point_list, vp.W, vp.H, g.rec, background,
-      img.final_T, img.n_contrib, out_color, out_depth, BlendBatch{0, 0, nullptr, 0}, nullptr, nullptr);
+      img.final_T, img.n_contrib, out_color, out_depth, BlendBatch{0, 0, nullptr, 0, (uint32_t)vp.P}, nullptr, nullptr);
   DGE_LAUNCHED(1);
   return cudaGetLastError();
 }
@@ -156,7 +156,7 @@ cudaError_t launch_render_forward_batched(const ViewParams& vp, const ViewBatch&
                                           float* out_color, float* out_depth, cudaStream_t stream,
                                           const float* extra, float* out_extra) {
   dim3 grid(vp.grid_x, vp.grid_y, vb.V);
-  const BlendBatch bb{vb.geom_stride, vb.img_stride, vb.seg_off, 0};
+  const BlendBatch bb{vb.geom_stride, vb.img_stride, vb.seg_off, 0, (uint32_t)vp.P};
   if (extra != nullptr && out_extra != nullptr)
     render_forward_kernel<true><<<grid, BL_THREADS, 0, stream>>>(img0.ranges, b.point_list, vp.W, vp.H, g0.rec,
                                                                 background, img0.final_T, img0.n_contrib, out_color,

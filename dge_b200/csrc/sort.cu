@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_kernel(
     const uint32_t k = s_keys[p];
     const uint32_t d = (k >> shift) & digit_mask;
     const uint32_t dst = s_base[d] + p;
+    DGE_CHECK(dst < n);
     keys_out[dst] = k;
     vals_out[dst] = s_vals[p];
   }

@@ -114,8 +114,9 @@ class FitModel:
         self.means2D_slice = slice(n, n + 3 * P)
         self.means2D.grad = self.flat_grad[self.means2D_slice].view(P, 3)
         # per-P caches of the fit step (lanes, batches, activations) belong to the old buffers
+        self._geom_version = getattr(self, "_geom_version", 0) + 1
         for attr in ("_lane_key", "_batch_key", "_acts", "_lanes", "_batches", "_acc", "_flags", "_lane_acc",
-                     "_lane_flags", "_min_chunks"):
+                     "_lane_flags", "_min_chunks", "_front"):
             if hasattr(self, attr):
                 delattr(self, attr)
         if not self.fused_adam:
@@ -281,18 +282,23 @@ class FitModel:
             "rotations": torch.nn.functional.normalize(p["rotation"]),
         }
 
-    def activations_fused(self):
+    def activations_fused(self, which: str = "all"):
         """The same activations from ONE kernel into persistent buffers (no autograd graph): their
-        backward is applied by dge_fit_backward_geom_raw's epilogue."""
+        backward is applied by dge_fit_backward_geom_raw's epilogue. which = "geometry"
+        (opacity / scaling / rotation only) or "features" (shs = cat(f_dc, f_rest) only) refreshes one half: the
+        pipelined multi-GPU step projects the next step's Gaussians before its features have been stepped."""
         if getattr(self, "_acts", None) is None:
             f32 = dict(dtype=torch.float32, device=self.device)
             self._acts = {"shs": torch.empty(self.P, 16, 3, **f32), "opacities": torch.empty(self.P, 1, **f32),
                           "scales": torch.empty(self.P, 3, **f32), "rotations": torch.empty(self.P, 4, **f32)}
         a, p = self._acts, self.params
-        L.check(L.load().dge_fit_activate(self.P, p["f_dc"].data_ptr(), p["f_rest"].data_ptr(),
-                                          p["opacity"].data_ptr(), p["scaling"].data_ptr(), p["rotation"].data_ptr(),
-                                          a["shs"].data_ptr(), a["opacities"].data_ptr(), a["scales"].data_ptr(),
-                                          a["rotations"].data_ptr(), L.stream_ptr(self.device)), "activate")
+        geo, feat = which in ("all", "geometry"), which in ("all", "features")
+        L.check(L.load().dge_fit_activate(self.P, p["f_dc"].data_ptr() if feat else None,
+                                          p["f_rest"].data_ptr() if feat else None,
+                                          p["opacity"].data_ptr() if geo else None, p["scaling"].data_ptr(),
+                                          p["rotation"].data_ptr(), a["shs"].data_ptr(), a["opacities"].data_ptr(),
+                                          a["scales"].data_ptr(), a["rotations"].data_ptr(), L.stream_ptr(self.device)),
+                "activate")
         return {"means3D": p["xyz"].detach(), **a}
 
     def training_setup(self, position_lr_max_steps, position_lr_init=0.00016, position_lr_final=0.000016,
@@ -340,6 +346,9 @@ class FitModel:
         rows=(r0, r1): only these Gaussians of the selected groups, r0 a multiple of 4; fused path only)."""
         if advance:
             self.step_count += 1
+        stepped = [nm for nm, _, _ in GROUPS if nm not in skip and (only is None or nm in only)]
+        if any(nm in ("xyz", "opacity", "scaling", "rotation") for nm in stepped):
+            self._geom_version = getattr(self, "_geom_version", 0) + 1  # a prefetched front half is stale now
         if not self.fused_adam:
             if self.grad_mask is not None:  # the reference's hooks (gaussian_model.py:837-856)
                 m = self.grad_mask.to(torch.float32)
@@ -572,14 +581,12 @@ class ViewBatch:
         self.cb_binning = L.ALLOC_FN(growing)
 
 
-def _batched_forward(model: FitModel, acts, cameras, bg, num_chunks=1, prune_lists=True, extra=None):
-    """Forward half of a step through the batched C-ABI: ONE launch per stage for all views of a chunk
-    (preprocess that reads the Gaussians once for all its cameras, segmented depth sort / binning, forward
-    blend). With num_chunks > 1 the views are split into that many chunks, each on its own stream, so
-    one chunk's bandwidth-bound stages (preprocess, sorts) overlap another's issue-bound blends.
-    `extra` [P] (DGE: gaussian.mask.float()): blended as a fourth channel into vb.sem, the image of DGE.forward's
-    second, mask-colour render of every view (DGE.py:198-204). Leaves images / depth / scratch in
-    model._batches and what the backward half needs in model._fw; the chunk streams are left running."""
+def _batched_front(model: FitModel, acts, cameras, num_chunks=1, prune_lists=True, with_colour=True):
+    """Front half of a step through the batched C-ABI: ONE launch per stage for all views of a chunk — preprocess
+    that reads the Gaussians once for all its cameras, segmented depth sort, binning (dge_fit_views_front). With
+    num_chunks > 1 the views are split into that many chunks, each on its own stream, so one chunk's
+    bandwidth-bound stages overlap another's issue-bound blends. with_colour=False leaves the SH colours out
+    (dge_fit_views_colour fills them in later: _batched_colour). Records in model._front what was projected."""
     lib = L.load()
     dev = model.device
     H, W = cameras[0].image_height, cameras[0].image_width
@@ -607,7 +614,6 @@ def _batched_forward(model: FitModel, acts, cameras, bg, num_chunks=1, prune_lis
     a = {k: v.detach() for k, v in acts.items()}
     ptrs = {k: v.data_ptr() for k, v in a.items()}
     M = a["shs"].shape[1]
-    bgp = bg.data_ptr()
     # cameras: one pinned [V,40] block, one H2D copy
     recs = [camera_record(cam) for cam in cameras]
     # records are memoised per camera: same objects <=> same cameras. The key HOLDS the records (an id()
@@ -619,22 +625,75 @@ def _batched_forward(model: FitModel, acts, cameras, bg, num_chunks=1, prune_lis
             model._cams_host[i].copy_(rec)
         model._cams.copy_(model._cams_host, non_blocking=True)
         model._cams_key = cams_key
-    ex = None if extra is None else extra.detach().to(dev, torch.float32).reshape(-1).contiguous()
-    acc_stride = P * 12
     for vb in batches:
         vb.stream.wait_stream(main)
-    # forward of every chunk (each call waits once for its instance counts)
+    # every chunk's front half (each call waits once for its instance counts)
     for vb in batches:
+        with torch.cuda.stream(vb.stream):
+            vb.R = L.check(lib.dge_fit_views_front(
+                vb.cb_geom, vb.cb_binning, vb.cb_img, None, P, model.sh_degree, M, vb.V, W, H, ptrs["means3D"],
+                ptrs["shs"] if with_colour else None, ptrs["opacities"], ptrs["scales"], 1.0, ptrs["rotations"],
+                vb.cams.data_ptr(), vb.radii_max.data_ptr(), vb.flags.data_ptr(), P, vb.num_rendered, int(prune_lists),
+                vb.stream_ptr), "fit views front")
+    model._front = dict(cams=tuple(recs), key=(key, bool(prune_lists)), geom_version=model._geom_version,
+                        coloured=with_colour, W=W, H=H, V=V, main=main)
+
+
+def _batched_colour(model: FitModel, acts):
+    """The SH colours of a front half that ran without them (after the features have been stepped)."""
+    lib = L.load()
+    fr, P = model._front, model.P
+    for vb in model._batches:
+        with torch.cuda.stream(vb.stream):
+            vb.stream.wait_stream(fr["main"])  # the feature activations were refreshed on the caller's stream
+            L.check(lib.dge_fit_views_colour(P, model.sh_degree, acts["shs"].shape[1], vb.V, acts["means3D"].data_ptr(),
+                                             acts["shs"].data_ptr(), vb.cams.data_ptr(), vb.geom.data_ptr(),
+                                             vb.flags.data_ptr(), P, vb.stream_ptr), "fit views colour")
+    fr["coloured"] = True
+
+
+def _batched_blend(model: FitModel, acts, bg, extra=None):
+    """The forward blend of the front half in model._front (all views of a chunk per launch). `extra` [P] (DGE:
+    gaussian.mask.float()): blended as a fourth channel into vb.sem, the image of DGE.forward's second,
+    mask-colour render of every view (DGE.py:198-204). Leaves images / depth / scratch in model._batches and what
+    the backward half needs in model._fw; the chunk streams are left running."""
+    lib = L.load()
+    fr, dev, P = model._front, model.device, model.P
+    assert fr["coloured"], "the front half has no colours yet (_batched_colour)"
+    W, H, V = fr["W"], fr["H"], fr["V"]
+    a = {k: v.detach() for k, v in acts.items()}
+    ptrs = {k: v.data_ptr() for k, v in a.items()}
+    ex = None if extra is None else extra.detach().to(dev, torch.float32).reshape(-1).contiguous()
+    bgp = bg.data_ptr()
+    acc_stride = P * 12
+    for vb in model._batches:
         with torch.cuda.stream(vb.stream):
             if ex is not None and getattr(vb, "sem", None) is None:
                 vb.sem = torch.empty(vb.V, 3, H, W, dtype=torch.float32, device=dev)
-            vb.R = L.check(lib.dge_fit_views_forward(
-                vb.cb_geom, vb.cb_binning, vb.cb_img, None, P, model.sh_degree, M, vb.V, bgp, W, H, ptrs["means3D"],
-                ptrs["shs"], ptrs["opacities"], ptrs["scales"], 1.0, ptrs["rotations"], vb.cams.data_ptr(),
-                vb.color.data_ptr(), vb.depth.data_ptr(), vb.radii_max.data_ptr(), vb.acc.data_ptr(), acc_stride,
-                vb.flags.data_ptr(), P, vb.num_rendered, None if ex is None else ex.data_ptr(),
-                None if ex is None else vb.sem.data_ptr(), int(prune_lists), vb.stream_ptr), "fit views forward")
-    model._fw = dict(acts=a, ptrs=ptrs, bg=bg, bg_black=_background_is_black(model, bg), W=W, H=H, V=V, main=main)
+            L.check(lib.dge_fit_views_blend(
+                P, vb.V, vb.R, bgp, W, H, vb.geom.data_ptr(), vb.binning.data_ptr(), vb.img.data_ptr(),
+                vb.color.data_ptr(), vb.depth.data_ptr(), vb.acc.data_ptr(), acc_stride,
+                None if ex is None else ex.data_ptr(), None if ex is None else vb.sem.data_ptr(), vb.stream_ptr),
+                "fit views blend")
+    model._fw = dict(acts=a, ptrs=ptrs, bg=bg, bg_black=_background_is_black(model, bg), W=W, H=H, V=V, main=fr["main"])
+
+
+def _front_is_valid(model: FitModel, cameras, num_chunks, prune_lists) -> bool:
+    """Does model._front hold the front half of exactly this step (same cameras, chunking and pruning, geometry
+    parameters untouched since)? True after the previous step prefetched it (fit_step(next_cameras=...))."""
+    fr = getattr(model, "_front", None)
+    if fr is None or len(cameras) == 0 or len(fr["cams"]) != len(cameras):
+        return False
+    V = len(cameras)
+    key = ((cameras[0].image_width, cameras[0].image_height, V, max(1, min(num_chunks, V))), bool(prune_lists))
+    return (fr["key"] == key and fr["geom_version"] == model._geom_version and
+            all(camera_record(c) is r for c, r in zip(cameras, fr["cams"])))
+
+
+def _batched_forward(model: FitModel, acts, cameras, bg, num_chunks=1, prune_lists=True, extra=None):
+    """Forward half of a step: front half (with colours) + forward blend."""
+    _batched_front(model, acts, cameras, num_chunks, prune_lists, with_colour=True)
+    _batched_blend(model, acts, bg, extra)
 
 
 def _batched_backward(model: FitModel, dL=None, geom_splits=1, on_range_done=None):
@@ -685,13 +744,20 @@ def _batched_backward(model: FitModel, dL=None, geom_splits=1, on_range_done=Non
     return radii_max
 
 
-def _batched_views(model: FitModel, acts, cameras, targets, bg, scale, host_inputs, num_chunks=1, prune_lists=True,
+def _batched_views(model: FitModel, cameras, targets, bg, scale, host_inputs, num_chunks=1, prune_lists=True,
                    geom_splits=1, on_range_done=None):
-    """The step's views through the batched C-ABI (_batched_forward, the fused L1 loss + gradient against
-    `targets`, _batched_backward). Returns (loss, max radii); leaves the step's raw-parameter gradients in
-    model.flat_grad."""
+    """The step's views through the batched C-ABI (front half — or the one the previous step prefetched, completed
+    with its colours —, forward blend, the fused L1 loss + gradient against `targets`, _batched_backward).
+    Returns (loss, max radii); leaves the step's raw-parameter gradients in model.flat_grad."""
     lib = L.load()
-    _batched_forward(model, acts, cameras, bg, num_chunks, prune_lists)
+    if _front_is_valid(model, cameras, num_chunks, prune_lists) and not model._front["coloured"]:
+        model._front["main"] = torch.cuda.current_stream(model.device)
+        acts = model.activations_fused("features")  # geometry activations date from the prefetch and are still valid
+        _batched_colour(model, acts)
+    else:
+        acts = model.activations_fused()
+        _batched_front(model, acts, cameras, num_chunks, prune_lists, with_colour=True)
+    _batched_blend(model, acts, bg)
     fw = model._fw
     W, H, main = fw["W"], fw["H"], fw["main"]
     batches, bounds = model._batches, model._chunk_bounds
@@ -966,7 +1032,7 @@ def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence
              process_group=None, lambda_l1: float = 10.0, host_inputs: bool = False, update_stats: bool = True,
              num_streams: int = 1, direct: Optional[bool] = None, batched: Optional[bool] = None,
              num_chunks: int = 1, prune_lists: bool = True, geom_splits: Optional[int] = None,
-             image_size: Optional[Sequence[int]] = None):
+             image_size: Optional[Sequence[int]] = None, next_cameras: Optional[Sequence[scene.Camera]] = None):
     """One optimisation step over this rank's views. `cameras`/`targets` are this rank's share;
     `global_batch` the number of views in the whole step (L1 is a mean over the global batch,
     DGE.py:672). With host_inputs the cameras/targets live in pinned host memory and are copied
@@ -981,7 +1047,14 @@ def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence
     (default) pushes ALL views of the step through each stage in one launch (_batched_views: the view
     is a grid dimension, the Gaussians are read once per step, one host wait per step); batched=False
     issues the views one by one round-robin on num_streams CUDA streams (_direct_views). The autograd path below is the reference-shaped one (per-view tensors,
-    torch ops for the loss, AccumulateGrad) and is what `rasterize` overrides go through."""
+    torch ops for the loss, AccumulateGrad) and is what `rasterize` overrides go through.
+
+    next_cameras (batched path): this rank's cameras of the NEXT step (fit.ViewSampler knows them). On several
+    GPUs the step then ends by projecting, depth-sorting and binning the next step's views — none of which needs
+    the SH coefficients — while the all-reduce of the f_rest gradient, three quarters of the step's bytes, is on
+    the wire; the next call finds that front half (same cameras), fills in the colours from the freshly stepped
+    features and goes straight to the blend. Results are those of the unpipelined step (same kernels, same
+    inputs); a front half that does not match the next call is simply recomputed."""
     dev = model.device
     if len(cameras) == 0:
         # this rank's share of the batch is empty (fewer views than ranks): it contributes zero gradients,
@@ -1007,8 +1080,8 @@ def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence
             early = _EarlyRestReduce(model, process_group) if (world > 1 and splits > 1) else None
             while True:
                 try:
-                    loss, radii_max = _batched_views(model, model.activations_fused(), cameras, targets, bg, scale,
-                                                     host_inputs, chunks, prune_lists, splits, early)
+                    loss, radii_max = _batched_views(model, cameras, targets, bg, scale, host_inputs, chunks,
+                                                     prune_lists, splits, early)
                     break
                 except RuntimeError as ex:
                     if "2^30" not in str(ex) or chunks >= len(cameras):
@@ -1020,7 +1093,12 @@ def fit_step(model: FitModel, cameras: Sequence[scene.Camera], targets: Sequence
             early = None
             loss, radii_max = _direct_views(model, model.activations_fused(), cameras, targets, bg, scale, host_inputs,
                                             num_streams)
-        return _finish_step(model, loss, radii_max, process_group, update_stats, early)
+        prefetch = None
+        if batched and next_cameras is not None and len(next_cameras) > 0:
+            def prefetch():
+                _batched_front(model, model.activations_fused("geometry"), next_cameras, chunks, prune_lists,
+                               with_colour=False)
+        return _finish_step(model, loss, radii_max, process_group, update_stats, early, prefetch=prefetch)
     model.zero_grad()
     acts_graph = model.activations()
     S = max(1, min(num_streams, len(cameras)))
@@ -1111,9 +1189,11 @@ class _EarlyRestReduce:
         self.done_rows = first + count
 
 
-def _finish_step(model, loss, radii_max, process_group, update_stats, early=None, adam=True):
+def _finish_step(model, loss, radii_max, process_group, update_stats, early=None, adam=True, prefetch=None):
     """The collective, the densification statistics and (adam=True) the optimiser step. With adam=False the
-    gradients are left reduced in model.flat_grad for a separate FitModel.adam_step() (DGEFitAdapter)."""
+    gradients are left reduced in model.flat_grad for a separate FitModel.adam_step() (DGEFitAdapter).
+    prefetch(): launches the next step's geometry front half; called once the geometry groups have been stepped,
+    i.e. while the f_rest gradient is still being reduced on several GPUs (fit_step's next_cameras)."""
     world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
     pending = None
     if world > 1:
@@ -1150,6 +1230,9 @@ def _finish_step(model, loss, radii_max, process_group, update_stats, early=None
         return loss
     if pending is not None and model.fused_adam:
         model.adam_step(skip=("f_rest",))
+        if prefetch is not None:
+            prefetch()  # next step's projection / depth sort / binning under the f_rest all-reduce
+            prefetch = None
         if early is not None and early.done_rows:
             for w in early.works:
                 w.wait()
@@ -1160,7 +1243,13 @@ def _finish_step(model, loss, radii_max, process_group, update_stats, early=None
     else:
         for w in (early.works if early is not None else []):
             w.wait()
-        model.adam_step()
+        if model.fused_adam and prefetch is not None:
+            # one process: the same order of work as on several (geometry groups, front half, features)
+            model.adam_step(skip=("f_rest",))
+            prefetch()
+            model.adam_step(only=("f_rest",), advance=False)
+        else:
+            model.adam_step()
     return loss
 
 

@@ -206,6 +206,25 @@ int dge_fit_views_forward(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffe
                           const float* cams, float* out_color, float* out_depth, int* radii_max, float* acc,
                           size_t acc_stride_floats, uint8_t* flags, size_t flags_stride, int* num_rendered_host,
                           const float* extra, float* out_extra, int prune_lists, void* stream);
+/* The same call in three pieces, for callers that want to start a step's projection, depth sort and binning before
+ * its SH coefficients are final (multi-GPU fit: they run under the all-reduce of the f_rest gradient, fit.py):
+ *   dge_fit_views_front  = batched preprocess + segment offsets + depth sort + binning; shs == NULL leaves the
+ *                          colours out of the blend records (flags then carry the visibility bit only). Returns
+ *                          R_total.
+ *   dge_fit_views_colour = SH -> rgb + clamp bits of every visible (view, Gaussian) pair into the records and
+ *                          flags of a front half that ran with shs == NULL (bit-identical to the fused path).
+ *   dge_fit_views_blend  = the forward blend of a front half (and the zeroing of acc beside it).
+ * dge_fit_views_forward == dge_fit_views_front (with shs) + dge_fit_views_blend. */
+int dge_fit_views_front(dge_alloc_fn geometryBuffer, dge_alloc_fn binningBuffer, dge_alloc_fn imageBuffer,
+                        void* alloc_ctx, int P, int D, int M, int V, int width, int height, const float* means3D,
+                        const float* shs, const float* opacities, const float* scales, float scale_modifier,
+                        const float* rotations, const float* cams, int* radii_max, uint8_t* flags,
+                        size_t flags_stride, int* num_rendered_host, int prune_lists, void* stream);
+int dge_fit_views_colour(int P, int D, int M, int V, const float* means3D, const float* shs, const float* cams,
+                         char* geom_buffer, uint8_t* flags, size_t flags_stride, void* stream);
+int dge_fit_views_blend(int P, int V, int R_total, const float* background, int width, int height, char* geom_buffer,
+                        char* binning_buffer, char* image_buffer, float* out_color, float* out_depth, float* acc,
+                        size_t acc_stride_floats, const float* extra, float* out_extra, void* stream);
 /* dL_dpix is [V,3,H,W]; the three blobs are the ones dge_fit_views_forward filled. */
 int dge_fit_views_backward_blend(int P, int V, int R_total, const float* background, int background_is_black,
                                  int width, int height, char* geom_buffer, char* binning_buffer,
@@ -227,6 +246,7 @@ int dge_fit_views_apply_weights(dge_alloc_fn geometryBuffer, dge_alloc_fn binnin
  * for the whole model in one pass — shs[P,16,3] = cat(f_dc[P,1,3], f_rest[P,15,3]), opacities =
  * sigmoid, scales = exp, rotations = normalize — and dge_fit_backward_geom with their backward in
  * its epilogue: the seven outputs are gradients w.r.t. the RAW parameters, every row written. */
+/* (dge_fit_activate: f_dc == f_rest == NULL skips the features, opacity_raw == NULL the other three.) */
 int dge_fit_activate(int P, const float* f_dc, const float* f_rest, const float* opacity_raw,
                      const float* scaling_raw, const float* rotation_raw, float* shs,
                      float* opacities, float* scales, float* rotations, void* stream);

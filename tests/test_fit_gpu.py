@@ -443,3 +443,33 @@ def test_dge_fit_adapter_training_step(cuda):
     before = model.flat.clone()
     ad.optimizer_step()
     assert not torch.equal(before, model.flat) and model.step_count == 1
+
+
+@pytest.mark.parametrize("chunks", [1, 2])
+def test_prefetched_front_half_gives_the_same_step(cuda, chunks):
+    """fit_step(next_cameras=...): the next step's projection / depth sort / binning launched at the end of a step
+    (geometry only, before the features are stepped), completed with dge_fit_views_colour at the start of the
+    next — the step it produces must be the unpipelined one: images bit-identical, loss and gradients equal."""
+    a, cams, targets, bg = _setup(cuda, True, 60000, 200, 136, 6, 0.03)
+    b, _, _, _ = _setup(cuda, True, 60000, 200, 136, 6, 0.03)
+    other = [scene.camera_to(c, cuda) for c in scene.ring_cameras(9, 200, 136)[3:9]]
+    fit.fit_step(a, cams, targets, bg, global_batch=6, num_chunks=chunks, next_cameras=other)
+    assert a._front is not None and not a._front["coloured"]           # geometry-only front half of `other`
+    for name in ("flat", "exp_avg", "exp_avg_sq", "xyz_gradient_accum", "denom", "max_radii2D"):
+        getattr(b, name).copy_(getattr(a, name))
+    b.step_count = a.step_count
+    la = fit.fit_step(a, other, targets, bg, global_batch=6, num_chunks=chunks, next_cameras=cams)
+    lb = fit.fit_step(b, other, targets, bg, global_batch=6, num_chunks=chunks)
+    torch.cuda.synchronize()
+    for va, vb in zip(a._batches, b._batches):
+        assert torch.equal(va.color, vb.color) and torch.equal(va.depth, vb.depth)
+        assert list(va.num_rendered) == list(vb.num_rendered)
+        assert torch.equal(va.flags, vb.flags)
+    assert abs(float(la) - float(lb)) <= 1e-6 * abs(float(lb))
+    for name, sl in list(a.slices.items()) + [("means2D", a.means2D_slice)]:
+        ok, msg = util.grad_ok(a.flat_grad[sl].cpu().numpy(), b.flat_grad[sl].cpu().numpy())
+        assert ok, (name, msg)
+    assert torch.equal(a.max_radii2D, b.max_radii2D) and torch.equal(a.denom, b.denom)
+    # a front half prefetched for other cameras than the next call's is not used
+    lc = fit.fit_step(a, other, targets, bg, global_batch=6, num_chunks=chunks)   # `cams` was prefetched
+    assert torch.isfinite(lc) and a._front["coloured"]
