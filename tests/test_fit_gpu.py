@@ -458,7 +458,7 @@ def test_prefetched_front_half_gives_the_same_step(cuda, chunks):
     for name in ("flat", "exp_avg", "exp_avg_sq", "xyz_gradient_accum", "denom", "max_radii2D"):
         getattr(b, name).copy_(getattr(a, name))
     b.step_count = a.step_count
-    la = fit.fit_step(a, other, targets, bg, global_batch=6, num_chunks=chunks, next_cameras=cams)
+    la = fit.fit_step(a, other, targets, bg, global_batch=6, num_chunks=chunks)   # finds the prefetched front half
     lb = fit.fit_step(b, other, targets, bg, global_batch=6, num_chunks=chunks)
     torch.cuda.synchronize()
     for va, vb in zip(a._batches, b._batches):
@@ -471,5 +471,7 @@ def test_prefetched_front_half_gives_the_same_step(cuda, chunks):
         assert ok, (name, msg)
     assert torch.equal(a.max_radii2D, b.max_radii2D) and torch.equal(a.denom, b.denom)
     # a front half prefetched for other cameras than the next call's is not used
+    fit.fit_step(a, other, targets, bg, global_batch=6, num_chunks=chunks, next_cameras=cams)
+    assert not a._front["coloured"]
     lc = fit.fit_step(a, other, targets, bg, global_batch=6, num_chunks=chunks)   # `cams` was prefetched
     assert torch.isfinite(lc) and a._front["coloured"]
