@@ -5,6 +5,7 @@ raises, and nothing under dge_b200/ imports oracle/.
 """
 import ctypes as C
 import os
+import threading
 
 import torch
 
@@ -122,6 +123,26 @@ class Arena:
             self.bufs[i] = t
             return t.data_ptr()
         return alloc
+
+
+_ARENAS = {}
+
+
+def arena(device, n=3):
+    """A per-device Arena whose ctypes trampolines are created ONCE (building a CFUNCTYPE costs tens of
+    microseconds, and the per-view API used to build three per call). The caller takes the tensors of this call
+    with take(): the arena then forgets them, so their lifetime is the caller's (ctx.save_for_backward)."""
+    key = (str(device), n, threading.get_ident())  # per thread: autograd runs backwards on its own
+    a = _ARENAS.get(key)
+    if a is None:
+        a = _ARENAS[key] = Arena(device, n)
+    a.bufs = [None] * n
+    return a
+
+
+def take(a):
+    bufs, a.bufs = a.bufs, [None] * len(a.bufs)
+    return bufs
 
 
 def stream_ptr(device=None):

@@ -59,7 +59,7 @@ def _forward_call(rs, means3D, colors_precomp, opacities, scales, rotations, cov
     color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
     depth = torch.empty((1, H, W), dtype=torch.float32, device=dev)
     radii = torch.empty((P,), dtype=torch.int32, device=dev)
-    arena = L.Arena(dev)
+    arena = L.arena(dev)
     with torch.cuda.device(dev):
         rc = lib.dge_rasterize_forward(
             arena.cbs[0], arena.cbs[1], arena.cbs[2], None, P, int(rs.sh_degree), M, L.ptr(bg), W, H,
@@ -67,9 +67,10 @@ def _forward_call(rs, means3D, colors_precomp, opacities, scales, rotations, cov
             float(rs.scale_modifier), L.ptr(rotations), L.ptr(cov3Ds_precomp), L.ptr(view), L.ptr(proj),
             L.ptr(campos), float(rs.tanfovx), float(rs.tanfovy), int(bool(rs.prefiltered)),
             L.ptr(color), L.ptr(depth), L.ptr(radii), int(bool(rs.debug)), L.stream_ptr(dev))
+    bufs = L.take(arena)
     L.check(rc, "rasterize_gaussians")
     empty = torch.empty(0, dtype=torch.uint8, device=dev)
-    geom, binning, img = (b if b is not None else empty for b in arena.bufs)
+    geom, binning, img = (b if b is not None else empty for b in bufs)
     return rc, color, depth, radii, geom, binning, img
 
 
@@ -96,7 +97,7 @@ def _backward_call(rs, means3D, radii, colors_precomp, scales, rotations, cov3Ds
     if P != 0:
         grad_out_color = _f32c(grad_out_color)
         bg, view, proj, campos = _f32c(rs.bg), _f32c(rs.viewmatrix), _f32c(rs.projmatrix), _f32c(rs.campos)
-        arena = L.Arena(dev, 1)
+        arena = L.arena(dev, 1)
         with torch.cuda.device(dev):
             rc = lib.dge_rasterize_backward(
                 arena.cbs[0], None, P, int(rs.sh_degree), M, int(num_rendered), L.ptr(bg), W, H,
@@ -106,6 +107,7 @@ def _backward_call(rs, means3D, radii, colors_precomp, scales, rotations, cov3Ds
                 L.ptr(grad_out_color), L.ptr(dL_dmeans2D), None, L.ptr(dL_dopacity), L.ptr(dL_dcolors),
                 L.ptr(dL_dmeans3D), L.ptr(dL_dcov3D), L.ptr(dL_dsh), L.ptr(dL_dscales), L.ptr(dL_drotations),
                 0, int(bool(rs.debug)), L.stream_ptr(dev))
+        L.take(arena)  # the scratch of the blend-stage sums is dead once the call has been queued (stream-ordered free)
         L.check(rc, "rasterize_gaussians_backward")
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
 
@@ -265,7 +267,7 @@ class GaussianRasterizer(nn.Module):
         rotations, cov3Ds_precomp, image_weights = _f32c(rotations), _f32c(cov3Ds_precomp), _f32c(image_weights)
         bg, view, proj, campos = _f32c(rs.bg), _f32c(rs.viewmatrix), _f32c(rs.projmatrix), _f32c(rs.campos)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
-        arena = L.Arena(dev)
+        arena = L.arena(dev)
         with torch.cuda.device(dev):
             rc = lib.dge_apply_weights(
                 arena.cbs[0], arena.cbs[1], arena.cbs[2], None, P, int(rs.sh_degree), M, L.ptr(bg), W, H,
@@ -274,4 +276,5 @@ class GaussianRasterizer(nn.Module):
                 L.ptr(campos), float(rs.tanfovx), float(rs.tanfovy), int(bool(rs.prefiltered)),
                 L.ptr(image_weights), L.ptr(radii), L.ptr(cnt), int(num_channels), int(bool(rs.debug)),
                 L.stream_ptr(dev))
+        L.take(arena)
         L.check(rc, "apply_weights")

@@ -14,6 +14,8 @@ ap.add_argument("--P", type=int, default=1_000_000)
 ap.add_argument("--res", type=int, default=512)
 ap.add_argument("--streams", type=int, default=0, help="0 = batched path")
 ap.add_argument("--out", default="")
+ap.add_argument("--pipeline", action="store_true", help="fit_step(next_cameras=cams): prefetch the next step's front half")
+ap.add_argument("--timeline", action="store_true", help="print every device activity of the profiled step")
 ap.add_argument("--e2e", action="store_true", help="pinned host inputs + loss read back each step; prints the idle gaps")
 args = ap.parse_args()
 rank = int(os.environ.get("RANK", "0"))
@@ -33,7 +35,8 @@ elif args.streams == 0:
     targets = torch.stack(targets)
 model = fit.FitModel(g, dev, fused_adam=True)
 bg = torch.zeros(3, device=dev)
-kw = dict(global_batch=args.views, num_streams=max(args.streams, 1), batched=args.streams == 0, host_inputs=args.e2e)
+kw = dict(global_batch=args.views, num_streams=max(args.streams, 1), batched=args.streams == 0, host_inputs=args.e2e,
+          next_cameras=cams if args.pipeline else None)
 for _ in range(3):
     fit.fit_step(model, cams, targets, bg, **kw).item()
 torch.cuda.synchronize()
@@ -74,6 +77,10 @@ if args.e2e or "RANK" in os.environ:
         if s_ - end > 15:
             print(f"gap {s_ - end:8.1f} us before {n_[:50]} at {(s_ - iv[0][0]) / 1e3:.3f} ms")
         end = max(end, e_)
+if args.timeline:
+    t0 = iv[0][0]
+    for s_, e_, n_ in iv:
+        print(f"{(s_ - t0) / 1e3:8.3f} .. {(e_ - t0) / 1e3:8.3f} ms  {(e_ - s_):8.1f} us  {n_.split('(')[0][:70]}")
 if args.out:
     json.dump([(s - iv[0][0], e - iv[0][0], n.split("(")[0][:40]) for s, e, n in iv], open(args.out, "w"))
 if "RANK" in os.environ:
