@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(BL_THREADS) apply_weights_kernel(
       const uint32_t e = s.list[warp][i];  // warp-uniform
       const int j = e & 0xFF;
       const float4 a = s.rec[j][0];  // x, y, conic.x, conic.y
-      const float4 b = s.rec[j][1];  // conic.z, power threshold, opacity, depth
+      const float4 b = s.rec[j][1];  // conic.z, power threshold, opacity, -
       float wsum[CH];
 #pragma unroll
       for (int c = 0; c < CH; c++) wsum[c] = 0.0f;

@@ -191,7 +191,7 @@ __global__ void debug_keys_kernel(uint32_t R, const uint32_t* __restrict__ tile_
                                   uint64_t* __restrict__ keys_out) {
   const uint32_t i = blockIdx.x * 256u + threadIdx.x;
   if (i >= R) return;
-  keys_out[i] = ((uint64_t)tile_ids[i] << 32) | __float_as_uint(rec[(size_t)point_list[i] * REC_F4 + 1].w);
+  keys_out[i] = ((uint64_t)tile_ids[i] << 32) | __float_as_uint(rec[(size_t)point_list[i] * REC_F4 + 2].w);
 }
 
 cudaError_t launch_depth_sort(int P, GeomState& g, cudaStream_t stream) {

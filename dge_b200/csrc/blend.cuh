@@ -162,12 +162,12 @@ __device__ __forceinline__ int compact_batch(BlendSmem& s, int warp, int lane, i
     const int k = c * 32 + lane;
     uint32_t qm = 0;
     if (k < count) {
-      const float4 a = s.rec[k][0], c = s.rec[k][2], d = s.rec[k][3];
+      const float4 a = s.rec[k][0], c = s.rec[k][1], d = s.rec[k][3];  // c: conic.z, threshold, opacity, hx
       // x - hx, x + hx, y - hy, y + hy
       const float4 bx = make_float4(a.x - c.w, a.x + c.w, a.y - d.x, a.y + d.x);
       if (bx.y >= X0 && bx.x <= X1 && bx.w >= Y0 && bx.z <= Y1) {
         qm = allowed(k);
-        if (qm) qm &= quad_mask(a, s.rec[k][1].x, bx, d.y, d.z, d.w, X0, Y0);
+        if (qm) qm &= quad_mask(a, c.x, bx, d.y, d.z, d.w, X0, Y0);
       }
     }
     const uint32_t m = __ballot_sync(0xFFFFFFFFu, qm != 0);

@@ -228,8 +228,9 @@ enum { ACC_SX = 0, ACC_SY, ACC_SXX, ACC_SXY, ACC_SYY, ACC_OPACITY, ACC_R, ACC_G,
 
 // ---- the 64-byte blend record of a Gaussian in a view (written by preprocess) ----
 //  q0: x, y (pixel-space centre), conic.x, conic.y
-//  q1: conic.z, power threshold, opacity, view-space depth
-//  q2: r, g, b, hx
+//  q1: conic.z, power threshold, opacity, hx
+//  q2: r, g, b, view-space depth   (the one quarter that depends on the SH coefficients: dge_fit_views_colour
+//      rewrites it as a whole when the projection ran before the features were final)
 //  q3: hy, -cy/cz, -cy/cx, limit on the quadratic form (< 0: the exact quadrant cull does not apply)
 // (hx, hy): half-extents of the box outside which alpha < 1/255 for certain (-inf = never visible).
 constexpr int REC_F4 = 4;
@@ -254,8 +255,8 @@ __device__ __forceinline__ void pack_record(float4* q, float x, float y, float h
   const bool exact = cx > 0.0f && cz > 0.0f && det > 1e-3f * ac && thr < 0.0f;
   const float kappa = exact ? __fdividef(ac, det) : 1.0f;
   q[0] = make_float4(x, y, cx, cy);
-  q[1] = make_float4(cz, thr, opacity, depth);
-  q[2] = make_float4(r, g, b, hx);
+  q[1] = make_float4(cz, thr, opacity, hx);
+  q[2] = make_float4(r, g, b, depth);
   q[3] = make_float4(hy, exact ? __fdividef(-cy, cz) : 0.0f, exact ? __fdividef(-cy, cx) : 0.0f,
                      exact ? -thr * (1.0f + 2e-5f * kappa) + 1e-4f : -1.0f);
 }

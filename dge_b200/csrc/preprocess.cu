@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(PRE_B_THREADS, PRE_B_MIN_CTAS) preprocess_batc
         // others are not emitted — 27 % fewer instances at config 2, identical images and gradients.
         // The rect only ever SHRINKS (the 3-sigma square still clips, as in the reference); radii,
         // visibility flags and statistics are untouched.
-        const float x = o.rec[0].x, y = o.rec[0].y, hx = o.rec[2].w, hy = o.rec[3].x;
+        const float x = o.rec[0].x, y = o.rec[0].y, hx = o.rec[1].w, hy = o.rec[3].x;
         // (float -> int conversions saturate; the min() keeps the + 1 from overflowing for hx = +inf)
         const int bx0 = max(0, (int)floorf((x - hx) * 0.0625f)), bx1 = min((int)floorf((x + hx) * 0.0625f), 1 << 20) + 1;
         const int by0 = max(0, (int)floorf((y - hy) * 0.0625f)), by1 = min((int)floorf((y + hy) * 0.0625f), 1 << 20) + 1;
@@ -421,9 +421,13 @@ __global__ void __launch_bounds__(PRE_B_THREADS, PRE_B_MIN_CTAS) colour_batched_
   if (idx >= P) return;
   const float px = __ldg(means3D + 3 * idx), py = __ldg(means3D + 3 * idx + 1), pz = __ldg(means3D + 3 * idx + 2);
   bool loaded = false;
-  for (int view = 0; view < V; view++) {
-    uint8_t* fp = flags + (size_t)view * flags_stride + idx;
-    if (!(*fp & 1u)) continue;
+  // four views at a time: their flag bytes are loaded together (one coalesced byte per lane and view) before
+  // any is looked at
+  for (int v0 = 0; v0 < V; v0 += 4) {
+    uint32_t fl[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) fl[k] = v0 + k < V ? (uint32_t)flags[(size_t)(v0 + k) * flags_stride + idx] : 0u;
+    if (!((fl[0] | fl[1] | fl[2] | fl[3]) & 1u)) continue;
     if (!loaded) {  // Gaussians no view sees never touch their 192 bytes of SH
       const float* base = shs + 48 * (size_t)idx;
       float4 v[12];
@@ -434,14 +438,19 @@ __global__ void __launch_bounds__(PRE_B_THREADS, PRE_B_MIN_CTAS) colour_batched_
       for (int k = 0; k < 48; k++) s_sh[k * PRE_B_THREADS] = f[k];
       loaded = true;
     }
-    const float* cam = s_cam + view * 40;
-    float rgb[3];
-    const uint8_t cl = sh_color(D, px, py, pz, cam[32], cam[33], cam[34],
-                                [&](int k, int c) { return s_sh[(3 * k + c) * PRE_B_THREADS]; }, rgb);
-    float4* q2 = shift_ptr(rec0, (size_t)view * geom_stride) + (size_t)idx * REC_F4 + 2;
-    const float hx = q2->w;
-    *q2 = make_float4(rgb[0], rgb[1], rgb[2], hx);
-    *fp = (uint8_t)(1u | ((uint32_t)cl << 1));
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (!(fl[k] & 1u)) continue;
+      const int view = v0 + k;
+      const float* cam = s_cam + view * 40;
+      float rgb[3];
+      const uint8_t cl = sh_color(D, px, py, pz, cam[32], cam[33], cam[34],
+                                  [&](int kk, int c) { return s_sh[(3 * kk + c) * PRE_B_THREADS]; }, rgb);
+      // the record's third quarter as a whole (r, g, b, view-space depth): a full 16-byte store, nothing read back
+      const float depth = xform_row(cam, 2, px, py, pz);
+      shift_ptr(rec0, (size_t)view * geom_stride)[(size_t)idx * REC_F4 + 2] = make_float4(rgb[0], rgb[1], rgb[2], depth);
+      flags[(size_t)view * flags_stride + idx] = (uint8_t)(1u | ((uint32_t)cl << 1));
+    }
   }
 }
 

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(BL_THREADS, HAS_BG ? 12 : DGE_BWD_MIN_CTAS) re
       const int j = e & 0xFF;
       const uint32_t pos = hi - 1 - j;  // 0-based list position
       const float4 a = s.rec[j][0];   // x, y, conic.x, conic.y
-      const float4 b = s.rec[j][1];   // conic.z, power threshold, opacity, depth
+      const float4 b = s.rec[j][1];   // conic.z, power threshold, opacity, -
       const float cd0 = s.rec[j][2].x, cd1 = s.rec[j][2].y, cd2 = s.rec[j][2].z;  // r, g, b
       const float opacity = b.z;
 

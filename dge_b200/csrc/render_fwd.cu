@@ -96,8 +96,8 @@ __global__ void __launch_bounds__(BL_THREADS, EXTRA ? 12 : DGE_FWD_MIN_CTAS) ren
       const uint32_t e = s.list[warp][i];  // warp-uniform
       const int j = e & 0xFF;
       const float4 a = s.rec[j][0];   // x, y, conic.x, conic.y
-      const float4 b = s.rec[j][1];   // conic.z, power threshold, opacity, depth
-      const float4 cd = s.rec[j][2];  // r, g, b, -
+      const float4 b = s.rec[j][1];   // conic.z, power threshold, opacity, -
+      const float4 cd = s.rec[j][2];  // r, g, b, depth
 #pragma unroll
       for (int p = 0; p < 4; p++) {
         if (!(e & (0x100u << p))) continue;  // warp-uniform branch
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(BL_THREADS, EXTRA ? 12 : DGE_FWD_MIN_CTAS) ren
         C[p][0] = BFMA(T[p], BMUL(alpha, cd.x), C[p][0]);
         C[p][1] = BFMA(T[p], BMUL(alpha, cd.y), C[p][1]);
         C[p][2] = BFMA(T[p], BMUL(alpha, cd.z), C[p][2]);
-        Dp[p] = BFMA(T[p], BMUL(alpha, b.w), Dp[p]);
+        Dp[p] = BFMA(T[p], BMUL(alpha, cd.w), Dp[p]);
         if (EXTRA) E[p] = BFMA(T[p], BMUL(alpha, s.rec[j][REC_F4].y), E[p]);
         T[p] = test_T;
         last[p] = base - range.x + j + 1;

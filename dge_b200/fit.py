@@ -1204,16 +1204,19 @@ def _finish_step(model, loss, radii_max, process_group, update_stats, early=None
         a0, a1 = model.slices["f_rest"].start, model.slices["f_rest"].stop
         sent = early.done_rows if early is not None else 0  # f_rest rows already on the wire
         ar = lambda t, op=dist.ReduceOp.SUM: dist.all_reduce(t, op=op, group=process_group, async_op=True)
-        # what the statistics and the small groups need goes first
-        works = [ar(model.flat_grad[a1:]), ar(radii_max, dist.ReduceOp.MAX), ar(loss), ar(model.flat_grad[:a0])]
+        # what the statistics and the GEOMETRY groups need goes first (the next step's projection can start on
+        # them); the features — f_dc, then f_rest — follow
+        x1, dc = model.slices["xyz"].stop, model.slices["f_dc"]
+        works = [ar(model.flat_grad[a1:]), ar(radii_max, dist.ReduceOp.MAX), ar(loss), ar(model.flat_grad[:x1])]
+        late_dc = ar(model.flat_grad[dc.start:dc.stop])
         # f_rest in REST_PIECES row ranges: Adam on a piece runs under the next piece's transfer, so only
         # the last piece's Adam is left exposed after the wire goes quiet
         P = model.P
         cuts = [sent] + [max(sent, (P * k // REST_PIECES) // 4 * 4) for k in range(1, REST_PIECES)] + [P]
         rest = [(r0, r1, ar(model.flat_grad[a0 + 45 * r0:a0 + 45 * r1])) for r0, r1 in zip(cuts[:-1], cuts[1:]) if r1 > r0]
         if not model.fused_adam:
-            works += [w for _, _, w in rest]
-            rest = []
+            works += [late_dc] + [w for _, _, w in rest]
+            rest, late_dc = [], None
         pending = rest
         for w in works:
             w.wait()
@@ -1225,14 +1228,17 @@ def _finish_step(model, loss, radii_max, process_group, update_stats, early=None
             model.xyz_gradient_accum += torch.where(vis[:, None], gnorm, torch.zeros_like(gnorm))
             model.denom += vis[:, None].to(model.denom.dtype)
     if not adam:
-        for w in ([w for _, _, w in pending] if pending else []) + (early.works if early is not None else []):
+        for w in ([w for _, _, w in pending] if pending else []) + (early.works if early is not None else []) + (
+                [late_dc] if (world > 1 and late_dc is not None) else []):
             w.wait()
         return loss
     if pending is not None and model.fused_adam:
-        model.adam_step(skip=("f_rest",))
+        model.adam_step(skip=("f_dc", "f_rest"))
         if prefetch is not None:
-            prefetch()  # next step's projection / depth sort / binning under the f_rest all-reduce
+            prefetch()  # next step's projection / depth sort / binning under the features' all-reduce
             prefetch = None
+        late_dc.wait()
+        model.adam_step(only=("f_dc",), advance=False)
         if early is not None and early.done_rows:
             for w in early.works:
                 w.wait()
@@ -1245,9 +1251,9 @@ def _finish_step(model, loss, radii_max, process_group, update_stats, early=None
             w.wait()
         if model.fused_adam and prefetch is not None:
             # one process: the same order of work as on several (geometry groups, front half, features)
-            model.adam_step(skip=("f_rest",))
+            model.adam_step(skip=("f_dc", "f_rest"))
             prefetch()
-            model.adam_step(only=("f_rest",), advance=False)
+            model.adam_step(only=("f_dc", "f_rest"), advance=False)
         else:
             model.adam_step()
     return loss

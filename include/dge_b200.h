@@ -114,7 +114,7 @@ size_t dge_backward_scratch_bytes(int P);
 /* Inspection of the opaque scratch blobs — used by the parity tests to compare
  * every intermediate with the reference's (DGR/cuda_rasterizer/rasterizer_impl.cu:135-175).
  * geom: out[0]=records float4[P][4]: one 64-byte blend record per Gaussian — (x, y, conic.x, conic.y |
- *       conic.z, power threshold, opacity, view-space depth | r, g, b, hx | hy, cull constants x3);
+ *       conic.z, power threshold, opacity, hx | r, g, b, view-space depth | hy, cull constants x3);
  *       out[1]=out[2]=NULL (reserved); out[3]=rect
  *       ushort4[P] (min.x,min.y,max.x,max.y), out[4]=clamped uint8[P] (bit ch),
  *       out[5]=depth_order uint32[P] (Gaussian ids sorted by depth bits),

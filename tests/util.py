@@ -75,11 +75,11 @@ def ours_intermediates(rs, g, dev, colors_precomp=None, cov3D_precomp=None):
     lib.dge_geom_pointers(geom.data_ptr(), P, gp)
     o = {"num_rendered": R, "radii": radii, "out_color": color, "out_depth": depth}
     # one 64-byte record per Gaussian (include/dge_b200.h: dge_geom_pointers): x, y, conic.x, conic.y |
-    # conic.z, power threshold, opacity, depth | r, g, b, hx | hy, cull constants
+    # conic.z, power threshold, opacity, hx | r, g, b, depth | hy, cull constants
     rec = view(geom, gp[0], torch.float32, 16 * P).view(P, 16)
     o["means2D"] = rec[:, 0:2]
     o["conic_opacity"] = torch.stack([rec[:, 2], rec[:, 3], rec[:, 4], rec[:, 6]], 1)
-    o["rgb"], o["depths"] = rec[:, 8:11], rec[:, 7]
+    o["rgb"], o["depths"] = rec[:, 8:11], rec[:, 11]
     o["rect"] = view(geom, gp[3], torch.int16, 4 * P).view(P, 4).to(torch.int32) & 0xFFFF
     cl = view(geom, gp[4], torch.uint8, P)
     o["clamped"] = torch.stack([(cl >> c) & 1 for c in range(3)], 1)
