@@ -30,6 +30,12 @@ from . import scene
 GROUPS = [("xyz", 3, (3,)), ("f_dc", 3, (1, 3)), ("f_rest", 45, (15, 3)), ("opacity", 1, (1,)),
           ("scaling", 3, (3,)), ("rotation", 4, (4,))]
 FLOATS_PER_GAUSSIAN = sum(g[1] for g in GROUPS)  # 59
+# Order of the groups INSIDE the flat parameter / gradient / Adam buffers: the features first, then everything a
+# projection needs, so that "geometry gradients + screen-space gradient + loss" is ONE contiguous all-reduce (the
+# part the next step's front half waits for) and "f_dc + f_rest" another (three quarters of the bytes, which that
+# front half runs under).
+LAYOUT = ("f_dc", "f_rest", "xyz", "opacity", "scaling", "rotation")
+GEOMETRY_GROUPS = ("xyz", "opacity", "scaling", "rotation")
 # gaussiansplatting/arguments/__init__.py:72-81 (OptimizationParams: position_lr_init, feature_lr, opacity_lr,
 # scaling_lr, rotation_lr; f_rest at feature_lr / 20, gaussian_model.py:344); configs/dge.yaml scales them by 1
 DEFAULT_LRS = {"xyz": 0.00016, "f_dc": 0.0125, "f_rest": 0.0125 / 20.0, "opacity": 0.05, "scaling": 0.005,
@@ -91,14 +97,15 @@ class FitModel:
         pad4 = lambda x: (x + 3) // 4 * 4
         n = sum(pad4(k * P) for _, k, _ in GROUPS)
         self.flat = torch.zeros(n, dtype=torch.float32, device=device)
-        # gradient buffer: 59P parameter grads followed by the 3P screen-space gradient sum
-        self.flat_grad = torch.zeros(n + 3 * P, dtype=torch.float32, device=device)
+        # gradient buffer: 59P parameter grads, the 3P screen-space gradient sum, and (last 4 floats) the step's
+        # loss, which rides in the same all-reduce
+        self.flat_grad = torch.zeros(n + pad4(3 * P) + 4, dtype=torch.float32, device=device)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=device)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=device)
         self.slices = {}
         self.params = {}
         off = 0
-        for name, k, tail in GROUPS:
+        for name, k, tail in sorted(GROUPS, key=lambda g: LAYOUT.index(g[0])):
             sl = slice(off, off + k * P)
             self.slices[name] = sl
             p = self.flat[sl].view(P, *tail)
@@ -113,6 +120,10 @@ class FitModel:
         self.means2D = torch.zeros(P, 3, dtype=torch.float32, device=device, requires_grad=True)
         self.means2D_slice = slice(n, n + 3 * P)
         self.means2D.grad = self.flat_grad[self.means2D_slice].view(P, 3)
+        self.loss_slot = self.flat_grad[n + pad4(3 * P):n + pad4(3 * P) + 1]
+        # [early_slice]: geometry groups + screen-space gradient + loss; [late_slice]: the features
+        self.late_slice = slice(self.slices["f_dc"].start, self.slices["f_rest"].stop)
+        self.early_slice = slice(self.slices["xyz"].start, n + pad4(3 * P) + 4)
         # per-P caches of the fit step (lanes, batches, activations) belong to the old buffers
         self._geom_version = getattr(self, "_geom_version", 0) + 1
         for attr in ("_lane_key", "_batch_key", "_acts", "_lanes", "_batches", "_acc", "_flags", "_lane_acc",
@@ -347,7 +358,7 @@ class FitModel:
         if advance:
             self.step_count += 1
         stepped = [nm for nm, _, _ in GROUPS if nm not in skip and (only is None or nm in only)]
-        if any(nm in ("xyz", "opacity", "scaling", "rotation") for nm in stepped):
+        if any(nm in GEOMETRY_GROUPS for nm in stepped):
             self._geom_version = getattr(self, "_geom_version", 0) + 1  # a prefetched front half is stale now
         if not self.fused_adam:
             if self.grad_mask is not None:  # the reference's hooks (gaussian_model.py:837-856)
@@ -1195,22 +1206,27 @@ def _finish_step(model, loss, radii_max, process_group, update_stats, early=None
     prefetch(): launches the next step's geometry front half; called once the geometry groups have been stepped,
     i.e. while the f_rest gradient is still being reduced on several GPUs (fit_step's next_cameras)."""
     world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
-    pending = None
+    pending, geometry_stepped = None, False
     if world > 1:
         # THE collective: 59P parameter grads + 3P screen-space grads, SUM (SURVEY.md §8e) — issued as
         # contiguous pieces of the flat buffer so that the optimiser can start on the small parameter
         # groups (and the statistics on the screen-space gradient) while the 45P floats of f_rest, three
         # quarters of the bytes, are still on the wire; MAX over the radii, SUM over the loss.
-        a0, a1 = model.slices["f_rest"].start, model.slices["f_rest"].stop
+        a0 = model.slices["f_rest"].start
         sent = early.done_rows if early is not None else 0  # f_rest rows already on the wire
         ar = lambda t, op=dist.ReduceOp.SUM: dist.all_reduce(t, op=op, group=process_group, async_op=True)
-        # what the statistics and the GEOMETRY groups need goes first (the next step's projection can start on
-        # them); the features — f_dc, then f_rest — follow
-        x1, dc = model.slices["xyz"].stop, model.slices["f_dc"]
-        works = [ar(model.flat_grad[a1:]), ar(radii_max, dist.ReduceOp.MAX), ar(loss), ar(model.flat_grad[:x1])]
+        # what the next step's projection waits for goes first, as ONE call: the geometry groups' gradients, the
+        # screen-space gradient and the loss are contiguous in the flat buffer (LAYOUT). Then the radii (MAX; only
+        # the statistics need them), then the features: f_dc, and f_rest in REST_PIECES row ranges (Adam on a
+        # piece runs under the next piece's transfer)
+        model.loss_slot.copy_(loss.reshape(1))
+        loss = model.loss_slot[0]
+        if prefetch is not None:
+            radii_max = radii_max.clone()  # the prefetched front half reuses the chunks' radii buffers
+        works = [ar(model.flat_grad[model.early_slice])]
+        radii_work = ar(radii_max, dist.ReduceOp.MAX)
+        dc = model.slices["f_dc"]
         late_dc = ar(model.flat_grad[dc.start:dc.stop])
-        # f_rest in REST_PIECES row ranges: Adam on a piece runs under the next piece's transfer, so only
-        # the last piece's Adam is left exposed after the wire goes quiet
         P = model.P
         cuts = [sent] + [max(sent, (P * k // REST_PIECES) // 4 * 4) for k in range(1, REST_PIECES)] + [P]
         rest = [(r0, r1, ar(model.flat_grad[a0 + 45 * r0:a0 + 45 * r1])) for r0, r1 in zip(cuts[:-1], cuts[1:]) if r1 > r0]
@@ -1220,6 +1236,14 @@ def _finish_step(model, loss, radii_max, process_group, update_stats, early=None
         pending = rest
         for w in works:
             w.wait()
+        if prefetch is not None and adam and model.fused_adam:
+            # the geometry groups are final once stepped: project / sort / bin the next step's views now, under
+            # the features' all-reduce (the statistics below do not touch what the front half reads)
+            model.adam_step(only=GEOMETRY_GROUPS)
+            prefetch()
+            prefetch, geometry_stepped = None, True
+        radii_work.wait()
+        loss = loss.clone()
     if update_stats:
         with torch.no_grad():  # DGE.py:266-284, gaussian_model.py:811-815
             vis = radii_max > 0
@@ -1233,10 +1257,8 @@ def _finish_step(model, loss, radii_max, process_group, update_stats, early=None
             w.wait()
         return loss
     if pending is not None and model.fused_adam:
-        model.adam_step(skip=("f_dc", "f_rest"))
-        if prefetch is not None:
-            prefetch()  # next step's projection / depth sort / binning under the features' all-reduce
-            prefetch = None
+        if not geometry_stepped:
+            model.adam_step(only=GEOMETRY_GROUPS)
         late_dc.wait()
         model.adam_step(only=("f_dc",), advance=False)
         if early is not None and early.done_rows:
@@ -1251,7 +1273,7 @@ def _finish_step(model, loss, radii_max, process_group, update_stats, early=None
             w.wait()
         if model.fused_adam and prefetch is not None:
             # one process: the same order of work as on several (geometry groups, front half, features)
-            model.adam_step(skip=("f_dc", "f_rest"))
+            model.adam_step(only=GEOMETRY_GROUPS)
             prefetch()
             model.adam_step(only=("f_dc", "f_rest"), advance=False)
         else:
