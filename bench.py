@@ -281,6 +281,37 @@ def dge_style_step(m, rasterize, make_settings, cams, targets, bg, global_batch,
     return loss.detach()
 
 
+def fit_restorer(model):
+    """restore() puts a fit.FitModel back to the state it has now (parameters, Adam, statistics): the fit moves the
+    Gaussians — and with them the instances per view — step by step, so every timed region starts from the SAME
+    state, the initial scene, and `value` and `e2e` time the same steps."""
+    snap = {k: getattr(model, k).clone() for k in ("flat", "exp_avg", "exp_avg_sq", "xyz_gradient_accum", "denom",
+                                                     "max_radii2D")}
+
+    def restore():
+        torch.cuda.synchronize()
+        for k, v in snap.items():
+            getattr(model, k).copy_(v)
+        model.step_count = 0
+        model._geom_version += 1  # a prefetched front half belongs to the old parameters
+    return restore
+
+
+def dge_restorer(model):
+    """The same for a DGEStyleModel (reference arm, drop-in loop)."""
+    tensors = [model._xyz, model._features_dc, model._features_rest, model._opacity, model._scaling, model._rotation,
+               model.xyz_gradient_accum, model.denom, model.max_radii2D]
+    snap = [t.detach().clone() for t in tensors]
+
+    def restore():
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            for t, v in zip(tensors, snap):
+                t.copy_(v)
+        model.optimizer.state.clear()  # Adam restarts at step 0 with zero moments
+    return restore
+
+
 class Workload:
     """The synthetic scene, this rank's cameras (pinned host and device copies) and its target images."""
 
@@ -337,11 +368,14 @@ def run_reference(args, cfg):
                               wl.targets_host if host else wl.targets_dev, wl.bg, V, host, dev)
 
     barrier = torch.cuda.synchronize
+    restore = dge_restorer(model)  # every timed region starts from the initial scene
+
     W_ = max(args.warmup, 3)
     for _ in range(W_):
         step(False)
     barrier()
-    # workload statistics of this arm's own forward (untimed)
+    # workload statistics of this arm's own forward (untimed), on the initial scene
+    restore()
     with torch.no_grad():
         Rs, Pvs = [], []
         for cam in wl.cams_dev[:4]:
@@ -352,9 +386,13 @@ def run_reference(args, cfg):
             Rs.append(int(rasterize.cls.last_R))
             Pvs.append(int((radii > 0).sum()))
     stats = {"P": P, "P_visible": sum(Pvs) / len(Pvs), "R": sum(Rs) / len(Rs), "views_sampled": len(Rs)}
+    restore()
+    for _ in range(W_):
+        step(False)
     total, per = timed_steps(lambda: step(False), args.steps, barrier, probe)
     mhz = probe.mhz()
     res = summarize(total, per, V)
+    restore()
     for _ in range(W_):
         step(True).item()
     last = [None]
@@ -509,12 +547,15 @@ def measure_fit(args, cfg, d, views_global, K, W_, name, scaling, device_targets
                             wl.bg, global_batch=views_global, host_inputs=host, image_size=(W, H),
                             next_cameras=cams if d.world > 1 else None)
 
+    restore = fit_restorer(model)
     for _ in range(W_):
         step(False)
     total, per = timed_steps(lambda: step(False), K, d.barrier)
+    restore()
     for _ in range(W_):
         step(True).item()
     total2, per2 = timed_steps(lambda: step(True).item(), K, d.barrier)
+    restore()
     total, total2 = d.max_([total, total2])
     res, e2e = summarize(total, per, views_global), summarize(total2, per2, views_global)
     stats = sample_view_stats(model, wl, n=2) if wl.cams_dev else {}
@@ -555,14 +596,16 @@ def measure_dropin(args, cfg, dev, K, W_):
                               wl.targets_host if host else wl.targets_dev, wl.bg, V, host, dev)
 
     barrier = torch.cuda.synchronize
+    restore = dge_restorer(model)
     for _ in range(W_):
         step(False)
     total, per = timed_steps(lambda: step(False), K, barrier)
+    restore()
     for _ in range(W_):
         step(True).item()
     total2, per2 = timed_steps(lambda: step(True).item(), K, barrier)
     res, e2e = summarize(total, per, V), summarize(total2, per2, V)
-    del model
+    del model, restore
     torch.cuda.empty_cache()
     boundary = measure_boundary(rasterize, make_settings, wl, dev, K, W_)
     del wl
@@ -725,12 +768,15 @@ def run_ours(args, cfg):
                             geom_splits=args.geom_splits or None, image_size=(W, H),
                             next_cameras=cams if (pipeline and batched) else None)
 
+    restore = fit_restorer(model)  # every timed region starts from the initial scene
+
     W_ = max(args.warmup, 3)
     for _ in range(W_):
         step(False)
     d.barrier()
 
-    # ---- diagnostic pass (untimed): per-stage device time, R and P_v of this rank's views
+    # ---- diagnostic pass (untimed) on the initial scene: per-stage device time, R and P_v of this rank's views
+    restore()
     lib.dge_profile_enable((1 << 7) - 1)
     step(False)
     torch.cuda.synchronize()
@@ -740,10 +786,12 @@ def run_ours(args, cfg):
     stage_total = {n: ms[i] for i, n in enumerate(STAGE_NAMES) if cnt[i]}
     stage_launches = {n: int(cnt[i]) for i, n in enumerate(STAGE_NAMES) if cnt[i]}
     lib.dge_profile_enable(0)
+    restore()
     stats = sample_view_stats(model, wl)
     dominant = max((k for k in stage_total if k in ("preprocess", "render_fwd", "render_bwd", "geom_bwd", "binning")),
                    key=lambda k: stage_total[k])  # largest share of the step
-    for _ in range(2):  # settle the caching allocator again after the diagnostic allocations
+    restore()
+    for _ in range(W_):  # (also settles the caching allocator again after the diagnostic allocations)
         step(False)
     # the dominant stage is event-timed live, inside the timed region, on the stream it is launched on
     lib.dge_profile_enable(1 << STAGE_NAMES.index(dominant))
@@ -783,8 +831,9 @@ def run_ours(args, cfg):
             "views_per_launch": units,
             "note": "blend kernels are issue bound, not HBM bound (SURVEY.md §8d); see DESIGN.md"}
 
-    # ---- timed region 2: K steps end to end (pinned host inputs copied inside, loss read back),
-    # after its own W warm-up steps (the first host-input step allocates the staging buffers)
+    # ---- timed region 2: K steps end to end (pinned host inputs copied inside, loss read back), from the
+    # same initial state, after its own W warm-up steps (the first host-input step allocates the staging buffers)
+    restore()
     for _ in range(W_):
         step(True).item()
     last = [None]
