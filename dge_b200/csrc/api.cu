@@ -272,7 +272,7 @@ using namespace dge;
 extern "C" {
 
 const char* dge_last_error(void) { return g_err; }
-int dge_abi_version(void) { return 12; }
+int dge_abi_version(void) { return 13; }
 unsigned long long dge_launch_count(void) { return g_kernel_launches; }
 
 int dge_clock_probe(unsigned long long* out, void* stream_) {

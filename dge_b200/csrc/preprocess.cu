@@ -279,7 +279,8 @@ cudaError_t launch_preprocess(const ViewParams& vp, const float* means3D, const 
 // ---- fit step: all V views of a step in ONE pass over the Gaussians -------------------------------
 // The 236 B of per-Gaussian inputs (192 B of them SH) and cov3D are view-independent: a thread loads
 // them once, then projects its Gaussian into every view of the step (cameras in shared memory) and
-// writes the per-view records: ~20x less input traffic than V per-view launches. Also produces the
+// writes the per-view records: ~20x less input traffic than V per-view launches. All inputs arrive through
+// 16-byte loads: the quaternion and the 12 SH quads per thread, positions and scales per CTA (below). Also produces the
 // running max of the radii over the views (max_radii2D statistics) instead of V radii arrays.
 constexpr int PRE_B_THREADS = 128;
 constexpr int PRE_B_MIN_CTAS = 6;  // 80 registers: the 48 SH floats live in shared memory, not registers
@@ -295,17 +296,38 @@ __global__ void __launch_bounds__(PRE_B_THREADS, PRE_B_MIN_CTAS) preprocess_batc
   float* s_sh = s_cam + V * 41 + threadIdx.x;
   for (int k = threadIdx.x; k < V * 40; k += blockDim.x) s_cam[k] = cams[k];
   for (int k = threadIdx.x; k < V; k += blockDim.x) s_tiles[k] = 0;
+  // The [P,3] inputs (positions, scales) are AoS with a 12-byte stride: the CTA's 128 rows of each are one
+  // contiguous, 16-byte aligned block of 96 float4 — loaded as such (coalesced 16-byte loads) and handed out
+  // through shared memory at a 3-word stride, which is conflict-free.
+  __shared__ __align__(16) float s_in[2][3 * PRE_B_THREADS];
+  {
+    const size_t first = (size_t)blockIdx.x * PRE_B_THREADS;
+    const int nflt = 3 * min(PRE_B_THREADS, vp.P - (int)first);
+    const float* src[2] = {means3D + 3 * first, scales + 3 * first};
+#pragma unroll
+    for (int a = 0; a < 2; a++) {
+      const bool aligned = (reinterpret_cast<uintptr_t>(src[a]) & 15) == 0;
+      for (int j = threadIdx.x; j < 3 * PRE_B_THREADS / 4; j += blockDim.x) {
+        if (aligned && 4 * j + 3 < nflt) {
+          reinterpret_cast<float4*>(s_in[a])[j] = ldg4(src[a] + 4 * j);
+        } else {
+          for (int e = 0; e < 4; e++)
+            if (4 * j + e < nflt) s_in[a][4 * j + e] = __ldg(src[a] + 4 * j + e);
+        }
+      }
+    }
+  }
   __syncthreads();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = idx < vp.P;
   float px = 0.f, py = 0.f, pz = 0.f, opac = 0.f;
   float cov3[6];
   if (live) {
-    px = __ldg(means3D + 3 * idx);
-    py = __ldg(means3D + 3 * idx + 1);
-    pz = __ldg(means3D + 3 * idx + 2);
+    px = s_in[0][3 * threadIdx.x];
+    py = s_in[0][3 * threadIdx.x + 1];
+    pz = s_in[0][3 * threadIdx.x + 2];
     const float4 q = ldg4(rotations + 4 * (size_t)idx);
-    cov3d_from_scale_rot(__ldg(scales + 3 * idx), __ldg(scales + 3 * idx + 1), __ldg(scales + 3 * idx + 2),
+    cov3d_from_scale_rot(s_in[1][3 * threadIdx.x], s_in[1][3 * threadIdx.x + 1], s_in[1][3 * threadIdx.x + 2],
                          vp.scale_modifier, q, cov3);
     opac = __ldg(opacities + idx);
     if (shs != nullptr) {  // nullptr: no colour (mask back-projection, K13 of the reference)

@@ -86,37 +86,50 @@ class FitModel:
         self.max_radii2D = torch.zeros(P, dtype=torch.int32, device=device)
         self.grad_mask: Optional[torch.Tensor] = None  # uint8 [P], local editing
 
+    @staticmethod
+    def _layout(P):
+        """Offsets of the groups inside the flat buffers for P Gaussians: (total floats, {name: slice}). Every
+        group starts on a 16-byte boundary (float4 accesses in the kernels: rotation rows, vectorised Adam),
+        whatever P is; order as LAYOUT."""
+        pad4 = lambda x: (x + 3) // 4 * 4
+        off, slices = 0, {}
+        for name, k, _ in sorted(GROUPS, key=lambda g: LAYOUT.index(g[0])):
+            slices[name] = slice(off, off + k * P)
+            off += pad4(k * P)
+        return off, slices
+
     def _allocate(self, raw, exp_avg=None, exp_avg_sq=None):
         """(Re)builds the flat parameter / gradient / Adam-state buffers for the raw parameter tensors
         `raw` (name -> [P, ...]); exp_avg / exp_avg_sq: optional per-group Adam state to carry over."""
         device = self.device
         P = raw["xyz"].shape[0]
-        self.P = P
-        # every group starts on a 16-byte boundary inside the flat buffers (float4 accesses in the
-        # kernels: rotation rows, vectorised Adam), whatever P is
+        n, slices = self._layout(P)
+        flat, m, v = (torch.zeros(n, dtype=torch.float32, device=device) for _ in range(3))
+        for name, k, tail in GROUPS:
+            sl = slices[name]
+            flat[sl].view(P, *tail).copy_(raw[name].detach().to(device).reshape(P, *tail))
+            if exp_avg is not None:
+                m[sl].copy_(exp_avg[name].reshape(-1))
+                v[sl].copy_(exp_avg_sq[name].reshape(-1))
+        self._bind(P, flat, m, v, carry_state=exp_avg is not None)
+
+    def _bind(self, P, flat, exp_avg, exp_avg_sq, carry_state=False):
+        """Makes `flat` / `exp_avg` / `exp_avg_sq` (laid out by _layout(P)) the model's state: parameter leaves
+        and their gradients as views, a fresh gradient buffer, caches of the old buffers dropped."""
+        device = self.device
         pad4 = lambda x: (x + 3) // 4 * 4
-        n = sum(pad4(k * P) for _, k, _ in GROUPS)
-        self.flat = torch.zeros(n, dtype=torch.float32, device=device)
+        n, self.slices = self._layout(P)
+        self.P, self.flat, self.exp_avg, self.exp_avg_sq = P, flat, exp_avg, exp_avg_sq
         # gradient buffer: 59P parameter grads, the 3P screen-space gradient sum, and (last 4 floats) the step's
         # loss, which rides in the same all-reduce
         self.flat_grad = torch.zeros(n + pad4(3 * P) + 4, dtype=torch.float32, device=device)
-        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=device)
-        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=device)
-        self.slices = {}
         self.params = {}
-        off = 0
-        for name, k, tail in sorted(GROUPS, key=lambda g: LAYOUT.index(g[0])):
-            sl = slice(off, off + k * P)
-            self.slices[name] = sl
+        for name, k, tail in GROUPS:
+            sl = self.slices[name]
             p = self.flat[sl].view(P, *tail)
-            p.copy_(raw[name].detach().to(device).reshape(P, *tail))
             p.requires_grad_(True)  # a leaf: `flat` itself never requires grad
             p.grad = self.flat_grad[sl].view(P, *tail)
             self.params[name] = p
-            if exp_avg is not None:
-                self.exp_avg[sl].copy_(exp_avg[name].reshape(-1))
-                self.exp_avg_sq[sl].copy_(exp_avg_sq[name].reshape(-1))
-            off += pad4(k * P)
         self.means2D = torch.zeros(P, 3, dtype=torch.float32, device=device, requires_grad=True)
         self.means2D_slice = slice(n, n + 3 * P)
         self.means2D.grad = self.flat_grad[self.means2D_slice].view(P, 3)
@@ -134,7 +147,7 @@ class FitModel:
             # the reference's optimiser, verbatim (gaussian_model.py:374)
             groups = [{"params": [self.params[nm]], "lr": self.lrs[nm], "name": nm} for nm, _, _ in GROUPS]
             self.optimizer = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
-            if exp_avg is not None:
+            if carry_state:
                 for nm, _, _ in GROUPS:
                     sl, pp = self.slices[nm], self.params[nm]
                     self.optimizer.state[pp] = {"step": torch.tensor(float(self.step_count)),
@@ -193,7 +206,7 @@ class FitModel:
     # -- gaussian_model.py:543-807
     @torch.no_grad()
     def densify_and_prune(self, max_grad, max_densify_percent, min_opacity, extent, max_screen_size,
-                          percent_dense=0.01, N=2, generator=None, normal_samples=None):
+                          percent_dense=0.01, N=2, generator=None, normal_samples=None, device_kernels=None):
         """GaussianModel.densify_and_prune (gaussiansplatting/scene/gaussian_model.py:770-797) on the
         flat-buffer replica: clone small Gaussians with a large accumulated screen-space gradient
         (:728-768), split large ones into N samples (:675-726), prune transparent / oversized ones
@@ -203,7 +216,11 @@ class FitModel:
         are touched, as in the reference (:774, :795). The flat buffers are rebuilt for the new count.
         Multi-GPU replicas stay identical when every rank passes a generator seeded alike (the
         reference draws from the global CUDA generator, :685-687). normal_samples: the N(0,1)-scaled
-        draw to use instead (tests). Returns (P_before, P_after_clone, P_after_split, P_after_prune)."""
+        draw to use instead (tests). Returns (P_before, P_after_clone, P_after_split, P_after_prune).
+        On a CUDA device with the fused optimiser (device_kernels, default) the decisions, the compaction, the
+        clone / split appends and the Adam-state surgery are TWO kernels over the flat buffers
+        (csrc/densify.cu: dge_densify_select / dge_densify_gather) instead of the boolean-mask gathers and
+        torch.cat re-allocations below; same rows in the same order (tests/test_fit_gpu.py)."""
         dev = self.device
         raw = {k: v.detach() for k, v in self.params.items()}
         m = {k: self.adam_state(k)[0].detach().clone() for k in raw}
@@ -217,6 +234,11 @@ class FitModel:
             valid_percent = len(grads.nonzero()) * max_densify_percent / grads.shape[0]
             thresold_value = torch.quantile(grads, 1 - valid_percent)
             grads[grads < thresold_value] = 0.0
+        if device_kernels is None:
+            device_kernels = dev.type == "cuda" and self.fused_adam
+        if device_kernels:
+            return self._densify_on_device(grads, max_grad, min_opacity, extent, max_screen_size, percent_dense, N,
+                                           generator, normal_samples)
 
         def extend(new):  # cat_tensors_to_optimizer (:609-640)
             for k in raw:
@@ -281,6 +303,56 @@ class FitModel:
         self.grad_mask = mask.to(torch.uint8).contiguous() if had_mask else None
         del P2_all
         return P0, P1, P2, P3
+
+    @torch.no_grad()
+    def _densify_on_device(self, grads, max_grad, min_opacity, extent, max_screen_size, percent_dense, N, generator,
+                           normal_samples):
+        """densify_and_prune's data movement as two kernels (csrc/densify.cu). `grads`: the masked / thresholded
+        accumulated gradients [P,1] the torch path computes (gaussian_model.py:770-781)."""
+        lib, dev, P0 = L.load(), self.device, self.P
+        st = L.stream_ptr(dev)
+        g = grads.reshape(-1).to(torch.float32).contiguous()
+        keep = torch.empty(4, P0, dtype=torch.int32, device=dev)
+        sel = torch.empty(P0, dtype=torch.uint8, device=dev)
+        mask = self.grad_mask
+        prune_size = float(0.1 * extent) if max_screen_size else -1.0
+        L.check(lib.dge_densify_select(P0, g.data_ptr(), self.params["scaling"].data_ptr(), self.params["opacity"].data_ptr(),
+                                       None if mask is None else mask.data_ptr(), float(max_grad),
+                                       float(percent_dense * extent), float(min_opacity), prune_size, int(N),
+                                       keep.data_ptr(), sel.data_ptr(), st), "densify select")
+        incl = torch.cumsum(keep, dim=1, dtype=torch.int32)
+        scan = (incl - keep).contiguous()
+        K_orig, K_clone, K_child, K_split = (int(x) for x in incl[:, -1].tolist())
+        n_clone = int((sel & 1).sum())
+        if normal_samples is not None:
+            samples = normal_samples.to(dev, torch.float32).contiguous()
+        else:  # the draw of densify_and_split (:685-687): N(0, scale) per split-selected Gaussian and copy
+            stds = torch.exp(self.params["scaling"].detach())[(sel & 2) != 0].repeat(N, 1)
+            samples = torch.normal(mean=torch.zeros((stds.size(0), 3), device=dev), std=stds, generator=generator)
+        assert samples.shape[0] == N * K_split
+        P3 = K_orig + K_clone + N * K_child
+        n, slices = self._layout(P3)
+        new = [torch.zeros(n, dtype=torch.float32, device=dev) for _ in range(3)]
+        names = [nm for nm, _, _ in GROUPS]
+        widths = (L.C.c_int * 6)(*[k for _, k, _ in GROUPS])
+        old = [self.flat, self.exp_avg, self.exp_avg_sq]
+        src = (L.C.c_void_p * 18)(*[old[a][self.slices[nm]].data_ptr() for a in range(3) for nm in names])
+        dst = (L.C.c_void_p * 18)(*[new[a][slices[nm]].data_ptr() if P3 else 0 for a in range(3) for nm in names])
+        had_mask = mask is not None
+        mask_out = torch.empty(P3, dtype=torch.uint8, device=dev) if had_mask else None
+        if P3:
+            L.check(lib.dge_densify_gather(P0, int(N), keep.data_ptr(), scan.data_ptr(), K_orig, K_clone, K_child, K_split,
+                                           src, dst, widths, names.index("xyz"), names.index("scaling"),
+                                           names.index("rotation"), samples.data_ptr() if K_split else None,
+                                           None if mask is None else mask.data_ptr(),
+                                           None if mask_out is None else mask_out.data_ptr(), st), "densify gather")
+        self._bind(P3, new[0], new[1], new[2])
+        self.xyz_gradient_accum = torch.zeros(P3, 1, device=dev)
+        self.denom = torch.zeros(P3, 1, device=dev)
+        self.max_radii2D = torch.zeros(P3, dtype=torch.int32, device=dev)
+        self.grad_mask = mask_out if had_mask else None
+        P1 = P0 + n_clone
+        return P0, P1, P1 + (N - 1) * K_split, P3
 
     # -- gaussian_model.py:221-258
     def activations(self):

@@ -273,6 +273,28 @@ int dge_fused_adam(float* param, const float* grad, float* exp_avg,
                    float beta2, float eps, int step, const uint8_t* mask,
                    int stride, void* stream);
 
+/* ---- densification on the flat fit buffers ----
+ * GaussianModel.densify_and_prune (gaussiansplatting/scene/gaussian_model.py:543-807) as two passes.
+ * dge_densify_select: per Gaussian the clone / split / prune decisions from its (masked, thresholded) accumulated
+ *   gradient `grad` [P], raw scaling [P,3], raw opacity [P] and the edit mask (uint8 [P] or NULL): clone if
+ *   |grad| >= max_grad and max(scale) <= size_threshold (= percent_dense * extent), split if grad >= max_grad and
+ *   max(scale) > size_threshold; prune (inside the mask) if sigmoid(opacity) < min_opacity or, with prune_size >= 0
+ *   (= 0.1 * extent), max(scale) > prune_size — the children with their scale / (0.8 N). keep [4][P] int32: the
+ *   original stays | its clone stays | its children stay | split-selected; sel [P]: bit 0 cloned, bit 1 split.
+ * dge_densify_gather: with scan = exclusive scans of keep's four rows and their totals K_*, writes the new
+ *   parameter / exp_avg / exp_avg_sq blocks of the six groups (src / dst: [3 buffers][6 groups] pointers, widths[6]
+ *   floats per Gaussian; g_* = indices of the xyz, scaling, rotation groups) in the reference's row order
+ *   [kept originals | kept clones | children copy 0 .. N-1], the children at R(q) sample + xyz with
+ *   samples [N][K_split][3] (the draw of :685-687) and log(scale / (0.8 N)), new rows with zero Adam moments
+ *   (cat_tensors_to_optimizer :609-640), and the new edit mask. */
+int dge_densify_select(int P, const float* grad, const float* scaling_raw, const float* opacity_raw,
+                       const uint8_t* mask, float max_grad, float size_threshold, float min_opacity,
+                       float prune_size, int N, int* keep, uint8_t* sel, void* stream);
+int dge_densify_gather(int P, int N, const int* keep, const int* scan, int K_orig, int K_clone, int K_child,
+                       int K_split, const float* const* src, float* const* dst, const int* widths, int g_xyz,
+                       int g_scaling, int g_rotation, const float* samples, const uint8_t* mask_in,
+                       uint8_t* mask_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -475,3 +475,92 @@ def test_prefetched_front_half_gives_the_same_step(cuda, chunks):
     assert not a._front["coloured"]
     lc = fit.fit_step(a, other, targets, bg, global_batch=6, num_chunks=chunks)   # `cams` was prefetched
     assert torch.isfinite(lc) and a._front["coloured"]
+
+
+def _state_for_densify(cuda, seed_mask=True):
+    model, cams, targets, bg = _setup(cuda, True, 40000, 200, 136, 4, 0.05)
+    if seed_mask:
+        model.set_grad_mask(torch.rand(model.P, generator=torch.Generator().manual_seed(8)) < 0.7)
+    for _ in range(3):
+        fit.fit_step(model, cams, targets, bg, global_batch=4)
+    return model
+
+
+@pytest.mark.parametrize("masked,max_screen", [(True, 5), (False, 5), (True, 0)])
+def test_device_densify_equals_torch_path(cuda, masked, max_screen):
+    """csrc/densify.cu (dge_densify_select / dge_densify_gather: decisions, compaction, clone / split appends and
+    Adam-state surgery as two kernels over the flat buffers) against the torch path of FitModel.densify_and_prune,
+    which tests/test_densify.py pins bit-exactly to the reference's own code: same counts, same rows in the same
+    order — parameters, both Adam moments, edit mask identical; only the split children's positions (a 3x3
+    product whose accumulation order torch leaves to cuBLAS) are compared to an ulp."""
+    a = _state_for_densify(cuda, masked)
+    b = _state_for_densify(cuda, masked)
+    for name in ("flat", "exp_avg", "exp_avg_sq", "xyz_gradient_accum", "denom", "max_radii2D"):
+        getattr(b, name).copy_(getattr(a, name))
+    P0 = a.P
+    scale_med = float(torch.exp(a.params["scaling"]).max(dim=1).values.median())
+    extent = scale_med / 0.01          # percent_dense * extent = the median size: clones AND splits occur
+    gmed = float((a.xyz_gradient_accum / a.denom.clamp_min(1)).median())
+    args = (gmed, 0.5, 0.3, extent, max_screen)
+    ca = a.densify_and_prune(*args, generator=torch.Generator(device=cuda).manual_seed(3), device_kernels=True)
+    cb = b.densify_and_prune(*args, generator=torch.Generator(device=cuda).manual_seed(3), device_kernels=False)
+    torch.cuda.synchronize()
+    print("densify counts (before, after clone, after split, after prune):", ca)
+    assert ca == cb and ca[1] > ca[0] and ca[2] > ca[1] and ca[3] < ca[2] and a.P == b.P == ca[3] != P0
+    n_child_rows = None
+    for name in a.params:
+        pa, pb = a.params[name].detach(), b.params[name].detach()
+        if name == "xyz":
+            same = (pa == pb).all(dim=1)
+            n_child_rows = int((~same).sum())
+            torch.testing.assert_close(pa, pb, rtol=2e-6, atol=1e-7)
+            first_diff = int(torch.nonzero(~same)[0]) if n_child_rows else a.P
+            assert same[:first_diff].all()   # originals and clones are copies: exact; differences only among the children
+        else:
+            assert torch.equal(pa, pb), name
+        for ma, mb in zip(a.adam_state(name), b.adam_state(name)):
+            assert torch.equal(ma, mb), name
+    print(f"children whose position differs in the last bit from torch's bmm: {n_child_rows} of {ca[3]}")
+    assert (a.grad_mask is None) == (b.grad_mask is None)
+    if masked:
+        assert torch.equal(a.grad_mask, b.grad_mask)
+    assert not a.xyz_gradient_accum.any() and not a.denom.any() and not a.max_radii2D.any()
+    # the rebuilt model keeps fitting
+    _, cams, targets, bg = _setup(cuda, True, 40000, 200, 136, 4, 0.05)
+    la = fit.fit_step(a, cams, targets, bg, global_batch=4)
+    assert torch.isfinite(la)
+
+
+def test_densify_fixtures_on_device(cuda):
+    """The reference's own densification (fixtures of oracle/make_densify_golden.py, produced by its code on the
+    CPU) through the device kernels: counts, parameters, Adam moments and mask as in the fixture (positions and
+    log-scales of the split children to an ulp: CPU vs GPU libm)."""
+    import glob, os
+    import numpy as np
+    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "densify_*.npz")))
+    assert files
+    names = [g[0] for g in fit.GROUPS]
+    for path in files:
+        z = np.load(path)
+        max_grad, pct, min_opacity, extent, max_screen, percent_dense = (float(x) for x in z["hyper"])
+        P = z["in_xyz"].shape[0]
+        model = fit.FitModel(scene.make_gaussians(P, seed=1), cuda)
+        model.step_count = int(z["adam_step"][0])
+        model._allocate({n: torch.from_numpy(z["in_" + n]) for n in names}, {n: torch.from_numpy(z["in_m_" + n]) for n in names},
+                        {n: torch.from_numpy(z["in_v_" + n]) for n in names})
+        model.xyz_gradient_accum = torch.from_numpy(z["in_xyz_gradient_accum"]).to(cuda)
+        model.denom = torch.from_numpy(z["in_denom"]).to(cuda)
+        model.max_radii2D = torch.from_numpy(z["in_max_radii2D"]).to(torch.int32).to(cuda)
+        model.set_grad_mask(torch.from_numpy(z["in_mask"]))
+        counts = model.densify_and_prune(max_grad, pct, min_opacity, extent, int(max_screen), percent_dense=percent_dense,
+                                         normal_samples=torch.from_numpy(z["normal_samples"]), device_kernels=True)
+        assert list(counts) == [int(c) for c in z["counts"]], path
+        for n in names:
+            got = model.params[n].detach().cpu().numpy()
+            if n in ("xyz", "scaling"):
+                np.testing.assert_allclose(got, z["out_" + n], rtol=3e-6, atol=1e-6, err_msg=n)
+            else:
+                assert np.array_equal(got, z["out_" + n]), (path, n)
+            m, v = model.adam_state(n)
+            assert np.array_equal(m.cpu().numpy(), z["out_m_" + n]) and np.array_equal(v.cpu().numpy(), z["out_v_" + n]), n
+        assert np.array_equal(model.grad_mask.bool().cpu().numpy(), z["out_mask"])
