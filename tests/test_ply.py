@@ -1,5 +1,8 @@
 """PLY files in the reference's on-disk layout (dge_b200/ply.py; gaussian_model.py:396-445, :447-540)."""
+import os
+
 import numpy as np
+import pytest
 import torch
 
 from dge_b200 import fit, ply, scene
@@ -40,3 +43,54 @@ def test_round_trip(tmp_path):
     assert again.P == model.P
     for k in model.params:
         assert torch.equal(again.params[k], model.params[k]), k
+
+
+REF = "/root/reference/gaussiansplatting"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree only exists in the build container")
+def test_files_interchange_with_the_reference_save_and_load(tmp_path):
+    """The reference's OWN GaussianModel.save_ply / load_ply (gaussian_model.py:410-445, :455-551), loaded unchanged
+    from the reference tree with `plyfile` replaced by tests/mini_plyfile.py (the package is not in this image):
+    a file the reference writes loads here to the reference model's tensors, and a file written here loads in the
+    reference to ours — bit for bit, features in the [P, coeffs, 3] layout both sides use in memory."""
+    import sys
+    import types
+    from tests import mini_plyfile
+    from tests.test_reference_callers import _cpu_for_cuda, _load, _stub
+    saved = dict(sys.modules)
+    try:
+        _stub("gaussiansplatting"), _stub("gaussiansplatting.utils"), _stub("gaussiansplatting.scene")
+        _load("gaussiansplatting.utils.general_utils", REF + "/utils/general_utils.py")
+        _load("gaussiansplatting.utils.system_utils", REF + "/utils/system_utils.py")
+        _load("gaussiansplatting.utils.sh_utils", REF + "/utils/sh_utils.py")
+        sys.modules["plyfile"] = mini_plyfile
+        _stub("simple_knn"), _stub("simple_knn._C", distCUDA2=None)
+        _stub("gaussiansplatting.utils.graphics_utils", BasicPointCloud=object)
+        _stub("gaussiansplatting.gaussian_renderer", camera2rasterizer=None)
+        _stub("gaussiansplatting.knn", K_nearest_neighbors=None)
+        GaussianModel = _load("gaussiansplatting.scene.gaussian_model", REF + "/scene/gaussian_model.py").GaussianModel
+        g = scene.make_gaussians(53, seed=9)
+        ours = fit.FitModel(g, torch.device("cpu"))
+        with _cpu_for_cuda():
+            # ours -> file -> the reference's load_ply
+            path_a = str(tmp_path / "ours" / "point_cloud.ply")
+            ours.save_ply(path_a)
+            ref = GaussianModel(3, 0.0, 0.05, 1.0)
+            ref.load_ply(path_a)
+            assert ref.max_sh_degree == 3 and ref.active_sh_degree == 3
+            pairs = [("xyz", ref._xyz), ("f_dc", ref._features_dc), ("f_rest", ref._features_rest), ("opacity", ref._opacity),
+                     ("scaling", ref._scaling), ("rotation", ref._rotation)]
+            for name, t in pairs:
+                assert torch.equal(t.detach(), ours.params[name].detach()), name
+            # the reference's save_ply -> file -> ours
+            path_b = str(tmp_path / "ref" / "point_cloud.ply")
+            ref.save_ply(path_b)
+        raw = ply.load_ply(path_b)
+        for name, t in pairs:
+            assert torch.equal(raw[name].reshape(t.shape), t.detach()), name
+        assert open(path_a, "rb").read() == open(path_b, "rb").read()   # and the two files are the same bytes
+    finally:
+        for k in list(sys.modules):
+            if k not in saved:
+                del sys.modules[k]
