@@ -425,7 +425,7 @@ def test_dge_fit_adapter_training_step(cuda):
     assert torch.equal(out["semantic_render"], torch.stack(sems, 0))
     assert torch.equal(out["masks"], torch.norm(torch.stack(sems, 0), dim=1) > 0.8)
     assert torch.equal(out["radii"], radii) and torch.equal(out["visibility_filter"], radii > 0)
-    assert abs(float(loss) - float(loss_ref)) <= 1e-6 * abs(float(loss_ref))
+    assert abs(float(loss.detach()) - float(loss_ref.detach())) <= 1e-6 * abs(float(loss_ref.detach()))
     # gradients: raw parameters + the summed screen-space gradient (DGE.py:269-276)
     vs_grad = sum(v.grad for v in vsp)
     for name, sl in model.slices.items():
@@ -498,7 +498,7 @@ def test_device_densify_equals_torch_path(cuda, masked, max_screen):
     for name in ("flat", "exp_avg", "exp_avg_sq", "xyz_gradient_accum", "denom", "max_radii2D"):
         getattr(b, name).copy_(getattr(a, name))
     P0 = a.P
-    scale_med = float(torch.exp(a.params["scaling"]).max(dim=1).values.median())
+    scale_med = float(torch.exp(a.params["scaling"].detach()).max(dim=1).values.median())
     extent = scale_med / 0.01          # percent_dense * extent = the median size: clones AND splits occur
     gmed = float((a.xyz_gradient_accum / a.denom.clamp_min(1)).median())
     args = (gmed, 0.5, 0.3, extent, max_screen)
