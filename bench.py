@@ -493,8 +493,36 @@ class Dist:
         self.dist, self.dev = dist, dev
         self.rank = int(os.environ.get("RANK", "0"))
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.nccl_log = None
         if self.world > 1:
+            if self.rank == 0 and "NCCL_DEBUG" not in os.environ:
+                # which transport / algorithm family NCCL set up (NVLS on NVSwitch?): rank 0's one-off INIT lines,
+                # written to a file (nothing is logged per collective, so the timed steps are not disturbed)
+                import tempfile
+                self.nccl_log = os.path.join(tempfile.gettempdir(), f"dge_b200_nccl_{os.getpid()}.log")
+                os.environ.update(NCCL_DEBUG="INFO", NCCL_DEBUG_SUBSYS="INIT", NCCL_DEBUG_FILE=self.nccl_log)
             dist.init_process_group("nccl", device_id=dev)
+
+    def nccl_summary(self):
+        """{version, nvls, channels...} read off rank 0's NCCL INIT log; None on one GPU or when NCCL_DEBUG was set
+        by the caller."""
+        if not self.nccl_log or not os.path.exists(self.nccl_log):
+            return None
+        import re
+        text = open(self.nccl_log, errors="replace").read()
+        out = {"version": ".".join(str(v) for v in torch.cuda.nccl.version()), "nvls": False}
+        m = re.search(r"NVLS multicast support is (\w+)", text)
+        if m:
+            out["nvls_multicast"] = m.group(1)
+        m = re.search(r"(\d+) coll channels, (\d+) collnet channels, (\d+) nvls channels, (\d+) p2p channels", text)
+        if m:
+            out.update(coll_channels=int(m.group(1)), nvls_channels=int(m.group(3)), p2p_channels=int(m.group(4)))
+            out["nvls"] = int(m.group(3)) > 0
+        elif re.search(r"Connected NVLS", text):
+            out["nvls"] = True
+        out["init_lines"] = [l.split("NCCL INFO ", 1)[-1][:160] for l in text.splitlines()
+                             if re.search(r"NVLS|coll channels|Connected all|threadThresholds", l)][:8]
+        return out
 
     def barrier(self):
         if self.world > 1:
@@ -913,6 +941,9 @@ def run_ours(args, cfg):
             rates["reference_equivalent_sort_keys_per_s"] = vpl * stats.get("R", 0.0) / (
                 (stage_ms["binning"] + stage_ms["depth_sort"]) * 1e-3)
     out["rates"] = rates
+    nccl = d.nccl_summary()
+    if nccl:
+        out["nccl"] = nccl
     if extras:
         out["extras"] = extras
     if not args.no_cpu_baseline and world == 1 and wl.targets_all is not None:  # rank 0 at N=1 only

@@ -11,7 +11,7 @@
 
 namespace dge {
 
-unsigned long long g_kernel_launches = 0;
+std::atomic<unsigned long long> g_kernel_launches{0};
 
 static thread_local char g_err[512] = "";
 
@@ -20,19 +20,24 @@ enum { ST_PREPROCESS = 0, ST_DEPTH_SORT, ST_BINNING, ST_RENDER_FWD, ST_RENDER_BW
        ST_APPLY_WEIGHTS, ST_COUNT };
 static unsigned g_profile_mask = 0;
 struct EvPair { cudaEvent_t a, b; };
+static std::mutex g_ev_mutex;  // the event lists are shared by every thread that calls into the library
 static std::vector<EvPair> g_ev_free;
 static std::vector<EvPair> g_ev_used[ST_COUNT];
 struct StageScope {
   int st; cudaStream_t s; bool on; EvPair ev;
   StageScope(int st_, cudaStream_t s_) : st(st_), s(s_), on((g_profile_mask >> st_) & 1u) {
     if (!on) return;
-    if (g_ev_free.empty()) { cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); }
-    else { ev = g_ev_free.back(); g_ev_free.pop_back(); }
+    {
+      std::lock_guard<std::mutex> lock(g_ev_mutex);
+      if (g_ev_free.empty()) { cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); }
+      else { ev = g_ev_free.back(); g_ev_free.pop_back(); }
+    }
     cudaEventRecord(ev.a, s);
   }
   ~StageScope() {
     if (!on) return;
     cudaEventRecord(ev.b, s);
+    std::lock_guard<std::mutex> lock(g_ev_mutex);
     g_ev_used[st].push_back(ev);
   }
 };
@@ -273,7 +278,7 @@ extern "C" {
 
 const char* dge_last_error(void) { return g_err; }
 int dge_abi_version(void) { return 13; }
-unsigned long long dge_launch_count(void) { return g_kernel_launches; }
+unsigned long long dge_launch_count(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
 
 int dge_clock_probe(unsigned long long* out, void* stream_) {
   clock_probe_kernel<<<DGE_NUM_SMS * 8, 32, 0, (cudaStream_t)stream_>>>(out);
@@ -285,20 +290,25 @@ void dge_profile_enable(unsigned stage_mask) { g_profile_mask = stage_mask; }
 // Sums (and clears) the event-timed durations recorded since the last call.
 // ms_out / count_out have DGE_NUM_STAGES entries. Synchronises on the recorded events.
 int dge_profile_read(float* ms_out, int* count_out) {
+  std::vector<EvPair> used[ST_COUNT];
+  {
+    std::lock_guard<std::mutex> lock(g_ev_mutex);
+    for (int st = 0; st < ST_COUNT; st++) used[st].swap(g_ev_used[st]);
+  }
   for (int st = 0; st < ST_COUNT; st++) {
     float total = 0.f;
-    for (const EvPair& ev : g_ev_used[st]) {
+    for (const EvPair& ev : used[st]) {
       cudaError_t e = cudaEventSynchronize(ev.b);
       float ms = 0.f;
       if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ev.a, ev.b);
       if (e != cudaSuccess) return fail("profile read", e);
       total += ms;
-      g_ev_free.push_back(ev);
     }
     ms_out[st] = total;
-    count_out[st] = (int)g_ev_used[st].size();
-    g_ev_used[st].clear();
+    count_out[st] = (int)used[st].size();
   }
+  std::lock_guard<std::mutex> lock(g_ev_mutex);
+  for (int st = 0; st < ST_COUNT; st++) g_ev_free.insert(g_ev_free.end(), used[st].begin(), used[st].end());
   return 0;
 }
 

@@ -1,5 +1,6 @@
 // Shared declarations of the dge_b200 CUDA library (sm_100a only).
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
@@ -31,8 +32,8 @@
 namespace dge {
 
 // Number of kernels this library has launched (read by bench.py through dge_launch_count()).
-extern unsigned long long g_kernel_launches;
-#define DGE_LAUNCHED(n) (::dge::g_kernel_launches += (n))
+extern std::atomic<unsigned long long> g_kernel_launches;  // (forward and autograd threads both launch)
+#define DGE_LAUNCHED(n) (::dge::g_kernel_launches.fetch_add((n), std::memory_order_relaxed))
 
 // ---------------------------------------------------------------- scratch ---
 // Our own layout of the three opaque blobs (the reference's is
