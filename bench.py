@@ -293,7 +293,7 @@ def fit_restorer(model):
         for k, v in snap.items():
             getattr(model, k).copy_(v)
         model.step_count = 0
-        model._geom_version += 1  # a prefetched front half belongs to the old parameters
+        model.parameters_changed()  # a prefetched front half belongs to the old parameters
     return restore
 
 

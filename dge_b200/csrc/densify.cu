@@ -73,7 +73,9 @@ __global__ void __launch_bounds__(256) densify_gather_kernel(
   const bool k_orig = keep[i] != 0, k_clone = keep[P + i] != 0, k_child = keep[2 * P + i] != 0;
   if (!(k_orig || k_clone || k_child)) return;
   const float p = b.src[0][g][(size_t)i * w + k];
+  [[maybe_unused]] const size_t rows_out = (size_t)K_orig + K_clone + (size_t)N * K_child;
   if (k_orig) {
+    DGE_CHECK(scan[i] < K_orig);
     const size_t d = (size_t)scan[i] * w + k;
     b.dst[0][g][d] = p;
     b.dst[1][g][d] = b.src[1][g][(size_t)i * w + k];  // the original keeps its Adam moments (_prune_optimizer :568-587)
@@ -82,6 +84,7 @@ __global__ void __launch_bounds__(256) densify_gather_kernel(
   }
   if (k_clone) {  // densify_and_clone: a copy with zero moments (cat_tensors_to_optimizer :609-640)
     const size_t row = (size_t)K_orig + scan[P + i];
+    DGE_CHECK(scan[P + i] < K_clone && row < rows_out);
     const size_t d = row * w + k;
     b.dst[0][g][d] = p;
     b.dst[1][g][d] = 0.0f;
@@ -117,6 +120,7 @@ __global__ void __launch_bounds__(256) densify_gather_kernel(
     }
     for (int n = 0; n < N; n++) {
       const size_t row = (size_t)K_orig + K_clone + (size_t)n * K_child + scan[2 * P + i];
+      DGE_CHECK(scan[2 * P + i] < K_child && rank < K_split && row < rows_out);
       float v = p;
       if (g == b.g_xyz) {
         const float* s = samples + 3 * ((size_t)n * K_split + rank);

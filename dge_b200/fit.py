@@ -195,6 +195,12 @@ class FitModel:
         self.max_radii2D = sd["max_radii2D"].to(dev).clone()
         self.set_grad_mask(sd.get("grad_mask"))
 
+    def parameters_changed(self):
+        """To be called after editing geometry parameters in place from outside (anything but adam_step,
+        densify_and_prune and load_state_dict, which do it themselves): a front half prefetched for the next
+        step (fit_step's next_cameras) belongs to the old parameters and must not be used."""
+        self._geom_version = getattr(self, "_geom_version", 0) + 1
+
     def adam_state(self, name):
         """(exp_avg, exp_avg_sq) of a parameter group, shaped like the parameter."""
         if not self.fused_adam and self.params[name] in self.optimizer.state:
