@@ -35,6 +35,17 @@ import sys
 import threading
 import time
 
+# Several GPUs: which transport / algorithm family NCCL sets up (NVLS on NVSwitch?) goes on the JSON line. Rank 0's one-off
+# INIT lines are sent to a file — nothing is logged per collective, the timed steps are not disturbed. The variables have
+# to be in the environment before the NCCL library first looks at them, hence before torch is imported.
+NCCL_LOG = None
+NCCL_DEBUG_WAS = os.environ.get("NCCL_DEBUG")
+if (int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("RANK", "0") == "0"
+        and (NCCL_DEBUG_WAS or "").upper() not in ("INFO", "TRACE") and "NCCL_DEBUG_FILE" not in os.environ):
+    import tempfile
+    NCCL_LOG = os.path.join(tempfile.gettempdir(), f"dge_b200_nccl_{os.getpid()}.log")
+    os.environ.update(NCCL_DEBUG="INFO", NCCL_DEBUG_SUBSYS="INIT", NCCL_DEBUG_FILE=NCCL_LOG)
+
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -493,24 +504,21 @@ class Dist:
         self.dist, self.dev = dist, dev
         self.rank = int(os.environ.get("RANK", "0"))
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
-        self.nccl_log = None
+        self.nccl_log = NCCL_LOG
         if self.world > 1:
-            if self.rank == 0 and "NCCL_DEBUG" not in os.environ:
-                # which transport / algorithm family NCCL set up (NVLS on NVSwitch?): rank 0's one-off INIT lines,
-                # written to a file (nothing is logged per collective, so the timed steps are not disturbed)
-                import tempfile
-                self.nccl_log = os.path.join(tempfile.gettempdir(), f"dge_b200_nccl_{os.getpid()}.log")
-                os.environ.update(NCCL_DEBUG="INFO", NCCL_DEBUG_SUBSYS="INIT", NCCL_DEBUG_FILE=self.nccl_log)
             dist.init_process_group("nccl", device_id=dev)
 
     def nccl_summary(self):
         """{version, nvls, channels...} read off rank 0's NCCL INIT log; None on one GPU or when NCCL_DEBUG was set
         by the caller."""
-        if not self.nccl_log or not os.path.exists(self.nccl_log):
+        if not self.nccl_log:
             return None
+        if not os.path.exists(self.nccl_log):
+            return {"version": ".".join(str(v) for v in torch.cuda.nccl.version()), "log": "no INIT log was written"}
         import re
         text = open(self.nccl_log, errors="replace").read()
-        out = {"version": ".".join(str(v) for v in torch.cuda.nccl.version()), "nvls": False}
+        out = {"version": ".".join(str(v) for v in torch.cuda.nccl.version()), "nvls": False,
+               "NCCL_DEBUG_before": NCCL_DEBUG_WAS}
         m = re.search(r"NVLS multicast support is (\w+)", text)
         if m:
             out["nvls_multicast"] = m.group(1)
