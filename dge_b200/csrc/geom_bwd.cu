@@ -631,28 +631,14 @@ __global__ void __launch_bounds__(128, 4) geom_backward_batched_kernel(
 
 // GaussianModel's activations (gaussian_model.py:221-258) for the whole model in one pass:
 // shs = cat(f_dc, f_rest), opacity = sigmoid, scaling = exp, rotation = normalize (eps 1e-12).
-__global__ void __launch_bounds__(256) activate_kernel(int P, const float* __restrict__ f_dc,
-                                                       const float* __restrict__ f_rest,
-                                                       const float* __restrict__ opacity_raw,
+__global__ void __launch_bounds__(256) activate_kernel(int P, const float* __restrict__ opacity_raw,
                                                        const float* __restrict__ scaling_raw,
                                                        const float* __restrict__ rotation_raw,
-                                                       float* __restrict__ shs, float* __restrict__ opacities,
-                                                       float* __restrict__ scales, float* __restrict__ rotations,
-                                                       int which) {  // bit 0: opacity / scaling / rotation, bit 1: features
+                                                       float* __restrict__ opacities, float* __restrict__ scales,
+                                                       float* __restrict__ rotations) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= P) return;
   const size_t i = (size_t)idx;
-  if (which & 2) {  // features: shs = cat(f_dc, f_rest)
-    float v[48];
-#pragma unroll
-    for (int k = 0; k < 3; k++) v[k] = __ldg(f_dc + 3 * i + k);
-#pragma unroll
-    for (int k = 0; k < 45; k++) v[3 + k] = __ldg(f_rest + 45 * i + k);
-#pragma unroll
-    for (int j = 0; j < 12; j++)
-      reinterpret_cast<float4*>(shs + 48 * i)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-  }
-  if (!(which & 1)) return;
   opacities[i] = 1.0f / (1.0f + expf(-__ldg(opacity_raw + i)));
 #pragma unroll
   for (int k = 0; k < 3; k++) scales[3 * i + k] = expf(__ldg(scaling_raw + 3 * i + k));
@@ -661,16 +647,43 @@ __global__ void __launch_bounds__(256) activate_kernel(int P, const float* __res
   reinterpret_cast<float4*>(rotations)[i] = make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);
 }
 
+// shs = cat(f_dc, f_rest): one thread per float4 of the output (a Gaussian's 48 floats are 12 of them), so that a
+// warp reads one contiguous run of f_rest and writes 512 contiguous bytes (one thread per Gaussian touched 32
+// different 180-byte rows per load instruction: 38 % of the copy bandwidth)
+__global__ void __launch_bounds__(256) cat_features_kernel(size_t n4, const float* __restrict__ f_dc,
+                                                           const float* __restrict__ f_rest,
+                                                           float4* __restrict__ shs) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n4) return;
+  const size_t i = j / 12;
+  const int c = (int)(j - i * 12) * 4;  // first of this thread's four coefficient slots, 0 .. 44
+  float4 v;
+  if (c == 0) {
+    v = make_float4(__ldg(f_dc + 3 * i), __ldg(f_dc + 3 * i + 1), __ldg(f_dc + 3 * i + 2), __ldg(f_rest + 45 * i));
+  } else {
+    const float* r = f_rest + 45 * i + (c - 3);
+    v = make_float4(__ldg(r), __ldg(r + 1), __ldg(r + 2), __ldg(r + 3));
+  }
+  shs[j] = v;
+}
+
 cudaError_t launch_activate(int P, const float* f_dc, const float* f_rest, const float* opacity_raw,
                             const float* scaling_raw, const float* rotation_raw, float* shs,
                             float* opacities, float* scales, float* rotations, cudaStream_t stream) {
   // either half may be left out (NULL inputs): the geometry activations of the next step run before its
   // features have been stepped (multi-GPU pipelining, fit.py)
   const int which = (opacity_raw != nullptr ? 1 : 0) | (f_dc != nullptr ? 2 : 0);
-  if (which == 0) return cudaSuccess;
-  activate_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw,
-                                                       shs, opacities, scales, rotations, which);
-  DGE_LAUNCHED(1);
+  if (which & 2) {
+    const size_t n4 = (size_t)P * 12;
+    cat_features_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(n4, f_dc, f_rest,
+                                                                        reinterpret_cast<float4*>(shs));
+    DGE_LAUNCHED(1);
+  }
+  if (which & 1) {
+    activate_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, opacity_raw, scaling_raw, rotation_raw, opacities, scales,
+                                                         rotations);
+    DGE_LAUNCHED(1);
+  }
   return cudaGetLastError();
 }
 
