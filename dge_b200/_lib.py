@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # DGE_B200_LIB: an alternative build of the SAME library (A/B measurements of kernel variants)
 LIB_PATH = os.environ.get("DGE_B200_LIB") or os.path.join(_HERE, "_build", "libdge_b200.so")
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
@@ -65,6 +65,7 @@ _SIGNATURES = {
     "dge_densify_gather": (_i, [_i, _i, _p, _p, _i, _i, _i, _i, C.POINTER(_p), C.POINTER(_p), C.POINTER(_i), _i, _i, _i,
                                 _p, _p, _p, _p]),
     "dge_l1_loss_grad": (_i, [_p, _p, C.c_size_t, _f, _p, _p, _p]),
+    "dge_fit_update_stats": (_i, [_i, _p, _p, _p, _p, _p, _p]),
     "dge_fused_adam": (_i, [_p, _p, _p, _p, C.c_size_t, _f, _f, _f, _f, _i, _p, _i, _p]),
 }
 EXPORTS = tuple(_SIGNATURES)

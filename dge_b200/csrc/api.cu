@@ -277,7 +277,7 @@ using namespace dge;
 extern "C" {
 
 const char* dge_last_error(void) { return g_err; }
-int dge_abi_version(void) { return 13; }
+int dge_abi_version(void) { return 14; }
 unsigned long long dge_launch_count(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
 
 int dge_clock_probe(unsigned long long* out, void* stream_) {
@@ -755,6 +755,13 @@ int dge_debug_sorted_keys(char* geom_buffer, char* binning_buffer, int P, int R,
 int dge_l1_loss_grad(const float* image, const float* target, size_t n, float scale, float* grad,
                      float* loss_accum, void* stream_) {
   CK("l1 loss", launch_l1_loss_grad(image, target, n, scale, grad, loss_accum, (cudaStream_t)stream_));
+  return 0;
+}
+
+int dge_fit_update_stats(int P, const int* radii_max, const float* means2D_grad, int* max_radii2D,
+                         float* xyz_gradient_accum, float* denom, void* stream_) {
+  CK("update stats", launch_update_stats(P, radii_max, means2D_grad, max_radii2D, xyz_gradient_accum, denom,
+                                         (cudaStream_t)stream_));
   return 0;
 }
 

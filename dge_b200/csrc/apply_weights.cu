@@ -244,4 +244,32 @@ cudaError_t launch_l1_loss_grad(const float* image, const float* target, size_t 
   return cudaGetLastError();
 }
 
+// Densification statistics of one step (threestudio/systems/DGE.py:266-284 + GaussianModel.add_densification_stats,
+// gaussiansplatting/scene/gaussian_model.py:811-815) for the whole model in one pass: for the Gaussians some view of
+// the step saw (max over the views of radii > 0): max_radii2D = max(max_radii2D, radii), xyz_gradient_accum +=
+// |screen-space gradient (x, y)|, denom += 1. Replaces ten elementwise / reduce launches of torch.
+__global__ void __launch_bounds__(256) update_stats_kernel(int P, const int* __restrict__ radii_max,
+                                                           const float* __restrict__ m2d_grad,
+                                                           int* __restrict__ max_radii2D,
+                                                           float* __restrict__ xyz_gradient_accum,
+                                                           float* __restrict__ denom) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const int r = radii_max[i];
+  if (r <= 0) return;
+  max_radii2D[i] = max(max_radii2D[i], r);
+  const float gx = m2d_grad[3 * (size_t)i], gy = m2d_grad[3 * (size_t)i + 1];
+  xyz_gradient_accum[i] += sqrtf(gx * gx + gy * gy);
+  denom[i] += 1.0f;
+}
+
+cudaError_t launch_update_stats(int P, const int* radii_max, const float* m2d_grad, int* max_radii2D,
+                                float* xyz_gradient_accum, float* denom, cudaStream_t stream) {
+  if (P == 0) return cudaSuccess;
+  update_stats_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, radii_max, m2d_grad, max_radii2D, xyz_gradient_accum,
+                                                           denom);
+  DGE_LAUNCHED(1);
+  return cudaGetLastError();
+}
+
 }  // namespace dge

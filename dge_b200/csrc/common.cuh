@@ -206,6 +206,8 @@ size_t carve_binning_batched(char* base, uint32_t R_total, int V, int T, BinStat
 size_t binning_batched_workspace_bytes(uint32_t R_total, int V, int T);
 cudaError_t launch_l1_loss_grad(const float* image, const float* target, size_t n, float scale,
                                 float* grad, float* loss_accum, cudaStream_t stream);
+cudaError_t launch_update_stats(int P, const int* radii_max, const float* m2d_grad, int* max_radii2D,
+                                float* xyz_gradient_accum, float* denom, cudaStream_t stream);
 cudaError_t launch_apply_weights_render(const ViewParams& vp, const GeomState& g, const BinState& b,
                                         const ImgState& img, float* weights, int* cnt,
                                         const float* image_weights, int num_channels,

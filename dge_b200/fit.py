@@ -1322,7 +1322,17 @@ def _finish_step(model, loss, radii_max, process_group, update_stats, early=None
             prefetch, geometry_stepped = None, True
         radii_work.wait()
         loss = loss.clone()
-    if update_stats:
+    fused_stats = (update_stats and model.device.type == "cuda" and model.fused_adam
+                   and radii_max.dtype == torch.int32 and model.max_radii2D.dtype == torch.int32
+                   and model.xyz_gradient_accum.dtype == model.denom.dtype == torch.float32
+                   and all(t.is_cuda and t.is_contiguous() for t in (radii_max, model.max_radii2D,
+                                                                     model.xyz_gradient_accum, model.denom)))
+    if fused_stats:
+        # DGE.py:266-284, gaussian_model.py:811-815 in one pass (the torch statements below are ten launches)
+        L.check(L.load().dge_fit_update_stats(
+            model.P, radii_max.data_ptr(), model.means2D.grad.data_ptr(), model.max_radii2D.data_ptr(),
+            model.xyz_gradient_accum.data_ptr(), model.denom.data_ptr(), L.stream_ptr(model.device)), "update stats")
+    elif update_stats:
         with torch.no_grad():  # DGE.py:266-284, gaussian_model.py:811-815
             vis = radii_max > 0
             model.max_radii2D = torch.where(vis, torch.maximum(model.max_radii2D, radii_max), model.max_radii2D)

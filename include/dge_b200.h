@@ -263,6 +263,13 @@ int dge_fit_backward_geom_raw(int P, int D, int V, const float* cams, int width,
  * grad[i] = scale * sign(image[i] - target[i]); *loss_accum += scale * sum |image - target|. */
 int dge_l1_loss_grad(const float* image, const float* target, size_t n, float scale,
                      float* grad, float* loss_accum, void* stream);
+/* Densification statistics of one step (threestudio/systems/DGE.py:266-284, GaussianModel.add_densification_stats
+ * gaussiansplatting/scene/gaussian_model.py:811-815) in one pass over the model: where radii_max[i] > 0 (some view of
+ * the step saw Gaussian i; radii_max = max over the step's views, after the MAX all-reduce on several GPUs):
+ * max_radii2D[i] = max(max_radii2D[i], radii_max[i]); xyz_gradient_accum[i] += |means2D_grad[i].xy| (the summed
+ * screen-space gradient, [P,3] floats); denom[i] += 1. In place. */
+int dge_fit_update_stats(int P, const int* radii_max, const float* means2D_grad, int* max_radii2D,
+                         float* xyz_gradient_accum, float* denom, void* stream);
 /*
  * Fused Adam over one flat fp32 parameter block (torch.optim.Adam semantics,
  * gaussiansplatting/scene/gaussian_model.py:374: eps=1e-15, no weight decay,
