@@ -221,6 +221,8 @@ static cudaError_t zero_acc_async(float* acc, size_t acc_stride_floats, int P, i
   std::lock_guard<std::mutex> lock(g_zero_mutex);
   cudaError_t e;
   if (g_zero_stream == nullptr) {
+    // (default priority: at the highest one the memset's blocks displace the forward blend's from the start and
+    // that kernel takes 0.10 ms longer; as it is, the memset fills the slots the blend's tail leaves free)
     if ((e = cudaStreamCreateWithFlags(&g_zero_stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
     if ((e = cudaEventCreateWithFlags(&g_zero_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
     for (AccZero& z : g_zero) {

@@ -65,10 +65,13 @@ struct SegArgs {
   int seg_in_x;
 };
 
-// Digit histograms of every pass in one read of the keys.
+// Digit histograms of every pass in one read of the keys; the pass count is a template parameter so that the digit
+// extraction unrolls (0.081 -> 0.065 ms for config 2's 20 M depth keys). The top digit of a depth key takes only a
+// handful of values; aggregating it per warp first (match.any) was measured and changes nothing: shared-memory
+// atomics on one address are already combined per warp by the hardware.
+template <int PASSES>
 __global__ void __launch_bounds__(256) sort_histogram_kernel(const uint32_t* __restrict__ keys,
-                                                             uint32_t n, int num_passes,
-                                                             int num_bits,
+                                                             uint32_t n, int num_bits,
                                                              uint32_t* __restrict__ hist, SegArgs sa) {
   __shared__ uint32_t sh[MAX_PASSES * RADIX];
   {
@@ -85,19 +88,22 @@ __global__ void __launch_bounds__(256) sort_histogram_kernel(const uint32_t* __r
   }
   for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += blockDim.x) sh[i] = 0;
   __syncthreads();
+  const int per = (num_bits + PASSES - 1) / PASSES;  // even split, see sort_pairs
   const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const uint32_t k = keys[i];
-    for (int p = 0; p < num_passes; p++) {
-      const int per = (num_bits + num_passes - 1) / num_passes;  // even split, see sort_pairs
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride) {
+    const uint32_t i = base + threadIdx.x;
+    const bool valid = i < n;
+    const uint32_t k = valid ? keys[i] : 0u;
+#pragma unroll
+    for (int p = 0; p < PASSES; p++) {
       const int shift = p * per;
       const int bits = min(per, num_bits - shift);
       const uint32_t d = (k >> shift) & ((1u << bits) - 1u);
-      atomicAdd(&sh[p * RADIX + d], 1u);
+      if (valid) atomicAdd(&sh[p * RADIX + d], 1u);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < num_passes * RADIX; i += blockDim.x)
+  for (int i = threadIdx.x; i < PASSES * RADIX; i += blockDim.x)
     if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 
@@ -329,7 +335,12 @@ cudaError_t sort_pairs_segmented(uint32_t* keys[2], uint32_t* vals[2], uint32_t 
   const SegArgs sa = {seg_stride_bytes, seg_off, seg_in_x};
   int cur = passes & 1;
   const int hist_blocks = (int)min((uint32_t)(DGE_NUM_SMS * 4), (n + 2047) / 2048);
-  sort_histogram_kernel<<<dim3(hist_blocks, segs), 256, 0, stream>>>(keys[cur], n, passes, num_bits, hist, sa);
+  switch (passes) {
+    case 1: sort_histogram_kernel<1><<<dim3(hist_blocks, segs), 256, 0, stream>>>(keys[cur], n, num_bits, hist, sa); break;
+    case 2: sort_histogram_kernel<2><<<dim3(hist_blocks, segs), 256, 0, stream>>>(keys[cur], n, num_bits, hist, sa); break;
+    case 3: sort_histogram_kernel<3><<<dim3(hist_blocks, segs), 256, 0, stream>>>(keys[cur], n, num_bits, hist, sa); break;
+    default: sort_histogram_kernel<4><<<dim3(hist_blocks, segs), 256, 0, stream>>>(keys[cur], n, num_bits, hist, sa); break;
+  }
   for (int p = 0; p < passes; p++) {
     // Digits of equal width (10 tile-id bits -> 5+5, not 8+2): a pass over few, long digit runs
     // writes whole lines and ranks without bank conflicts (measured 30 us vs 59 us per pass).
