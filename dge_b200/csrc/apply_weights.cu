@@ -212,16 +212,29 @@ cudaError_t launch_fused_adam(float* param, const float* grad, float* m, float* 
 // Fused L1 loss and its gradient for one rendered view (DGE.py:672: 10 * L1 over the batch):
 // grad = scale * sign(image - target), *loss_accum += scale * sum|image - target|.
 // Replaces sub / abs / sum / mul and their four backward kernels.
+template <bool VEC>
 __global__ void __launch_bounds__(256) l1_loss_grad_kernel(const float* __restrict__ image,
                                                            const float* __restrict__ target, size_t n,
                                                            float scale, float* __restrict__ grad,
                                                            float* __restrict__ loss_accum) {
   float local = 0.f;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float d = image[i] - target[i];
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (size_t)gridDim.x * blockDim.x;
+  auto one = [&](float a, float b) {
+    const float d = a - b;
     local += fabsf(d);
-    grad[i] = d > 0.f ? scale : (d < 0.f ? -scale : 0.f);
+    return d > 0.f ? scale : (d < 0.f ? -scale : 0.f);
+  };
+  size_t done = 0;
+  if (VEC) {  // all three pointers 16-byte aligned: 128-bit accesses, the n % 4 tail below
+    const size_t n4 = n / 4;
+    for (size_t i = tid; i < n4; i += nthreads) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(image) + i);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(target) + i);
+      reinterpret_cast<float4*>(grad)[i] = make_float4(one(a.x, b.x), one(a.y, b.y), one(a.z, b.z), one(a.w, b.w));
+    }
+    done = n4 * 4;
   }
+  for (size_t i = done + tid; i < n; i += nthreads) grad[i] = one(image[i], target[i]);
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, o);
   __shared__ float ws[8];
@@ -239,7 +252,12 @@ cudaError_t launch_l1_loss_grad(const float* image, const float* target, size_t 
                                 float* grad, float* loss_accum, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
   const unsigned blocks = (unsigned)((n + 256 * 8 - 1) / (256 * 8));
-  l1_loss_grad_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, stream>>>(image, target, n, scale, grad, loss_accum);
+  const bool vec = ((reinterpret_cast<uintptr_t>(image) | reinterpret_cast<uintptr_t>(target) |
+                     reinterpret_cast<uintptr_t>(grad)) & 15) == 0;
+  if (vec)
+    l1_loss_grad_kernel<true><<<blocks < 1 ? 1 : blocks, 256, 0, stream>>>(image, target, n, scale, grad, loss_accum);
+  else
+    l1_loss_grad_kernel<false><<<blocks < 1 ? 1 : blocks, 256, 0, stream>>>(image, target, n, scale, grad, loss_accum);
   DGE_LAUNCHED(1);
   return cudaGetLastError();
 }

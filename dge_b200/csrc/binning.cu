@@ -21,8 +21,12 @@ __device__ __forceinline__ uint32_t rect_count(ushort4 r) {
   return (uint32_t)(r.z - r.x) * (uint32_t)(r.w - r.y);
 }
 
-// block sums of tiles_touched taken in depth order
-__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(
+// block sums of tiles_touched taken in depth order. A block covers SCAN_THREADS consecutive ranks with
+// SCAN_THREADS / 4 threads, four ranks each: the two dependent loads per rank (order -> rect, a random 8-byte
+// gather) are latency, and with one rank per thread a warp had one gather in flight (0.121 ms for config 2's 20 M
+// ranks at 26 % of the issue rate and of the DRAM bandwidth); with four they overlap.
+constexpr int SCAN_RED_THREADS = SCAN_THREADS / 4;
+__global__ void __launch_bounds__(SCAN_RED_THREADS) scan_reduce_kernel(
     int P, const uint32_t* __restrict__ order, const ushort4* __restrict__ rect,
     uint32_t* __restrict__ block_sums, size_t view_stride) {
   if (blockIdx.y) {  // view of a batch (fit step): same arrays, view_stride bytes per view further on
@@ -31,17 +35,25 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(
     rect = shift_ptr(rect, sh);
     block_sums = shift_ptr(block_sums, sh);
   }
-  const int r = blockIdx.x * SCAN_THREADS + threadIdx.x;
+  const int r0 = blockIdx.x * SCAN_THREADS + threadIdx.x;
+  uint32_t gid[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int r = r0 + k * SCAN_RED_THREADS;
+    gid[k] = r < P ? order[r] : 0xFFFFFFFFu;
+  }
   uint32_t c = 0;
-  if (r < P) c = rect_count(rect[order[r]]);
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (gid[k] != 0xFFFFFFFFu) c += rect_count(rect[gid[k]]);
   c = __reduce_add_sync(0xFFFFFFFFu, c);
-  __shared__ uint32_t ws[SCAN_THREADS / 32];
+  __shared__ uint32_t ws[SCAN_RED_THREADS / 32];
   if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t t = 0;
 #pragma unroll
-    for (int i = 0; i < SCAN_THREADS / 32; i++) t += ws[i];
+    for (int i = 0; i < SCAN_RED_THREADS / 32; i++) t += ws[i];
     block_sums[blockIdx.x] = t;
   }
 }
@@ -214,7 +226,7 @@ cudaError_t launch_binning(const ViewParams& vp, int R, GeomState& g, BinState& 
   const int P = vp.P;
   const int blocks = (P + SCAN_THREADS - 1) / SCAN_THREADS;
   const uint32_t* order = g.sort_val[0];
-  scan_reduce_kernel<<<blocks, SCAN_THREADS, 0, stream>>>(P, order, g.rect, g.block_sums, 0);
+  scan_reduce_kernel<<<blocks, SCAN_RED_THREADS, 0, stream>>>(P, order, g.rect, g.block_sums, 0);
   scan_block_sums_kernel<<<1, 1024, 0, stream>>>(blocks, g.block_sums, 0);
   const int bits = tile_bits(T);
   const int passes = sort_num_passes(bits);
@@ -786,7 +798,7 @@ cudaError_t launch_binning_batched(const ViewParams& vp, const ViewBatch& vb, ui
   const int P = vp.P;
   const int blocks = (P + SCAN_THREADS - 1) / SCAN_THREADS;
   const uint32_t* order = g0.sort_val[0];
-  scan_reduce_kernel<<<dim3(blocks, vb.V), SCAN_THREADS, 0, stream>>>(P, order, g0.rect, g0.block_sums,
+  scan_reduce_kernel<<<dim3(blocks, vb.V), SCAN_RED_THREADS, 0, stream>>>(P, order, g0.rect, g0.block_sums,
                                                                       vb.geom_stride);
   scan_block_sums_kernel<<<vb.V, 1024, 0, stream>>>(blocks, g0.block_sums, vb.geom_stride);
   const int bits = tile_bits(T);
