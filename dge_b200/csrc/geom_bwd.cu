@@ -409,8 +409,16 @@ constexpr int MAX_BATCH_VIEWS = 64;
 // scaling = exp(raw), opacity = sigmoid(raw), rotation = normalize(raw), features = cat(f_dc, f_rest)),
 // i.e. the activations' backward is applied in the epilogue and dL/dsh is split into f_dc / f_rest
 // rows (dL_dsh -> f_dc [P,1,3], dL_drest -> f_rest [P,15,3]); every row is written (no accumulate).
+// A/B switches (tests/gpu_r2_ab.sh), measured at config 2: 3 / 4 / 5 CTAs per SM (168 registers without spills / 128
+// / 96): 0.525 / 0.498 / 0.572 ms; pass-1 groups of 2 / 4 / 8 views: 0.559 / 0.498 / 0.496 ms.
+#ifndef DGE_GEOM_MIN_CTAS
+#define DGE_GEOM_MIN_CTAS 4
+#endif
+#ifndef DGE_GEOM_GROUP
+#define DGE_GEOM_GROUP 4
+#endif
 template <bool RAW>
-__global__ void __launch_bounds__(128, 4) geom_backward_batched_kernel(
+__global__ void __launch_bounds__(128, DGE_GEOM_MIN_CTAS) geom_backward_batched_kernel(
     int P, int D, int M, int V, const float* __restrict__ cams, int W, int H, float scale_modifier,
     const float* __restrict__ acc, size_t acc_stride, const uint8_t* __restrict__ flags, size_t flags_stride,
     const float* __restrict__ means3D,
@@ -452,19 +460,20 @@ __global__ void __launch_bounds__(128, 4) geom_backward_batched_kernel(
   // Four views at a time, all loads of a level issued before any is used: walked one view after the
   // other, the dependent loads per view put 2 V memory round trips on every thread's critical path —
   // that latency, not bandwidth, was the kernel's time.
-  for (int v0 = 0; v0 < V; v0 += 4) {
-    uint32_t fl[4];
+  constexpr int GRP = DGE_GEOM_GROUP;
+  for (int v0 = 0; v0 < V; v0 += GRP) {
+    uint32_t fl[GRP];
 #pragma unroll
-    for (int k = 0; k < 4; k++) fl[k] = v0 + k < V ? (uint32_t)__ldg(flags + (size_t)(v0 + k) * flags_stride + i) : 0u;
+    for (int k = 0; k < GRP; k++) fl[k] = v0 + k < V ? (uint32_t)__ldg(flags + (size_t)(v0 + k) * flags_stride + i) : 0u;
     unsigned vis = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++)
+    for (int k = 0; k < GRP; k++)
       if (fl[k] & 1u) vis |= 1u << k;
     if (!vis) continue;
     any = true;
-    float4 a0[4], a1[4], a2[4];
+    float4 a0[GRP], a1[GRP], a2[GRP];
 #pragma unroll
-    for (int k = 0; k < 4; k++)
+    for (int k = 0; k < GRP; k++)
       if ((vis >> k) & 1u) {
         const float4* row = reinterpret_cast<const float4*>(acc + (size_t)(v0 + k) * acc_stride) + 3 * i;
         a0[k] = __ldg(row);
@@ -472,7 +481,7 @@ __global__ void __launch_bounds__(128, 4) geom_backward_batched_kernel(
         a2[k] = __ldg(row + 2);
       }
 #pragma unroll
-    for (int k = 0; k < 4; k++)
+    for (int k = 0; k < GRP; k++)
       if (((vis >> k) & 1u) &&
           (a0[k].x != 0.f || a0[k].y != 0.f || a0[k].z != 0.f || a0[k].w != 0.f || a1[k].x != 0.f || a1[k].y != 0.f ||
            a1[k].z != 0.f || a1[k].w != 0.f || a2[k].x != 0.f))
