@@ -65,6 +65,31 @@ def test_fused_activations_match_torch(cuda):
     assert torch.equal(got["shs"], want["shs"].detach())  # a concatenation: exact
 
 
+def test_update_stats_kernel_equals_the_torch_statements(cuda):
+    """dge_fit_update_stats against the statements it replaces (threestudio/systems/DGE.py:266-284,
+    gaussian_model.py:811-815): max_radii2D and denom exactly, the accumulated gradient norm to an ulp; rows of
+    Gaussians no view saw are untouched. P is not a multiple of the block size."""
+    from dge_b200 import _lib as L
+    Pn = 100_003
+    gen = torch.Generator().manual_seed(21)
+    radii = torch.randint(0, 40, (Pn,), generator=gen, dtype=torch.int32)
+    radii = torch.where(torch.rand(Pn, generator=gen) < 0.3, torch.zeros_like(radii), radii).to(cuda)
+    g2 = (torch.randn(Pn, 3, generator=gen) * 1e-3).to(cuda)
+    max_r = torch.randint(0, 40, (Pn,), generator=gen, dtype=torch.int32).to(cuda)
+    accum, denom = torch.rand(Pn, 1, generator=gen).to(cuda), torch.randint(0, 9, (Pn, 1), generator=gen).float().to(cuda)
+    vis = radii > 0
+    want_r = torch.where(vis, torch.maximum(max_r, radii), max_r)
+    gn = g2[:, :2].norm(dim=-1, keepdim=True)
+    want_a = accum + torch.where(vis[:, None], gn, torch.zeros_like(gn))
+    want_d = denom + vis[:, None].float()
+    L.check(L.load().dge_fit_update_stats(Pn, radii.data_ptr(), g2.data_ptr(), max_r.data_ptr(), accum.data_ptr(),
+                                          denom.data_ptr(), L.stream_ptr(cuda)), "update stats")
+    torch.cuda.synchronize()
+    assert torch.equal(max_r, want_r) and torch.equal(denom, want_d)
+    torch.testing.assert_close(accum, want_a, rtol=2e-7, atol=0)
+    assert torch.equal(accum[~vis], want_a[~vis])
+
+
 @pytest.mark.parametrize("streams,bgv,batched", [(1, 0.0, False), (3, 0.0, False), (2, 0.4, False), (1, 0.0, True),
                                                  (1, 0.4, True), (2, 0.0, True)])
 def test_direct_path_matches_autograd_path(cuda, streams, bgv, batched):
