@@ -134,9 +134,11 @@ class FitModel:
         self.means2D_slice = slice(n, n + 3 * P)
         self.means2D.grad = self.flat_grad[self.means2D_slice].view(P, 3)
         self.loss_slot = self.flat_grad[n + pad4(3 * P):n + pad4(3 * P) + 1]
-        # [early_slice]: geometry groups + screen-space gradient + loss; [late_slice]: the features
+        # [early_slice]: the geometry groups, what the next step's projection waits for; [stats_slice]: screen-space
+        # gradient + loss (statistics and the returned loss only); [late_slice]: the features
         self.late_slice = slice(self.slices["f_dc"].start, self.slices["f_rest"].stop)
-        self.early_slice = slice(self.slices["xyz"].start, n + pad4(3 * P) + 4)
+        self.early_slice = slice(self.slices["xyz"].start, n)
+        self.stats_slice = slice(n, n + pad4(3 * P) + 4)
         # per-P caches of the fit step (lanes, batches, activations) belong to the old buffers
         self._geom_version = getattr(self, "_geom_version", 0) + 1
         for attr in ("_lane_key", "_batch_key", "_acts", "_lanes", "_batches", "_acc", "_flags", "_lane_acc",
@@ -1293,16 +1295,17 @@ def _finish_step(model, loss, radii_max, process_group, update_stats, early=None
         a0 = model.slices["f_rest"].start
         sent = early.done_rows if early is not None else 0  # f_rest rows already on the wire
         ar = lambda t, op=dist.ReduceOp.SUM: dist.all_reduce(t, op=op, group=process_group, async_op=True)
-        # what the next step's projection waits for goes first, as ONE call: the geometry groups' gradients, the
-        # screen-space gradient and the loss are contiguous in the flat buffer (LAYOUT). Then the radii (MAX; only
-        # the statistics need them), then the features: f_dc, and f_rest in REST_PIECES row ranges (Adam on a
-        # piece runs under the next piece's transfer)
+        # what the next step's projection waits for goes first, as ONE call: the geometry groups' gradients are
+        # contiguous in the flat buffer (LAYOUT). Then what only the statistics and the caller need — the radii (MAX)
+        # and, in one call, the screen-space gradient + the loss —, then the features: f_dc, and f_rest in
+        # REST_PIECES row ranges (Adam on a piece runs under the next piece's transfer)
         model.loss_slot.copy_(loss.reshape(1))
         loss = model.loss_slot[0]
         if prefetch is not None:
             radii_max = radii_max.clone()  # the prefetched front half reuses the chunks' radii buffers
         works = [ar(model.flat_grad[model.early_slice])]
         radii_work = ar(radii_max, dist.ReduceOp.MAX)
+        stats_work = ar(model.flat_grad[model.stats_slice])
         dc = model.slices["f_dc"]
         late_dc = ar(model.flat_grad[dc.start:dc.stop])
         P = model.P
@@ -1321,6 +1324,7 @@ def _finish_step(model, loss, radii_max, process_group, update_stats, early=None
             prefetch()
             prefetch, geometry_stepped = None, True
         radii_work.wait()
+        stats_work.wait()
         loss = loss.clone()
     fused_stats = (update_stats and model.device.type == "cuda" and model.fused_adam
                    and radii_max.dtype == torch.int32 and model.max_radii2D.dtype == torch.int32
