@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(1024) scan_block_sums_kernel(int n, uint32_t* 
 // Emits the (tile id, Gaussian id) pairs of 256 depth-consecutive Gaussians.
 // Offsets come from a CTA scan + the scanned block sums; each warp then writes its
 // Gaussians' instances cooperatively (lane k handles the k-th instance of the warp,
-// source Gaussian found by a 5-step search over the warp's 32 offsets) so the stores
+// source Gaussian found from a ballot of the Gaussians' first positions) so the stores
 // are coalesced however skewed the per-Gaussian tile counts are.
 __global__ void __launch_bounds__(SCAN_THREADS) expand_kernel(
     int P, int grid_x, const uint32_t* __restrict__ order, const ushort4* __restrict__ rect,
@@ -144,30 +144,43 @@ __global__ void __launch_bounds__(SCAN_THREADS) expand_kernel(
     if (w < warp) wbase += ws[w];
   const uint32_t incl = wbase + x;
   if (r < P) offsets[r] = incl;
-  s_off[warp][lane] = incl - cnt;
-  s_gid[warp][lane] = gid;
-  s_rect[warp][lane] = rc;
-  // row = j / w through a float reciprocal: j, w < 2^16, so floor((j + 0.5) * (1/w)) is exact
-  s_invw[warp][lane] = __frcp_rn((float)max(1, (int)rc.z - (int)rc.x));
-  if (lane == 31) s_off[warp][32] = incl;
+  // The warp's Gaussians that emit anything, compacted in order: their first output position (relative to the
+  // warp's), id, rect and 1 / rect width. Lane k of an iteration then needs "the last start <= k": starts are
+  // distinct, so that is (#starts before the iteration's 32 positions) + (#head bits at or below k) - 1 — one
+  // ballot, one redux.or and two popcounts instead of a 5-step search through shared memory.
+  const uint32_t full = 0xFFFFFFFFu;
+  const uint32_t ne = __ballot_sync(full, cnt > 0);
+  const uint32_t wstart = __shfl_sync(full, incl - cnt, 0);
+  const uint32_t wtotal = __shfl_sync(full, incl, 31) - wstart;
+  if (cnt > 0) {
+    const int ci = __popc(ne & ((1u << lane) - 1u));
+    s_off[warp][ci] = incl - cnt - wstart;
+    s_gid[warp][ci] = gid;
+    s_rect[warp][ci] = rc;
+    // row = j / w through a float reciprocal: j, w < 2^16, so floor((j + 0.5) * (1/w)) is exact
+    s_invw[warp][ci] = __frcp_rn((float)((int)rc.z - (int)rc.x));
+  }
   __syncwarp();
-  const uint32_t wstart = s_off[warp][0];
-  const uint32_t wtotal = s_off[warp][32] - wstart;
-  for (uint32_t k = lane; k < wtotal; k += 32) {
-    const uint32_t target = wstart + k;
-    int l = 0;
-#pragma unroll
-    for (int step = 16; step >= 1; step >>= 1)
-      if (s_off[warp][l + step] <= target) l += step;
-    const uint32_t j = target - s_off[warp][l];
-    const ushort4 q = s_rect[warp][l];
-    const uint32_t w = q.z - q.x;
-    const uint32_t row = __float2uint_rz(((float)j + 0.5f) * s_invw[warp][l]);
-    const uint32_t ty = q.y + row, tx = q.x + (j - row * w);
-    DGE_CHECK(seg_off == nullptr || target < seg_off[blockIdx.y + 1] - seg_off[blockIdx.y]);
-    DGE_CHECK(j < (uint32_t)(q.z - q.x) * (uint32_t)(q.w - q.y) && tx < (uint32_t)grid_x);
-    keys_out[target] = ty * (uint32_t)grid_x + tx;
-    vals_out[target] = s_gid[warp][l];
+  const uint32_t my_start = lane < __popc(ne) ? s_off[warp][lane] : 0xFFFFFFFFu;
+  const uint32_t upto = full >> (31 - lane);  // bits 0 .. lane
+  for (uint32_t base = 0; base < wtotal; base += 32) {
+    const uint32_t rel = my_start - base;  // (wraps for starts before this iteration: not < 32)
+    const uint32_t heads = __reduce_or_sync(full, rel < 32u ? 1u << rel : 0u);
+    const int before = __popc(__ballot_sync(full, my_start < base));
+    const uint32_t k = base + lane;
+    if (k < wtotal) {
+      const int l = before + __popc(heads & upto) - 1;
+      const uint32_t j = k - s_off[warp][l];
+      const ushort4 q = s_rect[warp][l];
+      const uint32_t w = q.z - q.x;
+      const uint32_t row = __float2uint_rz(((float)j + 0.5f) * s_invw[warp][l]);
+      const uint32_t ty = q.y + row, tx = q.x + (j - row * w);
+      const uint32_t target = wstart + k;
+      DGE_CHECK(seg_off == nullptr || target < seg_off[blockIdx.y + 1] - seg_off[blockIdx.y]);
+      DGE_CHECK(l >= 0 && j < (uint32_t)(q.z - q.x) * (uint32_t)(q.w - q.y) && tx < (uint32_t)grid_x);
+      keys_out[target] = ty * (uint32_t)grid_x + tx;
+      vals_out[target] = s_gid[warp][l];
+    }
   }
 }
 
