@@ -10,6 +10,11 @@
 // below 2^24, so the result is bit-identical to the reference whatever the order.
 // The out-of-image read of image_weights in the reference (apply_weights.cu:279-283, before
 // its `inside` test) is guarded here; those values are never used.
+// Staged batch of the back-projection walk: 64 records like the forward blend (it stops early too; config 3:
+// 7.08 -> 6.93 ms per 40 views against 128)
+#ifndef DGE_BL_BATCH
+#define DGE_BL_BATCH 64
+#endif
 #include "blend.cuh"
 
 namespace dge {

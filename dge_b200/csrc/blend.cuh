@@ -23,7 +23,10 @@ constexpr int PX_STEP = 8;
 constexpr int PY_STEP = 4;
 constexpr int BL_THREADS = 64;
 constexpr int BL_WARPS = 2;
-constexpr int BL_BATCH = 128;
+#ifndef DGE_BL_BATCH
+#define DGE_BL_BATCH 128
+#endif
+constexpr int BL_BATCH = DGE_BL_BATCH;  // A/B switch (tests/gpu_r2_ab.sh)
 
 #define BMUL(a, b) __fmul_rn((a), (b))
 #define BADD(a, b) __fadd_rn((a), (b))
