@@ -27,7 +27,8 @@
 // 16 CTAs (32 warps) per SM at 64 registers: measured 2.39 / 2.32 / 2.25 ms per 20-view launch at 12 / 14 / 16
 // (config 2) — once the pair body shrank, hiding the staging and shared-memory latencies mattered more
 // than the 12 bytes of spills the tighter budget costs. (The HAS_BG variant — per-view API, whose launches
-// of ~1000 CTAs cannot fill the SMs anyway — keeps 80 registers.)
+// of ~1000 CTAs cannot fill the SMs anyway — keeps 80 registers.) Beyond 16 the spills win: 2.53 ms at 18 CTAs
+// (56 registers), 3.51 ms at 21 (40 registers).
 #ifndef DGE_BWD_MIN_CTAS
 #define DGE_BWD_MIN_CTAS 16
 #endif

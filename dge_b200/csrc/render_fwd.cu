@@ -28,7 +28,8 @@ namespace dge {
 // writes it, background added per channel, as a second image — DGE's "semantic" render of the edit
 // mask (threestudio/systems/DGE.py:198-204: render(..., override_color=mask repeated 3x)) for the price
 // of one FFMA per blended pair instead of a second preprocess + sort + blend of the same view.
-// measured at config 2, 20 views per launch: 1.67 / 1.60 / 1.55 ms at 12 / 14 / 16 CTAs per SM
+// measured at config 2, 20 views per launch: 1.67 / 1.60 / 1.55 ms at 12 / 14 / 16 CTAs per SM (with batches of 64
+// records: 1.53 at 16, 1.61 at 18 = 56 registers, 1.99 at 21 = 40 registers)
 #ifndef DGE_FWD_MIN_CTAS
 #define DGE_FWD_MIN_CTAS 16
 #endif
