@@ -283,7 +283,10 @@ cudaError_t launch_preprocess(const ViewParams& vp, const float* means3D, const 
 // 16-byte loads: the quaternion and the 12 SH quads per thread, positions and scales per CTA (below). Also produces the
 // running max of the radii over the views (max_radii2D statistics) instead of V radii arrays.
 constexpr int PRE_B_THREADS = 128;
-constexpr int PRE_B_MIN_CTAS = 6;  // 80 registers: the 48 SH floats live in shared memory, not registers
+#ifndef DGE_PRE_B_MIN_CTAS
+#define DGE_PRE_B_MIN_CTAS 6
+#endif
+constexpr int PRE_B_MIN_CTAS = DGE_PRE_B_MIN_CTAS;  // 80 registers: the 48 SH floats live in shared memory, not registers
 __global__ void __launch_bounds__(PRE_B_THREADS, PRE_B_MIN_CTAS) preprocess_batched_kernel(
     ViewParams vp, int V, const float* __restrict__ cams, const float* __restrict__ means3D,
     const float* __restrict__ scales, const float* __restrict__ rotations,
