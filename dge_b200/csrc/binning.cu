@@ -300,7 +300,10 @@ cudaError_t launch_depth_sort_batched(int P, const ViewBatch& vb, GeomState& g0,
 // Traffic per instance: 8 B written by expand, 4 + 8 B read, 4 B written (was 8 + 2 x 16 + 4 + 4).
 constexpr int PART_THREADS = 256;
 constexpr int PART_WARPS = PART_THREADS / 32;
-constexpr int PART_WARP_ITEMS = 512;
+#ifndef DGE_PART_WARP_ITEMS
+#define DGE_PART_WARP_ITEMS 512
+#endif
+constexpr int PART_WARP_ITEMS = DGE_PART_WARP_ITEMS;  // A/B switch: 256 / 512 / 1024 -> binning 1.028 / 0.825 / 0.831 ms (config 2)
 constexpr int PART_IPL = PART_WARP_ITEMS / 32;          // instances per lane, register resident
 constexpr int PART_RUN = PART_WARPS * PART_WARP_ITEMS;  // instances per CTA
 constexpr int PART_GROUPS = 16;                         // run groups of the two-level scan over runs
