@@ -19,7 +19,14 @@ constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_IPT_MIN = 8;   // items per thread: 8 for small inputs (more CTAs in flight), 16 otherwise
 constexpr int MAX_PASSES = 4;
-constexpr int LB_WINDOW = 16;
+// Status words loaded per look-back round trip. A/B (tests/gpu_r2_ab.sh, depth sort of config 2's 20 x 1 M keys with the
+// segment in grid.x): 2 / 4 / 6 / 8 / 12 / 16 / 24 / 32 -> 0.522 / 0.521 / 0.523 / 0.530 / 0.548 / 0.564 / 0.699 / 0.809 ms;
+// the per-view sorts, the back-projection and configs 4 / 5 are equal or faster at 4 as well. (16 dated from the
+// segment-in-grid.y layout, where a tile walked back over a whole wave of unfinished predecessors.)
+#ifndef DGE_LB_WINDOW
+#define DGE_LB_WINDOW 4
+#endif
+constexpr int LB_WINDOW = DGE_LB_WINDOW;
 constexpr uint32_t FLAG_AGG = 1u << 30, FLAG_PREFIX = 2u << 30, FLAG_MASK = 3u << 30;
 
 int sort_num_passes(int num_bits) { return (num_bits + RADIX_BITS - 1) / RADIX_BITS; }
