@@ -18,7 +18,7 @@ namespace dge {
 #ifndef DGE_SCAN_THREADS
 #define DGE_SCAN_THREADS 256
 #endif
-constexpr int SCAN_THREADS = DGE_SCAN_THREADS;  // A/B switch (<= 256: api.cu sizes block_sums for 256); 512: binning 0.829 -> 0.847 ms
+constexpr int SCAN_THREADS = DGE_SCAN_THREADS;  // A/B switch (>= 256 only: api.cu sizes block_sums for blocks of 256); 512: binning 0.829 -> 0.847 ms
 
 __device__ __forceinline__ uint32_t rect_count(ushort4 r) {
   return (uint32_t)(r.z - r.x) * (uint32_t)(r.w - r.y);
