@@ -230,9 +230,6 @@ class FitModel:
         (csrc/densify.cu: dge_densify_select / dge_densify_gather) instead of the boolean-mask gathers and
         torch.cat re-allocations below; same rows in the same order (tests/test_fit_gpu.py)."""
         dev = self.device
-        raw = {k: v.detach() for k, v in self.params.items()}
-        m = {k: self.adam_state(k)[0].detach().clone() for k in raw}
-        v = {k: self.adam_state(k)[1].detach().clone() for k in raw}
         P0 = self.P
         mask = torch.ones(P0, dtype=torch.bool, device=dev) if self.grad_mask is None else self.grad_mask.bool()
         grads = self.xyz_gradient_accum / self.denom
@@ -247,6 +244,9 @@ class FitModel:
         if device_kernels:
             return self._densify_on_device(grads, max_grad, min_opacity, extent, max_screen_size, percent_dense, N,
                                            generator, normal_samples)
+        raw = {k: v.detach() for k, v in self.params.items()}
+        m = {k: self.adam_state(k)[0].detach().clone() for k in raw}
+        v = {k: self.adam_state(k)[1].detach().clone() for k in raw}
 
         def extend(new):  # cat_tensors_to_optimizer (:609-640)
             for k in raw:
