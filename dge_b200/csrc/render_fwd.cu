@@ -33,8 +33,13 @@ namespace dge {
 #ifndef DGE_FWD_MIN_CTAS
 #define DGE_FWD_MIN_CTAS 16
 #endif
+// the variant with the fused semantic channel (tests/gpu_time_render_views.py, 20 views of config 2 forward only):
+// 3.69 / 3.59 / 3.56 ms at 12 / 14 / 16 CTAs per SM against 3.42 ms without the channel
+#ifndef DGE_FWD_EXTRA_MIN_CTAS
+#define DGE_FWD_EXTRA_MIN_CTAS 16
+#endif
 template <bool EXTRA>
-__global__ void __launch_bounds__(BL_THREADS, EXTRA ? 12 : DGE_FWD_MIN_CTAS) render_forward_kernel(
+__global__ void __launch_bounds__(BL_THREADS, EXTRA ? DGE_FWD_EXTRA_MIN_CTAS : DGE_FWD_MIN_CTAS) render_forward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
     const float4* __restrict__ rec, const float* __restrict__ background,
     float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
