@@ -26,11 +26,15 @@
 
 // 16 CTAs (32 warps) per SM at 64 registers: measured 2.39 / 2.32 / 2.25 ms per 20-view launch at 12 / 14 / 16
 // (config 2) — once the pair body shrank, hiding the staging and shared-memory latencies mattered more
-// than the 12 bytes of spills the tighter budget costs. (The HAS_BG variant — per-view API, whose launches
-// of ~1000 CTAs cannot fill the SMs anyway — keeps 80 registers.) Beyond 16 the spills win: 2.53 ms at 18 CTAs
+// than the 12 bytes of spills the tighter budget costs. (The HAS_BG variant has its own setting below.) Beyond 16 the spills win: 2.53 ms at 18 CTAs
 // (56 registers), 3.51 ms at 21 (40 registers).
 #ifndef DGE_BWD_MIN_CTAS
 #define DGE_BWD_MIN_CTAS 16
+#endif
+// the HAS_BG variant (non-black background; tests/gpu_time_fit_bg.py, config 2 with bg = 0.4): 2.49 / 2.37 / 2.44 ms
+// per 20-view launch at 12 / 14 / 16 CTAs per SM (80 / 72 / 64 registers)
+#ifndef DGE_BWD_BG_MIN_CTAS
+#define DGE_BWD_BG_MIN_CTAS 14
 #endif
 
 namespace dge {
@@ -39,7 +43,7 @@ namespace dge {
 // (backward.cu:526-529); for DGE's black background (DGE.py:87) that term, its division and
 // eight registers of per-pixel state disappear at compile time.
 template <bool HAS_BG>
-__global__ void __launch_bounds__(BL_THREADS, HAS_BG ? 12 : DGE_BWD_MIN_CTAS) render_backward_kernel(
+__global__ void __launch_bounds__(BL_THREADS, HAS_BG ? DGE_BWD_BG_MIN_CTAS : DGE_BWD_MIN_CTAS) render_backward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
     const float* __restrict__ background, const float4* __restrict__ rec,
     const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
