@@ -166,9 +166,16 @@ def test_apply_weights_vs_reference(cuda, CH, soft):
     g = scene.make_gaussians(P, seed=31, scale_median=0.03)
     gd = util.to_dev(g, cuda)
     if soft:
-        mask = torch.rand(CH, H, W, generator=torch.Generator().manual_seed(12)).contiguous().to(cuda)
+        mask = torch.rand(CH, H, W, generator=torch.Generator().manual_seed(12)).contiguous()
     else:
-        mask = scene.disc_mask(W, H, radius=50).repeat(CH, 1, 1).contiguous().to(cuda)
+        mask = scene.disc_mask(W, H, radius=50).repeat(CH, 1, 1).contiguous()
+    # The REFERENCE reads image_weights out of bounds for the partial tiles at the bottom edge (H = 136 is 8.5
+    # tiles; DGR/cuda_rasterizer/apply_weights.cu:279-283 indexes rows up to the tile-rounded height). Wherever
+    # the caching allocator happened to put the mask this went unnoticed — until it sat at the end of a segment
+    # and the reference faulted. The mask therefore lives at the front of a larger zero-filled buffer.
+    store = torch.zeros(CH * H * W + 32 * W, device=cuda)
+    store[:CH * H * W].copy_(mask.reshape(-1))
+    mask = store[:CH * H * W].view(CH, H, W)
     w_ours = torch.zeros(P, CH, device=cuda)
     c_ours = torch.zeros(P, 1, dtype=torch.int32, device=cuda)
     w_ref, c_ref = torch.zeros_like(w_ours), torch.zeros_like(c_ours)
